@@ -1,0 +1,210 @@
+"""Generate golden fixtures from the REAL reference modules (run in the build container only).
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+The reference's own PyTorch modules (imported from /root/reference via ref_loader.py) are constructed,
+loaded with the deterministic synthetic state dict `oracle.vgqa_oracle.synth_state_dict(seed)` (so the
+36 M weights are regenerated from a seed instead of stored), and driven exactly as
+`VSTGNet.forward` lines 114-181 drive them (vgqa/core/grounding_net.py), two decoder passes, then
+through `PostProcess` and `single_forward`'s dict building.  Outputs + decision margins are stored.
+
+torch version of the oracle run is recorded in every file (`torch_version`).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from oracle import vgqa_oracle as O  # noqa: E402
+from ref_loader import load_reference, make_cfg  # noqa: E402
+
+# name, T, H, W, L, seed, max_video_len, masked
+CASES = [
+    ("tiny_T3_3x4_L3", 3, 3, 4, 3, 0, 200, False),
+    ("ragged_T6_4x5_L7_masked", 6, 4, 5, 7, 1, 200, True),
+    ("cfg1_T32_7x7_L20_s0", 32, 7, 7, 20, 0, 200, False),
+    ("cfg1_T32_7x7_L20_s1", 32, 7, 7, 20, 1, 200, False),
+    ("cfg2_T64_7x7_L20_s0", 64, 7, 7, 20, 0, 200, False),
+    ("cfg2_T64_7x7_L20_s2", 64, 7, 7, 20, 2, 200, False),
+    ("yaml_T16_14x14_L20_s0", 16, 14, 14, 20, 0, 200, False),
+    ("cfg4_T256_7x7_L20_s0", 256, 7, 7, 20, 0, 256, False),
+    ("cfg5_T128_12x12_L64_s0", 128, 12, 12, 64, 0, 200, False),
+]
+
+
+class RefHotPath(torch.nn.Module):
+    """The reference sub-modules wired as VSTGNet.__init__ wires them (grounding_net.py:55-82)."""
+
+    def __init__(self, R, cfg):
+        super().__init__()
+        self.s_temporal_clas = R.build_TemporalSampling(256)
+        self.t_temporal_clas = R.build_TemporalSampling(256)
+        self.s_spatial_clas = R.build_SpatialActivation(256, cfg.DATASET.APP_NUM)
+        self.t_spatial_clas = R.build_SpatialActivation(256, cfg.DATASET.MOT_NUM)
+        self.ground_encoder = R.build_encoder(cfg)
+        self.ground_decoder = R.build_decoder(cfg)
+        self.temp_embed = R.MLP(256, 256, 2, 2, dropout=0.3)
+        self.bbox_embed = R.MLP(256, 256, 4, 3)
+        self.action_embed = R.MLP(256, 256, 1, 2, dropout=0.3)
+        self.ground_decoder.time_embed2 = self.action_embed
+        self.ground_decoder.decoder.bbox_embed = self.bbox_embed
+        self.theta = 0.45
+        self.R = R
+
+    @torch.no_grad()
+    def forward(self, vis, vid, pos, text, vis_mask, text_mask, iteration_rate=-1):
+        R = self.R
+        T = vis.shape[0]
+        vis_outputs = R.NestedTensor(vis, vis_mask.clone(), [T])
+        text_outputs = (text_mask, text, None)
+        dbg = {}
+        # ---- grounding_net.py:114-163, verbatim control flow ----
+        encoded_info = self.ground_encoder(videos=vis_outputs, vis_pos=pos, texts=text_outputs, vid=vid)
+        l = vid.size(-1) * vid.size(-2)
+        f_vid = encoded_info['encoded_feature'][-l:].permute(1, 2, 0).reshape(vid.size()).detach()
+        f_vis = encoded_info['encoded_feature'][:l].permute(1, 2, 0).reshape(vid.size()).detach()
+        f_text_cls = encoded_info['encoded_feature'][l:-l].mean(1).unsqueeze(0).detach()
+        logits_f_m = self.t_temporal_clas(f_vid, f_text_cls)
+        logits_f_a = self.s_temporal_clas(f_vis, f_text_cls)
+        att_sequences = (logits_f_m.sigmoid() + logits_f_a.sigmoid()) / 2
+        choose_index = torch.nonzero(att_sequences > self.theta).squeeze().tolist()
+        choose_index = [choose_index] if isinstance(choose_index, int) else choose_index
+        choose_index = choose_index or torch.nonzero(att_sequences > 0).squeeze().tolist()
+        dbg["choose_pass1"] = list(choose_index)
+        logits_r_m, att_map_t = self.t_spatial_clas(f_vid[choose_index], f_text_cls[:, :1])
+        logits_r_a, att_map_s = self.s_spatial_clas(f_vis[choose_index], f_text_cls[:, :1])
+        itq = (encoded_info['encoded_feature'][-l:].permute(1, 0, 2)[choose_index] * att_map_t.unsqueeze(2)).mean((0, 1))
+        isq = (encoded_info['encoded_feature'][:l].permute(1, 0, 2)[choose_index] * att_map_s.unsqueeze(2)).mean((0, 1))
+        dbg["itq1"], dbg["isq1"] = itq.clone(), isq.clone()
+        outputs_pos, outputs_time = self.ground_decoder(encoded_info=encoded_info, vis_pos=pos, isq=isq, itq=itq)
+        dbg["pass1_boxes"] = outputs_pos.flatten(1, 2).clone()
+        if iteration_rate < 0:
+            act1 = self.action_embed(outputs_time)[-1].squeeze().sigmoid()
+            dbg["actioness_pass1"] = act1.clone()
+            choose_index = torch.nonzero((act1 > 0.5).int()).squeeze().tolist()
+            choose_index = [choose_index] if isinstance(choose_index, int) else choose_index
+            choose_index = choose_index or torch.nonzero(att_sequences > 0).squeeze().tolist()
+            dbg["choose_pass2"] = list(choose_index)
+            logits_r_a, att_map_s = self.s_spatial_clas(f_vis[choose_index], f_text_cls[:, :1])
+            logits_r_m, att_map_t = self.t_spatial_clas(f_vid[choose_index], f_text_cls[:, :1])
+            itq = (encoded_info['encoded_feature'][-l:].permute(1, 0, 2)[choose_index] * att_map_t.unsqueeze(2)).mean((0, 1))
+            isq = (encoded_info['encoded_feature'][:l].permute(1, 0, 2)[choose_index] * att_map_s.unsqueeze(2)).mean((0, 1))
+            outputs_pos, outputs_time = self.ground_decoder(encoded_info=encoded_info, vis_pos=pos, isq=isq, itq=itq)
+        out = {}
+        outputs_coord = outputs_pos.flatten(1, 2)
+        out["pred_boxes"] = outputs_coord[-1]
+        out["logits_f_m"], out["logits_f_a"] = logits_f_m, logits_f_a
+        out["logits_r_a"], out["logits_r_m"] = logits_r_a, logits_r_m
+        sted = self.temp_embed(outputs_time)
+        actn = self.action_embed(outputs_time)
+        out["pred_sted"], out["pred_actioness"] = sted[-1], actn[-1]
+        out["aux_boxes"], out["aux_sted"], out["aux_actioness"] = outputs_coord, sted, actn
+        out["att_sequences"] = att_sequences.unsqueeze(0)
+        out["pr"] = (0, 0)
+        out["choose_index"] = list(choose_index)
+        dbg["encoded_feature"] = encoded_info["encoded_feature"]
+        dbg["frames_cls"] = encoded_info["frames_cls"]
+        dbg["att_map_s"], dbg["att_map_t"] = att_map_s, att_map_t
+        dbg["itq2"], dbg["isq2"] = itq, isq
+        return out, dbg
+
+
+def load_synth(model: torch.nn.Module, sd_np):
+    """load_state_dict(strict=False) of the synthetic weights; every synthetic key must exist in the
+    reference module with the same shape (this is the §8b weight-name contract check)."""
+    ref_sd = model.state_dict()
+    for k, v in sd_np.items():
+        assert k in ref_sd, f"synthetic key {k} not in reference state_dict"
+        assert tuple(ref_sd[k].shape) == tuple(v.shape), (k, ref_sd[k].shape, v.shape)
+    missing, unexpected = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd_np.items()}, strict=False)
+    assert not unexpected, unexpected
+    return missing
+
+
+masks_for = O.synth_masks
+
+
+def run_case(R, name, T, H, W, L, seed, max_len, masked, outdir):
+    cfg = make_cfg(max_video_len=max_len)
+    torch.manual_seed(0)
+    model = RefHotPath(R, cfg).eval()
+    sd = O.synth_state_dict(seed, max_video_len=max_len)
+    load_synth(model, sd)
+    vis, vid, _, text = O.synth_inputs(seed, T, H, W, L)
+    vis_mask, text_mask = masks_for(masked, T, H, W, L)
+    pos_t = R.PositionEmbeddingSine(128, normalize=True)(R.NestedTensor(torch.from_numpy(vis), torch.from_numpy(vis_mask), [T]))
+    out, dbg = model(torch.from_numpy(vis), torch.from_numpy(vid), pos_t, torch.from_numpy(text),
+                     torch.from_numpy(vis_mask), torch.from_numpy(text_mask))
+    # PostProcess + single_forward dicts (postprocessor.py:14-50; evaluator.py:56-92)
+    ori = (360, 640)
+    frame_ids = list(range(0, 2 * T, 2))
+    sizes = torch.tensor([list(ori)] * T)
+    boxes_px, att, steds, _ = R.PostProcess()(out, sizes, [frame_ids], [T])
+    att_np = out["att_sequences"].numpy()[0]
+    act1 = dbg["actioness_pass1"].numpy()
+    sted = out["pred_sted"].numpy()[0]
+    ls = O.log_softmax(sted[:, 0], 0)[:, None] + O.log_softmax(sted[:, 1], 0)[None, :]
+    ls = np.where(np.triu(np.ones((T, T), bool), 1), ls, -np.inf).reshape(-1)
+    top2 = np.sort(ls)[-2:] if T > 2 else np.array([ls.max() - 1.0, ls.max()])
+    ef = dbg["encoded_feature"].numpy()
+    rec = dict(
+        T=T, H=H, W=W, L=L, seed=seed, max_video_len=max_len, masked=int(masked),
+        torch_version=torch.__version__,
+        pos=pos_t.numpy()[:1] if not masked else pos_t.numpy(),
+        pred_boxes=out["pred_boxes"].numpy(), pred_sted=out["pred_sted"].numpy(),
+        pred_actioness=out["pred_actioness"].numpy(),
+        logits_f_m=out["logits_f_m"].numpy(), logits_f_a=out["logits_f_a"].numpy(),
+        logits_r_a=out["logits_r_a"].numpy(), logits_r_m=out["logits_r_m"].numpy(),
+        att_sequences=out["att_sequences"].numpy(),
+        aux_boxes=out["aux_boxes"].numpy(), aux_sted=out["aux_sted"].numpy(), aux_actioness=out["aux_actioness"].numpy(),
+        pass1_boxes=dbg["pass1_boxes"].numpy(), actioness_pass1=act1,
+        choose_pass1=np.asarray(dbg["choose_pass1"], np.int64), choose_pass2=np.asarray(dbg["choose_pass2"], np.int64),
+        itq1=dbg["itq1"].numpy(), isq1=dbg["isq1"].numpy(), itq2=dbg["itq2"].numpy(), isq2=dbg["isq2"].numpy(),
+        att_map_s=dbg["att_map_s"].numpy(), att_map_t=dbg["att_map_t"].numpy(),
+        frames_cls=dbg["frames_cls"].numpy(),
+        # encoder output: frames 0 and T-1 in full (S,256) as fp16 to keep the fixture small
+        enc_frame0=ef[:, 0].astype(np.float16), enc_frameN=ef[:, T - 1].astype(np.float16),
+        enc_abs_mean=np.float32(np.abs(ef).mean()),
+        post_boxes=boxes_px.numpy(), post_sted=np.asarray(steds, np.int64),
+        ori_size=np.asarray(ori, np.int64), frame_ids=np.asarray(frame_ids, np.int64),
+        margin_theta=np.float32(np.abs(att_np - 0.45).min()),
+        margin_act=np.float32(np.abs(act1 - 0.5).min()),
+        margin_sted_top2=np.float32(top2[-1] - top2[-2]),
+    )
+    np.savez_compressed(os.path.join(outdir, name + ".npz"), **rec)
+    print(f"{name}: K1={len(dbg['choose_pass1'])} K2={len(dbg['choose_pass2'])} sted={steds} "
+          f"margins theta={rec['margin_theta']:.4g} act={rec['margin_act']:.4g} top2={rec['margin_sted_top2']:.4g}")
+
+
+def interp_golden(R, outdir):
+    """Golden I/O for linear_interp / linear_interp_conf (evaluator.py:10-54)."""
+    rng = np.random.Generator(np.random.PCG64(7))
+    fids = [3, 4, 8, 9, 15, 16, 21]
+    boxes = {f: [rng.uniform(0, 500, 4).astype(np.float32).tolist()] for f in fids}
+    conf = {f: [float(rng.uniform())] for f in fids}
+    bi = R.linear_interp({k: [list(v[0])] for k, v in boxes.items()})
+    ci = R.linear_interp_conf({k: list(v) for k, v in conf.items()})
+    np.savez_compressed(os.path.join(outdir, "interp.npz"),
+                        fids=np.asarray(fids), boxes=np.asarray([boxes[f][0] for f in fids], np.float64),
+                        conf=np.asarray([conf[f][0] for f in fids], np.float64),
+                        out_fids=np.asarray(sorted(bi.keys())),
+                        out_boxes=np.asarray([bi[f][0] for f in sorted(bi.keys())], np.float64),
+                        out_conf=np.asarray([ci[f][0] for f in sorted(ci.keys())], np.float64))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    R = load_reference()
+    only = sys.argv[1:]
+    for c in CASES:
+        if only and not any(o in c[0] for o in only):
+            continue
+        run_case(R, *c, outdir=HERE)
+    if not only:
+        interp_golden(R, HERE)

@@ -1,0 +1,106 @@
+"""Import the reference's hot-path modules from /root/reference (THIS container only).
+
+Used by `make_golden.py` and by the optional oracle-vs-reference test; never on the GPU box
+(`/root/reference` does not exist there). Only the modules SURVEY.md §8(c) lists are imported:
+`vgqa.core.decoder.*`, `vgqa.core.language.bert_module`, `vgqa.core.model_utils`,
+`vgqa.core.vision.position_encoding`, `vgqa.core.postprocessor`, `vgqa.training.evaluator`
+(functions only), `vgqa.utils.{training_utils,box_ops}`.
+
+The package `__init__` files of `vgqa`, `vgqa.core`, `vgqa.core.language`, `vgqa.core.vision`,
+`vgqa.training`, `vgqa.utils` pull in decord / ffmpeg / timm / transformers / torchtext, none of which
+the hot path needs, so those packages are registered as bare namespace modules (their `__init__` is
+not executed) and `easydict` gets a 6-line stand-in.
+"""
+import importlib
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+REF_ROOT = os.environ.get("VGQA_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, "vgqa", "core", "decoder"))
+
+
+def _namespace_pkg(name: str, path: str):
+    if name in sys.modules:
+        return sys.modules[name]
+    mod = types.ModuleType(name)
+    mod.__path__ = [path]
+    mod.__package__ = name
+    sys.modules[name] = mod
+    parent, _, child = name.rpartition(".")
+    if parent:
+        setattr(sys.modules[parent], child, mod)
+    return mod
+
+
+def _install_shims():
+    if "easydict" not in sys.modules:
+        ed = types.ModuleType("easydict")
+
+        class EasyDict(dict):
+            def __init__(self, *a, **k):
+                super().__init__(*a, **k)
+                self.__dict__ = self
+
+        ed.EasyDict = EasyDict
+        sys.modules["easydict"] = ed
+    if "tqdm" not in sys.modules:
+        try:
+            import tqdm  # noqa: F401
+        except Exception:
+            tq = types.ModuleType("tqdm")
+            tq.tqdm = lambda x, *a, **k: x
+            sys.modules["tqdm"] = tq
+
+
+def load_reference():
+    """Returns a namespace with the reference classes/functions on the hot path."""
+    if not reference_available():
+        raise RuntimeError(f"reference not found at {REF_ROOT}")
+    _install_shims()
+    v = os.path.join(REF_ROOT, "vgqa")
+    _namespace_pkg("vgqa", v)
+    _namespace_pkg("vgqa.core", os.path.join(v, "core"))
+    _namespace_pkg("vgqa.core.language", os.path.join(v, "core", "language"))
+    _namespace_pkg("vgqa.core.vision", os.path.join(v, "core", "vision"))
+    _namespace_pkg("vgqa.utils", os.path.join(v, "utils"))
+    _namespace_pkg("vgqa.training", os.path.join(v, "training"))
+
+    ns = SimpleNamespace()
+    dec = importlib.import_module("vgqa.core.decoder")
+    ns.build_encoder = dec.build_encoder
+    ns.build_decoder = dec.build_decoder
+    ns.build_TemporalSampling = dec.build_TemporalSampling
+    ns.build_SpatialActivation = dec.build_SpatialActivation
+    mu = importlib.import_module("vgqa.core.model_utils")
+    ns.MLP = mu.MLP
+    ns.gen_sineembed_for_position = mu.gen_sineembed_for_position
+    pe = importlib.import_module("vgqa.core.vision.position_encoding")
+    ns.PositionEmbeddingSine = pe.PositionEmbeddingSine
+    tu = importlib.import_module("vgqa.utils.training_utils")
+    ns.NestedTensor = tu.NestedTensor
+    pp = importlib.import_module("vgqa.core.postprocessor")
+    ns.PostProcess = pp.PostProcess
+    ev = importlib.import_module("vgqa.training.evaluator")
+    ns.linear_interp = ev.linear_interp
+    ns.linear_interp_conf = ev.linear_interp_conf
+    ns.single_forward = ev.single_forward
+    return ns
+
+
+def make_cfg(max_video_len: int = 200, hidden=256, heads=8, ffn=2048, enc_layers=6, dec_layers=6):
+    """Attribute-tree stand-in for the yacs cfg: only the keys the hot path reads at construction
+    (vgqa/config/defaults.py:7,63-72; SOLVER.USE_ATTN :153)."""
+    vstg = SimpleNamespace(HIDDEN=hidden, HEADS=heads, FFN_DIM=ffn, DROPOUT=0.1, ENC_LAYERS=enc_layers,
+                           DEC_LAYERS=dec_layers, QUERY_DIM=4, FROM_SCRATCH=True,
+                           USE_LEARN_TIME_EMBED=False, USE_ACTION=True)
+    return SimpleNamespace(
+        INPUT=SimpleNamespace(MAX_VIDEO_LEN=max_video_len),
+        MODEL=SimpleNamespace(VSTG=vstg),
+        SOLVER=SimpleNamespace(USE_ATTN=False, USE_AUX_LOSS=True),
+        DATASET=SimpleNamespace(APP_NUM=20, MOT_NUM=34),
+    )

@@ -1,0 +1,74 @@
+"""CPU: the numpy oracle (oracle/vgqa_oracle.py) against golden vectors produced by the REAL reference
+modules (tests/golden/make_golden.py).  fp32 vs fp32 → tolerance 2e-4 abs (observed ≤ 5e-6)."""
+import numpy as np
+import pytest
+
+from oracle import vgqa_oracle as O
+from conftest import golden_path
+
+TOL = 2e-4
+SMALL = ["tiny_T3_3x4_L3", "ragged_T6_4x5_L7_masked", "cfg1_T32_7x7_L20_s0", "cfg1_T32_7x7_L20_s1",
+         "cfg2_T64_7x7_L20_s0", "yaml_T16_14x14_L20_s0"]
+
+
+def run_oracle(g):
+    T, H, W, L, seed = (int(g[k]) for k in ("T", "H", "W", "L", "seed"))
+    sd = O.synth_state_dict(seed, max_video_len=int(g["max_video_len"]))
+    vis, vid, _, text = O.synth_inputs(seed, T, H, W, L)
+    vm, tm = O.synth_masks(bool(g["masked"]), T, H, W, L)
+    pos = O.position_embedding_sine(vm)
+    return O.hot_path_forward(sd, vis, vid, pos, text, vm, tm, return_debug=True), pos
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_oracle_matches_reference_golden(name):
+    g = np.load(golden_path(name))
+    out, pos = run_oracle(g)
+    np.testing.assert_allclose(pos[: g["pos"].shape[0]], g["pos"], atol=1e-6)
+    for k in ("pred_boxes", "pred_sted", "pred_actioness", "logits_f_m", "logits_f_a", "logits_r_a",
+              "logits_r_m", "att_sequences"):
+        np.testing.assert_allclose(out[k], g[k], atol=TOL, err_msg=k)
+    assert out["debug"]["choose_pass1"] == g["choose_pass1"].tolist()
+    assert out["debug"]["choose_pass2"] == g["choose_pass2"].tolist()
+    aux_b = np.stack([a["pred_boxes"] for a in out["aux_outputs"]] + [out["pred_boxes"]])
+    np.testing.assert_allclose(aux_b, g["aux_boxes"], atol=TOL)
+    aux_s = np.stack([a["pred_sted"] for a in out["aux_outputs"]] + [out["pred_sted"]])
+    np.testing.assert_allclose(aux_s, g["aux_sted"], atol=TOL)
+    ef = out["debug"]["encoded_feature"]
+    np.testing.assert_allclose(ef[:, 0], g["enc_frame0"].astype(np.float32), atol=4e-3)
+    np.testing.assert_allclose(out["debug"]["frames_cls"], g["frames_cls"], atol=TOL)
+    # PostProcess + frame-id mapping (postprocessor.py:14-50)
+    T = int(g["T"])
+    sizes = np.tile(g["ori_size"][None].astype(np.float32), (T, 1))
+    boxes, _, steds, _ = O.postprocess(out["pred_boxes"], out["pred_sted"], out["att_sequences"], sizes,
+                                       [g["frame_ids"].tolist()], [T])
+    np.testing.assert_allclose(boxes, g["post_boxes"], atol=0.2)  # pixels (boxes×640)
+    assert steds == g["post_sted"].tolist()
+
+
+def test_interp_matches_reference_golden():
+    g = np.load(golden_path("interp"))
+    fids = g["fids"].tolist()
+    bi = O.linear_interp({f: [g["boxes"][i].tolist()] for i, f in enumerate(fids)})
+    ci = O.linear_interp_conf({f: [float(g["conf"][i])] for i, f in enumerate(fids)})
+    assert sorted(bi.keys()) == g["out_fids"].tolist()
+    np.testing.assert_allclose(np.asarray([bi[f][0] for f in sorted(bi)]), g["out_boxes"], rtol=1e-12)
+    np.testing.assert_allclose(np.asarray([ci[f][0] for f in sorted(ci)]), g["out_conf"], rtol=0)
+
+
+def test_interp_edge_cases():
+    assert O.linear_interp({5: [[1, 2, 3, 4]]}) == {5: [[1, 2, 3, 4]]}
+    assert O.linear_interp_conf({}) == {}
+    out = O.linear_interp({0: [[0, 0, 0, 0]], 4: [[4, 8, 12, 16]]})
+    assert out[1] == [[1, 2, 3, 4]] and out[3] == [[3, 6, 9, 12]]
+    c = O.linear_interp_conf({0: [0.1], 5: [0.9]})
+    assert [c[i][0] for i in range(6)] == [0.1, 0.1, 0.1, 0.9, 0.9, 0.9]
+
+
+def test_merge_predict_schema():
+    p1 = ({0: [[0.0, 0.0, 10.0, 10.0]], 4: [[4.0, 4.0, 14.0, 14.0]]}, {0: [0.5], 4: [0.7]}, [0, 5])
+    p2 = ({2: [[2.0, 2.0, 12.0, 12.0]], 6: [[6.0, 6.0, 16.0, 16.0]]}, {2: [0.6], 6: [0.8]}, [2, 7])
+    r = O.merge_predict(p1, p2, fps=2.0)
+    assert r["temporal"] == {"start": 0.0, "end": 3.5, "score": 1.0}
+    assert [t["frame"] for t in r["tube"]] == list(range(7))
+    assert r["tube"][1]["bbox"] == [1.0, 1.0, 11.0, 11.0] and r["tube"][1]["score"] == 0.5
