@@ -1,0 +1,35 @@
+// C-ABI entry points that expose single kernels for unit tests (tests/test_gemm_gpu.py etc.).
+#include <string>
+
+#include "common.h"
+
+namespace vg {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+const char* last_error_cstr() { return g_last_error.c_str(); }
+}  // namespace vg
+
+extern "C" {
+
+const char* vgqa_last_error(void) { return vg::last_error_cstr(); }
+
+// C = epilogue(A · W^T); all pointers are device pointers; see include/vgqa_b200.h.
+int vgqa_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, void* C, int ldc,
+                   int c_f32, const float* bias, int bias_period, int bias_ld, int act, const void* mul,
+                   int ldmul, const void* res, int ldres, const float* ln_w, const float* ln_b, float ln_eps,
+                   void* stream) {
+  try {
+    vg::GemmEpi ep;
+    ep.C = C; ep.ldc = ldc; ep.c_f32 = c_f32; ep.bias = bias; ep.bias_period = bias_period; ep.bias_ld = bias_ld;
+    ep.act = act; ep.mul = static_cast<const vg::bf16*>(mul); ep.ldmul = ldmul;
+    ep.res = static_cast<const vg::bf16*>(res); ep.ldres = ldres; ep.ln_w = ln_w; ep.ln_b = ln_b; ep.ln_eps = ln_eps;
+    vg::gemm_bf16_tn(static_cast<const vg::bf16*>(A), lda, static_cast<const vg::bf16*>(W), ldw, M, N, K, ep,
+                     static_cast<cudaStream_t>(stream));
+    return 0;
+  } catch (const std::exception& e) {
+    vg::set_last_error(e.what());
+    return 1;
+  }
+}
+
+}  // extern "C"

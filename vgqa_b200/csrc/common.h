@@ -1,0 +1,61 @@
+// Host-side shared declarations for the vgqa_b200 CUDA library (internal; the public C-ABI is
+// include/vgqa_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace vg {
+
+typedef __nv_bfloat16 bf16;
+
+void set_last_error(const std::string& s);
+
+struct Error : std::runtime_error {
+  explicit Error(const std::string& s) : std::runtime_error(s) {}
+};
+
+#define VG_CHECK(cond, msg)                                                                         \
+  do {                                                                                              \
+    if (!(cond)) throw ::vg::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + (msg)); \
+  } while (0)
+
+#define VG_CUDA(expr)                                                                               \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      throw ::vg::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + #expr + " -> " + \
+                        cudaGetErrorString(_e));                                                    \
+  } while (0)
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+// Epilogue of the tcgen05 GEMM:  v = acc + bias[(row % bias_period) * bias_ld + col];  v = act(v);
+// v *= mul[row, col];  v += res[row, col];  if (ln_w) v = LayerNorm_row(v) * ln_w + ln_b;  C[row, col] = v.
+struct GemmEpi {
+  void* C = nullptr;
+  int ldc = 0;
+  int c_f32 = 0;  // 0: bf16 output, 1: fp32 output
+  const float* bias = nullptr;
+  int bias_period = 1;
+  int bias_ld = 0;
+  int act = ACT_NONE;
+  const bf16* mul = nullptr;
+  int ldmul = 0;
+  const bf16* res = nullptr;
+  int ldres = 0;
+  const float* ln_w = nullptr;
+  const float* ln_b = nullptr;
+  float ln_eps = 1e-5f;
+};
+
+// C[M,N] = epilogue(A[M,K] (row-major, lda) * W[N,K]^T (row-major, ldw)).  K % 64 == 0, N % 64 == 0.
+void gemm_bf16_tn(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpi& ep,
+                  cudaStream_t stream);
+int gemm_launch_count();  // number of tcgen05 GEMM launches issued so far by this process
+
+}  // namespace vg
