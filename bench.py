@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py — grounding clips/sec on the VGQA hot path (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--clips B] [--impl reference]
+
+A step = one pass of the hot path (encoder → classifiers → 2 decoder passes → heads → PostProcess) over one batch
+of B synthetic clips of BASELINE.json configs[1]: 64 frames @224 (7x7 feature map), 20-token query, 6+6 layers,
+random-init (seeded synthetic) weights.  Prints ONE JSON line (rank 0).
+
+  value        clips/s with the inputs already resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e          clips/s through the C-ABI `vgqa_forward_host` with pinned HOST buffers (H2D + D2H inside the call)
+  roofline     the dominant kernel (tcgen05 FFN GEMM) timed alone with CUDA events: algorithmic FLOPs / duration
+  cpu_baseline the numpy oracle port timed on the host cores on a bounded sample (rank 0, N=1 only)
+  --impl reference : the reference arm = the oracle port on the host cores (the reference itself is PyTorch
+                     source under /root/reference which does not exist on the GPU box)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T, H, W, L = 64, 7, 7, 20
+WORKLOAD = "cfg2 grounding_vidstg.yaml@224: T=64 frames, 7x7 feature map, L=20 text tokens, 6 enc + 6 dec layers, 2 decoder passes"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def oracle_clips_per_sec(n_clips, seed=0):
+    """The numpy oracle port on the host cores (all BLAS threads): seconds per clip of the same workload."""
+    from oracle import vgqa_oracle as O
+    sd = O.synth_state_dict(seed)
+    times = []
+    for i in range(n_clips):
+        vis, vid, pos, text = O.synth_inputs(i, T, H, W, L)
+        t0 = time.perf_counter()
+        O.hot_path_forward(sd, vis, vid, pos, text)
+        times.append(time.perf_counter() - t0)
+    return n_clips / sum(times), times
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    t_steps = []
+    from oracle import vgqa_oracle as O
+    sd = O.synth_state_dict(0)
+    for i in range(args.warmup + args.steps):
+        vis, vid, pos, text = O.synth_inputs(i, T, H, W, L)
+        t0 = time.perf_counter()
+        O.hot_path_forward(sd, vis, vid, pos, text)
+        if i >= args.warmup:
+            t_steps.append(time.perf_counter() - t0)
+    v = len(t_steps) / sum(t_steps)
+    line = {"impl": "reference", "metric": "grounding clips/sec (64f@224)", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(t_steps) / len(t_steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "clips_per_step": 1},
+            "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+                             "sample": f"{len(t_steps)} clips of the same workload, one per step (numpy oracle port of the reference modules)"},
+            "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def time_dominant_kernel(B, pk):
+    """FFN1 GEMM of one encoder layer over the whole batch — gemm_tc_kernel<256>, M = B*T*S, N = 2048, K = 256."""
+    import torch
+    from vgqa_b200 import _lib
+    Lb = _lib.lib()
+    S = 2 * H * W + L
+    M, N, K = B * T * S, 2048, 256
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    Wt = (torch.randn(N, K, device="cuda") / 16).bfloat16()
+    bias = torch.zeros(N, device="cuda")
+    C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def launch():
+        _lib.check(Lb.vgqa_gemm_bf16(_lib.ptr(A), K, _lib.ptr(Wt), K, M, N, K, _lib.ptr(C), N, 0, _lib.ptr(bias), 1, N, 1,
+                                     None, 0, None, 0, None, None, 1e-5, st))
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) / reps * 1e-3
+    flops = 2.0 * M * N * K
+    ach = flops / dt / 1e12
+    return {"kernel": "gemm_tc_kernel<256> (encoder FFN linear1+ReLU, M=%d N=2048 K=256)" % M, "bound": "tensor",
+            "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+            "traffic": None, "peak_source": pk["source"] + ", burst (kernel timed alone)",
+            "algorithmic_flops_per_launch": flops, "launch_ms": dt * 1e3,
+            "hbm_gbs_at_algorithmic_bytes": (M * K * 2 + M * N * 2 + N * K * 2) / dt / 1e9}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--clips", type=int, default=64, help="clips per step per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-clips", type=int, default=4, help="clips of the bounded CPU-baseline sample")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from oracle import vgqa_oracle as O      # synthetic weights/inputs generator + cpu_baseline leg only
+    from vgqa_b200.engine import GroundingEngine, reference_flops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: vgqa_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.clips
+    pk = peaks()
+    eng = GroundingEngine(O.synth_state_dict(0), max_clips=B, max_frames=T, max_hw=H * W, max_text=L,
+                          use_cuda_graph=not args.no_graph)
+    # synthetic inputs: 8 distinct seeded clips tiled to B (per-rank offset), fp32 reference layouts
+    base = [O.synth_inputs(rank * 8 + i, T, H, W, L) for i in range(8)]
+    pos = torch.from_numpy(base[0][2][:1].copy())
+    h_vis = torch.from_numpy(np.stack([base[i % 8][0] for i in range(B)])).pin_memory()
+    h_vid = torch.from_numpy(np.stack([base[i % 8][1] for i in range(B)])).pin_memory()
+    h_text = torch.from_numpy(np.stack([base[i % 8][3][:, 0, :] for i in range(B)])).pin_memory()
+    h_sizes = torch.tensor([[360.0, 640.0]] * B).pin_memory()
+    h_pos = pos.pin_memory()
+    d_vis, d_vid, d_text, d_pos, d_sizes = (x.cuda() for x in (h_vis, h_vid, h_text, h_pos, h_sizes))
+    want = ["pred_boxes", "pred_sted", "pred_actioness", "att_sequences", "boxes_px", "sted_idx", "logits_r_a", "logits_r_m"]
+    d_outs = eng.alloc_outputs(B, T, H, W, L, want)
+    h_outs = eng.alloc_outputs(B, T, H, W, L, want, host=True)
+
+    def step_dev():
+        eng.forward(d_vis, d_vid, d_text, d_pos, ori_sizes_hw=d_sizes, outs=d_outs)
+
+    def step_host():
+        eng.forward_host(h_vis, h_vid, h_text, h_pos, ori_sizes_hw=h_sizes, outs=h_outs)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, device_events=True):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        sec = e0.elapsed_time(e1) * 1e-3 if device_events else wall
+        barrier()
+        if world > 1:
+            t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        return sec
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sec = timed(step_dev, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.last_launch_count
+    # e2e: host buffers through the C-ABI; the call synchronises, so wall clock == device time of the whole call
+    sec_e2e = timed(step_host, args.steps, device_events=False)
+    total_clips = B * world * args.steps
+    value = total_clips / sec
+    e2e = total_clips / sec_e2e
+    h2d = int(h_vis.numel() * 4 * 2 + h_text.numel() * 4 + h_pos.numel() * 4 + h_sizes.numel() * 4)
+    d2h = int(sum(v.numel() * v.element_size() for v in h_outs.values()))
+
+    if rank == 0:
+        flops_clip = reference_flops(T, H, W, L)
+        roof = time_dominant_kernel(B, pk)
+        line = {
+            "metric": "grounding clips/sec (64f@224, bf16)", "value": value, "unit": "clips/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "clips_per_step_per_gpu": B, "T": T, "H": H, "W": W, "L": L,
+                       "l2_policy": f"inputs larger than L2: {h2d / 1e6:.0f} MB of fp32 features per step",
+                       "cuda_graph": not args.no_graph, "parallelism": f"clips partitioned over {world} GPU(s), no data-path collective"},
+            "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * sec_e2e / args.steps},
+            "gpu_launches": int(launches) * args.steps,
+            "gpu_launches_per_step": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "algorithmic_gflop_per_clip": flops_clip / 1e9,
+            "algorithmic_tflops_whole_path": value / world * flops_clip / 1e12,
+            "frac_of_sustained_bf16_peak_whole_path": value / world * flops_clip / 1e12 / pk["bf16_tflops_sustained"],
+        }
+        if world == 1:
+            v, times = oracle_clips_per_sec(args.cpu_clips)
+            line["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{args.cpu_clips} clips of the same workload (numpy oracle port, fp32, all BLAS threads), {sum(times):.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+/* vgqa_b200 — C-ABI of the B200-native (sm_100a) VGQA grounding hot path.
+ *
+ * This is the drop-in boundary for the path BASELINE.json's north_star names: everything
+ * `VSTGNet.forward` does after the ResNet101 / Video-Swin / RoBERTa feature extractors
+ * (reference vgqa/core/grounding_net.py:114-202) plus `PostProcess.forward`
+ * (vgqa/core/postprocessor.py:14-50).  The reference has no FFI of its own (it is pure Python); the seam
+ * is its Python factory layer (vgqa/core/decoder/__init__.py:6-20, vgqa/core/__init__.py:8-54).  The Python
+ * mirror of that seam lives in vgqa_b200/modules.py and binds these symbols with ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions: plain pointers and sizes only; every entry point returns 0 on success and non-zero on
+ * failure, in which case vgqa_last_error() (thread-local) describes the problem — the Python side raises
+ * RuntimeError / AssertionError like the reference's asserts do.  No allocation happens inside
+ * vgqa_forward(): all workspace is owned by the context.  One context per device and per thread.
+ */
+#ifndef VGQA_B200_H_
+#define VGQA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vgqa_ctx vgqa_ctx;
+
+/* Model hyper-parameters (reference: vgqa/config/defaults.py:63-72, :7, :86-87) and workspace capacity. */
+typedef struct {
+  int enc_layers;    /* MODEL.VSTG.ENC_LAYERS (6) */
+  int dec_layers;    /* MODEL.VSTG.DEC_LAYERS (6) */
+  int hidden;        /* MODEL.VSTG.HIDDEN — must be 256 */
+  int heads;         /* MODEL.VSTG.HEADS  — must be 8   */
+  int ffn_dim;       /* MODEL.VSTG.FFN_DIM (2048), multiple of 256 */
+  int app_num;       /* DATASET.APP_NUM (20) — vocab of s_spatial_clas */
+  int mot_num;       /* DATASET.MOT_NUM (34) — vocab of t_spatial_clas */
+  int max_video_len; /* INPUT.MAX_VIDEO_LEN: the `te` buffers have max_video_len+1 rows */
+  int max_clips;     /* capacity: clips per forward call                                   */
+  int max_frames;    /* capacity: frames per clip (T), <= max_video_len + 1                */
+  int max_hw;        /* capacity: feature-map tokens per frame (H*W)                       */
+  int max_text;      /* capacity: text tokens (L)                                          */
+  int use_cuda_graph; /* 1: capture each (shape, pointer set) once and replay it           */
+} vgqa_config;
+
+/* Inputs of one forward call: `clips` independent clips (the reference is batch-1; a batch is N independent
+ * B=1 forwards, grounding_net.py:108-110).  All pointers are DEVICE pointers for vgqa_forward() and HOST
+ * pointers for vgqa_forward_host().  Layouts are the reference's own (NCHW fp32):
+ *   vis, vid : [clips, T, 256, H, W]  = input_proj(ResNet101 feats), input_proj2(Video-Swin feats)
+ *   text     : [clips, L, 256]        = text_encoder resizer output (reference shape (L,1,256) per clip)
+ *   pos      : [pos_frames, 256, H, W] PositionEmbeddingSine; pos_frames = 1 (shared by every frame — the case
+ *              of all-False masks) or clips*T (per frame)
+ *   vis_mask : [clips*T, H*W] uint8 (1 = padded) or NULL; text_mask: [clips, L] uint8 or NULL
+ *   ori_sizes_hw : [clips, 2] fp32 (h, w) for PostProcess box scaling, or NULL (boxes_px is then not written)
+ *   force_choose1/2 : optional [clips, T] fp32 0/1 masks overriding the pass-1 / pass-2 frame selection
+ *              (parity tests feed the reference's decisions through these); NULL in production.       */
+typedef struct {
+  int clips, T, H, W, L;
+  const float* vis;
+  const float* vid;
+  const float* text;
+  const float* pos;
+  int pos_frames;
+  const uint8_t* vis_mask;
+  const uint8_t* text_mask;
+  const float* ori_sizes_hw;
+  const float* force_choose1;
+  const float* force_choose2;
+  int iteration_rate; /* < 0 (inference): two decoder passes; >= 0: one pass (grounding_net.py:143) */
+} vgqa_inputs;
+
+/* Outputs (fp32 unless noted); any pointer may be NULL to skip that output.
+ *   pred_boxes [clips,T,4] cxcywh in (0,1); pred_sted [clips,T,2]; pred_actioness [clips,T];
+ *   logits_f_m / logits_f_a [clips,T]; logits_r_a [clips,app_num]; logits_r_m [clips,mot_num];
+ *   att_sequences [clips,T]; aux_boxes [dec_layers,clips,T,4]; aux_sted [dec_layers,clips,T,2];
+ *   aux_actioness [dec_layers,clips,T]; choose1 / choose2 [clips,T] 0/1 (frames selected in pass 1 / 2);
+ *   actioness_pass1 [clips,T] (sigmoid, pass 1); boxes_px [clips,T,4] xyxy pixels (PostProcess);
+ *   sted_idx int32 [clips,2] = argmax (start,end) frame indices (PostProcess);
+ *   encoded_feature [clips*T, S, 256] fp32 (frame-major; reference layout is (S,T,256)); frames_cls [clips*T,256] */
+typedef struct {
+  float* pred_boxes;
+  float* pred_sted;
+  float* pred_actioness;
+  float* logits_f_m;
+  float* logits_f_a;
+  float* logits_r_a;
+  float* logits_r_m;
+  float* att_sequences;
+  float* aux_boxes;
+  float* aux_sted;
+  float* aux_actioness;
+  float* choose1;
+  float* choose2;
+  float* actioness_pass1;
+  float* boxes_px;
+  int32_t* sted_idx;
+  float* encoded_feature;
+  float* frames_cls;
+} vgqa_outputs;
+
+const char* vgqa_last_error(void);
+
+/* Lifecycle. vgqa_set_weight copies one tensor of the reference state_dict (HOST fp32, reference key name,
+ * e.g. "ground_encoder.encoder.spatial_layers.0.self_attn.in_proj_weight"); unknown / unused keys are accepted
+ * and ignored (load_state_dict(strict=False) semantics, vgqa/inference/grounding.py:102-120).
+ * vgqa_finalize_weights packs them for the kernels (bf16, fused / absorbed layouts, constant tables) and fails
+ * if a key the hot path reads is missing. */
+int vgqa_create(const vgqa_config* cfg, vgqa_ctx** out);
+void vgqa_destroy(vgqa_ctx* ctx);
+int vgqa_set_weight(vgqa_ctx* ctx, const char* name, const float* data, const int64_t* shape, int ndim);
+int vgqa_finalize_weights(vgqa_ctx* ctx);
+
+/* The hot path on device-resident inputs/outputs, enqueued on `stream` (cudaStream_t). */
+int vgqa_forward(vgqa_ctx* ctx, const vgqa_inputs* in, const vgqa_outputs* out, void* stream);
+/* Same with HOST buffers: stages through pinned memory, H2D, forward, D2H, synchronises. */
+int vgqa_forward_host(vgqa_ctx* ctx, const vgqa_inputs* in, const vgqa_outputs* out);
+
+/* Counters: kernels launched by the last vgqa_forward call (graph replays count the captured launches). */
+int vgqa_last_launch_count(const vgqa_ctx* ctx);
+/* Algorithmic hot-path FLOPs per clip at (T,H,W,L) by the reference's op count (SURVEY.md §8d closed form). */
+double vgqa_reference_flops(int T, int H, int W, int L, int enc_layers, int dec_layers, int ffn_dim, int passes);
+
+/* Single-kernel entry points (unit tests; also usable as building blocks).  Device pointers, bf16 data. */
+int vgqa_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, void* C, int ldc, int c_f32,
+                   const float* bias, int bias_period, int bias_ld, int act, const void* mul, int ldmul,
+                   const void* res, int ldres, const float* ln_w, const float* ln_b, float ln_eps, void* stream);
+int vgqa_mha32(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int groups,
+               int Sq, int Sk, const uint8_t* kmask, float scale, void* stream);
+int vgqa_xattn1(const void* qt, const void* mem, long long frame_stride_rows, int F, int Mk, const void* posk,
+                long long posk_fstride, const void* q2, const void* kpos, int ldkpos, long long kpos_fstride,
+                const uint8_t* kmask, int ldmask, float scale, void* ctx_out, float* att_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGQA_B200_H_ */

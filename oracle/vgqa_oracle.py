@@ -128,7 +128,7 @@ def position_embedding_sine(mask: np.ndarray, num_pos_feats: int = 128, temperat
     pos_y = y_embed[:, :, :, None] / dim_t
     pos_x = np.stack((np.sin(pos_x[..., 0::2]), np.cos(pos_x[..., 1::2])), axis=4).reshape(*pos_x.shape[:3], -1)
     pos_y = np.stack((np.sin(pos_y[..., 0::2]), np.cos(pos_y[..., 1::2])), axis=4).reshape(*pos_y.shape[:3], -1)
-    return np.concatenate((pos_y, pos_x), axis=3).transpose(0, 3, 1, 2).astype(F32)
+    return np.ascontiguousarray(np.concatenate((pos_y, pos_x), axis=3).transpose(0, 3, 1, 2), dtype=F32)
 
 
 def seq_embedding_sine(max_len: int, d_model: int = 256) -> np.ndarray:
@@ -617,17 +617,23 @@ def hot_path_param_shapes(enc_layers=6, dec_layers=6, d=256, ffn=2048, max_video
 
 
 def synth_state_dict(seed: int = 0, **kw) -> Dict[str, np.ndarray]:
-    """Deterministic synthetic weights (numpy PCG64 — identical on every machine, no torch RNG):
-    matrices ~ xavier-uniform, biases ~ U(-0.05,0.05), LayerNorm weight ~ 1+U(-0.1,0.1);
-    `time_embed.te` is the real sine table. Used instead of the reference's torch init so that golden
-    fixtures stay small (the 36 M weights are regenerated, never stored)."""
+    """Deterministic synthetic weights (numpy PCG64 — identical on every machine, no torch RNG) with the SCALES of
+    the reference's own random init: encoder / decoder matrices ~ xavier_uniform (modal_encoder.py:36-39,
+    query_decoder.py:71-74); classifier, bbox/temp/action-head matrices ~ nn.Linear default U(±1/sqrt(fan_in))
+    (they are built outside / attached after the xavier reset, grounding_net.py:55-82).  Unlike the reference init,
+    biases are non-zero U(±0.05) and LayerNorm gains are 1+U(±0.1) so that every parameter is exercised.
+    `time_embed.te` is the real sine table.  Used instead of the reference's torch init so that golden fixtures
+    stay small (the 36 M weights are regenerated from the seed, never stored)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     sd: Dict[str, np.ndarray] = {}
     for name, shp in hot_path_param_shapes(**kw).items():
         if name.endswith("time_embed.te"):
             sd[name] = seq_embedding_sine(shp[0], shp[2])
         elif len(shp) >= 2:
-            bound = math.sqrt(6.0 / (shp[0] + shp[1]))
+            if name.startswith(("ground_encoder.", "ground_decoder.")):
+                bound = math.sqrt(6.0 / (shp[0] + shp[1]))
+            else:
+                bound = 1.0 / math.sqrt(shp[1])
             sd[name] = rng.uniform(-bound, bound, size=shp).astype(F32)
         elif ("norm" in name.lower() and name.endswith(".weight")) or name.endswith(("pos_fc.0.weight", "pos_fc.4.weight")):
             sd[name] = (1.0 + rng.uniform(-0.1, 0.1, size=shp)).astype(F32)

@@ -1,7 +1,7 @@
 // C-ABI entry points that expose single kernels for unit tests (tests/test_gemm_gpu.py etc.).
 #include <string>
 
-#include "common.h"
+#include "kernels.h"
 
 namespace vg {
 static thread_local std::string g_last_error;
@@ -25,6 +25,33 @@ int vgqa_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N,
     ep.res = static_cast<const vg::bf16*>(res); ep.ldres = ldres; ep.ln_w = ln_w; ep.ln_b = ln_b; ep.ln_eps = ln_eps;
     vg::gemm_bf16_tn(static_cast<const vg::bf16*>(A), lda, static_cast<const vg::bf16*>(W), ldw, M, N, K, ep,
                      static_cast<cudaStream_t>(stream));
+    return 0;
+  } catch (const std::exception& e) {
+    vg::set_last_error(e.what());
+    return 1;
+  }
+}
+
+int vgqa_mha32(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int groups,
+               int Sq, int Sk, const uint8_t* kmask, float scale, void* stream) {
+  try {
+    vg::mha32(static_cast<const vg::bf16*>(Q), ldq, static_cast<const vg::bf16*>(K), ldk, static_cast<const vg::bf16*>(V),
+              ldv, static_cast<vg::bf16*>(O), ldo, groups, Sq, Sk, kmask, scale, static_cast<cudaStream_t>(stream));
+    return 0;
+  } catch (const std::exception& e) {
+    vg::set_last_error(e.what());
+    return 1;
+  }
+}
+
+int vgqa_xattn1(const void* qt, const void* mem, long long frame_stride_rows, int F, int Mk, const void* posk,
+                long long posk_fstride, const void* q2, const void* kpos, int ldkpos, long long kpos_fstride,
+                const uint8_t* kmask, int ldmask, float scale, void* ctx_out, float* att_out, void* stream) {
+  try {
+    vg::xattn1(static_cast<const vg::bf16*>(qt), static_cast<const vg::bf16*>(mem), frame_stride_rows, F, Mk,
+               static_cast<const vg::bf16*>(posk), posk_fstride, static_cast<const vg::bf16*>(q2),
+               static_cast<const vg::bf16*>(kpos), ldkpos, kpos_fstride, kmask, ldmask, scale,
+               static_cast<vg::bf16*>(ctx_out), att_out, static_cast<cudaStream_t>(stream));
     return 0;
   } catch (const std::exception& e) {
     vg::set_last_error(e.what());

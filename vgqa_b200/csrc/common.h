@@ -35,7 +35,7 @@ struct Error : std::runtime_error {
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
 // Epilogue of the tcgen05 GEMM:  v = acc + bias[(row % bias_period) * bias_ld + col];  v = act(v);
-// v *= mul[row, col];  v += res[row, col];  if (ln_w) v = LayerNorm_row(v) * ln_w + ln_b;  C[row, col] = v.
+// v *= mul[row, col];  v += res[row, col] + res32[row, col];  if (ln_w) v = LayerNorm_row(v) * ln_w + ln_b;  C[row, col] = v.
 struct GemmEpi {
   void* C = nullptr;
   int ldc = 0;
@@ -48,6 +48,10 @@ struct GemmEpi {
   int ldmul = 0;
   const bf16* res = nullptr;
   int ldres = 0;
+  const float* res32 = nullptr;  // fp32 residual (added like `res`)
+  int ldres32 = 0;
+  float* C32 = nullptr;          // optional second, fp32 copy of the output (the fp32 residual stream)
+  int ldc32 = 0;
   const float* ln_w = nullptr;
   const float* ln_b = nullptr;
   float ln_eps = 1e-5f;

@@ -39,12 +39,14 @@ struct GemmCfg {
 
 struct EpiDev {
   void* C;
+  float* C32;
+  const float* res32;
   const float* bias;
   const bf16* mul;
   const bf16* res;
   const float* ln_w;
   const float* ln_b;
-  int ldc, c_f32, bias_period, bias_ld, act, ldmul, ldres;
+  int ldc, c_f32, bias_period, bias_ld, act, ldmul, ldres, ldres32, ldc32;
   float ln_eps;
 };
 
@@ -87,9 +89,22 @@ __device__ __forceinline__ void epi_transform(float (&v)[32], const EpiDev& ep, 
       v[8 * i + 4] += c.x; v[8 * i + 5] += c.y; v[8 * i + 6] += d.x; v[8 * i + 7] += d.y;
     }
   }
+  if (ep.res32 != nullptr) {
+    const float4* r4 = reinterpret_cast<const float4*>(ep.res32 + (size_t)row * ep.ldres32 + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 r = __ldg(r4 + i);
+      v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+    }
+  }
 }
 
 __device__ __forceinline__ void epi_store(const float (&v)[32], const EpiDev& ep, int row, int col0) {
+  if (ep.C32 != nullptr) {
+    float4* c4 = reinterpret_cast<float4*>(ep.C32 + (size_t)row * ep.ldc32 + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
   if (ep.c_f32) {
     float4* c4 = reinterpret_cast<float4*>(static_cast<float*>(ep.C) + (size_t)row * ep.ldc + col0);
 #pragma unroll
@@ -347,6 +362,7 @@ void gemm_bf16_tn(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, 
   ep.C = e.C; ep.bias = e.bias; ep.mul = e.mul; ep.res = e.res; ep.ln_w = e.ln_w; ep.ln_b = e.ln_b;
   ep.ldc = e.ldc; ep.c_f32 = e.c_f32; ep.bias_period = e.bias_period > 0 ? e.bias_period : 1;
   ep.bias_ld = e.bias_ld; ep.act = e.act; ep.ldmul = e.ldmul; ep.ldres = e.ldres; ep.ln_eps = e.ln_eps;
+  ep.C32 = e.C32; ep.ldc32 = e.ldc32; ep.res32 = e.res32; ep.ldres32 = e.ldres32;
   if (e.ln_w != nullptr) {
     VG_CHECK(N == 256, "gemm: the fused LayerNorm epilogue needs N == 256");
     launch_gemm<256>(A, lda, W, ldw, M, N, K, ep, stream);

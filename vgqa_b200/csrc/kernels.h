@@ -1,0 +1,55 @@
+// Launchers of the non-GEMM kernels (attention.cu, small.cu). Internal header.
+#pragma once
+#include "common.h"
+
+namespace vg {
+
+// ---- attention.cu
+void mha32(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int groups,
+           int Sq, int Sk, const uint8_t* kmask, float scale, cudaStream_t stream);
+void xattn1(const bf16* qt, const bf16* mem, long long frame_stride_rows, int F, int Mk, const bf16* posk,
+            long long posk_fstride, const bf16* q2, const bf16* kpos, int ldkpos, long long kpos_fstride,
+            const uint8_t* kmask, int ldmask, float scale, bf16* ctx, float* att, cudaStream_t stream);
+
+// ---- small.cu
+// NCHW fp32 features → token-major bf16 rows: X[(f*S + tok0 + p), c] = in[f, c, p]   (in may be broadcast: fstride 0)
+void nchw_to_tokens(const float* in, long long in_fstride, bf16* X, float* X32, int F, int S, int tok0, int P,
+                    cudaStream_t st);
+// X[(f*S + tok0 + l), :] = text[(f / T), l, :]   (text == nullptr → zeros)
+void text_to_tokens(const float* text, bf16* X, float* X32, int F, int T, int S, int tok0, int L, cudaStream_t st);
+// encoded_mask[f, :] = [vis_mask (with [f,0]=0) | text_mask[f/T] | vis_mask]
+void build_encoded_mask(const uint8_t* vis_mask, const uint8_t* text_mask, uint8_t* out, int F, int T, int P, int L,
+                        cudaStream_t st);
+// Xf = LayerNorm(X); frames_cls[f] = mean_s Xf; pool_vis/vid[f] = mean over the P vis / vid tokens
+void enc_finalize(const float* X32, const float* w, const float* b, float eps, bf16* Xf, float* frames_cls,
+                  bf16* pool_vis, bf16* pool_vid, float* pool_vis32, float* pool_vid32, int F, int S, int P, int L,
+                  cudaStream_t st);
+// ftext[b,l,:] = mean_t Xf[(b*T+t)*S + P + l, :];  q0[f,:] = ftext[f/T, 0, :]
+void text_mean(const bf16* Xf, bf16* ftext, bf16* q0, float* q0_32, int B, int T, int S, int P, int L, cudaStream_t st);
+// y[r, j] = act(x[r,:256] · w[j,:] + b[j]), j < N <= 64; act: 0 none, 1 sigmoid
+void rowvec_head(const bf16* x, int ldx, const float* w, const float* b, float* y, int ldy, int rows, int N, int act,
+                 cudaStream_t st);
+void select_pass1(const float* lfm, const float* lfa, float theta, const float* force_w, float* att, float* w,
+                  float* K, int B, int T, cudaStream_t st);
+void select_pass2(const float* act_sigmoid, const float* force_w, float* w, float* K, int B, int T, cudaStream_t st);
+// out[b, j] = sum_t w[b,t] x[(b,t), j] / K[b]
+void masked_mean_rows(const float* x, int ldx, const float* w, const float* K, float* out, int B, int T, int N,
+                      cudaStream_t st);
+// part[f, c] = w[f] * sum_p att[f,p] * Xf[(f*S + tok0 + p), c]
+void seed_partial(const bf16* Xf, const float* att, const float* w, float* part, int F, int S, int tok0, int P,
+                  cudaStream_t st);
+// q[b, c] = sum_t part[(b,t), c] / (K[b] * P);  tgt[(b,t), c] = bf16(q[b,c])
+void seed_reduce(const float* part, const float* K, float* q, bf16* tgt, int ldt, float* tgt32, int B, int T, int P,
+                 cudaStream_t st);
+// boxes[f] = sigmoid(BertLN4(relu(W · BertLN256(frames_cls[f]) + b)))
+void pos_fc_boxes(const float* frames_cls, const float* ln0w, const float* ln0b, const float* W, const float* b,
+                  const float* ln4w, const float* ln4b, float* boxes, int F, cudaStream_t st);
+void sine_embed(const float* boxes, bf16* sine, int F, cudaStream_t st);
+void ln_rows(const float* x, int ldx, const float* w, const float* b, float eps, bf16* y, int ldy, int rows,
+             cudaStream_t st);
+void copy_cols_bf16(const bf16* src, int lds, bf16* dst, int ldd, int rows, int cols, cudaStream_t st);
+// PostProcess (postprocessor.py:14-50): boxes → xyxy px (clamped), (start,end) = argmax_{s<e} ls[s] + le[e]
+void postprocess(const float* boxes, const float* sted, const float* sizes_hw, float* boxes_px, int* sted_idx, int B,
+                 int T, cudaStream_t st);
+
+}  // namespace vg

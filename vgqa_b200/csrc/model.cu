@@ -1,0 +1,990 @@
+// Context, weight packing and the forward orchestration of the grounding hot path.
+//
+// Restates VSTGNet.forward lines 114-202 (vgqa/core/grounding_net.py) + PostProcess on top of the kernels in
+// gemm_tc.cu / attention.cu / small.cu.  One launch sequence serves a whole batch of clips: every Linear is a
+// tcgen05 GEMM over (clips x frames [x tokens]) rows, the reference's host syncs (`nonzero().tolist()`,
+// grounding_net.py:126-128,144-150; `.item()`, postprocessor.py:44) are replaced by on-device 0/1 frame
+// weights, and the sequence is captured once into a CUDA graph per shape.
+//
+// Algebraic restructuring done at weight-pack time (fp32/fp64 on the host, then rounded to bf16):
+//   * positional adds are folded into fp32 bias tables: (x + pos) Wqk = x Wqk + (pos Wqk)     [encoder]
+//     and (tgt + te) Wqk = tgt Wqk + (te Wqk)                                                [TimeDecoder]
+//   * PosDecoder self-attention: the seven sa_* projections are multiplied into nn.MultiheadAttention's
+//     in_proj (query_decoder.py:282-294) → one K=512 GEMM over [tgt | query_pos] plus a te-table
+//   * every one-query-per-frame cross-attention has its key projection absorbed into the query
+//     (q~_h = Wk_h^T q_h) and its value projection into the output projection (W_vo = Wo · blockdiag(Wv_h)),
+//     so the memory-side Linear layers are never executed (attention.cu: xattn1).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/vgqa_b200.h"
+#include "kernels.h"
+
+namespace vg {
+
+const char* last_error_cstr();
+
+// ------------------------------------------------------------------------------------------------ host tensors
+struct HostT {
+  std::vector<int64_t> shape;
+  std::vector<float> v;
+  int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+static void parallel_for(int n, const std::function<void(int)>& fn) {
+  int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+  nt = std::min(nt, n);
+  if (nt <= 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&, t] { for (int i = t; i < n; i += nt) fn(i); });
+  for (auto& x : th) x.join();
+}
+
+// C[m,n] = A[m,k] * B[k,n]  (row-major, fp32 in, double accumulate)
+static std::vector<float> matmul(const float* A, const float* B, int m, int k, int n) {
+  std::vector<float> C((size_t)m * n);
+  parallel_for(m, [&](int i) {
+    std::vector<double> acc(n, 0.0);
+    for (int p = 0; p < k; ++p) {
+      const double a = A[(size_t)i * k + p];
+      const float* b = B + (size_t)p * n;
+      for (int j = 0; j < n; ++j) acc[j] += a * b[j];
+    }
+    for (int j = 0; j < n; ++j) C[(size_t)i * n + j] = (float)acc[j];
+  });
+  return C;
+}
+// y[m] = A[m,k] x[k] (+ b)
+static std::vector<float> matvec(const float* A, const float* x, const float* b, int m, int k) {
+  std::vector<float> y(m);
+  for (int i = 0; i < m; ++i) {
+    double acc = b ? b[i] : 0.0;
+    for (int p = 0; p < k; ++p) acc += (double)A[(size_t)i * k + p] * x[p];
+    y[i] = (float)acc;
+  }
+  return y;
+}
+
+// ------------------------------------------------------------------------------------------------ device arena
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, off = 0;
+  bool dry = false;  // dry run: only measure
+  void init(size_t bytes) {
+    VG_CUDA(cudaMalloc(&base, bytes));
+    VG_CUDA(cudaMemset(base, 0, bytes));
+    cap = bytes; off = 0; dry = false;
+  }
+  void* alloc(size_t bytes) {
+    off = (off + 255) & ~size_t(255);
+    if (dry) { off += bytes; return nullptr; }
+    VG_CHECK(off + bytes <= cap, "device arena exhausted");
+    void* p = base + off;
+    off += bytes;
+    return p;
+  }
+  template <class T> T* get(size_t n) { return static_cast<T*>(alloc(n * sizeof(T))); }
+  void release() { if (base) cudaFree(base); base = nullptr; }
+};
+
+struct Lin { bf16* W = nullptr; float* b = nullptr; int N = 0, K = 0; };
+struct LNp { float* w = nullptr; float* b = nullptr; };
+struct EncLayer { Lin qkv, tab, out, ff1, ff2; LNp ln1, ln2; };
+struct TsLayer { Lin q, o, inter, outp; LNp ln_a, ln_o; int kv_off; };
+struct SaLayer { Lin qabs, vo, inter, outp; LNp ln_a, ln_o; };
+struct Head { Lin t; LNp ln; float* dw = nullptr; float* db = nullptr; int vocab = 0; };
+struct TimeLayer { Lin qkv, out, qabs, vo, ff1, ff2; LNp ln1, ln3, ln4; float* tab = nullptr; };
+struct PosLayer { Lin sa, sa_out, q, sine, qabs, vo, ff1, ff2; LNp ln1, ln3, ln4; float* tab_sa = nullptr; };
+struct Mlp2 { Lin l0; float* w1 = nullptr; float* b1 = nullptr; int n1 = 0; };
+
+}  // namespace vg
+
+using namespace vg;
+
+struct vgqa_ctx {
+  vgqa_config cfg;
+  int device = 0;
+  bool finalized = false;
+  std::unordered_map<std::string, HostT> sd;
+  Arena warena, ws;
+  // ---- packed weights
+  std::vector<EncLayer> enc;
+  LNp enc_norm;
+  TsLayer ts[2][2];  // [0]=t (vid tokens), [1]=s (vis tokens)
+  Lin ts_kv;         // [2 cls * 2 layers * 512, 256] over f_text_cls
+  Head ts_head[2];
+  SaLayer sa[2][2];
+  Head sa_head[2];
+  std::vector<TimeLayer> tl;
+  std::vector<PosLayer> pl;
+  LNp time_norm;
+  Lin kpos_all;  // [dec_layers*256, 256]
+  Lin rph0, rph1, qs0, qs1, bb0, bb1;
+  float *bb2w = nullptr, *bb2b = nullptr;
+  Mlp2 temp_embed, action_embed;
+  float *pfc_ln0w, *pfc_ln0b, *pfc_W, *pfc_b, *pfc_ln4w, *pfc_ln4b;
+  // ---- workspace (device)
+  bf16 *X, *X1, *QKV, *AO, *HID, *Xf, *pos_enc, *kposb;
+  float *X32, *X1_32;  // fp32 residual stream of the encoder
+  float* enc_tab;
+  uint8_t* encmask;
+  float *in_vis, *in_vid, *in_text, *in_pos, *in_sizes, *in_f1, *in_f2;
+  uint8_t *in_vmask, *in_tmask;
+  float* frames_cls;
+  bf16 *pool[2], *ftext, *q0, *kv_ts;
+  float *pool32[2], *q0_32, *c_h32[2], *c_a32[2];
+  bf16 *c_h[2], *c_q[2], *c_ctx[2], *c_a[2], *c_i[2], *c_qabs[2], *c_ctx8[2];  // per-classifier scratch
+  float *logit_f[2], *att_seq, *w1, *w2, *K1, *K2, *attmap[2], *logit_rows[2], *logits_r[2], *part[2], *seedq[2];
+  float *t_tgt32, *t_x32, *t_x2_32, *p_tgt32, *p_x32, *p_x2_32;
+  bf16 *t_tgt, *t_qkv, *t_ao, *t_x, *t_qabs, *t_ctx8, *t_x2, *t_hid, *t_inter, *t_hs;
+  bf16 *p_cat, *p_sine, *p_h, *p_s256, *p_qkv, *p_ao, *p_q, *p_q2, *p_qabs, *p_ctx8, *p_x2, *p_hid, *p_b1, *p_b2;
+  float *boxes0, *anchors, *sted_all, *act_all, *act1, *boxes_px;
+  int* sted_idx;
+  // staging for vgqa_forward_host
+  uint8_t* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  cudaStream_t host_stream = nullptr;
+  cudaStream_t exec_stream = nullptr;  // graphs are captured and replayed here (the legacy stream cannot be captured)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // graph cache
+  struct GraphEntry { cudaGraphExec_t exec; int launches; };
+  std::map<std::vector<uint64_t>, GraphEntry> graphs;
+  int last_launches = 0;
+  int launches = 0;  // running count inside one forward
+};
+
+namespace vg {
+
+// ------------------------------------------------------------------------------------------------ packing helpers
+struct Packer {
+  vgqa_ctx* c;
+  const HostT& get(const std::string& name, std::initializer_list<int64_t> shape = {}) {
+    auto it = c->sd.find(name);
+    VG_CHECK(it != c->sd.end(), "missing weight '" + name + "' (set it with vgqa_set_weight before finalize)");
+    if (shape.size()) {
+      std::vector<int64_t> s(shape);
+      VG_CHECK(it->second.shape == s, "weight '" + name + "' has an unexpected shape");
+    }
+    return it->second;
+  }
+  float* f32(const float* v, size_t n) {
+    float* d = c->warena.get<float>(n);
+    VG_CUDA(cudaMemcpy(d, v, n * sizeof(float), cudaMemcpyHostToDevice));
+    return d;
+  }
+  float* f32(const std::vector<float>& v) { return f32(v.data(), v.size()); }
+  bf16* b16(const float* v, size_t n) {
+    std::vector<bf16> h(n);
+    for (size_t i = 0; i < n; ++i) h[i] = __float2bfloat16(v[i]);
+    bf16* d = c->warena.get<bf16>(n);
+    VG_CUDA(cudaMemcpy(d, h.data(), n * sizeof(bf16), cudaMemcpyHostToDevice));
+    return d;
+  }
+  Lin lin(const float* W, const float* b, int N, int K) {
+    Lin l; l.N = N; l.K = K; l.W = b16(W, (size_t)N * K); l.b = b ? f32(b, N) : nullptr; return l;
+  }
+  Lin lin(const std::string& p, int N, int K) {
+    return lin(get(p + ".weight", {N, K}).v.data(), get(p + ".bias", {N}).v.data(), N, K);
+  }
+  LNp ln(const std::string& p, int n = 256) {
+    LNp l; l.w = f32(get(p + ".weight", {n}).v); l.b = f32(get(p + ".bias", {n}).v); return l;
+  }
+};
+
+// W_abs[h*256 + j, i] = sum_{c in head h} Wk[c, j] * Wq[c, i];  b_abs[h*256 + j] = sum_c Wk[c, j] * bq[c]
+static void absorb_qk(const float* Wk, const float* Wq, const float* bq, int Kq, std::vector<float>& W,
+                      std::vector<float>& b) {
+  W.assign((size_t)2048 * Kq, 0.f);
+  b.assign(2048, 0.f);
+  parallel_for(2048, [&](int r) {
+    const int h = r >> 8, j = r & 255;
+    std::vector<double> acc(Kq, 0.0);
+    double bb = 0.0;
+    for (int c = h * 32; c < h * 32 + 32; ++c) {
+      const double wk = Wk[(size_t)c * 256 + j];
+      const float* q = Wq + (size_t)c * Kq;
+      for (int i = 0; i < Kq; ++i) acc[i] += wk * q[i];
+      bb += wk * bq[c];
+    }
+    for (int i = 0; i < Kq; ++i) W[(size_t)r * Kq + i] = (float)acc[i];
+    b[r] = (float)bb;
+  });
+}
+// W_vo[o, h*256 + j] = sum_{c in head h} Wo[o, c] * Wv[c, j];  b_vo[o] = sum_c Wo[o, c] bv[c] + bo[o]
+static void absorb_vo(const float* Wo, const float* bo, const float* Wv, const float* bv, std::vector<float>& W,
+                      std::vector<float>& b) {
+  W.assign((size_t)256 * 2048, 0.f);
+  b.assign(256, 0.f);
+  parallel_for(256, [&](int o) {
+    for (int h = 0; h < 8; ++h) {
+      std::vector<double> acc(256, 0.0);
+      for (int c = h * 32; c < h * 32 + 32; ++c) {
+        const double wo = Wo[(size_t)o * 256 + c];
+        const float* v = Wv + (size_t)c * 256;
+        for (int j = 0; j < 256; ++j) acc[j] += wo * v[j];
+      }
+      for (int j = 0; j < 256; ++j) W[(size_t)o * 2048 + h * 256 + j] = (float)acc[j];
+    }
+    double bb = bo[o];
+    for (int c = 0; c < 256; ++c) bb += (double)Wo[(size_t)o * 256 + c] * bv[c];
+    b[o] = (float)bb;
+  });
+}
+
+static void pack_weights(vgqa_ctx* c) {
+  Packer P{c};
+  const vgqa_config& cfg = c->cfg;
+  const int F = cfg.ffn_dim, Tm = cfg.max_video_len + 1;
+  c->warena.init((size_t)320 << 20);
+  // ---------------- encoder (modal_encoder.py:143-178)
+  c->enc.resize(cfg.enc_layers);
+  for (int l = 0; l < cfg.enc_layers; ++l) {
+    const std::string p = "ground_encoder.encoder.spatial_layers." + std::to_string(l) + ".";
+    EncLayer& e = c->enc[l];
+    const HostT& w = P.get(p + "self_attn.in_proj_weight", {768, 256});
+    const HostT& b = P.get(p + "self_attn.in_proj_bias", {768});
+    e.qkv = P.lin(w.v.data(), nullptr, 768, 256);
+    std::vector<float> wt(w.v);
+    std::fill(wt.begin() + (size_t)512 * 256, wt.end(), 0.f);  // V gets no positional term
+    e.tab = P.lin(wt.data(), b.v.data(), 768, 256);
+    e.out = P.lin(p + "self_attn.out_proj", 256, 256);
+    e.ff1 = P.lin(p + "linear1", F, 256);
+    e.ff2 = P.lin(p + "linear2", 256, F);
+    e.ln1 = P.ln(p + "norm1");
+    e.ln2 = P.ln(p + "norm2");
+  }
+  c->enc_norm = P.ln("ground_encoder.encoder.norm");
+  // ---------------- classifiers (classifier.py, bert_module.py)
+  const char* ts_names[2] = {"t_temporal_clas", "s_temporal_clas"};
+  const char* sa_names[2] = {"t_spatial_clas", "s_spatial_clas"};
+  auto head = [&](const std::string& p, int vocab) {
+    Head h;
+    h.t = P.lin(p + ".head.transform.dense", 256, 256);
+    h.ln = P.ln(p + ".head.transform.LayerNorm");
+    h.dw = P.f32(P.get(p + ".head.decoder.weight", {vocab, 256}).v);
+    h.db = P.f32(P.get(p + ".head.bias", {vocab}).v);
+    h.vocab = vocab;
+    return h;
+  };
+  std::vector<float> kvW((size_t)2048 * 256), kvB(2048);
+  for (int k = 0; k < 2; ++k) {
+    for (int i = 0; i < 2; ++i) {
+      const std::string p = std::string(ts_names[k]) + ".layer_ca." + std::to_string(i) + ".";
+      TsLayer& t = c->ts[k][i];
+      t.q = P.lin(p + "attention.self.query", 256, 256);
+      t.kv_off = (k * 2 + i) * 512;
+      const HostT& wk = P.get(p + "attention.self.key.weight", {256, 256});
+      const HostT& wv = P.get(p + "attention.self.value.weight", {256, 256});
+      std::copy(wk.v.begin(), wk.v.end(), kvW.begin() + (size_t)t.kv_off * 256);
+      std::copy(wv.v.begin(), wv.v.end(), kvW.begin() + (size_t)(t.kv_off + 256) * 256);
+      const HostT& bk = P.get(p + "attention.self.key.bias", {256});
+      const HostT& bv = P.get(p + "attention.self.value.bias", {256});
+      std::copy(bk.v.begin(), bk.v.end(), kvB.begin() + t.kv_off);
+      std::copy(bv.v.begin(), bv.v.end(), kvB.begin() + t.kv_off + 256);
+      t.o = P.lin(p + "attention.output.dense", 256, 256);
+      t.ln_a = P.ln(p + "attention.output.LayerNorm");
+      t.inter = P.lin(p + "hidden_intermediate.dense", 256, 256);
+      t.outp = P.lin(p + "output.dense", 256, 256);
+      t.ln_o = P.ln(p + "output.LayerNorm");
+    }
+    c->ts_head[k] = head(ts_names[k], 1);
+  }
+  c->ts_kv = P.lin(kvW.data(), kvB.data(), 2048, 256);
+  std::vector<float> Wa, ba, Wv, bv;
+  for (int k = 0; k < 2; ++k) {
+    for (int i = 0; i < 2; ++i) {
+      const std::string p = std::string(sa_names[k]) + ".layer_ca." + std::to_string(i) + ".";
+      SaLayer& s = c->sa[k][i];
+      absorb_qk(P.get(p + "attention.self.key.weight", {256, 256}).v.data(),
+                P.get(p + "attention.self.query.weight", {256, 256}).v.data(),
+                P.get(p + "attention.self.query.bias", {256}).v.data(), 256, Wa, ba);
+      s.qabs = P.lin(Wa.data(), ba.data(), 2048, 256);
+      absorb_vo(P.get(p + "attention.output.dense.weight", {256, 256}).v.data(),
+                P.get(p + "attention.output.dense.bias", {256}).v.data(),
+                P.get(p + "attention.self.value.weight", {256, 256}).v.data(),
+                P.get(p + "attention.self.value.bias", {256}).v.data(), Wv, bv);
+      s.vo = P.lin(Wv.data(), bv.data(), 256, 2048);
+      s.ln_a = P.ln(p + "attention.output.LayerNorm");
+      s.inter = P.lin(p + "hidden_intermediate.dense", 256, 256);
+      s.outp = P.lin(p + "output.dense", 256, 256);
+      s.ln_o = P.ln(p + "output.LayerNorm");
+    }
+    c->sa_head[k] = head(sa_names[k], k == 0 ? cfg.mot_num : cfg.app_num);
+  }
+  // ---------------- decoders (query_decoder.py)
+  const std::string g = "ground_decoder.";
+  const HostT& te = P.get(g + "time_embed.te", {Tm, 1, 256});
+  c->tl.resize(cfg.dec_layers);
+  c->pl.resize(cfg.dec_layers);
+  std::vector<float> kposW((size_t)cfg.dec_layers * 256 * 256), kposB((size_t)cfg.dec_layers * 256);
+  for (int l = 0; l < cfg.dec_layers; ++l) {
+    {  // ---- TimeDecoderLayer (:425-486)
+      const std::string p = g + "time_decoder.layers." + std::to_string(l) + ".";
+      TimeLayer& t = c->tl[l];
+      const HostT& w = P.get(p + "self_attn.in_proj_weight", {768, 256});
+      const HostT& b = P.get(p + "self_attn.in_proj_bias", {768});
+      t.qkv = P.lin(w.v.data(), nullptr, 768, 256);
+      // table[t] = [Wq;Wk] te_t + b  (v rows: bias only)   — folds `tgt + query_time` (:466)
+      std::vector<float> tab((size_t)Tm * 768);
+      parallel_for(Tm, [&](int ti) {
+        for (int n = 0; n < 768; ++n) {
+          double acc = b.v[n];
+          if (n < 512)
+            for (int k2 = 0; k2 < 256; ++k2) acc += (double)w.v[(size_t)n * 256 + k2] * te.v[(size_t)ti * 256 + k2];
+          tab[(size_t)ti * 768 + n] = (float)acc;
+        }
+      });
+      t.tab = P.f32(tab);
+      t.out = P.lin(p + "self_attn.out_proj", 256, 256);
+      t.ln1 = P.ln(p + "norm1");
+      const HostT& cw = P.get(p + "cross_attn_image.in_proj_weight", {768, 256});
+      const HostT& cb = P.get(p + "cross_attn_image.in_proj_bias", {768});
+      absorb_qk(cw.v.data() + (size_t)256 * 256, cw.v.data(), cb.v.data(), 256, Wa, ba);
+      t.qabs = P.lin(Wa.data(), ba.data(), 2048, 256);
+      absorb_vo(P.get(p + "cross_attn_image.out_proj.weight", {256, 256}).v.data(),
+                P.get(p + "cross_attn_image.out_proj.bias", {256}).v.data(), cw.v.data() + (size_t)512 * 256,
+                cb.v.data() + 512, Wv, bv);
+      t.vo = P.lin(Wv.data(), bv.data(), 256, 2048);
+      t.ln3 = P.ln(p + "norm3");
+      t.ff1 = P.lin(p + "linear1", F, 256);
+      t.ff2 = P.lin(p + "linear2", 256, F);
+      t.ln4 = P.ln(p + "norm4");
+    }
+    {  // ---- PosDecoderLayer (:208-375)
+      const std::string p = g + "decoder.layers." + std::to_string(l) + ".";
+      PosLayer& q = c->pl[l];
+      const HostT& iw = P.get(p + "self_attn.in_proj_weight", {768, 256});
+      const HostT& ib = P.get(p + "self_attn.in_proj_bias", {768});
+      auto W = [&](const char* n) -> const float* { return P.get(p + n + ".weight", {256, 256}).v.data(); };
+      auto Bv = [&](const char* n) -> const float* { return P.get(p + n + ".bias", {256}).v.data(); };
+      // Wsa [768, 512] over [tgt | query_pos]
+      std::vector<float> Wsa((size_t)768 * 512, 0.f), tab((size_t)Tm * 768);
+      const char* cont[3] = {"sa_qcontent_proj", "sa_kcontent_proj", "sa_v_proj"};
+      const char* posn[2] = {"sa_qpos_proj", "sa_kpos_proj"};
+      const char* timn[2] = {"sa_qtime_proj", "sa_ktime_proj"};
+      for (int part = 0; part < 3; ++part) {
+        const float* Win = iw.v.data() + (size_t)part * 256 * 256;
+        std::vector<float> m1 = matmul(Win, W(cont[part]), 256, 256, 256);
+        for (int r = 0; r < 256; ++r)
+          std::copy(m1.begin() + (size_t)r * 256, m1.begin() + (size_t)(r + 1) * 256,
+                    Wsa.begin() + (size_t)(part * 256 + r) * 512);
+        std::vector<float> bsum(256);
+        for (int i = 0; i < 256; ++i) bsum[i] = Bv(cont[part])[i];
+        std::vector<float> mt;
+        if (part < 2) {
+          std::vector<float> m2 = matmul(Win, W(posn[part]), 256, 256, 256);
+          for (int r = 0; r < 256; ++r)
+            std::copy(m2.begin() + (size_t)r * 256, m2.begin() + (size_t)(r + 1) * 256,
+                      Wsa.begin() + (size_t)(part * 256 + r) * 512 + 256);
+          for (int i = 0; i < 256; ++i) bsum[i] += Bv(posn[part])[i] + Bv(timn[part])[i];
+          mt = matmul(Win, W(timn[part]), 256, 256, 256);  // Win * Wtime
+        }
+        std::vector<float> b0 = matvec(Win, bsum.data(), ib.v.data() + part * 256, 256, 256);
+        parallel_for(Tm, [&](int ti) {
+          for (int n = 0; n < 256; ++n) {
+            double acc = b0[n];
+            if (part < 2)
+              for (int k2 = 0; k2 < 256; ++k2) acc += (double)mt[(size_t)n * 256 + k2] * te.v[(size_t)ti * 256 + k2];
+            tab[(size_t)ti * 768 + part * 256 + n] = (float)acc;
+          }
+        });
+      }
+      q.sa = P.lin(Wsa.data(), nullptr, 768, 512);
+      q.tab_sa = P.f32(tab);
+      q.sa_out = P.lin(p + "self_attn.out_proj", 256, 256);
+      q.ln1 = P.ln(p + "norm1");
+      // cross-attention query side
+      const float* Wcq = W("ca_qcontent_proj");
+      const float* bcq = Bv("ca_qcontent_proj");
+      const float* Wkc = W("ca_kcontent_proj");
+      if (l == 0) {
+        // A = [query_pos | x] (K = 512): q = Wqpos qpos + Wcq x + (bqpos + bcq)   (:311-313)
+        const float* Wqp = W("ca_qpos_proj");
+        const float* bqp = Bv("ca_qpos_proj");
+        std::vector<float> Wq((size_t)256 * 512), bq(256);
+        for (int r = 0; r < 256; ++r) {
+          std::copy(Wqp + (size_t)r * 256, Wqp + (size_t)(r + 1) * 256, Wq.begin() + (size_t)r * 512);
+          std::copy(Wcq + (size_t)r * 256, Wcq + (size_t)(r + 1) * 256, Wq.begin() + (size_t)r * 512 + 256);
+          bq[r] = bqp[r] + bcq[r];
+        }
+        q.q = P.lin(Wq.data(), bq.data(), 256, 512);
+        absorb_qk(Wkc, Wq.data(), bq.data(), 512, Wa, ba);
+        q.qabs = P.lin(Wa.data(), ba.data(), 2048, 512);
+      } else {
+        absorb_qk(Wkc, Wcq, bcq, 256, Wa, ba);
+        q.qabs = P.lin(Wa.data(), ba.data(), 2048, 256);
+      }
+      q.sine = P.lin(p + "ca_qpos_sine_proj", 256, 256);
+      absorb_vo(P.get(p + "cross_attn.out_proj.weight", {256, 256}).v.data(),
+                P.get(p + "cross_attn.out_proj.bias", {256}).v.data(), W("ca_v_proj"), Bv("ca_v_proj"), Wv, bv);
+      q.vo = P.lin(Wv.data(), bv.data(), 256, 2048);
+      q.ln3 = P.ln(p + "norm3");
+      q.ff1 = P.lin(p + "linear1", F, 256);
+      q.ff2 = P.lin(p + "linear2", 256, F);
+      q.ln4 = P.ln(p + "norm4");
+      std::copy(W("ca_kpos_proj"), W("ca_kpos_proj") + 65536, kposW.begin() + (size_t)l * 65536);
+      std::copy(Bv("ca_kpos_proj"), Bv("ca_kpos_proj") + 256, kposB.begin() + (size_t)l * 256);
+    }
+  }
+  c->kpos_all = P.lin(kposW.data(), kposB.data(), cfg.dec_layers * 256, 256);
+  c->time_norm = P.ln(g + "time_decoder.norm");
+  c->rph0 = P.lin(g + "decoder.ref_point_head.layers.0", 256, 512);
+  c->rph1 = P.lin(g + "decoder.ref_point_head.layers.1", 256, 256);
+  c->qs0 = P.lin(g + "decoder.query_scale.layers.0", 256, 256);
+  c->qs1 = P.lin(g + "decoder.query_scale.layers.1", 256, 256);
+  c->bb0 = P.lin("bbox_embed.layers.0", 256, 256);
+  c->bb1 = P.lin("bbox_embed.layers.1", 256, 256);
+  c->bb2w = P.f32(P.get("bbox_embed.layers.2.weight", {4, 256}).v);
+  c->bb2b = P.f32(P.get("bbox_embed.layers.2.bias", {4}).v);
+  c->temp_embed.l0 = P.lin("temp_embed.layers.0", 256, 256);
+  c->temp_embed.w1 = P.f32(P.get("temp_embed.layers.1.weight", {2, 256}).v);
+  c->temp_embed.b1 = P.f32(P.get("temp_embed.layers.1.bias", {2}).v);
+  c->temp_embed.n1 = 2;
+  c->action_embed.l0 = P.lin("action_embed.layers.0", 256, 256);
+  c->action_embed.w1 = P.f32(P.get("action_embed.layers.1.weight", {1, 256}).v);
+  c->action_embed.b1 = P.f32(P.get("action_embed.layers.1.bias", {1}).v);
+  c->action_embed.n1 = 1;
+  c->pfc_ln0w = P.f32(P.get(g + "pos_fc.0.weight", {256}).v);
+  c->pfc_ln0b = P.f32(P.get(g + "pos_fc.0.bias", {256}).v);
+  c->pfc_W = P.f32(P.get(g + "pos_fc.2.weight", {4, 256}).v);
+  c->pfc_b = P.f32(P.get(g + "pos_fc.2.bias", {4}).v);
+  c->pfc_ln4w = P.f32(P.get(g + "pos_fc.4.weight", {4}).v);
+  c->pfc_ln4b = P.f32(P.get(g + "pos_fc.4.bias", {4}).v);
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+static void carve_workspace(vgqa_ctx* c);
+static void alloc_workspace(vgqa_ctx* c) {
+  c->ws.dry = true; c->ws.off = 0;
+  carve_workspace(c);
+  const size_t bytes = c->ws.off + 4096;
+  c->ws.init(bytes);
+  carve_workspace(c);
+}
+static void carve_workspace(vgqa_ctx* c) {
+  const vgqa_config& g = c->cfg;
+  const size_t B = g.max_clips, T = g.max_frames, P = g.max_hw, L = g.max_text;
+  const size_t F = B * T, S = 2 * P + L, R = F * S, FF = g.ffn_dim, D = g.dec_layers;
+  Arena& a = c->ws;
+  c->X = a.get<bf16>(R * 256); c->X1 = a.get<bf16>(R * 256); c->QKV = a.get<bf16>(R * 768); c->AO = a.get<bf16>(R * 256);
+  c->HID = a.get<bf16>(R * FF); c->Xf = a.get<bf16>(R * 256);
+  c->X32 = a.get<float>(R * 256); c->X1_32 = a.get<float>(R * 256);
+  c->pos_enc = a.get<bf16>(R * 256); c->kposb = a.get<bf16>(R * 1536); c->enc_tab = a.get<float>(R * 768);
+  c->encmask = a.get<uint8_t>(R);
+  c->in_vis = a.get<float>(F * 256 * P); c->in_vid = a.get<float>(F * 256 * P); c->in_text = a.get<float>(B * L * 256);
+  c->in_pos = a.get<float>(F * 256 * P); c->in_sizes = a.get<float>(B * 2); c->in_f1 = a.get<float>(F); c->in_f2 = a.get<float>(F);
+  c->in_vmask = a.get<uint8_t>(F * P); c->in_tmask = a.get<uint8_t>(B * L);
+  c->frames_cls = a.get<float>(F * 256);
+  c->ftext = a.get<bf16>(B * L * 256); c->q0 = a.get<bf16>(F * 256); c->kv_ts = a.get<bf16>(B * L * 2048);
+  for (int k = 0; k < 2; ++k) {
+    c->pool[k] = a.get<bf16>(F * 256); c->pool32[k] = a.get<float>(F * 256);
+    c->c_h32[k] = a.get<float>(F * 256); c->c_a32[k] = a.get<float>(F * 256);
+    c->c_h[k] = a.get<bf16>(F * 256); c->c_q[k] = a.get<bf16>(F * 256); c->c_ctx[k] = a.get<bf16>(F * 256);
+    c->c_a[k] = a.get<bf16>(F * 256); c->c_i[k] = a.get<bf16>(F * 256);
+    c->c_qabs[k] = a.get<bf16>(F * 2048); c->c_ctx8[k] = a.get<bf16>(F * 2048);
+    c->logit_f[k] = a.get<float>(F); c->attmap[k] = a.get<float>(F * P); c->logit_rows[k] = a.get<float>(F * 64);
+    c->logits_r[k] = a.get<float>(B * 64); c->part[k] = a.get<float>(F * 256); c->seedq[k] = a.get<float>(B * 256);
+  }
+  c->q0_32 = a.get<float>(F * 256);
+  c->t_tgt32 = a.get<float>(F * 256); c->t_x32 = a.get<float>(F * 256); c->t_x2_32 = a.get<float>(F * 256);
+  c->p_tgt32 = a.get<float>(F * 256); c->p_x32 = a.get<float>(F * 256); c->p_x2_32 = a.get<float>(F * 256);
+  c->att_seq = a.get<float>(F); c->w1 = a.get<float>(F); c->w2 = a.get<float>(F); c->K1 = a.get<float>(B); c->K2 = a.get<float>(B);
+  c->t_tgt = a.get<bf16>(F * 256); c->t_qkv = a.get<bf16>(F * 768); c->t_ao = a.get<bf16>(F * 256); c->t_x = a.get<bf16>(F * 256);
+  c->t_qabs = a.get<bf16>(F * 2048); c->t_ctx8 = a.get<bf16>(F * 2048); c->t_x2 = a.get<bf16>(F * 256);
+  c->t_hid = a.get<bf16>(F * FF); c->t_inter = a.get<bf16>(D * F * 256); c->t_hs = a.get<bf16>(D * F * 256);
+  c->p_cat = a.get<bf16>(F * 768); c->p_sine = a.get<bf16>(F * 512); c->p_h = a.get<bf16>(F * 256); c->p_s256 = a.get<bf16>(F * 256);
+  c->p_qkv = a.get<bf16>(F * 768); c->p_ao = a.get<bf16>(F * 256); c->p_q = a.get<bf16>(F * 256); c->p_q2 = a.get<bf16>(F * 256);
+  c->p_qabs = a.get<bf16>(F * 2048); c->p_ctx8 = a.get<bf16>(F * 2048); c->p_x2 = a.get<bf16>(F * 256);
+  c->p_hid = a.get<bf16>(F * FF); c->p_b1 = a.get<bf16>(F * 256); c->p_b2 = a.get<bf16>(F * 256);
+  c->boxes0 = a.get<float>(F * 4); c->anchors = a.get<float>(D * F * 4); c->sted_all = a.get<float>(D * F * 2);
+  c->act_all = a.get<float>(D * F); c->act1 = a.get<float>(F); c->boxes_px = a.get<float>(F * 4);
+  c->sted_idx = a.get<int>(B * 2);
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+struct Fwd {
+  vgqa_ctx* c;
+  cudaStream_t st;
+  int B, T, P, L, S, F, R;
+  void gemm(const bf16* A, int lda, const Lin& w, int M, const GemmEpi& ep) {
+    gemm_bf16_tn(A, lda, w.W, w.K, M, w.N, w.K, ep, st);
+    ++c->launches;
+  }
+  // C = act(A W^T + b)
+  void linear(const bf16* A, int lda, const Lin& w, int M, bf16* C, int ldc, int act = ACT_NONE) {
+    GemmEpi ep; ep.C = C; ep.ldc = ldc; ep.bias = w.b; ep.bias_period = 1; ep.bias_ld = w.N; ep.act = act;
+    gemm(A, lda, w, M, ep);
+  }
+  // C (bf16) and C32 (fp32 residual stream, ld 256) = LN(res32 + act(A W^T + b))
+  void linear_res_ln(const bf16* A, int lda, const Lin& w, int M, const float* res32, const LNp& ln, float eps,
+                     bf16* C, int ldc, float* C32, int act = ACT_NONE) {
+    GemmEpi ep; ep.C = C; ep.ldc = ldc; ep.bias = w.b; ep.bias_period = 1; ep.bias_ld = w.N; ep.act = act;
+    ep.res32 = res32; ep.ldres32 = 256; ep.C32 = C32; ep.ldc32 = 256; ep.ln_w = ln.w; ep.ln_b = ln.b; ep.ln_eps = eps;
+    gemm(A, lda, w, M, ep);
+  }
+  void count(int n = 1) { c->launches += n; }
+};
+
+static void run_encoder(Fwd& f, const vgqa_inputs& in, bool have_mask, int pos_rows) {
+  vgqa_ctx* c = f.c;
+  cudaStream_t st = f.st;
+  const int S = f.S, P = f.P, L = f.L, R = f.R, F = f.F;
+  // tokens: [vis | text | vid] per frame (modal_encoder.py:64)
+  nchw_to_tokens(in.vis, (long long)256 * P, c->X, c->X32, F, S, 0, P, st);
+  text_to_tokens(in.text, c->X, c->X32, F, f.T, S, P, L, st);
+  nchw_to_tokens(in.vid, (long long)256 * P, c->X, c->X32, F, S, P + L, P, st);
+  // positional rows: [pos | 0 | pos] (modal_encoder.py:66)
+  const int pf = in.pos_frames;
+  nchw_to_tokens(in.pos, (long long)256 * P, c->pos_enc, nullptr, pf, S, 0, P, st);
+  text_to_tokens(nullptr, c->pos_enc, nullptr, pf, 1, S, P, L, st);
+  nchw_to_tokens(in.pos, (long long)256 * P, c->pos_enc, nullptr, pf, S, P + L, P, st);
+  f.count(6);
+  if (have_mask) { build_encoded_mask(in.vis_mask, in.text_mask, c->encmask, F, f.T, P, L, st); f.count(); }
+  const uint8_t* km = have_mask ? c->encmask : nullptr;
+  bf16* x = c->X;
+  for (size_t l = 0; l < c->enc.size(); ++l) {
+    EncLayer& e = c->enc[l];
+    {  // table = pos_enc [Wq;Wk;0]^T + in_proj_bias  (fp32)
+      GemmEpi ep; ep.C = c->enc_tab; ep.ldc = 768; ep.c_f32 = 1; ep.bias = e.tab.b; ep.bias_ld = 768;
+      f.gemm(c->pos_enc, 256, e.tab, pos_rows, ep);
+    }
+    {  // QKV = x Wqkv^T + table[row % pos_rows]
+      GemmEpi ep; ep.C = c->QKV; ep.ldc = 768; ep.bias = c->enc_tab; ep.bias_period = pos_rows; ep.bias_ld = 768;
+      f.gemm(x, 256, e.qkv, R, ep);
+    }
+    mha32(c->QKV, 768, c->QKV + 256, 768, c->QKV + 512, 768, c->AO, 256, F, S, S, km, 0.17677669529663687f, st);
+    f.count();
+    f.linear_res_ln(c->AO, 256, e.out, R, c->X32, e.ln1, 1e-5f, c->X1, 256, c->X1_32);
+    f.linear(c->X1, 256, e.ff1, R, c->HID, e.ff1.N, ACT_RELU);
+    f.linear_res_ln(c->HID, e.ff2.K, e.ff2, R, c->X1_32, e.ln2, 1e-5f, c->X, 256, c->X32);
+    x = c->X;
+  }
+  enc_finalize(c->X32, c->enc_norm.w, c->enc_norm.b, 1e-5f, c->Xf, c->frames_cls, c->pool[1], c->pool[0], c->pool32[1],
+               c->pool32[0], F, S, P, L, st);
+  text_mean(c->Xf, c->ftext, c->q0, c->q0_32, f.B, f.T, S, P, L, st);
+  f.count(2);
+}
+
+// TemporalSampling (classifier.py:32-37): k = 0 → t_temporal_clas on vid tokens, 1 → s_temporal_clas on vis tokens
+static void run_temporal_sampling(Fwd& f) {
+  vgqa_ctx* c = f.c;
+  const int F = f.F;
+  f.linear(c->ftext, 256, c->ts_kv, f.B * f.L, c->kv_ts, 2048);
+  for (int k = 0; k < 2; ++k) {
+    const bf16* h = c->pool[k];
+    const float* h32 = c->pool32[k];
+    for (int i = 0; i < 2; ++i) {
+      TsLayer& t = c->ts[k][i];
+      f.linear(h, 256, t.q, F, c->c_q[k], 256);
+      mha32(c->c_q[k], 256, c->kv_ts + t.kv_off, 2048, c->kv_ts + t.kv_off + 256, 2048, c->c_ctx[k], 256, f.B, f.T, f.L,
+            nullptr, 0.17677669529663687f, f.st);
+      f.count();
+      f.linear_res_ln(c->c_ctx[k], 256, t.o, F, h32, t.ln_a, 1e-12f, c->c_a[k], 256, c->c_a32[k]);
+      f.linear(c->c_a[k], 256, t.inter, F, c->c_i[k], 256, ACT_GELU);
+      f.linear_res_ln(c->c_i[k], 256, t.outp, F, c->c_a32[k], t.ln_o, 1e-12f, c->c_h[k], 256, c->c_h32[k]);
+      h = c->c_h[k]; h32 = c->c_h32[k];
+    }
+    Head& hd = c->ts_head[k];
+    f.linear_res_ln(h, 256, hd.t, F, nullptr, hd.ln, 1e-12f, c->c_a[k], 256, nullptr, ACT_GELU);
+    rowvec_head(c->c_a[k], 256, hd.dw, hd.db, c->logit_f[k], 1, F, 1, 0, f.st);
+    f.count();
+  }
+}
+
+// SpatialActivation + query seeding (classifier.py:64-81; grounding_net.py:131-136)
+static void run_spatial_seed(Fwd& f, const float* w, const float* K) {
+  vgqa_ctx* c = f.c;
+  const int F = f.F, P = f.P, S = f.S;
+  for (int k = 0; k < 2; ++k) {
+    const int tok0 = k == 0 ? P + f.L : 0;  // t_* reads vid tokens, s_* reads vis tokens
+    const bf16* q = c->q0;
+    const float* q32 = c->q0_32;
+    for (int i = 0; i < 2; ++i) {
+      SaLayer& s = c->sa[k][i];
+      f.linear(q, 256, s.qabs, F, c->c_qabs[k], 2048);
+      xattn1(c->c_qabs[k], c->Xf + (size_t)tok0 * 256, S, F, P, nullptr, 0, nullptr, nullptr, 0, 0, nullptr, 0,
+             0.17677669529663687f, c->c_ctx8[k], i == 1 ? c->attmap[k] : nullptr, f.st);
+      f.count();
+      f.linear_res_ln(c->c_ctx8[k], 2048, s.vo, F, q32, s.ln_a, 1e-12f, c->c_a[k], 256, c->c_a32[k]);
+      f.linear(c->c_a[k], 256, s.inter, F, c->c_i[k], 256, ACT_GELU);
+      f.linear_res_ln(c->c_i[k], 256, s.outp, F, c->c_a32[k], s.ln_o, 1e-12f, c->c_h[k], 256, c->c_h32[k]);
+      q = c->c_h[k]; q32 = c->c_h32[k];
+    }
+    Head& hd = c->sa_head[k];
+    f.linear_res_ln(q, 256, hd.t, F, nullptr, hd.ln, 1e-12f, c->c_a[k], 256, nullptr, ACT_GELU);
+    rowvec_head(c->c_a[k], 256, hd.dw, hd.db, c->logit_rows[k], 64, F, hd.vocab, 0, f.st);
+    masked_mean_rows(c->logit_rows[k], 64, w, K, c->logits_r[k], f.B, f.T, hd.vocab, f.st);
+    seed_partial(c->Xf, c->attmap[k], w, c->part[k], F, S, tok0, P, f.st);
+    // k = 0: init temporal query → TimeDecoder tgt; k = 1: init spatial query → PosDecoder tgt (cat cols 0..255)
+    seed_reduce(c->part[k], K, c->seedq[k], k == 0 ? c->t_tgt : c->p_cat, k == 0 ? 256 : 768,
+                k == 0 ? c->t_tgt32 : c->p_tgt32, f.B, f.T, P, f.st);
+    f.count(4);
+  }
+}
+
+static void run_decoders(Fwd& f, bool have_mask, int pos_frames) {
+  vgqa_ctx* c = f.c;
+  cudaStream_t st = f.st;
+  const int F = f.F, P = f.P, L = f.L, S = f.S, T = f.T, M = P + L;
+  const int D = (int)c->tl.size();
+  const long long pos_fs = pos_frames > 1 ? (long long)S * 256 : 0;
+  // anchors from frames_cls (query_decoder.py:92-94)
+  pos_fc_boxes(c->frames_cls, c->pfc_ln0w, c->pfc_ln0b, c->pfc_W, c->pfc_b, c->pfc_ln4w, c->pfc_ln4b, c->boxes0, F, st);
+  f.count();
+  // ---------------- TimeDecoder (query_decoder.py:379-486), memory = [text | vid] tokens
+  for (int l = 0; l < D; ++l) {
+    TimeLayer& t = c->tl[l];
+    { GemmEpi ep; ep.C = c->t_qkv; ep.ldc = 768; ep.bias = t.tab; ep.bias_period = T; ep.bias_ld = 768;
+      f.gemm(c->t_tgt, 256, t.qkv, F, ep); }
+    mha32(c->t_qkv, 768, c->t_qkv + 256, 768, c->t_qkv + 512, 768, c->t_ao, 256, f.B, T, T, nullptr, 0.17677669529663687f, st);
+    f.linear_res_ln(c->t_ao, 256, t.out, F, c->t_tgt32, t.ln1, 1e-5f, c->t_x, 256, c->t_x32);
+    f.linear(c->t_x, 256, t.qabs, F, c->t_qabs, 2048);
+    // keys = mem + pos_t (:474); mask = encoded_mask[:, :-P] applied positionally (:100,476)
+    xattn1(c->t_qabs, c->Xf + (size_t)P * 256, S, F, M, c->pos_enc + (size_t)P * 256, pos_fs, nullptr, nullptr, 0, 0,
+           have_mask ? c->encmask : nullptr, S, 0.17677669529663687f, c->t_ctx8, nullptr, st);
+    f.linear_res_ln(c->t_ctx8, 2048, t.vo, F, c->t_x32, t.ln3, 1e-5f, c->t_x2, 256, c->t_x2_32);
+    f.linear(c->t_x2, 256, t.ff1, F, c->t_hid, t.ff1.N, ACT_RELU);
+    f.linear_res_ln(c->t_hid, t.ff2.K, t.ff2, F, c->t_x2_32, t.ln4, 1e-5f, c->t_tgt, 256, c->t_tgt32);
+    ln_rows(c->t_tgt32, 256, c->time_norm.w, c->time_norm.b, 1e-5f, c->t_inter + (size_t)l * F * 256, 256, F, st);  // :412
+    f.count(3);
+  }
+  // ---------------- PosDecoder (query_decoder.py:129-375), memory = [vis | text] tokens
+  { GemmEpi ep; ep.C = c->kposb; ep.ldc = 1536; ep.bias = c->kpos_all.b; ep.bias_ld = c->kpos_all.N;
+    f.gemm(c->pos_enc, 256, c->kpos_all, pos_frames * S, ep); }  // ca_kpos_proj(pos_s) for all layers (:309)
+  const float* boxes = c->boxes0;
+  for (int l = 0; l < D; ++l) {
+    PosLayer& q = c->pl[l];
+    sine_embed(boxes, c->p_sine, F, st);                                        // :169
+    f.count();
+    f.linear(c->p_sine, 512, c->rph0, F, c->p_h, 256, ACT_RELU);                // ref_point_head (:170)
+    f.linear(c->p_h, 256, c->rph1, F, c->p_cat + 256, 768);
+    const bf16* s256 = c->p_sine;
+    int lds = 512;
+    if (l > 0) {                                                                // query_scale (:176-179)
+      f.linear(c->p_cat, 768, c->qs0, F, c->p_h, 256, ACT_RELU);
+      GemmEpi ep; ep.C = c->p_s256; ep.ldc = 256; ep.bias = c->qs1.b; ep.bias_ld = 256; ep.mul = c->p_sine; ep.ldmul = 512;
+      f.gemm(c->p_h, 256, c->qs1, F, ep);
+      s256 = c->p_s256; lds = 256;
+    }
+    { GemmEpi ep; ep.C = c->p_qkv; ep.ldc = 768; ep.bias = q.tab_sa; ep.bias_period = T; ep.bias_ld = 768;
+      f.gemm(c->p_cat, 768, q.sa, F, ep); }                                     // 7 sa_* projs ∘ in_proj (:282-294)
+    mha32(c->p_qkv, 768, c->p_qkv + 256, 768, c->p_qkv + 512, 768, c->p_ao, 256, f.B, T, T, nullptr, 0.17677669529663687f, st);
+    f.linear_res_ln(c->p_ao, 256, q.sa_out, F, c->p_tgt32, q.ln1, 1e-5f, c->p_cat + 512, 768, c->p_x32);  // x → cat[:,512:]
+    const bf16* qa = l == 0 ? c->p_cat + 256 : c->p_cat + 512;                  // [qpos | x] or x
+    const bf16* q2res = nullptr;
+    if (l == 0) { f.linear(qa, 768, q.q, F, c->p_q, 256); q2res = c->p_q; }      // :305,311-313
+    { GemmEpi ep; ep.C = c->p_q2; ep.ldc = 256; ep.bias = q.sine.b; ep.bias_ld = 256; ep.res = q2res; ep.ldres = 256;
+      f.gemm(s256, lds, q.sine, F, ep); }                                       // ca_qpos_sine_proj (:320)
+    f.linear(qa, 768, q.qabs, F, c->p_qabs, 2048);
+    xattn1(c->p_qabs, c->Xf, S, F, M, nullptr, 0, c->p_q2, c->kposb + (size_t)l * 256, 1536, pos_frames > 1 ? (long long)S * 1536 : 0,
+           nullptr, 0, 0.125f, c->p_ctx8, nullptr, st);                         // (512/8)^-0.5 (attention.py:151)
+    f.linear_res_ln(c->p_ctx8, 2048, q.vo, F, c->p_x32, q.ln3, 1e-5f, c->p_x2, 256, c->p_x2_32);
+    f.linear(c->p_x2, 256, q.ff1, F, c->p_hid, q.ff1.N, ACT_RELU);
+    f.linear_res_ln(c->p_hid, q.ff2.K, q.ff2, F, c->p_x2_32, q.ln4, 1e-5f, c->p_cat, 768, c->p_tgt32);
+    f.linear(c->p_cat, 768, c->bb0, F, c->p_b1, 256, ACT_RELU);                 // bbox_embed (:188-192)
+    f.linear(c->p_b1, 256, c->bb1, F, c->p_b2, 256, ACT_RELU);
+    float* anc = c->anchors + (size_t)l * F * 4;
+    rowvec_head(c->p_b2, 256, c->bb2w, c->bb2b, anc, 4, F, 4, 1, st);
+    boxes = anc;
+    f.count(3);
+  }
+}
+
+static std::string shape_str(const vgqa_inputs& in) {
+  return "clips=" + std::to_string(in.clips) + " T=" + std::to_string(in.T) + " H=" + std::to_string(in.H) +
+         " W=" + std::to_string(in.W) + " L=" + std::to_string(in.L);
+}
+
+static void check_inputs(vgqa_ctx* c, const vgqa_inputs& in) {
+  VG_CHECK(c->finalized, "vgqa_finalize_weights has not been called");
+  VG_CHECK(in.clips >= 1 && in.T >= 2 && in.H >= 1 && in.W >= 1 && in.L >= 1, "bad shape: " + shape_str(in));
+  VG_CHECK(in.clips <= c->cfg.max_clips && in.T <= c->cfg.max_frames && in.H * in.W <= c->cfg.max_hw &&
+               in.L <= c->cfg.max_text,
+           "shape exceeds the context capacity: " + shape_str(in));
+  VG_CHECK(in.T <= c->cfg.max_video_len + 1,
+           "T exceeds INPUT.MAX_VIDEO_LEN+1 rows of the time embedding (reference raises RuntimeError too)");
+  VG_CHECK(in.vis && in.vid && in.text && in.pos, "vis/vid/text/pos must be non-null");
+  VG_CHECK(in.pos_frames == 1 || in.pos_frames == in.clips * in.T, "pos_frames must be 1 or clips*T");
+}
+
+static void forward_body(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out, cudaStream_t st) {
+  Fwd f;
+  f.c = c; f.st = st; f.B = in.clips; f.T = in.T; f.P = in.H * in.W; f.L = in.L; f.S = 2 * f.P + f.L;
+  f.F = f.B * f.T; f.R = f.F * f.S;
+  const int F = f.F, D = (int)c->tl.size();
+  const bool have_mask = in.vis_mask != nullptr || in.text_mask != nullptr;
+  const int pos_rows = in.pos_frames * f.S;
+  c->launches = 0;
+  run_encoder(f, in, have_mask, pos_rows);
+  run_temporal_sampling(f);
+  select_pass1(c->logit_f[0], c->logit_f[1], 0.45f, in.force_choose1, c->att_seq, c->w1, c->K1, f.B, f.T, st);
+  f.count();
+  run_spatial_seed(f, c->w1, c->K1);
+  run_decoders(f, have_mask, in.pos_frames);
+  const float* wfinal = c->w1;
+  if (in.iteration_rate < 0) {  // grounding_net.py:143-163
+    f.linear(c->t_inter + (size_t)(D - 1) * F * 256, 256, c->action_embed.l0, F, c->t_hs, 256, ACT_RELU);
+    rowvec_head(c->t_hs, 256, c->action_embed.w1, c->action_embed.b1, c->act1, 1, F, 1, 1, st);  // sigmoid
+    select_pass2(c->act1, in.force_choose2, c->w2, c->K2, f.B, f.T, st);
+    f.count(2);
+    run_spatial_seed(f, c->w2, c->K2);
+    run_decoders(f, have_mask, in.pos_frames);
+    wfinal = c->w2;
+  }
+  // heads over all decoder layers (grounding_net.py:177-181)
+  f.linear(c->t_inter, 256, c->temp_embed.l0, D * F, c->t_hs, 256, ACT_RELU);
+  rowvec_head(c->t_hs, 256, c->temp_embed.w1, c->temp_embed.b1, c->sted_all, 2, D * F, 2, 0, st);
+  f.linear(c->t_inter, 256, c->action_embed.l0, D * F, c->t_hs, 256, ACT_RELU);
+  rowvec_head(c->t_hs, 256, c->action_embed.w1, c->action_embed.b1, c->act_all, 1, D * F, 1, 0, st);
+  f.count(2);
+  const float* last_boxes = c->anchors + (size_t)(D - 1) * F * 4;
+  const float* last_sted = c->sted_all + (size_t)(D - 1) * F * 2;
+  if (in.ori_sizes_hw != nullptr) {
+    postprocess(last_boxes, last_sted, in.ori_sizes_hw, c->boxes_px, c->sted_idx, f.B, f.T, st);
+    f.count();
+  }
+  // ---- outputs
+  auto cp = [&](void* dst, const void* src, size_t bytes) {
+    if (dst != nullptr) VG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+  };
+  cp(out.pred_boxes, last_boxes, (size_t)F * 4 * 4);
+  cp(out.pred_sted, last_sted, (size_t)F * 2 * 4);
+  cp(out.pred_actioness, c->act_all + (size_t)(D - 1) * F, (size_t)F * 4);
+  cp(out.logits_f_m, c->logit_f[0], (size_t)F * 4);
+  cp(out.logits_f_a, c->logit_f[1], (size_t)F * 4);
+  cp(out.att_sequences, c->att_seq, (size_t)F * 4);
+  cp(out.aux_boxes, c->anchors, (size_t)D * F * 4 * 4);
+  cp(out.aux_sted, c->sted_all, (size_t)D * F * 2 * 4);
+  cp(out.aux_actioness, c->act_all, (size_t)D * F * 4);
+  cp(out.choose1, c->w1, (size_t)F * 4);
+  cp(out.choose2, wfinal, (size_t)F * 4);
+  cp(out.actioness_pass1, c->act1, (size_t)F * 4);
+  if (in.ori_sizes_hw != nullptr) {
+    cp(out.boxes_px, c->boxes_px, (size_t)F * 4 * 4);
+    cp(out.sted_idx, c->sted_idx, (size_t)f.B * 2 * 4);
+  }
+  if (out.logits_r_m) VG_CUDA(cudaMemcpy2DAsync(out.logits_r_m, c->cfg.mot_num * 4, c->logits_r[0], c->cfg.mot_num * 4,
+                                                c->cfg.mot_num * 4, f.B, cudaMemcpyDeviceToDevice, st));
+  if (out.logits_r_a) VG_CUDA(cudaMemcpy2DAsync(out.logits_r_a, c->cfg.app_num * 4, c->logits_r[1], c->cfg.app_num * 4,
+                                                c->cfg.app_num * 4, f.B, cudaMemcpyDeviceToDevice, st));
+  cp(out.frames_cls, c->frames_cls, (size_t)F * 256 * 4);
+}
+
+}  // namespace vg
+
+// bf16 → fp32 debug copy of the encoder output
+__global__ void bf16_to_f32_kernel(const vg::bf16* in, float* out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+extern "C" {
+
+int vgqa_create(const vgqa_config* cfg, vgqa_ctx** out) {
+  try {
+    VG_CHECK(cfg != nullptr && out != nullptr, "null argument");
+    VG_CHECK(cfg->hidden == 256 && cfg->heads == 8, "this build supports MODEL.VSTG.HIDDEN=256, HEADS=8 only");
+    VG_CHECK(cfg->ffn_dim > 0 && cfg->ffn_dim % 256 == 0, "FFN_DIM must be a multiple of 256");
+    VG_CHECK(cfg->enc_layers >= 1 && cfg->dec_layers >= 1, "layer counts must be >= 1");
+    VG_CHECK(cfg->app_num >= 1 && cfg->app_num <= 64 && cfg->mot_num >= 1 && cfg->mot_num <= 64, "vocab sizes must be in [1,64]");
+    VG_CHECK(cfg->max_clips >= 1 && cfg->max_frames >= 2 && cfg->max_hw >= 1 && cfg->max_text >= 1, "bad capacity");
+    VG_CHECK(cfg->max_frames <= cfg->max_video_len + 1, "max_frames exceeds max_video_len + 1");
+    int ndev = 0;
+    VG_CUDA(cudaGetDeviceCount(&ndev));
+    VG_CHECK(ndev > 0, "no CUDA device: vgqa_b200 has no CPU fallback");
+    vgqa_ctx* c = new vgqa_ctx();
+    c->cfg = *cfg;
+    VG_CUDA(cudaGetDevice(&c->device));
+    cudaDeviceProp prop;
+    VG_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    VG_CHECK(prop.major == 10, std::string("vgqa_b200 is built for sm_100a only; found ") + prop.name);
+    *out = c;
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+void vgqa_destroy(vgqa_ctx* c) {
+  if (!c) return;
+  for (auto& g : c->graphs) cudaGraphExecDestroy(g.second.exec);
+  if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->host_stream) cudaStreamDestroy(c->host_stream);
+  if (c->exec_stream) cudaStreamDestroy(c->exec_stream);
+  if (c->ev_in) cudaEventDestroy(c->ev_in);
+  if (c->ev_out) cudaEventDestroy(c->ev_out);
+  c->warena.release();
+  c->ws.release();
+  delete c;
+}
+
+int vgqa_set_weight(vgqa_ctx* c, const char* name, const float* data, const int64_t* shape, int ndim) {
+  try {
+    VG_CHECK(c && name && data && (shape || ndim == 0), "null argument");
+    VG_CHECK(!c->finalized, "weights are already finalized");
+    HostT t;
+    t.shape.assign(shape, shape + ndim);
+    t.v.assign(data, data + t.numel());
+    c->sd[name] = std::move(t);
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_finalize_weights(vgqa_ctx* c) {
+  try {
+    VG_CHECK(c && !c->finalized, "bad context");
+    vg::pack_weights(c);
+    vg::alloc_workspace(c);
+    c->sd.clear();
+    c->finalized = true;
+    VG_CUDA(cudaDeviceSynchronize());
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_forward(vgqa_ctx* c, const vgqa_inputs* in, const vgqa_outputs* out, void* stream) {
+  try {
+    VG_CHECK(c && in && out, "null argument");
+    vg::check_inputs(c, *in);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (out->encoded_feature) VG_CHECK(!c->cfg.use_cuda_graph, "encoded_feature output is not available in graph mode");
+    if (!c->cfg.use_cuda_graph) {
+      vg::forward_body(c, *in, *out, st);
+      if (out->encoded_feature) {
+        const size_t n = (size_t)in->clips * in->T * (2 * in->H * in->W + in->L) * 256;
+        bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->Xf, out->encoded_feature, n);
+      }
+      c->last_launches = c->launches;
+      return 0;
+    }
+    // graph mode: captured and replayed on the context's own stream, ordered after / before `st` with events
+    if (!c->exec_stream) {
+      VG_CUDA(cudaStreamCreateWithFlags(&c->exec_stream, cudaStreamNonBlocking));
+      VG_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+      VG_CUDA(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
+    }
+    cudaStream_t ex = c->exec_stream;
+    // key = every scalar and pointer that is baked into the captured launches
+    std::vector<uint64_t> key = {(uint64_t)in->clips, (uint64_t)in->T, (uint64_t)in->H, (uint64_t)in->W, (uint64_t)in->L,
+                                 (uint64_t)in->pos_frames, (uint64_t)(in->iteration_rate < 0)};
+    for (const void* q : {(const void*)in->vis, (const void*)in->vid, (const void*)in->text, (const void*)in->pos,
+                          (const void*)in->vis_mask, (const void*)in->text_mask, (const void*)in->ori_sizes_hw,
+                          (const void*)in->force_choose1, (const void*)in->force_choose2})
+      key.push_back((uint64_t)(uintptr_t)q);
+    for (const void* q : {(const void*)out->pred_boxes, (const void*)out->pred_sted, (const void*)out->pred_actioness,
+                          (const void*)out->logits_f_m, (const void*)out->logits_f_a, (const void*)out->logits_r_a,
+                          (const void*)out->logits_r_m, (const void*)out->att_sequences, (const void*)out->aux_boxes,
+                          (const void*)out->aux_sted, (const void*)out->aux_actioness, (const void*)out->choose1,
+                          (const void*)out->choose2, (const void*)out->actioness_pass1, (const void*)out->boxes_px,
+                          (const void*)out->sted_idx, (const void*)out->frames_cls})
+      key.push_back((uint64_t)(uintptr_t)q);
+    VG_CUDA(cudaEventRecord(c->ev_in, st));
+    VG_CUDA(cudaStreamWaitEvent(ex, c->ev_in, 0));
+    auto it = c->graphs.find(key);
+    if (it == c->graphs.end()) {
+      vg::forward_body(c, *in, *out, ex);  // eager warm-up (sets function attributes, validates)
+      VG_CUDA(cudaStreamSynchronize(ex));
+      cudaGraph_t graph = nullptr;
+      VG_CUDA(cudaStreamBeginCapture(ex, cudaStreamCaptureModeThreadLocal));
+      try {
+        vg::forward_body(c, *in, *out, ex);
+      } catch (...) {
+        cudaStreamEndCapture(ex, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      VG_CUDA(cudaStreamEndCapture(ex, &graph));
+      vgqa_ctx::GraphEntry ge;
+      VG_CUDA(cudaGraphInstantiate(&ge.exec, graph, 0));
+      cudaGraphDestroy(graph);
+      ge.launches = c->launches;
+      if (c->graphs.size() >= 16) {
+        for (auto& g : c->graphs) cudaGraphExecDestroy(g.second.exec);
+        c->graphs.clear();
+      }
+      it = c->graphs.emplace(key, ge).first;
+    }
+    VG_CUDA(cudaGraphLaunch(it->second.exec, ex));
+    VG_CUDA(cudaEventRecord(c->ev_out, ex));
+    VG_CUDA(cudaStreamWaitEvent(st, c->ev_out, 0));
+    c->last_launches = it->second.launches;
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_forward_host(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outputs* hout) {
+  try {
+    VG_CHECK(c && hin && hout, "null argument");
+    vg::check_inputs(c, *hin);
+    if (!c->host_stream) VG_CUDA(cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking));
+    cudaStream_t st = c->host_stream;
+    const size_t B = hin->clips, T = hin->T, P = (size_t)hin->H * hin->W, L = hin->L, F = B * T;
+    const size_t D = c->tl.size();
+    auto h2d = [&](void* dst, const void* src, size_t bytes) {
+      VG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    };
+    vgqa_inputs din = *hin;
+    h2d(c->in_vis, hin->vis, F * 256 * P * 4); din.vis = c->in_vis;
+    h2d(c->in_vid, hin->vid, F * 256 * P * 4); din.vid = c->in_vid;
+    h2d(c->in_text, hin->text, B * L * 256 * 4); din.text = c->in_text;
+    h2d(c->in_pos, hin->pos, (size_t)hin->pos_frames * 256 * P * 4); din.pos = c->in_pos;
+    if (hin->vis_mask) { h2d(c->in_vmask, hin->vis_mask, F * P); din.vis_mask = c->in_vmask; }
+    if (hin->text_mask) { h2d(c->in_tmask, hin->text_mask, B * L); din.text_mask = c->in_tmask; }
+    if (hin->ori_sizes_hw) { h2d(c->in_sizes, hin->ori_sizes_hw, B * 2 * 4); din.ori_sizes_hw = c->in_sizes; }
+    if (hin->force_choose1) { h2d(c->in_f1, hin->force_choose1, F * 4); din.force_choose1 = c->in_f1; }
+    if (hin->force_choose2) { h2d(c->in_f2, hin->force_choose2, F * 4); din.force_choose2 = c->in_f2; }
+    vgqa_outputs none;
+    std::memset(&none, 0, sizeof(none));
+    int rc = vgqa_forward(c, &din, &none, st);
+    if (rc != 0) return rc;
+    auto d2h = [&](void* dst, const void* src, size_t bytes) {
+      if (dst != nullptr) VG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    };
+    d2h(hout->pred_boxes, c->anchors + (D - 1) * F * 4, F * 16);
+    d2h(hout->pred_sted, c->sted_all + (D - 1) * F * 2, F * 8);
+    d2h(hout->pred_actioness, c->act_all + (D - 1) * F, F * 4);
+    d2h(hout->logits_f_m, c->logit_f[0], F * 4);
+    d2h(hout->logits_f_a, c->logit_f[1], F * 4);
+    d2h(hout->logits_r_m, c->logits_r[0], B * c->cfg.mot_num * 4);
+    d2h(hout->logits_r_a, c->logits_r[1], B * c->cfg.app_num * 4);
+    d2h(hout->att_sequences, c->att_seq, F * 4);
+    d2h(hout->aux_boxes, c->anchors, D * F * 16);
+    d2h(hout->aux_sted, c->sted_all, D * F * 8);
+    d2h(hout->aux_actioness, c->act_all, D * F * 4);
+    d2h(hout->choose1, c->w1, F * 4);
+    d2h(hout->choose2, hin->iteration_rate < 0 ? c->w2 : c->w1, F * 4);
+    d2h(hout->actioness_pass1, c->act1, F * 4);
+    if (hin->ori_sizes_hw) {
+      d2h(hout->boxes_px, c->boxes_px, F * 16);
+      d2h(hout->sted_idx, c->sted_idx, B * 8);
+    }
+    d2h(hout->frames_cls, c->frames_cls, F * 256 * 4);
+    VG_CHECK(hout->encoded_feature == nullptr, "encoded_feature is only available through vgqa_forward");
+    VG_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_last_launch_count(const vgqa_ctx* c) { return c ? c->last_launches : 0; }
+
+double vgqa_reference_flops(int T, int H, int W, int L, int enc_layers, int dec_layers, int ffn, int passes) {
+  // 2*MACs of the reference modules: encoder + TemporalSampling + passes*(SpatialActivation + decoders)
+  const double d = 256, P = (double)H * W, S = 2 * P + L, M = P + L, F = ffn, Tt = T;
+  const double enc = enc_layers * (Tt * S * (2 * d * 3 * d + 2 * d * d + 4 * d * F) + Tt * 4 * S * S * d);
+  const double ts = 2 * (2 * (2 * (Tt * d * d + 2 * L * d * d) + 4 * Tt * L * d + 2 * 3 * Tt * d * d) + 2 * Tt * d * d + 2 * Tt * d);
+  const double sp = 2 * (2 * (2 * (Tt * d * d + 2 * Tt * P * d * d) + 4 * Tt * P * d + 2 * 3 * Tt * d * d) + 2 * Tt * d * d);
+  const double qside = 2 * Tt * d * d;  // one 256x256 Linear over T rows
+  const double timed = dec_layers * (2 * 2 * Tt * M * d * d + 4 * qside + 4 * Tt * Tt * d + qside + 4 * Tt * M * d + qside +
+                                     4 * Tt * d * F);
+  const double posd = dec_layers * (3 * 2 * Tt * M * d * d + 11 * qside + 4 * Tt * Tt * d + 4 * Tt * M * d * 1.5 + 3 * qside +
+                                    4 * Tt * d * F + 4 * qside + 2 * qside);
+  return enc + ts + passes * (sp + timed + posd);
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+"""GroundingEngine — Python owner of one `vgqa_ctx` (include/vgqa_b200.h).
+
+PyTorch is used only for device memory and streams; all math runs in libvgqa_b200.so.  There is no CPU or
+eager-PyTorch fallback: if the library or a B200 is missing the constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Mapping, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import c_float, c_int, c_void_p
+
+
+class VgqaConfig(ctypes.Structure):
+    _fields_ = [(n, c_int) for n in (
+        "enc_layers", "dec_layers", "hidden", "heads", "ffn_dim", "app_num", "mot_num", "max_video_len",
+        "max_clips", "max_frames", "max_hw", "max_text", "use_cuda_graph")]
+
+
+class VgqaInputs(ctypes.Structure):
+    _fields_ = [("clips", c_int), ("T", c_int), ("H", c_int), ("W", c_int), ("L", c_int),
+                ("vis", c_void_p), ("vid", c_void_p), ("text", c_void_p), ("pos", c_void_p), ("pos_frames", c_int),
+                ("vis_mask", c_void_p), ("text_mask", c_void_p), ("ori_sizes_hw", c_void_p),
+                ("force_choose1", c_void_p), ("force_choose2", c_void_p), ("iteration_rate", c_int)]
+
+
+OUTPUT_FIELDS = ("pred_boxes", "pred_sted", "pred_actioness", "logits_f_m", "logits_f_a", "logits_r_a", "logits_r_m",
+                 "att_sequences", "aux_boxes", "aux_sted", "aux_actioness", "choose1", "choose2", "actioness_pass1",
+                 "boxes_px", "sted_idx", "encoded_feature", "frames_cls")
+
+
+class VgqaOutputs(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in OUTPUT_FIELDS]
+
+
+def _declare(L):
+    if getattr(L, "_vgqa_engine_declared", False):
+        return
+    L.vgqa_create.restype = c_int
+    L.vgqa_create.argtypes = [ctypes.POINTER(VgqaConfig), ctypes.POINTER(c_void_p)]
+    L.vgqa_destroy.restype = None
+    L.vgqa_destroy.argtypes = [c_void_p]
+    L.vgqa_set_weight.restype = c_int
+    L.vgqa_set_weight.argtypes = [c_void_p, ctypes.c_char_p, c_void_p, ctypes.POINTER(ctypes.c_int64), c_int]
+    L.vgqa_finalize_weights.restype = c_int
+    L.vgqa_finalize_weights.argtypes = [c_void_p]
+    L.vgqa_forward.restype = c_int
+    L.vgqa_forward.argtypes = [c_void_p, ctypes.POINTER(VgqaInputs), ctypes.POINTER(VgqaOutputs), c_void_p]
+    L.vgqa_forward_host.restype = c_int
+    L.vgqa_forward_host.argtypes = [c_void_p, ctypes.POINTER(VgqaInputs), ctypes.POINTER(VgqaOutputs)]
+    L.vgqa_last_launch_count.restype = c_int
+    L.vgqa_last_launch_count.argtypes = [c_void_p]
+    L.vgqa_reference_flops.restype = ctypes.c_double
+    L.vgqa_reference_flops.argtypes = [c_int] * 8
+    L._vgqa_engine_declared = True
+
+
+def reference_flops(T, H, W, L, enc_layers=6, dec_layers=6, ffn_dim=2048, passes=2) -> float:
+    L_ = _lib.lib()
+    _declare(L_)
+    return float(L_.vgqa_reference_flops(T, H, W, L, enc_layers, dec_layers, ffn_dim, passes))
+
+
+class GroundingEngine:
+    """Owns the packed weights + workspace for up to (max_clips, max_frames, max_hw, max_text)."""
+
+    def __init__(self, state_dict: Mapping[str, object], *, max_clips=1, max_frames=64, max_hw=49, max_text=32,
+                 enc_layers=6, dec_layers=6, ffn_dim=2048, app_num=20, mot_num=34, max_video_len=200,
+                 use_cuda_graph=False, device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("vgqa_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self._L = _lib.lib()
+        _declare(self._L)
+        if device is not None:
+            torch.cuda.set_device(device)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        torch.cuda.init()
+        torch.zeros(1, device=self.device)  # make sure the primary context exists
+        self.cfg = VgqaConfig(enc_layers, dec_layers, 256, 8, ffn_dim, app_num, mot_num, max_video_len, max_clips,
+                              max_frames, max_hw, max_text, 1 if use_cuda_graph else 0)
+        self._ctx = c_void_p()
+        _lib.check(self._L.vgqa_create(ctypes.byref(self.cfg), ctypes.byref(self._ctx)))
+        self.load_state_dict(state_dict)
+
+    # -- weights ------------------------------------------------------------------------------------
+    def load_state_dict(self, state_dict: Mapping[str, object]):
+        """Feeds every tensor of a reference state_dict (reference key names; extra keys are ignored by the
+        library) and packs them."""
+        for name, t in state_dict.items():
+            if isinstance(t, torch.Tensor):
+                a = t.detach().to("cpu", torch.float32).contiguous().numpy()
+            else:
+                a = np.ascontiguousarray(np.asarray(t), dtype=np.float32)
+            if a.dtype != np.float32:
+                continue
+            shape = (ctypes.c_int64 * max(a.ndim, 1))(*a.shape)
+            _lib.check(self._L.vgqa_set_weight(self._ctx, name.encode(), a.ctypes.data_as(c_void_p), shape, a.ndim))
+        _lib.check(self._L.vgqa_finalize_weights(self._ctx))
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._L.vgqa_destroy(self._ctx)
+            self._ctx = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- forward ------------------------------------------------------------------------------------
+    def output_shapes(self, B, T, H, W, L):
+        D = self.cfg.dec_layers
+        return {
+            "pred_boxes": (B, T, 4), "pred_sted": (B, T, 2), "pred_actioness": (B, T), "logits_f_m": (B, T),
+            "logits_f_a": (B, T), "logits_r_a": (B, self.cfg.app_num), "logits_r_m": (B, self.cfg.mot_num),
+            "att_sequences": (B, T), "aux_boxes": (D, B, T, 4), "aux_sted": (D, B, T, 2), "aux_actioness": (D, B, T),
+            "choose1": (B, T), "choose2": (B, T), "actioness_pass1": (B, T), "boxes_px": (B, T, 4), "sted_idx": (B, 2),
+            "encoded_feature": (B * T, 2 * H * W + L, 256), "frames_cls": (B * T, 256),
+        }
+
+    def alloc_outputs(self, B, T, H, W, L, want=None, host=False) -> Dict[str, torch.Tensor]:
+        want = set(want or [f for f in OUTPUT_FIELDS if f != "encoded_feature"])
+        outs = {}
+        for k, shp in self.output_shapes(B, T, H, W, L).items():
+            if k not in want:
+                continue
+            dt = torch.int32 if k == "sted_idx" else torch.float32
+            outs[k] = (torch.zeros(shp, dtype=dt).pin_memory() if host else torch.zeros(shp, dtype=dt, device=self.device))
+        return outs
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else c_void_p(t.data_ptr())
+
+    def _pack_io(self, vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force1, force2, iteration_rate, outs):
+        B, T, d, H, W = vis.shape
+        assert d == 256 and tuple(vid.shape) == tuple(vis.shape), "vis/vid must be [clips, T, 256, H, W]"
+        Lt = text.shape[1]
+        assert tuple(text.shape) == (B, Lt, 256), "text must be [clips, L, 256]"
+        assert pos.shape[0] in (1, B * T) and tuple(pos.shape[1:]) == (256, H, W), "pos must be [1 or clips*T, 256, H, W]"
+        for t in (vis, vid, text, pos):
+            assert t.dtype == torch.float32 and t.is_contiguous()
+        inp = VgqaInputs(B, T, H, W, Lt, self._p(vis), self._p(vid), self._p(text), self._p(pos), pos.shape[0],
+                         self._p(vis_mask), self._p(text_mask), self._p(ori_sizes_hw), self._p(force1), self._p(force2),
+                         iteration_rate)
+        out = VgqaOutputs(**{k: self._p(outs.get(k)) for k in OUTPUT_FIELDS})
+        return inp, out
+
+    def forward(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, ori_sizes_hw=None, force_choose1=None,
+                force_choose2=None, iteration_rate=-1, outs=None, want=None):
+        """Device-resident inputs (fp32 CUDA tensors, reference layouts); enqueues on the current stream."""
+        B, T, _, H, W = vis.shape
+        if outs is None:
+            outs = self.alloc_outputs(B, T, H, W, text.shape[1], want)
+            if ori_sizes_hw is None:
+                outs.pop("boxes_px", None), outs.pop("sted_idx", None)
+        inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force_choose1, force_choose2,
+                                 iteration_rate, outs)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self._L.vgqa_forward(self._ctx, ctypes.byref(inp), ctypes.byref(out), c_void_p(st)))
+        return outs
+
+    def forward_host(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, ori_sizes_hw=None,
+                     force_choose1=None, force_choose2=None, iteration_rate=-1, outs=None, want=None):
+        """Host buffers (CPU tensors, ideally pinned): H2D + forward + D2H inside the call (synchronous)."""
+        B, T, _, H, W = vis.shape
+        if outs is None:
+            outs = self.alloc_outputs(B, T, H, W, text.shape[1], want, host=True)
+            if ori_sizes_hw is None:
+                outs.pop("boxes_px", None), outs.pop("sted_idx", None)
+        inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force_choose1, force_choose2,
+                                 iteration_rate, outs)
+        _lib.check(self._L.vgqa_forward_host(self._ctx, ctypes.byref(inp), ctypes.byref(out)))
+        return outs
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self._L.vgqa_last_launch_count(self._ctx))
