@@ -37,7 +37,7 @@ __device__ __forceinline__ uint32_t swz64(int row, int chunk) { return row * 64 
 
 __global__ void __launch_bounds__(128) mha32_kernel(const Mha32Params p) {
   extern __shared__ __align__(16) uint8_t sm[];
-  const int g = blockIdx.x, h = blockIdx.y;
+  const int g = blockIdx.x >> 3, h = blockIdx.x & 7;  // the 8 heads of a group run together → K/V lines shared in L2
   const int Sq = p.Sq, Sk = p.Sk;
   const int Sq_pad = (Sq + 15) & ~15, Sk_pad = (Sk + 63) & ~63;
   uint8_t* sQ = sm;
@@ -180,7 +180,7 @@ void mha32(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ld
     VG_CUDA(cudaFuncSetAttribute(mha32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  mha32_kernel<<<dim3(groups, 8), 128, smem, stream>>>(p);
+  mha32_kernel<<<groups * 8, 128, smem, stream>>>(p);
   VG_CUDA(cudaGetLastError());
 }
 

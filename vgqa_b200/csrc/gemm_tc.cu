@@ -34,7 +34,8 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct EpiDev {
@@ -121,13 +122,14 @@ __device__ __forceinline__ void epi_store(const float (&v)[32], const EpiDev& ep
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const EpiDev ep, int M, int N, int K) {
+               const __grid_constant__ CUtensorMap tma_c, const EpiDev ep, int M, int N, int K) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_stage_out = smem + Cfg::kStages * Cfg::kStageBytes;  // 1024-aligned (stage sizes are multiples of 1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage_out + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
@@ -144,6 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_c);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -222,15 +225,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       uint32_t raw[32];
       float v[32];
       if (!do_ln) {
+        // TMEM → registers → 128B-swizzled smem slab (32 rows x 128 B per warp) → TMA store; double-buffered per warp
+        uint8_t* my_stage = smem_stage_out + (warp - 2) * 8192;
+        const int cols_per_unit = ep.c_f32 ? 32 : 64;   // 128 B of output per row
+        const int units = BN / cols_per_unit;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          tmem_ld32(taddr + c * 32, raw);
-          tmem_ld_wait();
+        for (int u = 0; u < units; ++u) {
+          uint8_t* buf = my_stage + (u & 1) * 4096;
+          if (lane == 0) tma_store_wait_read<1>();      // the store issued two units ago has drained this buffer
+          __syncwarp();
+          const int halves = ep.c_f32 ? 1 : 2;
+          for (int hf = 0; hf < halves; ++hf) {
+            const int col = u * cols_per_unit + hf * 32;
+            tmem_ld32(taddr + col, raw);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          if (valid) {
-            epi_transform(v, ep, row, n0 + c * 32);
-            epi_store(v, ep, row, n0 + c * 32);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+            if (valid) epi_transform(v, ep, row, n0 + col);
+            uint8_t* rowp = buf + lane * 128;
+            if (ep.c_f32) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(rowp + ((i ^ (lane & 7)) << 4)) =
+                    make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<uint4*>(rowp + (((hf * 4 + i) ^ (lane & 7)) << 4)) =
+                    make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                               pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tma_c, buf, n0 + u * cols_per_unit, m0 + quad * 32);
+            tma_store_commit();
           }
         }
       } else {
@@ -283,6 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   }
 
+  if (warp >= 2 && lane == 0) tma_store_wait_all<0>();  // smem must outlive the bulk stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -309,18 +340,20 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 2D bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows x 64 cols], 128B swizzle.
-static CUtensorMap make_tmap_2d(const bf16* ptr, int rows, int cols, int ld, int box_rows) {
+// 2D row-major [rows, cols] (bf16 or fp32) with row stride ld (elements); box = [box_rows x 128 bytes], 128B swizzle.
+static CUtensorMap make_tmap_2d(const void* ptr, int rows, int cols, int ld, int box_rows, bool f32 = false) {
   CUtensorMap m;
+  const size_t es = f32 ? 4 : 2;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(bf16)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   VG_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base pointer must be 16-byte aligned");
-  VG_CHECK((ld * sizeof(bf16)) % 16 == 0, "TMA row stride must be a multiple of 16 bytes");
-  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VG_CHECK((ld * es) % 16 == 0, "TMA row stride must be a multiple of 16 bytes");
+  CUresult r = get_encode()(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                            const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
   return m;
 }
@@ -340,9 +373,10 @@ static void launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, int M, i
   }
   CUtensorMap ta = make_tmap_2d(A, M, K, lda, BM);
   CUtensorMap tb = make_tmap_2d(W, N, K, ldw, BN);
+  CUtensorMap tc = make_tmap_2d(ep.C, M, N, ep.ldc, 32, ep.c_f32 != 0);
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tc_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, tb, ep, M, N, K);
+  gemm_tc_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, tb, tc, ep, M, N, K);
   VG_CUDA(cudaGetLastError());
   ++g_gemm_launches;
 }
