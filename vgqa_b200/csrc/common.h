@@ -52,6 +52,10 @@ struct GemmEpi {
   int ldres32 = 0;
   float* C32 = nullptr;          // optional second, fp32 copy of the output (the fp32 residual stream)
   int ldc32 = 0;
+  bf16* C2 = nullptr;            // LN path only: third output  bf16(LN(v) + add2[row % add2_period])  (x + pos for Q/K)
+  int ldc2 = 0;
+  const bf16* add2 = nullptr;    // [add2_period, 256] bf16
+  int add2_period = 1;
   const float* ln_w = nullptr;
   const float* ln_b = nullptr;
   float ln_eps = 1e-5f;
@@ -60,6 +64,10 @@ struct GemmEpi {
 // C[M,N] = epilogue(A[M,K] (row-major, lda) * W[N,K]^T (row-major, ldw)).  K % 64 == 0, N % 64 == 0.
 void gemm_bf16_tn(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpi& ep,
                   cudaStream_t stream);
+// Weight-stationary variant (gemm_ws.cu) — used automatically by gemm_bf16_tn when the problem qualifies.
+bool gemm_ws_supported(int N, int K, const GemmEpi& e);
+void gemm_ws(const bf16* A, const bf16* A2, int a_switch_col, int lda, const bf16* W, int ldw, int M, int N, int K,
+             const GemmEpi& e, cudaStream_t stream);
 int gemm_launch_count();  // number of tcgen05 GEMM launches issued so far by this process
 
 }  // namespace vg

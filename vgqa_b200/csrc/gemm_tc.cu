@@ -40,6 +40,9 @@ struct GemmCfg {
 
 struct EpiDev {
   void* C;
+  bf16* C2;
+  const bf16* add2;
+  int ldc2, add2_period;
   float* C32;
   const float* res32;
   const float* bias;
@@ -303,7 +306,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             v[4 * i + 2] = (__uint_as_float(raw[4 * i + 2]) - mean) * rstd * w.z + b.z;
             v[4 * i + 3] = (__uint_as_float(raw[4 * i + 3]) - mean) * rstd * w.w + b.w;
           }
-          if (valid) epi_store(v, ep, row, n0 + c * 32);
+          if (valid) {
+            epi_store(v, ep, row, n0 + c * 32);
+            if (ep.C2 != nullptr) {  // third output: LN(v) + positional rows (bf16)
+              const uint4* a4 = reinterpret_cast<const uint4*>(ep.add2 + (size_t)(row % ep.add2_period) * 256 + n0 + c * 32);
+              uint4* o4 = reinterpret_cast<uint4*>(ep.C2 + (size_t)row * ep.ldc2 + n0 + c * 32);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = __ldg(a4 + i);
+                float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+                o4[i] = make_uint4(pack_bf16(v[8 * i] + a.x, v[8 * i + 1] + a.y), pack_bf16(v[8 * i + 2] + b.x, v[8 * i + 3] + b.y),
+                                   pack_bf16(v[8 * i + 4] + cc.x, v[8 * i + 5] + cc.y), pack_bf16(v[8 * i + 6] + d.x, v[8 * i + 7] + d.y));
+              }
+            }
+          }
         }
       }
       tc_fence_before();
@@ -341,7 +357,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 2D row-major [rows, cols] (bf16 or fp32) with row stride ld (elements); box = [box_rows x 128 bytes], 128B swizzle.
-static CUtensorMap make_tmap_2d(const void* ptr, int rows, int cols, int ld, int box_rows, bool f32 = false) {
+CUtensorMap make_tmap_2d(const void* ptr, int rows, int cols, int ld, int box_rows, bool f32) {
   CUtensorMap m;
   const size_t es = f32 ? 4 : 2;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -361,6 +377,15 @@ static CUtensorMap make_tmap_2d(const void* ptr, int rows, int cols, int ld, int
 static int g_num_sms = 0;
 static int g_gemm_launches = 0;
 int gemm_launch_count() { return g_gemm_launches; }
+void count_gemm_launch() { ++g_gemm_launches; }
+int device_sm_count() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    VG_CUDA(cudaGetDevice(&dev));
+    VG_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return g_num_sms;
+}
 
 template <int BN>
 static void launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const EpiDev& ep,
@@ -371,8 +396,8 @@ static void launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, int M, i
     VG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  CUtensorMap ta = make_tmap_2d(A, M, K, lda, BM);
-  CUtensorMap tb = make_tmap_2d(W, N, K, ldw, BN);
+  CUtensorMap ta = make_tmap_2d(A, M, K, lda, BM, false);
+  CUtensorMap tb = make_tmap_2d(W, N, K, ldw, BN, false);
   CUtensorMap tc = make_tmap_2d(ep.C, M, N, ep.ldc, 32, ep.c_f32 != 0);
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
@@ -392,7 +417,12 @@ void gemm_bf16_tn(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, 
     VG_CUDA(cudaGetDevice(&dev));
     VG_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  if (gemm_ws_supported(N, K, e)) {
+    gemm_ws(A, nullptr, 0, lda, W, ldw, M, N, K, e, stream);
+    return;
+  }
   EpiDev ep;
+  ep.C2 = e.C2; ep.ldc2 = e.ldc2; ep.add2 = e.add2; ep.add2_period = e.add2_period > 0 ? e.add2_period : 1;
   ep.C = e.C; ep.bias = e.bias; ep.mul = e.mul; ep.res = e.res; ep.ln_w = e.ln_w; ep.ln_b = e.ln_b;
   ep.ldc = e.ldc; ep.c_f32 = e.c_f32; ep.bias_period = e.bias_period > 0 ? e.bias_period : 1;
   ep.bias_ld = e.bias_ld; ep.act = e.act; ep.ldmul = e.ldmul; ep.ldres = e.ldres; ep.ln_eps = e.ln_eps;

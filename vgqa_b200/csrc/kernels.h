@@ -13,10 +13,11 @@ void xattn1(const bf16* qt, const bf16* mem, long long frame_stride_rows, int F,
 
 // ---- small.cu
 // NCHW fp32 features → token-major bf16 rows: X[(f*S + tok0 + p), c] = in[f, c, p]   (in may be broadcast: fstride 0)
-void nchw_to_tokens(const float* in, long long in_fstride, bf16* X, float* X32, int F, int S, int tok0, int P,
-                    cudaStream_t st);
+void nchw_to_tokens(const float* in, long long in_fstride, bf16* X, float* X32, const float* pos, long long pos_fstride,
+                    bf16* XP, int F, int S, int tok0, int P, cudaStream_t st);
 // X[(f*S + tok0 + l), :] = text[(f / T), l, :]   (text == nullptr → zeros)
-void text_to_tokens(const float* text, bf16* X, float* X32, int F, int T, int S, int tok0, int L, cudaStream_t st);
+void text_to_tokens(const float* text, bf16* X, float* X32, bf16* XP, int F, int T, int S, int tok0, int L,
+                    cudaStream_t st);
 // encoded_mask[f, :] = [vis_mask (with [f,0]=0) | text_mask[f/T] | vis_mask]
 void build_encoded_mask(const uint8_t* vis_mask, const uint8_t* text_mask, uint8_t* out, int F, int T, int P, int L,
                         cudaStream_t st);

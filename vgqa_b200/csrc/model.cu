@@ -97,7 +97,7 @@ struct Arena {
 
 struct Lin { bf16* W = nullptr; float* b = nullptr; int N = 0, K = 0; };
 struct LNp { float* w = nullptr; float* b = nullptr; };
-struct EncLayer { Lin qkv, tab, out, ff1, ff2; LNp ln1, ln2; };
+struct EncLayer { Lin qkv, out, ff1, ff2; LNp ln1, ln2; };
 struct TsLayer { Lin q, o, inter, outp; LNp ln_a, ln_o; int kv_off; };
 struct SaLayer { Lin qabs, vo, inter, outp; LNp ln_a, ln_o; };
 struct Head { Lin t; LNp ln; float* dw = nullptr; float* db = nullptr; int vocab = 0; };
@@ -134,6 +134,7 @@ struct vgqa_ctx {
   // ---- workspace (device)
   bf16 *X, *X1, *QKV, *AO, *HID, *Xf, *pos_enc, *kposb;
   float *X32, *X1_32;  // fp32 residual stream of the encoder
+  bf16* XP;            // bf16(x + pos): A operand of the Q/K in-projection
   float* enc_tab;
   uint8_t* encmask;
   float *in_vis, *in_vid, *in_text, *in_pos, *in_sizes, *in_f1, *in_f2;
@@ -251,10 +252,7 @@ static void pack_weights(vgqa_ctx* c) {
     EncLayer& e = c->enc[l];
     const HostT& w = P.get(p + "self_attn.in_proj_weight", {768, 256});
     const HostT& b = P.get(p + "self_attn.in_proj_bias", {768});
-    e.qkv = P.lin(w.v.data(), nullptr, 768, 256);
-    std::vector<float> wt(w.v);
-    std::fill(wt.begin() + (size_t)512 * 256, wt.end(), 0.f);  // V gets no positional term
-    e.tab = P.lin(wt.data(), b.v.data(), 768, 256);
+    e.qkv = P.lin(w.v.data(), b.v.data(), 768, 256);
     e.out = P.lin(p + "self_attn.out_proj", 256, 256);
     e.ff1 = P.lin(p + "linear1", F, 256);
     e.ff2 = P.lin(p + "linear2", 256, F);
@@ -476,7 +474,7 @@ static void carve_workspace(vgqa_ctx* c) {
   Arena& a = c->ws;
   c->X = a.get<bf16>(R * 256); c->X1 = a.get<bf16>(R * 256); c->QKV = a.get<bf16>(R * 768); c->AO = a.get<bf16>(R * 256);
   c->HID = a.get<bf16>(R * FF); c->Xf = a.get<bf16>(R * 256);
-  c->X32 = a.get<float>(R * 256); c->X1_32 = a.get<float>(R * 256);
+  c->X32 = a.get<float>(R * 256); c->X1_32 = a.get<float>(R * 256); c->XP = a.get<bf16>(R * 256);
   c->pos_enc = a.get<bf16>(R * 256); c->kposb = a.get<bf16>(R * 1536); c->enc_tab = a.get<float>(R * 768);
   c->encmask = a.get<uint8_t>(R);
   c->in_vis = a.get<float>(F * 256 * P); c->in_vid = a.get<float>(F * 256 * P); c->in_text = a.get<float>(B * L * 256);
@@ -538,34 +536,35 @@ static void run_encoder(Fwd& f, const vgqa_inputs& in, bool have_mask, int pos_r
   cudaStream_t st = f.st;
   const int S = f.S, P = f.P, L = f.L, R = f.R, F = f.F;
   // tokens: [vis | text | vid] per frame (modal_encoder.py:64)
-  nchw_to_tokens(in.vis, (long long)256 * P, c->X, c->X32, F, S, 0, P, st);
-  text_to_tokens(in.text, c->X, c->X32, F, f.T, S, P, L, st);
-  nchw_to_tokens(in.vid, (long long)256 * P, c->X, c->X32, F, S, P + L, P, st);
+  const long long pos_fs = in.pos_frames > 1 ? (long long)256 * P : 0;
+  nchw_to_tokens(in.vis, (long long)256 * P, c->X, c->X32, in.pos, pos_fs, c->XP, F, S, 0, P, st);
+  text_to_tokens(in.text, c->X, c->X32, c->XP, F, f.T, S, P, L, st);
+  nchw_to_tokens(in.vid, (long long)256 * P, c->X, c->X32, in.pos, pos_fs, c->XP, F, S, P + L, P, st);
   // positional rows: [pos | 0 | pos] (modal_encoder.py:66)
   const int pf = in.pos_frames;
-  nchw_to_tokens(in.pos, (long long)256 * P, c->pos_enc, nullptr, pf, S, 0, P, st);
-  text_to_tokens(nullptr, c->pos_enc, nullptr, pf, 1, S, P, L, st);
-  nchw_to_tokens(in.pos, (long long)256 * P, c->pos_enc, nullptr, pf, S, P + L, P, st);
+  nchw_to_tokens(in.pos, (long long)256 * P, c->pos_enc, nullptr, nullptr, 0, nullptr, pf, S, 0, P, st);
+  text_to_tokens(nullptr, c->pos_enc, nullptr, nullptr, pf, 1, S, P, L, st);
+  nchw_to_tokens(in.pos, (long long)256 * P, c->pos_enc, nullptr, nullptr, 0, nullptr, pf, S, P + L, P, st);
   f.count(6);
   if (have_mask) { build_encoded_mask(in.vis_mask, in.text_mask, c->encmask, F, f.T, P, L, st); f.count(); }
   const uint8_t* km = have_mask ? c->encmask : nullptr;
-  bf16* x = c->X;
   for (size_t l = 0; l < c->enc.size(); ++l) {
     EncLayer& e = c->enc[l];
-    {  // table = pos_enc [Wq;Wk;0]^T + in_proj_bias  (fp32)
-      GemmEpi ep; ep.C = c->enc_tab; ep.ldc = 768; ep.c_f32 = 1; ep.bias = e.tab.b; ep.bias_ld = 768;
-      f.gemm(c->pos_enc, 256, e.tab, pos_rows, ep);
-    }
-    {  // QKV = x Wqkv^T + table[row % pos_rows]
-      GemmEpi ep; ep.C = c->QKV; ep.ldc = 768; ep.bias = c->enc_tab; ep.bias_period = pos_rows; ep.bias_ld = 768;
-      f.gemm(x, 256, e.qkv, R, ep);
+    {  // q,k = (x + pos) Wqk^T + b ; v = x Wv^T + b   (modal_encoder.py:171-172) — one launch, two A operands
+      GemmEpi ep; ep.C = c->QKV; ep.ldc = 768; ep.bias = e.qkv.b; ep.bias_ld = 768;
+      gemm_ws(c->XP, c->X, 512, 256, e.qkv.W, 256, R, 768, 256, ep, st);
+      f.count();
     }
     mha32(c->QKV, 768, c->QKV + 256, 768, c->QKV + 512, 768, c->AO, 256, F, S, S, km, 0.17677669529663687f, st);
     f.count();
     f.linear_res_ln(c->AO, 256, e.out, R, c->X32, e.ln1, 1e-5f, c->X1, 256, c->X1_32);
     f.linear(c->X1, 256, e.ff1, R, c->HID, e.ff1.N, ACT_RELU);
-    f.linear_res_ln(c->HID, e.ff2.K, e.ff2, R, c->X1_32, e.ln2, 1e-5f, c->X, 256, c->X32);
-    x = c->X;
+    {  // x = LN2(x1 + W2 relu(..) + b2); also emits x + pos for the next layer's Q/K projection
+      GemmEpi ep; ep.C = c->X; ep.ldc = 256; ep.bias = e.ff2.b; ep.bias_ld = 256; ep.res32 = c->X1_32; ep.ldres32 = 256;
+      ep.C32 = c->X32; ep.ldc32 = 256; ep.ln_w = e.ln2.w; ep.ln_b = e.ln2.b; ep.ln_eps = 1e-5f;
+      if (l + 1 < c->enc.size()) { ep.C2 = c->XP; ep.ldc2 = 256; ep.add2 = c->pos_enc; ep.add2_period = pos_rows; }
+      f.gemm(c->HID, e.ff2.K, e.ff2, R, ep);
+    }
   }
   enc_finalize(c->X32, c->enc_norm.w, c->enc_norm.b, 1e-5f, c->Xf, c->frames_cls, c->pool[1], c->pool[0], c->pool32[1],
                c->pool32[0], F, S, P, L, st);

@@ -9,16 +9,20 @@ namespace vg {
 // ---------------------------------------------------------------- layout: NCHW fp32 → token-major bf16
 // Replaces `flatten(2).permute(2,0,1)` + `torch.cat` of CrossModalEncoder.forward (modal_encoder.py:50-66).
 __global__ void __launch_bounds__(256) nchw_to_tokens_kernel(const float* __restrict__ in, long long in_fstride,
-                                                             bf16* __restrict__ X, float* __restrict__ X32, int S, int tok0,
-                                                             int P) {
+                                                             bf16* __restrict__ X, float* __restrict__ X32,
+                                                             const float* __restrict__ pos, long long pos_fstride,
+                                                             bf16* __restrict__ XP, int S, int tok0, int P) {
   __shared__ float tile[32][33];
   const int f = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  __shared__ float ptile[32][33];
   const float* src = in + (size_t)f * in_fstride;
+  const float* psrc = pos ? pos + (size_t)f * pos_fstride : nullptr;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int c = c0 + ty + 8 * k, p = p0 + tx;
     tile[ty + 8 * k][tx] = p < P ? src[(size_t)c * P + p] : 0.f;
+    if (psrc) ptile[ty + 8 * k][tx] = p < P ? psrc[(size_t)c * P + p] : 0.f;
   }
   __syncthreads();
 #pragma unroll
@@ -28,18 +32,20 @@ __global__ void __launch_bounds__(256) nchw_to_tokens_kernel(const float* __rest
       const size_t o = ((size_t)f * S + tok0 + p) * 256 + c0 + tx;
       X[o] = __float2bfloat16(tile[tx][ty + 8 * k]);
       if (X32 != nullptr) X32[o] = tile[tx][ty + 8 * k];
+      if (XP != nullptr) XP[o] = __float2bfloat16(tile[tx][ty + 8 * k] + ptile[tx][ty + 8 * k]);
     }
   }
 }
-void nchw_to_tokens(const float* in, long long in_fstride, bf16* X, float* X32, int F, int S, int tok0, int P,
-                    cudaStream_t st) {
+void nchw_to_tokens(const float* in, long long in_fstride, bf16* X, float* X32, const float* pos, long long pos_fstride,
+                    bf16* XP, int F, int S, int tok0, int P, cudaStream_t st) {
   dim3 grid((P + 31) / 32, 8, F);
-  nchw_to_tokens_kernel<<<grid, 256, 0, st>>>(in, in_fstride, X, X32, S, tok0, P);
+  nchw_to_tokens_kernel<<<grid, 256, 0, st>>>(in, in_fstride, X, X32, pos, pos_fstride, XP, S, tok0, P);
   VG_CUDA(cudaGetLastError());
 }
 
 __global__ void __launch_bounds__(256) text_to_tokens_kernel(const float* __restrict__ text, bf16* __restrict__ X,
-                                                             float* __restrict__ X32, int T, int S, int tok0, int L) {
+                                                             float* __restrict__ X32, bf16* __restrict__ XP, int T, int S,
+                                                             int tok0, int L) {
   const int f = blockIdx.x, b = f / T;
   for (int i = threadIdx.x; i < L * 64; i += 256) {
     const int l = i >> 6, c = (i & 63) * 4;
@@ -51,10 +57,12 @@ __global__ void __launch_bounds__(256) text_to_tokens_kernel(const float* __rest
     }
     *reinterpret_cast<uint2*>(X + ((size_t)f * S + tok0 + l) * 256 + c) = o;
     if (X32 != nullptr) *reinterpret_cast<float4*>(X32 + ((size_t)f * S + tok0 + l) * 256 + c) = v;
+    if (XP != nullptr) *reinterpret_cast<uint2*>(XP + ((size_t)f * S + tok0 + l) * 256 + c) = o;  // pos = 0 on text rows
   }
 }
-void text_to_tokens(const float* text, bf16* X, float* X32, int F, int T, int S, int tok0, int L, cudaStream_t st) {
-  text_to_tokens_kernel<<<F, 256, 0, st>>>(text, X, X32, T, S, tok0, L);
+void text_to_tokens(const float* text, bf16* X, float* X32, bf16* XP, int F, int T, int S, int tok0, int L,
+                    cudaStream_t st) {
+  text_to_tokens_kernel<<<F, 256, 0, st>>>(text, X, X32, XP, T, S, tok0, L);
   VG_CUDA(cudaGetLastError());
 }
 
