@@ -68,6 +68,9 @@ void gemm_bf16_tn(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, 
 bool gemm_ws_supported(int N, int K, const GemmEpi& e);
 void gemm_ws(const bf16* A, const bf16* A2, int a_switch_col, int lda, const bf16* W, int ldw, int M, int N, int K,
              const GemmEpi& e, cudaStream_t stream);
+// Residual + LayerNorm epilogue variant (gemm_ln.cu), N = 256.
+bool gemm_ln_supported(int N, int K, const GemmEpi& e);
+void gemm_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, const GemmEpi& e, cudaStream_t stream);
 int gemm_launch_count();  // number of tcgen05 GEMM launches issued so far by this process
 
 }  // namespace vg

@@ -417,6 +417,10 @@ void gemm_bf16_tn(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, 
     VG_CUDA(cudaGetDevice(&dev));
     VG_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  if (gemm_ln_supported(N, K, e)) {
+    gemm_ln(A, lda, W, ldw, M, K, e, stream);
+    return;
+  }
   if (gemm_ws_supported(N, K, e)) {
     gemm_ws(A, nullptr, 0, lda, W, ldw, M, N, K, e, stream);
     return;
