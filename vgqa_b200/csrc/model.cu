@@ -155,6 +155,8 @@ struct vgqa_ctx {
   cudaStream_t host_stream = nullptr;
   cudaStream_t exec_stream = nullptr;  // graphs are captured and replayed here (the legacy stream cannot be captured)
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaStream_t aux_stream = nullptr;   // second branch of the fork/join sections (classifier pairs, the two decoders)
+  cudaEvent_t fj[32] = {};
   // graph cache
   struct GraphEntry { cudaGraphExec_t exec; int launches; };
   std::map<std::vector<uint64_t>, GraphEntry> graphs;
@@ -510,8 +512,23 @@ static void carve_workspace(vgqa_ctx* c) {
 // ------------------------------------------------------------------------------------------------ forward
 struct Fwd {
   vgqa_ctx* c;
-  cudaStream_t st;
+  cudaStream_t st;          // stream the helpers below launch on (main or aux)
+  cudaStream_t main, aux;
+  int ev_i = 0;
   int B, T, P, L, S, F, R;
+  // independent sub-graphs (the two classifiers of a pair, TimeDecoder vs PosDecoder) run on two streams; under
+  // stream capture this becomes two parallel branches of the CUDA graph.
+  void fork() {
+    VG_CUDA(cudaEventRecord(c->fj[ev_i], main));
+    VG_CUDA(cudaStreamWaitEvent(aux, c->fj[ev_i], 0));
+    ev_i = (ev_i + 1) & 31;
+  }
+  void join() {
+    VG_CUDA(cudaEventRecord(c->fj[ev_i], aux));
+    VG_CUDA(cudaStreamWaitEvent(main, c->fj[ev_i], 0));
+    ev_i = (ev_i + 1) & 31;
+    st = main;
+  }
   void gemm(const bf16* A, int lda, const Lin& w, int M, const GemmEpi& ep) {
     gemm_bf16_tn(A, lda, w.W, w.K, M, w.N, w.K, ep, st);
     ++c->launches;
@@ -577,7 +594,9 @@ static void run_temporal_sampling(Fwd& f) {
   vgqa_ctx* c = f.c;
   const int F = f.F;
   f.linear(c->ftext, 256, c->ts_kv, f.B * f.L, c->kv_ts, 2048);
+  f.fork();
   for (int k = 0; k < 2; ++k) {
+    f.st = k == 0 ? f.main : f.aux;
     const bf16* h = c->pool[k];
     const float* h32 = c->pool32[k];
     for (int i = 0; i < 2; ++i) {
@@ -596,13 +615,16 @@ static void run_temporal_sampling(Fwd& f) {
     rowvec_head(c->c_a[k], 256, hd.dw, hd.db, c->logit_f[k], 1, F, 1, 0, f.st);
     f.count();
   }
+  f.join();
 }
 
 // SpatialActivation + query seeding (classifier.py:64-81; grounding_net.py:131-136)
 static void run_spatial_seed(Fwd& f, const float* w, const float* K) {
   vgqa_ctx* c = f.c;
   const int F = f.F, P = f.P, S = f.S;
+  f.fork();
   for (int k = 0; k < 2; ++k) {
+    f.st = k == 0 ? f.main : f.aux;
     const int tok0 = k == 0 ? P + f.L : 0;  // t_* reads vid tokens, s_* reads vis tokens
     const bf16* q = c->q0;
     const float* q32 = c->q0_32;
@@ -627,6 +649,7 @@ static void run_spatial_seed(Fwd& f, const float* w, const float* K) {
                 k == 0 ? c->t_tgt32 : c->p_tgt32, f.B, f.T, P, f.st);
     f.count(4);
   }
+  f.join();
 }
 
 static void run_decoders(Fwd& f, bool have_mask, int pos_frames) {
@@ -638,6 +661,7 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames) {
   // anchors from frames_cls (query_decoder.py:92-94)
   pos_fc_boxes(c->frames_cls, c->pfc_ln0w, c->pfc_ln0b, c->pfc_W, c->pfc_b, c->pfc_ln4w, c->pfc_ln4b, c->boxes0, F, st);
   f.count();
+  f.fork();
   // ---------------- TimeDecoder (query_decoder.py:379-486), memory = [text | vid] tokens
   for (int l = 0; l < D; ++l) {
     TimeLayer& t = c->tl[l];
@@ -655,7 +679,9 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames) {
     ln_rows(c->t_tgt32, 256, c->time_norm.w, c->time_norm.b, 1e-5f, c->t_inter + (size_t)l * F * 256, 256, F, st);  // :412
     f.count(3);
   }
-  // ---------------- PosDecoder (query_decoder.py:129-375), memory = [vis | text] tokens
+  // ---------------- PosDecoder (query_decoder.py:129-375), memory = [vis | text] tokens — second branch
+  f.st = f.aux;
+  st = f.aux;
   { GemmEpi ep; ep.C = c->kposb; ep.ldc = 1536; ep.bias = c->kpos_all.b; ep.bias_ld = c->kpos_all.N;
     f.gemm(c->pos_enc, 256, c->kpos_all, pos_frames * S, ep); }  // ca_kpos_proj(pos_s) for all layers (:309)
   const float* boxes = c->boxes0;
@@ -695,6 +721,7 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames) {
     boxes = anc;
     f.count(3);
   }
+  f.join();
 }
 
 static std::string shape_str(const vgqa_inputs& in) {
@@ -716,7 +743,11 @@ static void check_inputs(vgqa_ctx* c, const vgqa_inputs& in) {
 
 static void forward_body(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out, cudaStream_t st) {
   Fwd f;
-  f.c = c; f.st = st; f.B = in.clips; f.T = in.T; f.P = in.H * in.W; f.L = in.L; f.S = 2 * f.P + f.L;
+  if (!c->aux_stream) {
+    VG_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    for (auto& e : c->fj) VG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  f.c = c; f.st = st; f.main = st; f.aux = c->aux_stream; f.B = in.clips; f.T = in.T; f.P = in.H * in.W; f.L = in.L; f.S = 2 * f.P + f.L;
   f.F = f.B * f.T; f.R = f.F * f.S;
   const int F = f.F, D = (int)c->tl.size();
   const bool have_mask = in.vis_mask != nullptr || in.text_mask != nullptr;
@@ -816,6 +847,8 @@ void vgqa_destroy(vgqa_ctx* c) {
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->host_stream) cudaStreamDestroy(c->host_stream);
   if (c->exec_stream) cudaStreamDestroy(c->exec_stream);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  for (auto& e : c->fj) if (e) cudaEventDestroy(e);
   if (c->ev_in) cudaEventDestroy(c->ev_in);
   if (c->ev_out) cudaEventDestroy(c->ev_out);
   c->warena.release();
