@@ -124,6 +124,10 @@ int vgqa_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N,
                    const void* res, int ldres, const float* ln_w, const float* ln_b, float ln_eps, void* stream);
 int vgqa_mha32(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int groups,
                int Sq, int Sk, const uint8_t* kmask, float scale, void* stream);
+/* Encoder per-frame self-attention over the packed in-projection output QKV[F*S,768] → AO[F*S,256];
+ * use_tcgen05 = 1: TMEM/TMA kernel (S <= 128), 0: warp-MMA flash kernel (any S). */
+int vgqa_enc_attn(const void* QKV, void* AO, int F, int S, const uint8_t* kmask, float scale, int use_tcgen05,
+                  void* stream);
 int vgqa_xattn1(const void* qt, const void* mem, long long frame_stride_rows, int F, int Mk, const void* posk,
                 long long posk_fstride, const void* q2, const void* kpos, int ldkpos, long long kpos_fstride,
                 const uint8_t* kmask, int ldmask, float scale, void* ctx_out, float* att_out, void* stream);

@@ -89,3 +89,35 @@ def test_xattn1(F, S, tok0, Mk, use_pos, use_kpos, use_mask, want_att):
         a = p.sum(1).sigmoid()
         a = (a - a.min(1, keepdim=True)[0]) / (a.max(1, keepdim=True)[0] - a.min(1, keepdim=True)[0] + 1e-6)
         assert (att - a).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("F,S,masked", [(5, 118, False), (300, 118, False), (3, 128, False), (7, 47, True), (2, 3, False),
+                                        (4, 27, False), (9, 118, True)])
+def test_enc_attn_tcgen05(F, S, masked):
+    """tcgen05/TMEM per-frame attention vs torch fp32, and vs the warp-MMA kernel on the same data."""
+    from vgqa_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(F * 7 + S)
+    qkv = torch.randn(F * S, 768, device="cuda", generator=g).bfloat16()
+    mask_u8 = None
+    if masked:
+        mask = torch.rand(F, S, device="cuda", generator=g) < 0.3
+        mask[:, 0] = False
+        mask_u8 = mask.to(torch.uint8).contiguous()
+    scale = 1 / math.sqrt(32)
+    outs = []
+    for use_tc in (1, 0):
+        O = torch.full((F * S + 8, 256), 7.0, device="cuda", dtype=torch.bfloat16)   # canary rows after the end
+        _lib.check(L.vgqa_enc_attn(_lib.ptr(qkv), _lib.ptr(O), F, S, _lib.ptr(mask_u8), scale, use_tc, _stream()))
+        torch.cuda.synchronize()
+        assert float((O[F * S:].float() - 7.0).abs().max()) == 0.0
+        outs.append(O[:F * S].float())
+    q = qkv[:, :256].float().view(F, S, 8, 32).transpose(1, 2)
+    k = qkv[:, 256:512].float().view(F, S, 8, 32).transpose(1, 2)
+    v = qkv[:, 512:].float().view(F, S, 8, 32).transpose(1, 2)
+    s = q @ k.transpose(-1, -2) * scale
+    if masked:
+        s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(F * S, 256)
+    assert (outs[0] - ref).abs().max().item() < 2e-2
+    assert (outs[1] - ref).abs().max().item() < 2e-2

@@ -1,0 +1,64 @@
+"""Micro-benchmarks of single kernels through the C-ABI (CUDA events, L2-exceeding operands)."""
+import math
+import sys
+import os
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from vgqa_b200 import _lib
+
+L = _lib.lib()
+st = lambda: torch.cuda.current_stream().cuda_stream
+
+
+def timeit(fn, reps=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3  # us
+
+
+def bench_attn(F=4096, S=118):
+    qkv = torch.randn(F * S, 768, device="cuda").bfloat16()
+    O = torch.empty(F * S, 256, device="cuda", dtype=torch.bfloat16)
+    for use_tc in (1, 0):
+        t = timeit(lambda: _lib.check(L.vgqa_enc_attn(_lib.ptr(qkv), _lib.ptr(O), F, S, None, 1 / math.sqrt(32), use_tc, st())))
+        flops = 4.0 * S * S * 32 * 8 * F
+        byts = F * S * (768 + 256) * 2
+        print(f"enc_attn {'tcgen05' if use_tc else 'mma.sync'} F={F} S={S}: {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s  {byts / t / 1e3:7.1f} GB/s")
+
+
+def bench_gemm(M, N, K, ln=False, act=0, name=""):
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    W = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    b = torch.zeros(N, device="cuda")
+    C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    lw = torch.ones(N, device="cuda") if ln else None
+    t = timeit(lambda: _lib.check(L.vgqa_gemm_bf16(_lib.ptr(A), K, _lib.ptr(W), K, M, N, K, _lib.ptr(C), N, 0, _lib.ptr(b), 1, N, act,
+                                                   None, 0, None, 0, _lib.ptr(lw), _lib.ptr(b) if ln else None, 1e-5, st())))
+    flops = 2.0 * M * N * K
+    byts = (M * K + M * N + N * K) * 2
+    print(f"gemm {name} M={M} N={N} K={K} ln={ln}: {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s  {byts / t / 1e3:7.1f} GB/s")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["attn", "gemm"]
+    if "attn" in which:
+        bench_attn()
+        bench_attn(F=1024, S=118)
+    if "gemm" in which:
+        R = 64 * 64 * 118
+        bench_gemm(R, 768, 256, name="qkv")
+        bench_gemm(R, 2048, 256, act=1, name="ffn1")
+        bench_gemm(R, 256, 256, ln=True, name="outproj+ln (no residual)")
+        bench_gemm(R, 256, 2048, ln=True, name="ffn2+ln (no residual)")
+        bench_gemm(4096, 2048, 256, name="dec qabs")
+        bench_gemm(4096, 256, 2048, ln=True, name="dec vo+ln")

@@ -31,6 +31,8 @@ def _declare(L):
     L.vgqa_mha32.restype = c_int
     L.vgqa_mha32.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p, c_float, c_void_p]
+    L.vgqa_enc_attn.restype = c_int
+    L.vgqa_enc_attn.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_int, c_void_p]
     L.vgqa_xattn1.restype = c_int
     L.vgqa_xattn1.argtypes = [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, ctypes.c_longlong,
                               c_void_p, c_void_p, c_int, ctypes.c_longlong, c_void_p, c_int, c_float, c_void_p,

@@ -59,4 +59,20 @@ int vgqa_xattn1(const void* qt, const void* mem, long long frame_stride_rows, in
   }
 }
 
+int vgqa_enc_attn(const void* QKV, void* AO, int F, int S, const uint8_t* kmask, float scale, int use_tcgen05,
+                  void* stream) {
+  try {
+    const vg::bf16* q = static_cast<const vg::bf16*>(QKV);
+    if (use_tcgen05)
+      vg::enc_attn_tc(q, static_cast<vg::bf16*>(AO), F, S, kmask, scale, static_cast<cudaStream_t>(stream));
+    else
+      vg::mha32(q, 768, q + 256, 768, q + 512, 768, static_cast<vg::bf16*>(AO), 256, F, S, S, kmask, scale,
+                static_cast<cudaStream_t>(stream));
+    return 0;
+  } catch (const std::exception& e) {
+    vg::set_last_error(e.what());
+    return 1;
+  }
+}
+
 }  // extern "C"

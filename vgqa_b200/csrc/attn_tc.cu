@@ -1,0 +1,329 @@
+// Per-frame encoder self-attention on tcgen05 / TMEM / TMA (S <= 128 tokens per frame, 8 heads, head_dim 32).
+//
+// Reference: F.multi_head_attention_forward inside TransformerEncoderLayer (vgqa/core/decoder/modal_encoder.py:172).
+// Input is the packed in-projection output QKV[R, 768] (q | k | v), output AO[R, 256] (heads concatenated).
+//
+// One persistent CTA per SM walks over frames; the unit of work is (frame, head):
+//   warp 0      TMA producer: Q, K, V head slices (128 rows x 64 B, 64B-swizzled) through a 3D tensor map
+//               (cols, tokens, frames) whose token dimension is the true S, so rows >= S are zero-filled on load and
+//               clipped on store — no cross-frame contamination, no tail code.
+//   warp 1      tcgen05.mma issuer:  S = Q K^T (128x128x32, 2 UMMAs, K-major SW64 operands) into TMEM, and
+//               O = P V (128x32x128, 8 UMMAs; P is a K-major SW128 smem operand written by the softmax warps,
+//               V is an MN-major SW64 operand straight from the TMA tile).
+//   warps 2..9  two softmax warpgroups ping-ponging on alternate units, one score row per thread (TMEM lane):
+//               row max / exp2 / row sum without any shuffle, P packed to bf16 in shared memory, then the
+//               O epilogue (1/sum scaling, bf16, TMA store).
+// S and O are double-buffered in TMEM (2 x 128 + 2 x 32 columns) so the tensor core works on unit u+1 while the
+// softmax of unit u runs.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vg {
+
+static constexpr int kAtQkvBytes = 3 * 8192;      // Q, K, V: 128 rows x 64 B each
+static constexpr int kAtPBytes = 32768;           // P: 2 atoms of 128 rows x 128 B
+static constexpr int kAtOBytes = 8192;            // O staging: 128 rows x 64 B
+static constexpr int kAtStages = 4;                // Q/K/V ring depth (decoupled from the 2 TMEM buffers)
+static constexpr int kAtSmem = kAtStages * kAtQkvBytes + 2 * kAtPBytes + 2 * kAtOBytes + 1024 + 256;
+
+struct AttnTcParams {
+  const uint8_t* kmask;  // [F, S] or nullptr
+  int S, F;
+  float scale_log2e;
+};
+
+// K-major operand, rows of 64 B (32 bf16), 64B swizzle: 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw64_kmajor(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;  // SWIZZLE_64B
+  return d;
+}
+// MN-major operand (N contiguous): rows = K index, 64 B (32 bf16 of N) per row, 64B swizzle; 8-row K groups 512 B apart
+// (SBO); a single 32-wide MN block, so the leading-dimension offset is never used.
+__device__ __forceinline__ uint64_t umma_desc_sw64_mnmajor(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(512 >> 4) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// 2^x on the MUFU pipe, flush-to-zero, no range fix-up code (ex2(-inf) = +0)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(320, 1)
+enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_o,
+                   const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_qkv = smem;                               // [kAtStages][Q|K|V]
+  uint8_t* s_p = s_qkv + kAtStages * kAtQkvBytes;      // [2][2 atoms]
+  uint8_t* s_o = s_p + 2 * kAtPBytes;                  // [2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_o + 2 * kAtOBytes);
+  uint64_t* qkv_full = bars;                    // [kAtStages]
+  uint64_t* qkv_empty = bars + kAtStages;       // [kAtStages]
+  uint64_t* s_full = bars + 2 * kAtStages;      // [2]
+  uint64_t* p_full = s_full + 2;                // [2]
+  uint64_t* o_full = s_full + 4;                // [2]
+  uint64_t* t_free = s_full + 6;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S;
+  int my_frames = 0;
+  for (int f = blockIdx.x; f < p.F; f += gridDim.x) ++my_frames;
+  const int num_units = my_frames * 8;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_o);
+    for (int b = 0; b < kAtStages; ++b) {
+      mbar_init(&qkv_full[b], 1);
+      mbar_init(&qkv_empty[b], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&p_full[b], 128);
+      mbar_init(&o_full[b], 1);
+      mbar_init(&t_free[b], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int u = 0; u < num_units; ++u) {
+        const int st = u % kAtStages;
+        const int f = blockIdx.x + (u >> 3) * gridDim.x, h = u & 7;
+        mbar_wait(&qkv_empty[st], ((u / kAtStages) & 1) ^ 1);
+        mbar_expect_tx(&qkv_full[st], kAtQkvBytes);
+        uint8_t* dst = s_qkv + st * kAtQkvBytes;
+        tma_load_3d(dst, &tm_qkv, &qkv_full[st], h * 32, 0, f);
+        tma_load_3d(dst + 8192, &tm_qkv, &qkv_full[st], 256 + h * 32, 0, f);
+        tma_load_3d(dst + 16384, &tm_qkv, &qkv_full[st], 512 + h * 32, 0, f);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 32) | (1u << 16);  // B operand (V) is MN-major
+    for (int u = 0; u <= num_units; ++u) {
+      if (u < num_units) {
+        const int b = u & 1, st = u % kAtStages;
+        const uint32_t ph = (u >> 1) & 1;
+        mbar_wait(&qkv_full[st], (u / kAtStages) & 1);
+        mbar_wait(&t_free[b], ph ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t q_addr = smem_u32(s_qkv + st * kAtQkvBytes);
+          const uint64_t qd = umma_desc_sw64_kmajor(q_addr), kd = umma_desc_sw64_kmajor(q_addr + 8192);
+          umma_bf16(tmem_base + b * 128, qd, kd, idesc_s, 0u);
+          umma_bf16(tmem_base + b * 128, qd + 2, kd + 2, idesc_s, 1u);
+          umma_commit(&s_full[b]);
+        }
+        __syncwarp();
+      }
+      if (u >= 1) {
+        const int v = u - 1, b = v & 1, st = v % kAtStages;
+        const uint32_t ph = (v >> 1) & 1;
+        mbar_wait(&p_full[b], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t v_addr = smem_u32(s_qkv + st * kAtQkvBytes + 16384);
+          const uint32_t p_addr = smem_u32(s_p + b * kAtPBytes);
+          const uint64_t vd = umma_desc_sw64_mnmajor(v_addr);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // 8 x 16 keys
+            const uint64_t pd = umma_desc_sw128_kmajor(p_addr + (k >> 2) * 16384) + 2 * (k & 3);
+            umma_bf16(tmem_base + 256 + b * 32, pd, vd + (uint64_t)((k * 1024) >> 4), idesc_o, k ? 1u : 0u);
+          }
+          umma_commit(&o_full[b]);
+          umma_commit(&qkv_empty[st]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== softmax + output warpgroups =====================
+    const int wg = (warp - 2) >> 2;          // 0 or 1: handles units u with (u & 1) == wg
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;        // score row / token index within the frame
+    const int wg_tid = (warp - 2 - wg * 4) * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    uint8_t* p_buf = s_p + wg * kAtPBytes;
+    uint8_t* o_buf = s_o + wg * kAtOBytes;
+    for (int u = wg; u < num_units; u += 2) {
+      const int f = blockIdx.x + (u >> 3) * gridDim.x, h = u & 7;
+      const uint32_t ph = (u >> 1) & 1;
+      const uint8_t* km = p.kmask ? p.kmask + (size_t)f * S : nullptr;
+      mbar_wait(&s_full[wg], ph);
+      tc_fence_after();
+      const uint32_t t_s = tmem_base + lane_base + wg * 128;
+      uint32_t raw[32];
+      // Dead keys (index >= S, or padded by the key mask) are set to -inf once per chunk; everything after that is
+      // branch-free: max, then p = ex2(s*scale - base) with ex2(-inf) = 0.
+      auto load_chunk = [&](int c, float (&x)[32]) {
+        tmem_ld32(t_s + c * 32, raw);
+        tmem_ld_wait();
+        if (km != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int key = c * 32 + i;
+            x[i] = (key >= S || km[key] != 0) ? -INFINITY : __uint_as_float(raw[i]);
+          }
+        } else if (c * 32 + 32 > S) {
+          const int nvalid = S - c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = i < nvalid ? __uint_as_float(raw[i]) : -INFINITY;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(raw[i]);
+        }
+      };
+      float x[32];
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c * 32 < S; ++c) {
+        load_chunk(c, x);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, x[i]);
+      }
+      const float nbase = -(mx == -INFINITY ? 0.f : mx) * p.scale_log2e;
+      float sum = 0.f;
+      const uint32_t sw = static_cast<uint32_t>(row & 7) << 4;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+        if (c * 32 < S) {
+          load_chunk(c, x);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_approx(fmaf(x[2 * i], p.scale_log2e, nbase));
+            const float p1 = ex2_approx(fmaf(x[2 * i + 1], p.scale_log2e, nbase));
+            sum += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        }
+        uint8_t* rowp = p_buf + (c >> 1) * 16384 + row * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(rowp + ((static_cast<uint32_t>((c & 1) * 4 + i) << 4) ^ sw)) =
+              make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_full[wg]);
+      // O epilogue
+      mbar_wait(&o_full[wg], ph);
+      tc_fence_after();
+      tmem_ld32(tmem_base + lane_base + 256 + wg * 32, raw);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_free[wg]);   // S[wg] and O[wg] may be overwritten by unit u+2
+      const float inv = 1.f / sum;
+      if (wg_tid == 0) tma_store_wait_read<0>();  // the previous store of this warpgroup has drained o_buf
+      named_bar_sync(1 + wg, 128);
+      {
+        uint8_t* rowp = o_buf + row * 64;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(rowp + ((i ^ ((row >> 1) & 3)) << 4)) =
+              make_uint4(pack_bf16(__uint_as_float(raw[8 * i]) * inv, __uint_as_float(raw[8 * i + 1]) * inv),
+                         pack_bf16(__uint_as_float(raw[8 * i + 2]) * inv, __uint_as_float(raw[8 * i + 3]) * inv),
+                         pack_bf16(__uint_as_float(raw[8 * i + 4]) * inv, __uint_as_float(raw[8 * i + 5]) * inv),
+                         pack_bf16(__uint_as_float(raw[8 * i + 6]) * inv, __uint_as_float(raw[8 * i + 7]) * inv));
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + wg, 128);
+      if (wg_tid == 0) {
+        tma_store_3d(&tm_o, o_buf, h * 32, 0, f);
+        tma_store_commit();
+      }
+    }
+    if (wg_tid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+void* tensor_map_encode_fn();  // gemm_tc.cu
+int device_sm_count();
+
+// [F frames][S tokens][cols] bf16 with row stride ld; box = 32 cols x 128 tokens x 1 frame, 64B swizzle.
+static CUtensorMap make_tmap_frames(const bf16* ptr, int F, int S, int cols, int ld) {
+  CUtensorMap m;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)S, (cuuint64_t)F};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)S * ld * 2};
+  cuuint32_t box[3] = {32, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = reinterpret_cast<PFN_encodeTiled_t>(tensor_map_encode_fn())(
+      &m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), gdim, gstr, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3D) failed with CUresult " + std::to_string((int)r));
+  return m;
+}
+
+bool enc_attn_tc_supported(int S) { return S >= 1 && S <= 128; }
+
+// AO[f*S + s, h*32 + d] = softmax_s'(scale * q·k) v  over the S tokens of frame f; QKV is [F*S, 768] (q | k | v).
+void enc_attn_tc(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* kmask, float scale, cudaStream_t stream) {
+  VG_CHECK(enc_attn_tc_supported(S) && F > 0, "enc_attn_tc: S must be in [1,128]");
+  static bool attr_set = false;
+  if (!attr_set) {
+    VG_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    attr_set = true;
+  }
+  CUtensorMap tq = make_tmap_frames(QKV, F, S, 768, 768);
+  CUtensorMap to = make_tmap_frames(AO, F, S, 256, 256);
+  AttnTcParams p{kmask, S, F, scale * 1.4426950408889634f};
+  const int grid = F < device_sm_count() ? F : device_sm_count();
+  enc_attn_tc_kernel<<<grid, 320, kAtSmem, stream>>>(tq, to, p);
+  VG_CUDA(cudaGetLastError());
+}
+
+}  // namespace vg

@@ -356,6 +356,8 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+void* tensor_map_encode_fn() { return reinterpret_cast<void*>(get_encode()); }
+
 // 2D row-major [rows, cols] (bf16 or fp32) with row stride ld (elements); box = [box_rows x 128 bytes], 128B swizzle.
 CUtensorMap make_tmap_2d(const void* ptr, int rows, int cols, int ld, int box_rows, bool f32) {
   CUtensorMap m;

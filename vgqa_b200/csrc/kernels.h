@@ -11,6 +11,10 @@ void xattn1(const bf16* qt, const bf16* mem, long long frame_stride_rows, int F,
             long long posk_fstride, const bf16* q2, const bf16* kpos, int ldkpos, long long kpos_fstride,
             const uint8_t* kmask, int ldmask, float scale, bf16* ctx, float* att, cudaStream_t stream);
 
+// ---- attn_tc.cu: tcgen05 per-frame self-attention over the packed QKV buffer (S <= 128)
+bool enc_attn_tc_supported(int S);
+void enc_attn_tc(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* kmask, float scale, cudaStream_t stream);
+
 // ---- small.cu
 // NCHW fp32 features → token-major bf16 rows: X[(f*S + tok0 + p), c] = in[f, c, p]   (in may be broadcast: fstride 0)
 void nchw_to_tokens(const float* in, long long in_fstride, bf16* X, float* X32, const float* pos, long long pos_fstride,

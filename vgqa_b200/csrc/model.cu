@@ -572,7 +572,10 @@ static void run_encoder(Fwd& f, const vgqa_inputs& in, bool have_mask, int pos_r
       gemm_ws(c->XP, c->X, 512, 256, e.qkv.W, 256, R, 768, 256, ep, st);
       f.count();
     }
-    mha32(c->QKV, 768, c->QKV + 256, 768, c->QKV + 512, 768, c->AO, 256, F, S, S, km, 0.17677669529663687f, st);
+    if (enc_attn_tc_supported(S))   // tcgen05/TMEM kernel (7x7 .. 8x8 feature maps); larger frames use the warp-MMA flash kernel
+      enc_attn_tc(c->QKV, c->AO, F, S, km, 0.17677669529663687f, st);
+    else
+      mha32(c->QKV, 768, c->QKV + 256, 768, c->QKV + 512, 768, c->AO, 256, F, S, S, km, 0.17677669529663687f, st);
     f.count();
     f.linear_res_ln(c->AO, 256, e.out, R, c->X32, e.ln1, 1e-5f, c->X1, 256, c->X1_32);
     f.linear(c->X1, 256, e.ff1, R, c->HID, e.ff1.N, ACT_RELU);
