@@ -204,22 +204,24 @@ struct Xattn1Params {
 
 static constexpr int XROW = 264;  // padded smem row (elements): 528 B → conflict-free ldmatrix
 
-__global__ void __launch_bounds__(128) xattn1_kernel(const Xattn1Params p) {
+static constexpr int XNT = 256;   // 8 warps
+
+__global__ void __launch_bounds__(XNT) xattn1_kernel(const Xattn1Params p) {
   extern __shared__ __align__(16) uint8_t sm[];
   const int f = blockIdx.x;
   const int Mk = p.Mk, Mp = (Mk + 15) & ~15;
   bf16* sMem = reinterpret_cast<bf16*>(sm);                       // [Mp][XROW]
   bf16* sQ = sMem + (size_t)Mp * XROW;                            // [8][XROW]
   bf16* sP = sQ + 8 * XROW;                                       // [16][Mp + 8]
-  float* sS = reinterpret_cast<float*>(sP + 16 * (Mp + 8));       // [8][Mp]
-  bf16* sQ2 = reinterpret_cast<bf16*>(sS + 8 * Mp);               // [256]
-  float* sRed = reinterpret_cast<float*>(sQ2 + 256);              // [8]
+  float* sS = reinterpret_cast<float*>(sP + 16 * (Mp + 8));       // [2 K-halves][8][Mp]
+  bf16* sQ2 = reinterpret_cast<bf16*>(sS + 16 * Mp);              // [256]
+  float* sRed = reinterpret_cast<float*>(sQ2 + 256);              // [16]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bf16* gmem = p.mem + (size_t)f * p.frame_stride * 256;
   const bf16* gpos = p.posk ? p.posk + (size_t)f * p.posk_fstride : nullptr;
 
   // ---- fill: keys (mem [+ pos]) , absorbed queries, q2; zero pad rows and P rows 8..15
-  for (int i = tid; i < Mp * 32; i += 128) {
+  for (int i = tid; i < Mp * 32; i += XNT) {
     const int r = i >> 5, c = i & 31;
     bf16* dst = sMem + (size_t)r * XROW + c * 8;
     if (r < Mk) {
@@ -238,12 +240,12 @@ __global__ void __launch_bounds__(128) xattn1_kernel(const Xattn1Params p) {
       *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
     }
   }
-  for (int i = tid; i < 8 * 32; i += 128) {
-    const int r = i >> 5, c = i & 31;
+  {
+    const int r = tid >> 5, c = tid & 31;  // 8 rows x 32 chunks = 256 threads
     cp_async16(sQ + r * XROW + c * 8, p.qt + (size_t)f * 2048 + r * 256 + c * 8);
   }
   if (p.q2 != nullptr && tid < 32) cp_async16(sQ2 + tid * 8, p.q2 + (size_t)f * 256 + tid * 8);
-  for (int i = tid; i < 8 * (Mp + 8) / 2; i += 128) reinterpret_cast<uint32_t*>(sP + 8 * (Mp + 8))[i] = 0u;
+  for (int i = tid; i < 8 * (Mp + 8) / 2; i += XNT) reinterpret_cast<uint32_t*>(sP + 8 * (Mp + 8))[i] = 0u;
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
@@ -251,34 +253,40 @@ __global__ void __launch_bounds__(128) xattn1_kernel(const Xattn1Params p) {
   const uint32_t sMemA = smem_u32(sMem), sQA = smem_u32(sQ), sPA = smem_u32(sP);
   const int gid = lane >> 2, tq = lane & 3;
 
-  // ---- phase 1: scores[key][head] = mem[key,:] · q~[head,:]   (16 k-steps of 16 channels)
+  // ---- phase 1: scores[key][head] = mem[key,:] · q~[head,:].  Work item = (16-key block, K half of 128 channels);
+  //      two interleaved accumulators keep the HMMA dependency chains short.
   {
-    uint32_t bq[16][2];
+    const int kh = warp & 1;
+    uint32_t bq[8][2];
 #pragma unroll
-    for (int ks = 0; ks < 16; ++ks) {
+    for (int ks = 0; ks < 8; ++ks) {
       // B[k=channel][n=head]: q~ is [head][channel] → non-transposed ldmatrix, matrices (ch 0-7),(ch 8-15)
       const int row = lane & 7, half = (lane >> 3) & 1;
-      ldmatrix_x2(bq[ks], sQA + (row * XROW + ks * 16 + half * 8) * 2);
+      ldmatrix_x2(bq[ks], sQA + (row * XROW + kh * 128 + ks * 16 + half * 8) * 2);
     }
-    for (int kb = warp; kb * 16 < Mp; kb += 4) {
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int kb = warp >> 1; kb * 16 < Mp; kb += 4) {
+      float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+      const int row = kb * 16 + (lane & 15);
+      const uint32_t abase = sMemA + (row * XROW + kh * 128 + (lane >> 4) * 8) * 2;
 #pragma unroll
-      for (int ks = 0; ks < 16; ++ks) {
-        uint32_t a[4];
-        const int row = kb * 16 + (lane & 15);
-        ldmatrix_x4(a, sMemA + (row * XROW + ks * 16 + (lane >> 4) * 8) * 2);
-        mma_16816(d, a, bq[ks]);
+      for (int ks = 0; ks < 8; ks += 2) {
+        uint32_t a0[4], a1[4];
+        ldmatrix_x4(a0, abase + ks * 32);
+        ldmatrix_x4(a1, abase + (ks + 1) * 32);
+        mma_16816(d0, a0, bq[ks]);
+        mma_16816(d1, a1, bq[ks + 1]);
       }
+      float* pl = sS + kh * 8 * Mp;
       const int k0 = kb * 16 + gid, k1 = k0 + 8, h0 = tq * 2;
-      sS[h0 * Mp + k0] = d[0]; sS[(h0 + 1) * Mp + k0] = d[1];
-      sS[h0 * Mp + k1] = d[2]; sS[(h0 + 1) * Mp + k1] = d[3];
+      pl[h0 * Mp + k0] = d0[0] + d1[0]; pl[(h0 + 1) * Mp + k0] = d0[1] + d1[1];
+      pl[h0 * Mp + k1] = d0[2] + d1[2]; pl[(h0 + 1) * Mp + k1] = d0[3] + d1[3];
     }
   }
   __syncthreads();
   // ---- optional second score term: q2_h · kpos_h(m)  (32-d per head, SIMT; kpos is L1/L2 resident)
   if (p.kpos != nullptr) {
     const bf16* gk = p.kpos + (size_t)f * p.kpos_fstride;
-    for (int i = tid; i < Mk * 8; i += 128) {
+    for (int i = tid; i < Mk * 8; i += XNT) {
       const int m = i >> 3, h = i & 7;
       const uint4* kp = reinterpret_cast<const uint4*>(gk + (size_t)m * p.ldkpos + h * 32);
       const uint4* qp = reinterpret_cast<const uint4*>(sQ2 + h * 32);
@@ -296,35 +304,38 @@ __global__ void __launch_bounds__(128) xattn1_kernel(const Xattn1Params p) {
   }
   // the keys buffer held mem+pos: re-stage the plain memory rows for the value side (L2 hit)
   if (gpos != nullptr) {
-    for (int i = tid; i < Mk * 32; i += 128) {
+    for (int i = tid; i < Mk * 32; i += XNT) {
       const int r = i >> 5, c = i & 31;
       cp_async16(sMem + (size_t)r * XROW + c * 8, gmem + (size_t)r * 256 + c * 8);
     }
     cp_async_commit();
   }
-  // ---- phase 2: softmax over keys, one warp per two heads
+  // ---- phase 2: softmax over keys, one warp per head
   const uint8_t* km = p.kmask ? p.kmask + (size_t)f * p.ldmask : nullptr;
-  for (int h = warp; h < 8; h += 4) {
+  {
+    const int h = warp;
+    float* s0 = sS + h * Mp;
+    const float* s1 = sS + (8 + h) * Mp;
     float mx = -INFINITY;
     for (int m = lane; m < Mk; m += 32) {
-      float v = sS[h * Mp + m] * p.scale_log2e;
+      float v = (s0[m] + s1[m]) * p.scale_log2e;
       if (km != nullptr && km[m] != 0) v = -INFINITY;
-      sS[h * Mp + m] = v;
+      s0[m] = v;
       mx = fmaxf(mx, v);
     }
     mx = warp_max(mx);
     if (mx == -INFINITY) mx = 0.f;
     float sum = 0.f;
     for (int m = lane; m < Mk; m += 32) {
-      const float e = exp2f(sS[h * Mp + m] - mx);
-      sS[h * Mp + m] = e;
+      const float e = exp2f(s0[m] - mx);
+      s0[m] = e;
       sum += e;
     }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
     for (int m = lane; m < Mp; m += 32) {
-      const float pr = m < Mk ? sS[h * Mp + m] * inv : 0.f;
-      if (m < Mk) sS[h * Mp + m] = pr;
+      const float pr = m < Mk ? s0[m] * inv : 0.f;
+      if (m < Mk) s0[m] = pr;
       sP[h * (Mp + 8) + m] = __float2bfloat16(pr);
     }
   }
@@ -333,44 +344,46 @@ __global__ void __launch_bounds__(128) xattn1_kernel(const Xattn1Params p) {
   // ---- optional attention map: minmax(sigmoid(sum over heads))
   if (p.att != nullptr) {
     float lmin = INFINITY, lmax = -INFINITY;
-    for (int m = tid; m < Mk; m += 128) {
+    float* amap = sS + 8 * Mp;  // the second score plane is free now
+    for (int m = tid; m < Mk; m += XNT) {
       float a = 0.f;
 #pragma unroll
       for (int h = 0; h < 8; ++h) a += sS[h * Mp + m];
       a = 1.f / (1.f + __expf(-a));
-      sS[m] = a;  // row 0 is no longer needed as probabilities by this thread's keys (sP holds them)
+      amap[m] = a;
       lmin = fminf(lmin, a); lmax = fmaxf(lmax, a);
     }
     lmin = -warp_max(-lmin); lmax = warp_max(lmax);
-    if (lane == 0) { sRed[warp] = lmin; sRed[4 + warp] = lmax; }
+    if (lane == 0) { sRed[warp] = lmin; sRed[8 + warp] = lmax; }
     __syncthreads();
-    const float amin = fminf(fminf(sRed[0], sRed[1]), fminf(sRed[2], sRed[3]));
-    const float amax = fmaxf(fmaxf(sRed[4], sRed[5]), fmaxf(sRed[6], sRed[7]));
-    const float inv = 1.f / (amax - amin + 1e-6f);
-    for (int m = tid; m < Mk; m += 128) p.att[(size_t)f * Mk + m] = (sS[m] - amin) * inv;
-  }
-  // ---- phase 3: ctx[head][channel] = sum_key P[head][key] mem[key][channel]; warp w → channels [64w, 64w+64)
-  {
-    float d[8][4];
+    float amin = sRed[0], amax = sRed[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f;
+    for (int w = 1; w < 8; ++w) { amin = fminf(amin, sRed[w]); amax = fmaxf(amax, sRed[8 + w]); }
+    const float inv = 1.f / (amax - amin + 1e-6f);
+    for (int m = tid; m < Mk; m += XNT) p.att[(size_t)f * Mk + m] = (amap[m] - amin) * inv;
+  }
+  // ---- phase 3: ctx[head][channel] = sum_key P[head][key] mem[key][channel]; warp w → channels [32w, 32w+32)
+  {
+    float d[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f;
     for (int ks = 0; ks * 16 < Mp; ++ks) {
       uint32_t a[4];
       ldmatrix_x4(a, sPA + ((lane & 15) * (Mp + 8) + ks * 16 + (lane >> 4) * 8) * 2);
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {
+      for (int np = 0; np < 2; ++np) {
         uint32_t vf[4];
         const int row = ks * 16 + (lane & 15);
-        const int col = warp * 64 + np * 16 + (lane >> 4) * 8;
+        const int col = warp * 32 + np * 16 + (lane >> 4) * 8;
         ldmatrix_x4_trans(vf, sMemA + (row * XROW + col) * 2);
         uint32_t b0[2] = {vf[0], vf[1]}, b1[2] = {vf[2], vf[3]};
         mma_16816(d[np * 2 + 0], a, b0);
         mma_16816(d[np * 2 + 1], a, b1);
       }
     }
-    bf16* gc = p.ctx + (size_t)f * 2048 + gid * 256 + warp * 64 + tq * 2;  // rows 0..7 = heads
+    bf16* gc = p.ctx + (size_t)f * 2048 + gid * 256 + warp * 32 + tq * 2;  // rows 0..7 = heads
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) *reinterpret_cast<uint32_t*>(gc + nb * 8) = pack_bf16(d[nb][0], d[nb][1]);
+    for (int nb = 0; nb < 4; ++nb) *reinterpret_cast<uint32_t*>(gc + nb * 8) = pack_bf16(d[nb][0], d[nb][1]);
   }
 }
 
@@ -383,14 +396,14 @@ void xattn1(const bf16* qt, const bf16* mem, long long frame_stride_rows, int F,
   p.frame_stride = frame_stride_rows; p.posk_fstride = posk_fstride; p.kpos_fstride = kpos_fstride;
   p.Mk = Mk; p.ldkpos = ldkpos; p.ldmask = ldmask; p.scale_log2e = scale * kLog2e;
   const int Mp = (Mk + 15) & ~15;
-  const int smem = (Mp * XROW + 8 * XROW + 16 * (Mp + 8) + 256) * 2 + (8 * Mp + 8) * 4;
+  const int smem = (Mp * XROW + 8 * XROW + 16 * (Mp + 8) + 256) * 2 + (16 * Mp + 16) * 4;
   VG_CHECK(smem <= 220 * 1024, "xattn1: too many keys for the shared-memory resident kernel");
   static int configured = 0;
   if (smem > configured) {
     VG_CUDA(cudaFuncSetAttribute(xattn1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  xattn1_kernel<<<F, 128, smem, stream>>>(p);
+  xattn1_kernel<<<F, XNT, smem, stream>>>(p);
   VG_CUDA(cudaGetLastError());
 }
 
