@@ -65,6 +65,8 @@ typedef struct {
   const float* force_choose1;
   const float* force_choose2;
   int iteration_rate; /* < 0 (inference): two decoder passes; >= 0: one pass (grounding_net.py:143) */
+  int stop_after_encoder; /* 1: run CrossModalEncoder only (outputs encoded_feature / frames_cls) — the
+                             `build_encoder(cfg)` seam (vgqa/core/decoder/__init__.py:6-8) */
 } vgqa_inputs;
 
 /* Outputs (fp32 unless noted); any pointer may be NULL to skip that output.
@@ -112,6 +114,11 @@ int vgqa_finalize_weights(vgqa_ctx* ctx);
 int vgqa_forward(vgqa_ctx* ctx, const vgqa_inputs* in, const vgqa_outputs* out, void* stream);
 /* Same with HOST buffers: stages through pinned memory, H2D, forward, D2H, synchronises. */
 int vgqa_forward_host(vgqa_ctx* ctx, const vgqa_inputs* in, const vgqa_outputs* out);
+
+/* PostProcess.forward (vgqa/core/postprocessor.py:14-50) on device tensors: boxes [clips,T,4] cxcywh, sted [clips,T,2],
+ * sizes_hw [clips,2] → boxes_px [clips,T,4] xyxy pixels (clamped at 0), sted_idx int32 [clips,2] = argmax (start,end), start < end. */
+int vgqa_postprocess(const float* boxes, const float* sted, const float* sizes_hw, float* boxes_px, int32_t* sted_idx,
+                     int clips, int T, void* stream);
 
 /* Counters: kernels launched by the last vgqa_forward call (graph replays count the captured launches). */
 int vgqa_last_launch_count(const vgqa_ctx* ctx);

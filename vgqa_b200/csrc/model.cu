@@ -757,6 +757,10 @@ static void forward_body(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs&
   const int pos_rows = in.pos_frames * f.S;
   c->launches = 0;
   run_encoder(f, in, have_mask, pos_rows);
+  if (in.stop_after_encoder) {
+    if (out.frames_cls) VG_CUDA(cudaMemcpyAsync(out.frames_cls, c->frames_cls, (size_t)F * 256 * 4, cudaMemcpyDeviceToDevice, st));
+    return;
+  }
   run_temporal_sampling(f);
   select_pass1(c->logit_f[0], c->logit_f[1], 0.45f, in.force_choose1, c->att_seq, c->w1, c->K1, f.B, f.T, st);
   f.count();
@@ -888,8 +892,8 @@ int vgqa_forward(vgqa_ctx* c, const vgqa_inputs* in, const vgqa_outputs* out, vo
     VG_CHECK(c && in && out, "null argument");
     vg::check_inputs(c, *in);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (out->encoded_feature) VG_CHECK(!c->cfg.use_cuda_graph, "encoded_feature output is not available in graph mode");
-    if (!c->cfg.use_cuda_graph) {
+    // debug / seam outputs bypass the graph cache
+    if (!c->cfg.use_cuda_graph || out->encoded_feature != nullptr || in->stop_after_encoder) {
       vg::forward_body(c, *in, *out, st);
       if (out->encoded_feature) {
         const size_t n = (size_t)in->clips * in->T * (2 * in->H * in->W + in->L) * 256;
@@ -907,7 +911,8 @@ int vgqa_forward(vgqa_ctx* c, const vgqa_inputs* in, const vgqa_outputs* out, vo
     cudaStream_t ex = c->exec_stream;
     // key = every scalar and pointer that is baked into the captured launches
     std::vector<uint64_t> key = {(uint64_t)in->clips, (uint64_t)in->T, (uint64_t)in->H, (uint64_t)in->W, (uint64_t)in->L,
-                                 (uint64_t)in->pos_frames, (uint64_t)(in->iteration_rate < 0)};
+                                 (uint64_t)in->pos_frames, (uint64_t)(in->iteration_rate < 0),
+                                 (uint64_t)in->stop_after_encoder};
     for (const void* q : {(const void*)in->vis, (const void*)in->vid, (const void*)in->text, (const void*)in->pos,
                           (const void*)in->vis_mask, (const void*)in->text_mask, (const void*)in->ori_sizes_hw,
                           (const void*)in->force_choose1, (const void*)in->force_choose2})
@@ -1002,6 +1007,15 @@ int vgqa_forward_host(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outputs* h
     d2h(hout->frames_cls, c->frames_cls, F * 256 * 4);
     VG_CHECK(hout->encoded_feature == nullptr, "encoded_feature is only available through vgqa_forward");
     VG_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_postprocess(const float* boxes, const float* sted, const float* sizes_hw, float* boxes_px, int32_t* sted_idx,
+                     int clips, int T, void* stream) {
+  try {
+    VG_CHECK(boxes && sted && sizes_hw && boxes_px && sted_idx && clips >= 1 && T >= 2, "vgqa_postprocess: bad argument");
+    vg::postprocess(boxes, sted, sizes_hw, boxes_px, sted_idx, clips, T, static_cast<cudaStream_t>(stream));
     return 0;
   } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
 }

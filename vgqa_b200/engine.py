@@ -25,7 +25,8 @@ class VgqaInputs(ctypes.Structure):
     _fields_ = [("clips", c_int), ("T", c_int), ("H", c_int), ("W", c_int), ("L", c_int),
                 ("vis", c_void_p), ("vid", c_void_p), ("text", c_void_p), ("pos", c_void_p), ("pos_frames", c_int),
                 ("vis_mask", c_void_p), ("text_mask", c_void_p), ("ori_sizes_hw", c_void_p),
-                ("force_choose1", c_void_p), ("force_choose2", c_void_p), ("iteration_rate", c_int)]
+                ("force_choose1", c_void_p), ("force_choose2", c_void_p), ("iteration_rate", c_int),
+                ("stop_after_encoder", c_int)]
 
 
 OUTPUT_FIELDS = ("pred_boxes", "pred_sted", "pred_actioness", "logits_f_m", "logits_f_a", "logits_r_a", "logits_r_m",
@@ -54,6 +55,8 @@ def _declare(L):
     L.vgqa_forward_host.argtypes = [c_void_p, ctypes.POINTER(VgqaInputs), ctypes.POINTER(VgqaOutputs)]
     L.vgqa_last_launch_count.restype = c_int
     L.vgqa_last_launch_count.argtypes = [c_void_p]
+    L.vgqa_postprocess.restype = c_int
+    L.vgqa_postprocess.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
     L.vgqa_reference_flops.restype = ctypes.c_double
     L.vgqa_reference_flops.argtypes = [c_int] * 8
     L._vgqa_engine_declared = True
@@ -137,7 +140,8 @@ class GroundingEngine:
     def _p(t):
         return None if t is None else c_void_p(t.data_ptr())
 
-    def _pack_io(self, vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force1, force2, iteration_rate, outs):
+    def _pack_io(self, vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force1, force2, iteration_rate, outs,
+                 stop_after_encoder=0):
         B, T, d, H, W = vis.shape
         assert d == 256 and tuple(vid.shape) == tuple(vis.shape), "vis/vid must be [clips, T, 256, H, W]"
         Lt = text.shape[1]
@@ -147,9 +151,18 @@ class GroundingEngine:
             assert t.dtype == torch.float32 and t.is_contiguous()
         inp = VgqaInputs(B, T, H, W, Lt, self._p(vis), self._p(vid), self._p(text), self._p(pos), pos.shape[0],
                          self._p(vis_mask), self._p(text_mask), self._p(ori_sizes_hw), self._p(force1), self._p(force2),
-                         iteration_rate)
+                         iteration_rate, stop_after_encoder)
         out = VgqaOutputs(**{k: self._p(outs.get(k)) for k in OUTPUT_FIELDS})
         return inp, out
+
+    def encode(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None):
+        """CrossModalEncoder only: returns encoded_feature [clips*T, S, 256] (frame-major) and frames_cls [clips*T, 256]."""
+        B, T, _, H, W = vis.shape
+        outs = self.alloc_outputs(B, T, H, W, text.shape[1], ["encoded_feature", "frames_cls"])
+        inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, None, None, None, -1, outs, 1)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self._L.vgqa_forward(self._ctx, ctypes.byref(inp), ctypes.byref(out), c_void_p(st)))
+        return outs
 
     def forward(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, ori_sizes_hw=None, force_choose1=None,
                 force_choose2=None, iteration_rate=-1, outs=None, want=None):
