@@ -114,6 +114,11 @@ int vgqa_finalize_weights(vgqa_ctx* ctx);
 int vgqa_forward(vgqa_ctx* ctx, const vgqa_inputs* in, const vgqa_outputs* out, void* stream);
 /* Same with HOST buffers: stages through pinned memory, H2D, forward, D2H, synchronises. */
 int vgqa_forward_host(vgqa_ctx* ctx, const vgqa_inputs* in, const vgqa_outputs* out);
+/* Pipelined variant: enqueue uploads (own copy stream), the forward and the result downloads for `slot` (0 or 1) and
+ * return; the host output buffers are valid after vgqa_forward_host_wait(ctx, slot).  Alternating the two slots overlaps
+ * the H2D copy of call k+1 with the compute of call k.  Host buffers must stay alive (and should be pinned) until the wait. */
+int vgqa_forward_host_async(vgqa_ctx* ctx, const vgqa_inputs* in, const vgqa_outputs* out, int slot);
+int vgqa_forward_host_wait(vgqa_ctx* ctx, int slot);
 
 /* PostProcess.forward (vgqa/core/postprocessor.py:14-50) on device tensors: boxes [clips,T,4] cxcywh, sted [clips,T,2],
  * sizes_hw [clips,2] → boxes_px [clips,T,4] xyxy pixels (clamped at 0), sted_idx int32 [clips,2] = argmax (start,end), start < end. */

@@ -20,7 +20,7 @@ namespace vg {
 
 static constexpr int WBM = 128;
 static constexpr int WBK = 64;
-static constexpr int kWsStages = 3;
+static constexpr int kWsStages = 4;
 static constexpr int kWsEpiWarps = 8;
 
 struct WsParams {

@@ -137,8 +137,14 @@ struct vgqa_ctx {
   bf16* XP;            // bf16(x + pos): A operand of the Q/K in-projection
   float* enc_tab;
   uint8_t* encmask;
-  float *in_vis, *in_vid, *in_text, *in_pos, *in_sizes, *in_f1, *in_f2;
-  uint8_t *in_vmask, *in_tmask;
+  // host-path input staging, two slots so that the upload of call k+1 overlaps the compute of call k
+  struct HostSlot {
+    float *vis, *vid, *text, *pos, *sizes, *f1, *f2;
+    uint8_t *vmask, *tmask;
+    cudaEvent_t in_ready = nullptr, in_free = nullptr, done = nullptr;
+    bool used = false;
+  } hs[2];
+  cudaStream_t h2d_stream = nullptr;
   float* frames_cls;
   bf16 *pool[2], *ftext, *q0, *kv_ts;
   float *pool32[2], *q0_32, *c_h32[2], *c_a32[2];
@@ -479,9 +485,11 @@ static void carve_workspace(vgqa_ctx* c) {
   c->X32 = a.get<float>(R * 256); c->X1_32 = a.get<float>(R * 256); c->XP = a.get<bf16>(R * 256);
   c->pos_enc = a.get<bf16>(R * 256); c->kposb = a.get<bf16>(R * 1536); c->enc_tab = a.get<float>(R * 768);
   c->encmask = a.get<uint8_t>(R);
-  c->in_vis = a.get<float>(F * 256 * P); c->in_vid = a.get<float>(F * 256 * P); c->in_text = a.get<float>(B * L * 256);
-  c->in_pos = a.get<float>(F * 256 * P); c->in_sizes = a.get<float>(B * 2); c->in_f1 = a.get<float>(F); c->in_f2 = a.get<float>(F);
-  c->in_vmask = a.get<uint8_t>(F * P); c->in_tmask = a.get<uint8_t>(B * L);
+  for (auto& h : c->hs) {
+    h.vis = a.get<float>(F * 256 * P); h.vid = a.get<float>(F * 256 * P); h.text = a.get<float>(B * L * 256);
+    h.pos = a.get<float>(F * 256 * P); h.sizes = a.get<float>(B * 2); h.f1 = a.get<float>(F); h.f2 = a.get<float>(F);
+    h.vmask = a.get<uint8_t>(F * P); h.tmask = a.get<uint8_t>(B * L);
+  }
   c->frames_cls = a.get<float>(F * 256);
   c->ftext = a.get<bf16>(B * L * 256); c->q0 = a.get<bf16>(F * 256); c->kv_ts = a.get<bf16>(B * L * 2048);
   for (int k = 0; k < 2; ++k) {
@@ -853,6 +861,12 @@ void vgqa_destroy(vgqa_ctx* c) {
   for (auto& g : c->graphs) cudaGraphExecDestroy(g.second.exec);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->host_stream) cudaStreamDestroy(c->host_stream);
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  for (auto& h : c->hs) {
+    if (h.in_ready) cudaEventDestroy(h.in_ready);
+    if (h.in_free) cudaEventDestroy(h.in_free);
+    if (h.done) cudaEventDestroy(h.done);
+  }
   if (c->exec_stream) cudaStreamDestroy(c->exec_stream);
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   for (auto& e : c->fj) if (e) cudaEventDestroy(e);
@@ -958,31 +972,47 @@ int vgqa_forward(vgqa_ctx* c, const vgqa_inputs* in, const vgqa_outputs* out, vo
   } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
 }
 
-int vgqa_forward_host(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outputs* hout) {
+int vgqa_forward_host_async(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outputs* hout, int slot) {
   try {
-    VG_CHECK(c && hin && hout, "null argument");
+    VG_CHECK(c && hin && hout && (slot == 0 || slot == 1), "bad argument");
     vg::check_inputs(c, *hin);
-    if (!c->host_stream) VG_CUDA(cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking));
-    cudaStream_t st = c->host_stream;
+    VG_CHECK(hout->encoded_feature == nullptr, "encoded_feature is only available through vgqa_forward");
+    if (!c->host_stream) {
+      VG_CUDA(cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking));
+      VG_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+      for (auto& h : c->hs) {
+        VG_CUDA(cudaEventCreateWithFlags(&h.in_ready, cudaEventDisableTiming));
+        VG_CUDA(cudaEventCreateWithFlags(&h.in_free, cudaEventDisableTiming));
+        VG_CUDA(cudaEventCreateWithFlags(&h.done, cudaEventDisableTiming));
+      }
+    }
+    vgqa_ctx::HostSlot& h = c->hs[slot];
+    cudaStream_t st = c->host_stream, up = c->h2d_stream;
     const size_t B = hin->clips, T = hin->T, P = (size_t)hin->H * hin->W, L = hin->L, F = B * T;
     const size_t D = c->tl.size();
+    // uploads wait until the previous forward that read this slot has finished
+    if (h.used) VG_CUDA(cudaStreamWaitEvent(up, h.in_free, 0));
     auto h2d = [&](void* dst, const void* src, size_t bytes) {
-      VG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+      VG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, up));
     };
     vgqa_inputs din = *hin;
-    h2d(c->in_vis, hin->vis, F * 256 * P * 4); din.vis = c->in_vis;
-    h2d(c->in_vid, hin->vid, F * 256 * P * 4); din.vid = c->in_vid;
-    h2d(c->in_text, hin->text, B * L * 256 * 4); din.text = c->in_text;
-    h2d(c->in_pos, hin->pos, (size_t)hin->pos_frames * 256 * P * 4); din.pos = c->in_pos;
-    if (hin->vis_mask) { h2d(c->in_vmask, hin->vis_mask, F * P); din.vis_mask = c->in_vmask; }
-    if (hin->text_mask) { h2d(c->in_tmask, hin->text_mask, B * L); din.text_mask = c->in_tmask; }
-    if (hin->ori_sizes_hw) { h2d(c->in_sizes, hin->ori_sizes_hw, B * 2 * 4); din.ori_sizes_hw = c->in_sizes; }
-    if (hin->force_choose1) { h2d(c->in_f1, hin->force_choose1, F * 4); din.force_choose1 = c->in_f1; }
-    if (hin->force_choose2) { h2d(c->in_f2, hin->force_choose2, F * 4); din.force_choose2 = c->in_f2; }
+    h2d(h.vis, hin->vis, F * 256 * P * 4); din.vis = h.vis;
+    h2d(h.vid, hin->vid, F * 256 * P * 4); din.vid = h.vid;
+    h2d(h.text, hin->text, B * L * 256 * 4); din.text = h.text;
+    h2d(h.pos, hin->pos, (size_t)hin->pos_frames * 256 * P * 4); din.pos = h.pos;
+    if (hin->vis_mask) { h2d(h.vmask, hin->vis_mask, F * P); din.vis_mask = h.vmask; }
+    if (hin->text_mask) { h2d(h.tmask, hin->text_mask, B * L); din.text_mask = h.tmask; }
+    if (hin->ori_sizes_hw) { h2d(h.sizes, hin->ori_sizes_hw, B * 2 * 4); din.ori_sizes_hw = h.sizes; }
+    if (hin->force_choose1) { h2d(h.f1, hin->force_choose1, F * 4); din.force_choose1 = h.f1; }
+    if (hin->force_choose2) { h2d(h.f2, hin->force_choose2, F * 4); din.force_choose2 = h.f2; }
+    VG_CUDA(cudaEventRecord(h.in_ready, up));
+    VG_CUDA(cudaStreamWaitEvent(st, h.in_ready, 0));
     vgqa_outputs none;
     std::memset(&none, 0, sizeof(none));
     int rc = vgqa_forward(c, &din, &none, st);
     if (rc != 0) return rc;
+    VG_CUDA(cudaEventRecord(h.in_free, st));
+    h.used = true;
     auto d2h = [&](void* dst, const void* src, size_t bytes) {
       if (dst != nullptr) VG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
     };
@@ -1005,10 +1035,22 @@ int vgqa_forward_host(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outputs* h
       d2h(hout->sted_idx, c->sted_idx, B * 8);
     }
     d2h(hout->frames_cls, c->frames_cls, F * 256 * 4);
-    VG_CHECK(hout->encoded_feature == nullptr, "encoded_feature is only available through vgqa_forward");
-    VG_CUDA(cudaStreamSynchronize(st));
+    VG_CUDA(cudaEventRecord(h.done, st));
     return 0;
   } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_forward_host_wait(vgqa_ctx* c, int slot) {
+  try {
+    VG_CHECK(c && (slot == 0 || slot == 1), "bad argument");
+    if (c->hs[slot].done) VG_CUDA(cudaEventSynchronize(c->hs[slot].done));
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_forward_host(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outputs* hout) {
+  int rc = vgqa_forward_host_async(c, hin, hout, 0);
+  return rc != 0 ? rc : vgqa_forward_host_wait(c, 0);
 }
 
 int vgqa_postprocess(const float* boxes, const float* sted, const float* sizes_hw, float* boxes_px, int32_t* sted_idx,

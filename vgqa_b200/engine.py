@@ -53,6 +53,10 @@ def _declare(L):
     L.vgqa_forward.argtypes = [c_void_p, ctypes.POINTER(VgqaInputs), ctypes.POINTER(VgqaOutputs), c_void_p]
     L.vgqa_forward_host.restype = c_int
     L.vgqa_forward_host.argtypes = [c_void_p, ctypes.POINTER(VgqaInputs), ctypes.POINTER(VgqaOutputs)]
+    L.vgqa_forward_host_async.restype = c_int
+    L.vgqa_forward_host_async.argtypes = [c_void_p, ctypes.POINTER(VgqaInputs), ctypes.POINTER(VgqaOutputs), c_int]
+    L.vgqa_forward_host_wait.restype = c_int
+    L.vgqa_forward_host_wait.argtypes = [c_void_p, c_int]
     L.vgqa_last_launch_count.restype = c_int
     L.vgqa_last_launch_count.argtypes = [c_void_p]
     L.vgqa_postprocess.restype = c_int
@@ -190,6 +194,17 @@ class GroundingEngine:
                                  iteration_rate, outs)
         _lib.check(self._L.vgqa_forward_host(self._ctx, ctypes.byref(inp), ctypes.byref(out)))
         return outs
+
+    def forward_host_async(self, vis, vid, text, pos, *, outs, slot, vis_mask=None, text_mask=None, ori_sizes_hw=None,
+                           force_choose1=None, force_choose2=None, iteration_rate=-1):
+        """Pipelined host path: returns immediately; `outs` (pinned host tensors) are valid after `wait_host(slot)`."""
+        inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force_choose1, force_choose2,
+                                 iteration_rate, outs)
+        _lib.check(self._L.vgqa_forward_host_async(self._ctx, ctypes.byref(inp), ctypes.byref(out), slot))
+        return outs
+
+    def wait_host(self, slot: int):
+        _lib.check(self._L.vgqa_forward_host_wait(self._ctx, slot))
 
     @property
     def last_launch_count(self) -> int:
