@@ -49,11 +49,29 @@ def bench_gemm(M, N, K, ln=False, act=0, name=""):
     print(f"gemm {name} M={M} N={N} K={K} ln={ln}: {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s  {byts / t / 1e3:7.1f} GB/s")
 
 
+def bench_xattn(F=4096, S=118, tok0=0, Mk=69, use_pos=False, use_kpos=False, name=""):
+    mem_all = torch.randn(F, S, 256, device="cuda").bfloat16()
+    qt = (torch.randn(F, 8, 256, device="cuda") / 4).bfloat16()
+    pos = torch.randn(Mk, 256, device="cuda").bfloat16() if use_pos else None
+    q2 = torch.randn(F, 256, device="cuda").bfloat16() if use_kpos else None
+    kpos = torch.randn(Mk, 1536, device="cuda").bfloat16() if use_kpos else None
+    ctx = torch.zeros(F, 2048, device="cuda", dtype=torch.bfloat16)
+    mem = mem_all[:, tok0:tok0 + Mk]
+    t = timeit(lambda: _lib.check(L.vgqa_xattn1(_lib.ptr(qt), _lib.ptr(mem), S, F, Mk, _lib.ptr(pos), 0, _lib.ptr(q2), _lib.ptr(kpos), 1536,
+                                                0, None, 0, 0.125, _lib.ptr(ctx), None, st())))
+    byts = F * (Mk * 512 + 4096 + 4096)
+    print(f"xattn1 {name} F={F} Mk={Mk}: {t:8.1f} us  {byts / t / 1e3:7.1f} GB/s")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["attn", "gemm"]
     if "attn" in which:
         bench_attn()
         bench_attn(F=1024, S=118)
+    if "xattn" in which:
+        bench_xattn(Mk=49, tok0=69, name="spatial")
+        bench_xattn(Mk=69, tok0=0, use_kpos=True, name="pos-decoder")
+        bench_xattn(Mk=69, tok0=49, use_pos=True, name="time-decoder")
     if "gemm" in which:
         R = 64 * 64 * 118
         bench_gemm(R, 768, 256, name="qkv")

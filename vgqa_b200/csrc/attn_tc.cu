@@ -24,7 +24,8 @@ static constexpr int kAtQkvBytes = 3 * 8192;      // Q, K, V: 128 rows x 64 B ea
 static constexpr int kAtPBytes = 32768;           // P: 2 atoms of 128 rows x 128 B
 static constexpr int kAtOBytes = 8192;            // O staging: 128 rows x 64 B
 static constexpr int kAtStages = 4;                // Q/K/V ring depth (decoupled from the 2 TMEM buffers)
-static constexpr int kAtSmem = kAtStages * kAtQkvBytes + 2 * kAtPBytes + 2 * kAtOBytes + 1024 + 256;
+static constexpr int kAtOnesBytes = 8192;         // constant bf16 1.0 tile: extra V columns that make the MMA emit row sums
+static constexpr int kAtSmem = kAtStages * kAtQkvBytes + 2 * kAtPBytes + 2 * kAtOBytes + kAtOnesBytes + 1024 + 256;
 
 struct AttnTcParams {
   const uint8_t* kmask;  // [F, S] or nullptr
@@ -43,11 +44,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw64_kmajor(uint32_t smem_addr) {
   return d;
 }
 // MN-major operand (N contiguous): rows = K index, 64 B (32 bf16 of N) per row, 64B swizzle; 8-row K groups 512 B apart
-// (SBO); a single 32-wide MN block, so the leading-dimension offset is never used.
-__device__ __forceinline__ uint64_t umma_desc_sw64_mnmajor(uint32_t smem_addr) {
+// (SBO); the second MN block (columns 32..47 = the constant ones tile → row sums of P) sits LBO bytes after the first.
+__device__ __forceinline__ uint64_t umma_desc_sw64_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(512 >> 4) << 16;
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;   // next 32-wide MN block (the ones tile)
   d |= static_cast<uint64_t>(512 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(4) << 61;
@@ -66,11 +67,16 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
-// 2^x on the MUFU pipe, flush-to-zero, no range fix-up code (ex2(-inf) = +0)
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+// two 2^x per MUFU op on packed bf16 (ex2(-inf) = +0); the result is directly the bf16x2 word stored into P
+__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
   return y;
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -84,7 +90,8 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint8_t* s_qkv = smem;                               // [kAtStages][Q|K|V]
   uint8_t* s_p = s_qkv + kAtStages * kAtQkvBytes;      // [2][2 atoms]
   uint8_t* s_o = s_p + 2 * kAtPBytes;                  // [2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_o + 2 * kAtOBytes);
+  uint8_t* s_ones = s_o + 2 * kAtOBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + kAtOnesBytes);
   uint64_t* qkv_full = bars;                    // [kAtStages]
   uint64_t* qkv_empty = bars + kAtStages;       // [kAtStages]
   uint64_t* s_full = bars + 2 * kAtStages;      // [2]
@@ -115,6 +122,11 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp >= 2) {  // ones tile (bf16 1.0 = 0x3F80); uniform, so the swizzle pattern is irrelevant
+    for (int i = threadIdx.x - 64; i < kAtOnesBytes / 16; i += 256)
+      reinterpret_cast<uint4*>(s_ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -137,7 +149,7 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 32) | (1u << 16);  // B operand (V) is MN-major
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 48) | (1u << 16);  // B = [V | ones] is MN-major, N = 32 + 16
     for (int u = 0; u <= num_units; ++u) {
       if (u < num_units) {
         const int b = u & 1, st = u % kAtStages;
@@ -162,11 +174,11 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         if (elect_one()) {
           const uint32_t v_addr = smem_u32(s_qkv + st * kAtQkvBytes + 16384);
           const uint32_t p_addr = smem_u32(s_p + b * kAtPBytes);
-          const uint64_t vd = umma_desc_sw64_mnmajor(v_addr);
+          const uint64_t vd = umma_desc_sw64_mnmajor(v_addr, smem_u32(s_ones) - v_addr);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {  // 8 x 16 keys
             const uint64_t pd = umma_desc_sw128_kmajor(p_addr + (k >> 2) * 16384) + 2 * (k & 3);
-            umma_bf16(tmem_base + 256 + b * 32, pd, vd + (uint64_t)((k * 1024) >> 4), idesc_o, k ? 1u : 0u);
+            umma_bf16(tmem_base + 256 + b * 64, pd, vd + (uint64_t)((k * 1024) >> 4), idesc_o, k ? 1u : 0u);
           }
           umma_commit(&o_full[b]);
           umma_commit(&qkv_empty[st]);
@@ -220,7 +232,6 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, x[i]);
       }
       const float nbase = -(mx == -INFINITY ? 0.f : mx) * p.scale_log2e;
-      float sum = 0.f;
       const uint32_t sw = static_cast<uint32_t>(row & 7) << 4;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -228,12 +239,8 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         if (c * 32 < S) {
           load_chunk(c, x);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2_approx(fmaf(x[2 * i], p.scale_log2e, nbase));
-            const float p1 = ex2_approx(fmaf(x[2 * i + 1], p.scale_log2e, nbase));
-            sum += p0 + p1;
-            pk[i] = pack_bf16(p0, p1);
-          }
+          for (int i = 0; i < 16; ++i)   // two exponentials per MUFU op, result already packed bf16x2
+            pk[i] = ex2_bf16x2(pack_bf16(fmaf(x[2 * i], p.scale_log2e, nbase), fmaf(x[2 * i + 1], p.scale_log2e, nbase)));
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) pk[i] = 0u;
@@ -250,7 +257,8 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       // O epilogue
       mbar_wait(&o_full[wg], ph);
       tc_fence_after();
-      tmem_ld32(tmem_base + lane_base + 256 + wg * 32, raw);
+      tmem_ld32(tmem_base + lane_base + 256 + wg * 64, raw);
+      const float sum = __uint_as_float(tmem_ld1(tmem_base + lane_base + 256 + wg * 64 + 32));  // P · ones
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
