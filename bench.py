@@ -197,8 +197,17 @@ def main():
     d_outs = eng.alloc_outputs(B, T, H, W, L, want)
     h_outs = eng.alloc_outputs(B, T, H, W, L, want, host=True)
 
+    d_outs2 = [d_outs, eng.alloc_outputs(B, T, H, W, L, want)]
+    dev_i = [0]
+
     def step_dev():
-        eng.forward(d_vis, d_vid, d_text, d_pos, ori_sizes_hw=d_sizes, outs=d_outs)
+        # pipelined public API (two boundary slots): the decoder phase of step i overlaps the encoder phase of step i+1
+        slot = dev_i[0] & 1
+        eng.forward_async(d_vis, d_vid, d_text, d_pos, ori_sizes_hw=d_sizes, outs=d_outs2[slot], slot=slot)
+        dev_i[0] += 1
+
+    def drain_dev():
+        eng.wait(0), eng.wait(1)     # the current stream waits for both slots → the closing CUDA event covers all steps
 
     h_outs2 = [h_outs, eng.alloc_outputs(B, T, H, W, L, want, host=True)]
     host_i = [0]
@@ -232,9 +241,9 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
-        e1.record()
         if drain:
             drain()
+        e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         sec = e0.elapsed_time(e1) * 1e-3 if device_events else wall
@@ -248,7 +257,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    sec = timed(step_dev, args.steps)
+    sec = timed(step_dev, args.steps, drain=drain_dev)
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.last_launch_count
     # e2e: pinned host buffers through the C-ABI (vgqa_forward_host_async/_wait, two slots); timed by wall clock

@@ -112,6 +112,14 @@ int vgqa_finalize_weights(vgqa_ctx* ctx);
 
 /* The hot path on device-resident inputs/outputs, enqueued on `stream` (cudaStream_t). */
 int vgqa_forward(vgqa_ctx* ctx, const vgqa_inputs* in, const vgqa_outputs* out, void* stream);
+/* Pipelined variant.  The forward has two phases on internal streams — phase 0: CrossModalEncoder, phase 1: classifiers,
+ * decoders, heads — and the tensors between them are double-buffered in two `slot`s, so phase 1 of call k overlaps
+ * phase 0 of call k+1 when consecutive calls alternate slots.  vgqa_forward_async orders the work after everything
+ * already enqueued on `stream` and returns; the outputs are complete once vgqa_forward_wait has made `stream` wait
+ * (host_sync = 0) or blocked the host (host_sync = 1).  Inputs must stay valid until then.
+ * vgqa_forward(ctx, in, out, stream) == vgqa_forward_async(.., slot 0, stream) + vgqa_forward_wait(ctx, 0, stream, 0). */
+int vgqa_forward_async(vgqa_ctx* ctx, const vgqa_inputs* in, const vgqa_outputs* out, int slot, void* stream);
+int vgqa_forward_wait(vgqa_ctx* ctx, int slot, void* stream, int host_sync);
 /* Same with HOST buffers: stages through pinned memory, H2D, forward, D2H, synchronises. */
 int vgqa_forward_host(vgqa_ctx* ctx, const vgqa_inputs* in, const vgqa_outputs* out);
 /* Pipelined variant: enqueue uploads (own copy stream), the forward and the result downloads for `slot` (0 or 1) and

@@ -135,13 +135,12 @@ struct vgqa_ctx {
   bf16 *X, *X1, *QKV, *AO, *HID, *Xf, *pos_enc, *kposb;
   float *X32, *X1_32;  // fp32 residual stream of the encoder
   bf16* XP;            // bf16(x + pos): A operand of the Q/K in-projection
-  float* enc_tab;
   uint8_t* encmask;
   // host-path input staging, two slots so that the upload of call k+1 overlaps the compute of call k
   struct HostSlot {
     float *vis, *vid, *text, *pos, *sizes, *f1, *f2;
     uint8_t *vmask, *tmask;
-    cudaEvent_t in_ready = nullptr, in_free = nullptr, done = nullptr;
+    cudaEvent_t done = nullptr;
     bool used = false;
   } hs[2];
   cudaStream_t h2d_stream = nullptr;
@@ -159,8 +158,17 @@ struct vgqa_ctx {
   uint8_t* pinned = nullptr;
   size_t pinned_bytes = 0;
   cudaStream_t host_stream = nullptr;
-  cudaStream_t exec_stream = nullptr;  // graphs are captured and replayed here (the legacy stream cannot be captured)
-  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // The forward is split in two phases that run on their own streams: phase 0 = CrossModalEncoder (saturates the GPU),
+  // phase 1 = classifiers + decoders + heads (hundreds of small launches).  The tensors that cross the boundary are
+  // double-buffered ("slots") so that phase 1 of call k overlaps phase 0 of call k+1.
+  struct Boundary {
+    bf16 *Xf, *pool[2], *ftext, *q0, *pos_enc;
+    float *frames_cls, *pool32[2], *q0_32;
+    uint8_t* encmask;
+    cudaEvent_t ev_in = nullptr, enc_done = nullptr, dec_done = nullptr;
+    bool used = false;
+  } bd[2];
+  cudaStream_t enc_stream = nullptr, dec_stream = nullptr;
   cudaStream_t aux_stream = nullptr;   // second branch of the fork/join sections (classifier pairs, the two decoders)
   cudaEvent_t fj[32] = {};
   // graph cache
@@ -481,19 +489,22 @@ static void carve_workspace(vgqa_ctx* c) {
   const size_t F = B * T, S = 2 * P + L, R = F * S, FF = g.ffn_dim, D = g.dec_layers;
   Arena& a = c->ws;
   c->X = a.get<bf16>(R * 256); c->X1 = a.get<bf16>(R * 256); c->QKV = a.get<bf16>(R * 768); c->AO = a.get<bf16>(R * 256);
-  c->HID = a.get<bf16>(R * FF); c->Xf = a.get<bf16>(R * 256);
+  c->HID = a.get<bf16>(R * FF);
   c->X32 = a.get<float>(R * 256); c->X1_32 = a.get<float>(R * 256); c->XP = a.get<bf16>(R * 256);
-  c->pos_enc = a.get<bf16>(R * 256); c->kposb = a.get<bf16>(R * 1536); c->enc_tab = a.get<float>(R * 768);
-  c->encmask = a.get<uint8_t>(R);
+  c->kposb = a.get<bf16>(R * 1536);
+  for (auto& b : c->bd) {
+    b.Xf = a.get<bf16>(R * 256); b.pos_enc = a.get<bf16>(R * 256); b.encmask = a.get<uint8_t>(R);
+    b.frames_cls = a.get<float>(F * 256); b.ftext = a.get<bf16>(B * L * 256); b.q0 = a.get<bf16>(F * 256);
+    b.q0_32 = a.get<float>(F * 256);
+    for (int k = 0; k < 2; ++k) { b.pool[k] = a.get<bf16>(F * 256); b.pool32[k] = a.get<float>(F * 256); }
+  }
   for (auto& h : c->hs) {
     h.vis = a.get<float>(F * 256 * P); h.vid = a.get<float>(F * 256 * P); h.text = a.get<float>(B * L * 256);
     h.pos = a.get<float>(F * 256 * P); h.sizes = a.get<float>(B * 2); h.f1 = a.get<float>(F); h.f2 = a.get<float>(F);
     h.vmask = a.get<uint8_t>(F * P); h.tmask = a.get<uint8_t>(B * L);
   }
-  c->frames_cls = a.get<float>(F * 256);
-  c->ftext = a.get<bf16>(B * L * 256); c->q0 = a.get<bf16>(F * 256); c->kv_ts = a.get<bf16>(B * L * 2048);
+  c->kv_ts = a.get<bf16>(B * L * 2048);
   for (int k = 0; k < 2; ++k) {
-    c->pool[k] = a.get<bf16>(F * 256); c->pool32[k] = a.get<float>(F * 256);
     c->c_h32[k] = a.get<float>(F * 256); c->c_a32[k] = a.get<float>(F * 256);
     c->c_h[k] = a.get<bf16>(F * 256); c->c_q[k] = a.get<bf16>(F * 256); c->c_ctx[k] = a.get<bf16>(F * 256);
     c->c_a[k] = a.get<bf16>(F * 256); c->c_i[k] = a.get<bf16>(F * 256);
@@ -501,7 +512,6 @@ static void carve_workspace(vgqa_ctx* c) {
     c->logit_f[k] = a.get<float>(F); c->attmap[k] = a.get<float>(F * P); c->logit_rows[k] = a.get<float>(F * 64);
     c->logits_r[k] = a.get<float>(B * 64); c->part[k] = a.get<float>(F * 256); c->seedq[k] = a.get<float>(B * 256);
   }
-  c->q0_32 = a.get<float>(F * 256);
   c->t_tgt32 = a.get<float>(F * 256); c->t_x32 = a.get<float>(F * 256); c->t_x2_32 = a.get<float>(F * 256);
   c->p_tgt32 = a.get<float>(F * 256); c->p_x32 = a.get<float>(F * 256); c->p_x2_32 = a.get<float>(F * 256);
   c->att_seq = a.get<float>(F); c->w1 = a.get<float>(F); c->w2 = a.get<float>(F); c->K1 = a.get<float>(B); c->K2 = a.get<float>(B);
@@ -515,6 +525,14 @@ static void carve_workspace(vgqa_ctx* c) {
   c->boxes0 = a.get<float>(F * 4); c->anchors = a.get<float>(D * F * 4); c->sted_all = a.get<float>(D * F * 2);
   c->act_all = a.get<float>(D * F); c->act1 = a.get<float>(F); c->boxes_px = a.get<float>(F * 4);
   c->sted_idx = a.get<int>(B * 2);
+}
+
+// point the "current" boundary tensors at one of the two slots (host-side; launches are enqueued in host order)
+static void select_slot(vgqa_ctx* c, int slot) {
+  vgqa_ctx::Boundary& b = c->bd[slot];
+  c->Xf = b.Xf; c->pos_enc = b.pos_enc; c->encmask = b.encmask; c->frames_cls = b.frames_cls; c->ftext = b.ftext;
+  c->q0 = b.q0; c->q0_32 = b.q0_32;
+  for (int k = 0; k < 2; ++k) { c->pool[k] = b.pool[k]; c->pool32[k] = b.pool32[k]; }
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -752,10 +770,13 @@ static void check_inputs(vgqa_ctx* c, const vgqa_inputs& in) {
   VG_CHECK(in.pos_frames == 1 || in.pos_frames == in.clips * in.T, "pos_frames must be 1 or clips*T");
 }
 
-static void forward_body(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out, cudaStream_t st) {
+// phase 0: CrossModalEncoder (+ final norm, pooled means); phase 1: everything after it.
+static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out, int phase, cudaStream_t st) {
   Fwd f;
   if (!c->aux_stream) {
-    VG_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    VG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    VG_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_hi));
     for (auto& e : c->fj) VG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   f.c = c; f.st = st; f.main = st; f.aux = c->aux_stream; f.B = in.clips; f.T = in.T; f.P = in.H * in.W; f.L = in.L; f.S = 2 * f.P + f.L;
@@ -764,7 +785,10 @@ static void forward_body(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs&
   const bool have_mask = in.vis_mask != nullptr || in.text_mask != nullptr;
   const int pos_rows = in.pos_frames * f.S;
   c->launches = 0;
-  run_encoder(f, in, have_mask, pos_rows);
+  if (phase == 0) {
+    run_encoder(f, in, have_mask, pos_rows);
+    return;
+  }
   if (in.stop_after_encoder) {
     if (out.frames_cls) VG_CUDA(cudaMemcpyAsync(out.frames_cls, c->frames_cls, (size_t)F * 256 * 4, cudaMemcpyDeviceToDevice, st));
     return;
@@ -862,16 +886,17 @@ void vgqa_destroy(vgqa_ctx* c) {
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->host_stream) cudaStreamDestroy(c->host_stream);
   if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
-  for (auto& h : c->hs) {
-    if (h.in_ready) cudaEventDestroy(h.in_ready);
-    if (h.in_free) cudaEventDestroy(h.in_free);
+  for (auto& h : c->hs)
     if (h.done) cudaEventDestroy(h.done);
+  if (c->enc_stream) cudaStreamDestroy(c->enc_stream);
+  if (c->dec_stream) cudaStreamDestroy(c->dec_stream);
+  for (auto& b : c->bd) {
+    if (b.ev_in) cudaEventDestroy(b.ev_in);
+    if (b.enc_done) cudaEventDestroy(b.enc_done);
+    if (b.dec_done) cudaEventDestroy(b.dec_done);
   }
-  if (c->exec_stream) cudaStreamDestroy(c->exec_stream);
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   for (auto& e : c->fj) if (e) cudaEventDestroy(e);
-  if (c->ev_in) cudaEventDestroy(c->ev_in);
-  if (c->ev_out) cudaEventDestroy(c->ev_out);
   c->warena.release();
   c->ws.release();
   delete c;
@@ -901,75 +926,125 @@ int vgqa_finalize_weights(vgqa_ctx* c) {
   } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
 }
 
-int vgqa_forward(vgqa_ctx* c, const vgqa_inputs* in, const vgqa_outputs* out, void* stream) {
+}  // extern "C" (reopened below)
+
+namespace vg {
+
+static void ensure_streams(vgqa_ctx* c) {
+  if (c->enc_stream) return;
+  int prio_lo = 0, prio_hi = 0;
+  VG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  VG_CUDA(cudaStreamCreateWithPriority(&c->enc_stream, cudaStreamNonBlocking, prio_lo));
+  // phase 1 is a long chain of small kernels: give it priority so that its blocks are placed first whenever SMs free up
+  VG_CUDA(cudaStreamCreateWithPriority(&c->dec_stream, cudaStreamNonBlocking, prio_hi));
+  VG_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+  for (auto& b : c->bd) {
+    VG_CUDA(cudaEventCreateWithFlags(&b.ev_in, cudaEventDisableTiming));
+    VG_CUDA(cudaEventCreateWithFlags(&b.enc_done, cudaEventDisableTiming));
+    VG_CUDA(cudaEventCreateWithFlags(&b.dec_done, cudaEventDisableTiming));
+  }
+  for (auto& h : c->hs) VG_CUDA(cudaEventCreateWithFlags(&h.done, cudaEventDisableTiming));
+}
+
+// Enqueue one phase on `ex`: eagerly, or as a cached CUDA graph (one graph per phase / slot / shape / pointer set).
+static int run_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out, int phase, int slot, cudaStream_t ex,
+                     bool eager) {
+  if (eager) {
+    forward_phase(c, in, out, phase, ex);
+    return c->launches;
+  }
+  std::vector<uint64_t> key = {(uint64_t)phase, (uint64_t)slot, (uint64_t)in.clips, (uint64_t)in.T, (uint64_t)in.H,
+                               (uint64_t)in.W, (uint64_t)in.L, (uint64_t)in.pos_frames, (uint64_t)(in.iteration_rate < 0)};
+  for (const void* q : {(const void*)in.vis, (const void*)in.vid, (const void*)in.text, (const void*)in.pos,
+                        (const void*)in.vis_mask, (const void*)in.text_mask, (const void*)in.ori_sizes_hw,
+                        (const void*)in.force_choose1, (const void*)in.force_choose2})
+    key.push_back((uint64_t)(uintptr_t)q);
+  if (phase == 1)
+    for (const void* q : {(const void*)out.pred_boxes, (const void*)out.pred_sted, (const void*)out.pred_actioness,
+                          (const void*)out.logits_f_m, (const void*)out.logits_f_a, (const void*)out.logits_r_a,
+                          (const void*)out.logits_r_m, (const void*)out.att_sequences, (const void*)out.aux_boxes,
+                          (const void*)out.aux_sted, (const void*)out.aux_actioness, (const void*)out.choose1,
+                          (const void*)out.choose2, (const void*)out.actioness_pass1, (const void*)out.boxes_px,
+                          (const void*)out.sted_idx, (const void*)out.frames_cls})
+      key.push_back((uint64_t)(uintptr_t)q);
+  auto it = c->graphs.find(key);
+  if (it == c->graphs.end()) {
+    forward_phase(c, in, out, phase, ex);  // eager warm-up (sets function attributes, validates, produces valid data)
+    VG_CUDA(cudaStreamSynchronize(ex));
+    VG_CUDA(cudaStreamSynchronize(c->aux_stream));
+    cudaGraph_t graph = nullptr;
+    VG_CUDA(cudaStreamBeginCapture(ex, cudaStreamCaptureModeThreadLocal));
+    try {
+      forward_phase(c, in, out, phase, ex);
+    } catch (...) {
+      cudaStreamEndCapture(ex, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    VG_CUDA(cudaStreamEndCapture(ex, &graph));
+    vgqa_ctx::GraphEntry ge;
+    VG_CUDA(cudaGraphInstantiate(&ge.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    ge.launches = c->launches;
+    if (c->graphs.size() >= 32) {
+      VG_CUDA(cudaDeviceSynchronize());
+      for (auto& g : c->graphs) cudaGraphExecDestroy(g.second.exec);
+      c->graphs.clear();
+    }
+    it = c->graphs.emplace(key, ge).first;
+  }
+  VG_CUDA(cudaGraphLaunch(it->second.exec, ex));
+  return it->second.launches;
+}
+
+// Both phases of one call, for boundary slot `slot`, ordered after everything enqueued on `st` so far.
+static void forward_async(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out, int slot, cudaStream_t st) {
+  check_inputs(c, in);
+  ensure_streams(c);
+  select_slot(c, slot);
+  vgqa_ctx::Boundary& b = c->bd[slot];
+  const bool eager = !c->cfg.use_cuda_graph || out.encoded_feature != nullptr || in.stop_after_encoder;
+  VG_CUDA(cudaEventRecord(b.ev_in, st));
+  VG_CUDA(cudaStreamWaitEvent(c->enc_stream, b.ev_in, 0));
+  if (b.used) VG_CUDA(cudaStreamWaitEvent(c->enc_stream, b.dec_done, 0));  // phase 1 of the previous user of this slot
+  int launches = run_phase(c, in, out, 0, slot, c->enc_stream, eager);
+  VG_CUDA(cudaEventRecord(b.enc_done, c->enc_stream));
+  VG_CUDA(cudaStreamWaitEvent(c->dec_stream, b.enc_done, 0));
+  launches += run_phase(c, in, out, 1, slot, c->dec_stream, eager);
+  if (out.encoded_feature) {
+    const size_t n = (size_t)in.clips * in.T * (2 * in.H * in.W + in.L) * 256;
+    bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->dec_stream>>>(c->Xf, out.encoded_feature, n);
+  }
+  VG_CUDA(cudaEventRecord(b.dec_done, c->dec_stream));
+  b.used = true;
+  c->last_launches = launches;
+}
+
+}  // namespace vg
+
+extern "C" {
+
+int vgqa_forward_async(vgqa_ctx* c, const vgqa_inputs* in, const vgqa_outputs* out, int slot, void* stream) {
   try {
-    VG_CHECK(c && in && out, "null argument");
-    vg::check_inputs(c, *in);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // debug / seam outputs bypass the graph cache
-    if (!c->cfg.use_cuda_graph || out->encoded_feature != nullptr || in->stop_after_encoder) {
-      vg::forward_body(c, *in, *out, st);
-      if (out->encoded_feature) {
-        const size_t n = (size_t)in->clips * in->T * (2 * in->H * in->W + in->L) * 256;
-        bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->Xf, out->encoded_feature, n);
-      }
-      c->last_launches = c->launches;
-      return 0;
-    }
-    // graph mode: captured and replayed on the context's own stream, ordered after / before `st` with events
-    if (!c->exec_stream) {
-      VG_CUDA(cudaStreamCreateWithFlags(&c->exec_stream, cudaStreamNonBlocking));
-      VG_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
-      VG_CUDA(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
-    }
-    cudaStream_t ex = c->exec_stream;
-    // key = every scalar and pointer that is baked into the captured launches
-    std::vector<uint64_t> key = {(uint64_t)in->clips, (uint64_t)in->T, (uint64_t)in->H, (uint64_t)in->W, (uint64_t)in->L,
-                                 (uint64_t)in->pos_frames, (uint64_t)(in->iteration_rate < 0),
-                                 (uint64_t)in->stop_after_encoder};
-    for (const void* q : {(const void*)in->vis, (const void*)in->vid, (const void*)in->text, (const void*)in->pos,
-                          (const void*)in->vis_mask, (const void*)in->text_mask, (const void*)in->ori_sizes_hw,
-                          (const void*)in->force_choose1, (const void*)in->force_choose2})
-      key.push_back((uint64_t)(uintptr_t)q);
-    for (const void* q : {(const void*)out->pred_boxes, (const void*)out->pred_sted, (const void*)out->pred_actioness,
-                          (const void*)out->logits_f_m, (const void*)out->logits_f_a, (const void*)out->logits_r_a,
-                          (const void*)out->logits_r_m, (const void*)out->att_sequences, (const void*)out->aux_boxes,
-                          (const void*)out->aux_sted, (const void*)out->aux_actioness, (const void*)out->choose1,
-                          (const void*)out->choose2, (const void*)out->actioness_pass1, (const void*)out->boxes_px,
-                          (const void*)out->sted_idx, (const void*)out->frames_cls})
-      key.push_back((uint64_t)(uintptr_t)q);
-    VG_CUDA(cudaEventRecord(c->ev_in, st));
-    VG_CUDA(cudaStreamWaitEvent(ex, c->ev_in, 0));
-    auto it = c->graphs.find(key);
-    if (it == c->graphs.end()) {
-      vg::forward_body(c, *in, *out, ex);  // eager warm-up (sets function attributes, validates)
-      VG_CUDA(cudaStreamSynchronize(ex));
-      cudaGraph_t graph = nullptr;
-      VG_CUDA(cudaStreamBeginCapture(ex, cudaStreamCaptureModeThreadLocal));
-      try {
-        vg::forward_body(c, *in, *out, ex);
-      } catch (...) {
-        cudaStreamEndCapture(ex, &graph);
-        if (graph) cudaGraphDestroy(graph);
-        throw;
-      }
-      VG_CUDA(cudaStreamEndCapture(ex, &graph));
-      vgqa_ctx::GraphEntry ge;
-      VG_CUDA(cudaGraphInstantiate(&ge.exec, graph, 0));
-      cudaGraphDestroy(graph);
-      ge.launches = c->launches;
-      if (c->graphs.size() >= 16) {
-        for (auto& g : c->graphs) cudaGraphExecDestroy(g.second.exec);
-        c->graphs.clear();
-      }
-      it = c->graphs.emplace(key, ge).first;
-    }
-    VG_CUDA(cudaGraphLaunch(it->second.exec, ex));
-    VG_CUDA(cudaEventRecord(c->ev_out, ex));
-    VG_CUDA(cudaStreamWaitEvent(st, c->ev_out, 0));
-    c->last_launches = it->second.launches;
+    VG_CHECK(c && in && out && (slot == 0 || slot == 1), "bad argument");
+    vg::forward_async(c, *in, *out, slot, static_cast<cudaStream_t>(stream));
     return 0;
   } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_forward_wait(vgqa_ctx* c, int slot, void* stream, int host_sync) {
+  try {
+    VG_CHECK(c && (slot == 0 || slot == 1), "bad argument");
+    if (!c->bd[slot].used) return 0;
+    if (host_sync) VG_CUDA(cudaEventSynchronize(c->bd[slot].dec_done));
+    else VG_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), c->bd[slot].dec_done, 0));
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_forward(vgqa_ctx* c, const vgqa_inputs* in, const vgqa_outputs* out, void* stream) {
+  int rc = vgqa_forward_async(c, in, out, 0, stream);
+  return rc != 0 ? rc : vgqa_forward_wait(c, 0, stream, 0);
 }
 
 int vgqa_forward_host_async(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outputs* hout, int slot) {
@@ -977,21 +1052,13 @@ int vgqa_forward_host_async(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outp
     VG_CHECK(c && hin && hout && (slot == 0 || slot == 1), "bad argument");
     vg::check_inputs(c, *hin);
     VG_CHECK(hout->encoded_feature == nullptr, "encoded_feature is only available through vgqa_forward");
-    if (!c->host_stream) {
-      VG_CUDA(cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking));
-      VG_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
-      for (auto& h : c->hs) {
-        VG_CUDA(cudaEventCreateWithFlags(&h.in_ready, cudaEventDisableTiming));
-        VG_CUDA(cudaEventCreateWithFlags(&h.in_free, cudaEventDisableTiming));
-        VG_CUDA(cudaEventCreateWithFlags(&h.done, cudaEventDisableTiming));
-      }
-    }
+    vg::ensure_streams(c);
     vgqa_ctx::HostSlot& h = c->hs[slot];
-    cudaStream_t st = c->host_stream, up = c->h2d_stream;
+    cudaStream_t up = c->h2d_stream;
     const size_t B = hin->clips, T = hin->T, P = (size_t)hin->H * hin->W, L = hin->L, F = B * T;
     const size_t D = c->tl.size();
-    // uploads wait until the previous forward that read this slot has finished
-    if (h.used) VG_CUDA(cudaStreamWaitEvent(up, h.in_free, 0));
+    // uploads wait until the previous forward that read this slot's staging buffers has finished
+    if (c->bd[slot].used) VG_CUDA(cudaStreamWaitEvent(up, c->bd[slot].dec_done, 0));
     auto h2d = [&](void* dst, const void* src, size_t bytes) {
       VG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, up));
     };
@@ -1005,14 +1072,10 @@ int vgqa_forward_host_async(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outp
     if (hin->ori_sizes_hw) { h2d(h.sizes, hin->ori_sizes_hw, B * 2 * 4); din.ori_sizes_hw = h.sizes; }
     if (hin->force_choose1) { h2d(h.f1, hin->force_choose1, F * 4); din.force_choose1 = h.f1; }
     if (hin->force_choose2) { h2d(h.f2, hin->force_choose2, F * 4); din.force_choose2 = h.f2; }
-    VG_CUDA(cudaEventRecord(h.in_ready, up));
-    VG_CUDA(cudaStreamWaitEvent(st, h.in_ready, 0));
     vgqa_outputs none;
     std::memset(&none, 0, sizeof(none));
-    int rc = vgqa_forward(c, &din, &none, st);
-    if (rc != 0) return rc;
-    VG_CUDA(cudaEventRecord(h.in_free, st));
-    h.used = true;
+    vg::forward_async(c, din, none, slot, up);
+    cudaStream_t st = c->dec_stream;   // results are downloaded right behind phase 1, before the next call's phase 1
     auto d2h = [&](void* dst, const void* src, size_t bytes) {
       if (dst != nullptr) VG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
     };
@@ -1036,6 +1099,8 @@ int vgqa_forward_host_async(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outp
     }
     d2h(hout->frames_cls, c->frames_cls, F * 256 * 4);
     VG_CUDA(cudaEventRecord(h.done, st));
+    VG_CUDA(cudaEventRecord(c->bd[slot].dec_done, st));   // the slot is busy until the downloads are done, too
+    h.used = true;
     return 0;
   } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
 }
@@ -1043,7 +1108,7 @@ int vgqa_forward_host_async(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outp
 int vgqa_forward_host_wait(vgqa_ctx* c, int slot) {
   try {
     VG_CHECK(c && (slot == 0 || slot == 1), "bad argument");
-    if (c->hs[slot].done) VG_CUDA(cudaEventSynchronize(c->hs[slot].done));
+    if (c->hs[slot].used) VG_CUDA(cudaEventSynchronize(c->hs[slot].done));
     return 0;
   } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
 }

@@ -51,6 +51,10 @@ def _declare(L):
     L.vgqa_finalize_weights.argtypes = [c_void_p]
     L.vgqa_forward.restype = c_int
     L.vgqa_forward.argtypes = [c_void_p, ctypes.POINTER(VgqaInputs), ctypes.POINTER(VgqaOutputs), c_void_p]
+    L.vgqa_forward_async.restype = c_int
+    L.vgqa_forward_async.argtypes = [c_void_p, ctypes.POINTER(VgqaInputs), ctypes.POINTER(VgqaOutputs), c_int, c_void_p]
+    L.vgqa_forward_wait.restype = c_int
+    L.vgqa_forward_wait.argtypes = [c_void_p, c_int, c_void_p, c_int]
     L.vgqa_forward_host.restype = c_int
     L.vgqa_forward_host.argtypes = [c_void_p, ctypes.POINTER(VgqaInputs), ctypes.POINTER(VgqaOutputs)]
     L.vgqa_forward_host_async.restype = c_int
@@ -181,6 +185,20 @@ class GroundingEngine:
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(self._L.vgqa_forward(self._ctx, ctypes.byref(inp), ctypes.byref(out), c_void_p(st)))
         return outs
+
+    def forward_async(self, vis, vid, text, pos, *, outs, slot, vis_mask=None, text_mask=None, ori_sizes_hw=None,
+                      force_choose1=None, force_choose2=None, iteration_rate=-1):
+        """Pipelined device path: alternate slot 0/1 on consecutive calls; `outs` are complete after `wait(slot)`."""
+        inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force_choose1, force_choose2,
+                                 iteration_rate, outs)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self._L.vgqa_forward_async(self._ctx, ctypes.byref(inp), ctypes.byref(out), slot, c_void_p(st)))
+        return outs
+
+    def wait(self, slot: int, host_sync: bool = False):
+        """Make the current stream (or the host) wait for the call last issued on `slot`."""
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self._L.vgqa_forward_wait(self._ctx, slot, c_void_p(st), 1 if host_sync else 0))
 
     def forward_host(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, ori_sizes_hw=None,
                      force_choose1=None, force_choose2=None, iteration_rate=-1, outs=None, want=None):
