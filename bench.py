@@ -147,7 +147,9 @@ def time_dominant_kernel(B, pk):
     ach = flops / dt / 1e12
     return {"kernel": "gemm_ws_kernel<256> (encoder FFN linear1+ReLU, M=%d N=2048 K=256)" % M, "bound": "tensor",
             "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
-            "traffic": None, "peak_source": pk["source"] + ", burst (kernel timed alone)",
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
+            # (profiles/r01_gemm_ws_ncu.md), scaled to this batch size; algorithmic bytes are (M*K + M*N + N*K) * 2
+            "traffic": (248.6e6 + 1921.6e6) * (B / 64.0), "peak_source": pk["source"] + ", burst (kernel timed alone)",
             "algorithmic_flops_per_launch": flops, "launch_ms": dt * 1e3,
             "hbm_gbs_at_algorithmic_bytes": (M * K * 2 + M * N * 2 + N * K * 2) / dt / 1e9}
 
