@@ -128,6 +128,17 @@ int vgqa_forward_host(vgqa_ctx* ctx, const vgqa_inputs* in, const vgqa_outputs* 
 int vgqa_forward_host_async(vgqa_ctx* ctx, const vgqa_inputs* in, const vgqa_outputs* out, int slot);
 int vgqa_forward_host_wait(vgqa_ctx* ctx, int slot);
 
+/* Frame sharding of ONE long clip over `world` processes / GPUs: rank r passes its contiguous frames
+ * [r*T, (r+1)*T) as a clips = 1, T = local-frames call.  Encoder, classifiers, cross-attention, FFNs and heads are
+ * frame-local; the library calls `fn` for the few exchanges the path needs — op 0: all-gather of `count` elements per
+ * rank (recv holds world*count, rank-major), op 1: in-place all-reduce(sum) of `count` elements; dtype 0 = bf16, 1 = fp32;
+ * the call must be enqueued on `stream` (NCCL from torch.distributed in vgqa_b200/parallel.py).  Exchanges per call:
+ * text-token mean (1 all-reduce), frame-selection counts (2), classifier/seed sums (4), and the temporal self-attention
+ * K|V rows (one all-gather per decoder layer and decoder: 12 per pass).  Outputs are the local frames' rows; gather them
+ * and run vgqa_postprocess for the segment decode. */
+typedef void (*vgqa_exchange_fn)(void* user, int op, const void* send, void* recv, long long count, int dtype, void* stream);
+int vgqa_set_sharding(vgqa_ctx* ctx, int rank, int world, vgqa_exchange_fn fn, void* user);
+
 /* PostProcess.forward (vgqa/core/postprocessor.py:14-50) on device tensors: boxes [clips,T,4] cxcywh, sted [clips,T,2],
  * sizes_hw [clips,2] → boxes_px [clips,T,4] xyxy pixels (clamped at 0), sted_idx int32 [clips,2] = argmax (start,end), start < end. */
 int vgqa_postprocess(const float* boxes, const float* sted, const float* sizes_hw, float* boxes_px, int32_t* sted_idx,

@@ -30,22 +30,26 @@ void enc_finalize(const float* X32, const float* w, const float* b, float eps, b
                   bf16* pool_vis, bf16* pool_vid, float* pool_vis32, float* pool_vid32, int F, int S, int P, int L,
                   cudaStream_t st);
 // ftext[b,l,:] = mean_t Xf[(b*T+t)*S + P + l, :];  q0[f,:] = ftext[f/T, 0, :]
-void text_mean(const bf16* Xf, bf16* ftext, bf16* q0, float* q0_32, int B, int T, int S, int P, int L, cudaStream_t st);
+void text_sum(const bf16* Xf, float* sums, int B, int T, int S, int P, int L, cudaStream_t st);
+void text_finish(const float* sums, float inv_t_global, bf16* ftext, bf16* q0, float* q0_32, int B, int T, int L,
+                 cudaStream_t st);
 // y[r, j] = act(x[r,:256] · w[j,:] + b[j]), j < N <= 64; act: 0 none, 1 sigmoid
 void rowvec_head(const bf16* x, int ldx, const float* w, const float* b, float* y, int ldy, int rows, int N, int act,
                  cudaStream_t st);
 void select_pass1(const float* lfm, const float* lfa, float theta, const float* force_w, float* att, float* w,
                   float* K, int B, int T, cudaStream_t st);
 void select_pass2(const float* act_sigmoid, const float* force_w, float* w, float* K, int B, int T, cudaStream_t st);
-// out[b, j] = sum_t w[b,t] x[(b,t), j] / K[b]
-void masked_mean_rows(const float* x, int ldx, const float* w, const float* K, float* out, int B, int T, int N,
-                      cudaStream_t st);
+// applies the "no frame selected → every frame" fall-back with the (possibly all-reduced) count K
+void select_finish(float* w, float* K, int B, int T, int T_global, cudaStream_t st);
 // part[f, c] = w[f] * sum_p att[f,p] * Xf[(f*S + tok0 + p), c]
 void seed_partial(const bf16* Xf, const float* att, const float* w, float* part, int F, int S, int tok0, int P,
                   cudaStream_t st);
-// q[b, c] = sum_t part[(b,t), c] / (K[b] * P);  tgt[(b,t), c] = bf16(q[b,c])
-void seed_reduce(const float* part, const float* K, float* q, bf16* tgt, int ldt, float* tgt32, int B, int T, int P,
+// red[b] = [sum_t w x[(b,t), 0..N) (64 slots) | sum_t part[(b,t), 0..256)]
+void masked_sums(const float* logit_rows, int ldx, int N, const float* part, const float* w, float* red, int B, int T,
                  cudaStream_t st);
+// logits_r[b] = red[b][:N] / K[b];  q[b] = red[b][64:] / (K[b] * P);  tgt[(b,t), :] = q[b]
+void seed_finish(const float* red, const float* K, float* logits_r, int N, float* q, bf16* tgt, int ldt, float* tgt32,
+                 int B, int T, int P, cudaStream_t st);
 // boxes[f] = sigmoid(BertLN4(relu(W · BertLN256(frames_cls[f]) + b)))
 void pos_fc_boxes(const float* frames_cls, const float* ln0w, const float* ln0b, const float* W, const float* b,
                   const float* ln4w, const float* ln4b, float* boxes, int F, cudaStream_t st);

@@ -171,6 +171,12 @@ struct vgqa_ctx {
   cudaStream_t enc_stream = nullptr, dec_stream = nullptr;
   cudaStream_t aux_stream = nullptr;   // second branch of the fork/join sections (classifier pairs, the two decoders)
   cudaEvent_t fj[32] = {};
+  // frame sharding of one long clip over `sh_world` ranks (vgqa_set_sharding); exchanges go through the callback
+  int sh_rank = 0, sh_world = 1;
+  vgqa_exchange_fn sh_fn = nullptr;
+  void* sh_user = nullptr;
+  float *text_sums, *red[2];
+  bf16 *t_qkv_all, *p_qkv_all;   // all-gathered in-projection rows of the temporal self-attention
   // graph cache
   struct GraphEntry { cudaGraphExec_t exec; int launches; };
   std::map<std::vector<uint64_t>, GraphEntry> graphs;
@@ -504,6 +510,9 @@ static void carve_workspace(vgqa_ctx* c) {
     h.vmask = a.get<uint8_t>(F * P); h.tmask = a.get<uint8_t>(B * L);
   }
   c->kv_ts = a.get<bf16>(B * L * 2048);
+  c->text_sums = a.get<float>(B * L * 256);
+  c->red[0] = a.get<float>(B * 320); c->red[1] = a.get<float>(B * 320);
+  c->t_qkv_all = a.get<bf16>((size_t)(g.max_video_len + 1) * 768); c->p_qkv_all = a.get<bf16>((size_t)(g.max_video_len + 1) * 768);
   for (int k = 0; k < 2; ++k) {
     c->c_h32[k] = a.get<float>(F * 256); c->c_a32[k] = a.get<float>(F * 256);
     c->c_h[k] = a.get<bf16>(F * 256); c->c_q[k] = a.get<bf16>(F * 256); c->c_ctx[k] = a.get<bf16>(F * 256);
@@ -545,11 +554,13 @@ struct Fwd {
   // independent sub-graphs (the two classifiers of a pair, TimeDecoder vs PosDecoder) run on two streams; under
   // stream capture this becomes two parallel branches of the CUDA graph.
   void fork() {
+    if (aux == main) return;   // sharded mode: one stream, collectives stay in program order
     VG_CUDA(cudaEventRecord(c->fj[ev_i], main));
     VG_CUDA(cudaStreamWaitEvent(aux, c->fj[ev_i], 0));
     ev_i = (ev_i + 1) & 31;
   }
   void join() {
+    if (aux == main) { st = main; return; }
     VG_CUDA(cudaEventRecord(c->fj[ev_i], aux));
     VG_CUDA(cudaStreamWaitEvent(main, c->fj[ev_i], 0));
     ev_i = (ev_i + 1) & 31;
@@ -572,6 +583,16 @@ struct Fwd {
     gemm(A, lda, w, M, ep);
   }
   void count(int n = 1) { c->launches += n; }
+  bool sharded() const { return c->sh_world > 1; }
+  int T_global() const { return T * c->sh_world; }
+  // in-place sum over ranks of `n` fp32 values (no-op for a single rank)
+  void all_reduce_f32(float* buf, size_t n) {
+    if (sharded()) c->sh_fn(c->sh_user, 1, buf, buf, (long long)n, 1, st);
+  }
+  // recv[world][rows_local * cols] <- every rank's send[rows_local * cols] (bf16)
+  void all_gather_bf16(const bf16* send, bf16* recv, size_t elems_per_rank) {
+    c->sh_fn(c->sh_user, 0, send, recv, (long long)elems_per_rank, 0, st);
+  }
 };
 
 static void run_encoder(Fwd& f, const vgqa_inputs& in, bool have_mask, int pos_rows) {
@@ -614,8 +635,10 @@ static void run_encoder(Fwd& f, const vgqa_inputs& in, bool have_mask, int pos_r
   }
   enc_finalize(c->X32, c->enc_norm.w, c->enc_norm.b, 1e-5f, c->Xf, c->frames_cls, c->pool[1], c->pool[0], c->pool32[1],
                c->pool32[0], F, S, P, L, st);
-  text_mean(c->Xf, c->ftext, c->q0, c->q0_32, f.B, f.T, S, P, L, st);
-  f.count(2);
+  text_sum(c->Xf, c->text_sums, f.B, f.T, S, P, L, st);
+  f.all_reduce_f32(c->text_sums, (size_t)f.B * L * 256);
+  text_finish(c->text_sums, 1.f / (float)f.T_global(), c->ftext, c->q0, c->q0_32, f.B, f.T, L, st);
+  f.count(3);
 }
 
 // TemporalSampling (classifier.py:32-37): k = 0 → t_temporal_clas on vid tokens, 1 → s_temporal_clas on vis tokens
@@ -671,10 +694,11 @@ static void run_spatial_seed(Fwd& f, const float* w, const float* K) {
     Head& hd = c->sa_head[k];
     f.linear_res_ln(q, 256, hd.t, F, nullptr, hd.ln, 1e-12f, c->c_a[k], 256, nullptr, ACT_GELU);
     rowvec_head(c->c_a[k], 256, hd.dw, hd.db, c->logit_rows[k], 64, F, hd.vocab, 0, f.st);
-    masked_mean_rows(c->logit_rows[k], 64, w, K, c->logits_r[k], f.B, f.T, hd.vocab, f.st);
     seed_partial(c->Xf, c->attmap[k], w, c->part[k], F, S, tok0, P, f.st);
+    masked_sums(c->logit_rows[k], 64, hd.vocab, c->part[k], w, c->red[k], f.B, f.T, f.st);
+    f.all_reduce_f32(c->red[k], (size_t)f.B * 320);
     // k = 0: init temporal query → TimeDecoder tgt; k = 1: init spatial query → PosDecoder tgt (cat cols 0..255)
-    seed_reduce(c->part[k], K, c->seedq[k], k == 0 ? c->t_tgt : c->p_cat, k == 0 ? 256 : 768,
+    seed_finish(c->red[k], K, c->logits_r[k], hd.vocab, c->seedq[k], k == 0 ? c->t_tgt : c->p_cat, k == 0 ? 256 : 768,
                 k == 0 ? c->t_tgt32 : c->p_tgt32, f.B, f.T, P, f.st);
     f.count(4);
   }
@@ -694,9 +718,13 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames) {
   // ---------------- TimeDecoder (query_decoder.py:379-486), memory = [text | vid] tokens
   for (int l = 0; l < D; ++l) {
     TimeLayer& t = c->tl[l];
-    { GemmEpi ep; ep.C = c->t_qkv; ep.ldc = 768; ep.bias = t.tab; ep.bias_period = T; ep.bias_ld = 768;
+    { GemmEpi ep; ep.C = c->t_qkv; ep.ldc = 768; ep.bias = t.tab + (size_t)c->sh_rank * T * 768; ep.bias_period = T; ep.bias_ld = 768;
       f.gemm(c->t_tgt, 256, t.qkv, F, ep); }
-    mha32(c->t_qkv, 768, c->t_qkv + 256, 768, c->t_qkv + 512, 768, c->t_ao, 256, f.B, T, T, nullptr, 0.17677669529663687f, st);
+    {  // temporal self-attention across ALL frames of the clip: a sharded clip all-gathers the K|V rows (§8e)
+      const bf16* kv = c->t_qkv;
+      if (f.sharded()) { f.all_gather_bf16(c->t_qkv, c->t_qkv_all, (size_t)T * 768); kv = c->t_qkv_all; }
+      mha32(c->t_qkv, 768, kv + 256, 768, kv + 512, 768, c->t_ao, 256, f.B, T, f.T_global(), nullptr, 0.17677669529663687f, st);
+    }
     f.linear_res_ln(c->t_ao, 256, t.out, F, c->t_tgt32, t.ln1, 1e-5f, c->t_x, 256, c->t_x32);
     f.linear(c->t_x, 256, t.qabs, F, c->t_qabs, 2048);
     // keys = mem + pos_t (:474); mask = encoded_mask[:, :-P] applied positionally (:100,476)
@@ -728,9 +756,13 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames) {
       f.gemm(c->p_h, 256, c->qs1, F, ep);
       s256 = c->p_s256; lds = 256;
     }
-    { GemmEpi ep; ep.C = c->p_qkv; ep.ldc = 768; ep.bias = q.tab_sa; ep.bias_period = T; ep.bias_ld = 768;
+    { GemmEpi ep; ep.C = c->p_qkv; ep.ldc = 768; ep.bias = q.tab_sa + (size_t)c->sh_rank * T * 768; ep.bias_period = T; ep.bias_ld = 768;
       f.gemm(c->p_cat, 768, q.sa, F, ep); }                                     // 7 sa_* projs ∘ in_proj (:282-294)
-    mha32(c->p_qkv, 768, c->p_qkv + 256, 768, c->p_qkv + 512, 768, c->p_ao, 256, f.B, T, T, nullptr, 0.17677669529663687f, st);
+    {
+      const bf16* kv = c->p_qkv;
+      if (f.sharded()) { f.all_gather_bf16(c->p_qkv, c->p_qkv_all, (size_t)T * 768); kv = c->p_qkv_all; }
+      mha32(c->p_qkv, 768, kv + 256, 768, kv + 512, 768, c->p_ao, 256, f.B, T, f.T_global(), nullptr, 0.17677669529663687f, st);
+    }
     f.linear_res_ln(c->p_ao, 256, q.sa_out, F, c->p_tgt32, q.ln1, 1e-5f, c->p_cat + 512, 768, c->p_x32);  // x → cat[:,512:]
     const bf16* qa = l == 0 ? c->p_cat + 256 : c->p_cat + 512;                  // [qpos | x] or x
     const bf16* q2res = nullptr;
@@ -768,6 +800,11 @@ static void check_inputs(vgqa_ctx* c, const vgqa_inputs& in) {
            "T exceeds INPUT.MAX_VIDEO_LEN+1 rows of the time embedding (reference raises RuntimeError too)");
   VG_CHECK(in.vis && in.vid && in.text && in.pos, "vis/vid/text/pos must be non-null");
   VG_CHECK(in.pos_frames == 1 || in.pos_frames == in.clips * in.T, "pos_frames must be 1 or clips*T");
+  if (c->sh_world > 1) {
+    VG_CHECK(in.clips == 1, "frame sharding handles one clip per call");
+    VG_CHECK(in.T * c->sh_world <= c->cfg.max_video_len + 1, "sharded clip exceeds INPUT.MAX_VIDEO_LEN+1 frames");
+    VG_CHECK(in.ori_sizes_hw == nullptr, "PostProcess of a sharded clip runs on the gathered outputs (vgqa_postprocess)");
+  }
 }
 
 // phase 0: CrossModalEncoder (+ final norm, pooled means); phase 1: everything after it.
@@ -779,7 +816,7 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
     VG_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_hi));
     for (auto& e : c->fj) VG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  f.c = c; f.st = st; f.main = st; f.aux = c->aux_stream; f.B = in.clips; f.T = in.T; f.P = in.H * in.W; f.L = in.L; f.S = 2 * f.P + f.L;
+  f.c = c; f.st = st; f.main = st; f.aux = c->sh_world > 1 ? st : c->aux_stream; f.B = in.clips; f.T = in.T; f.P = in.H * in.W; f.L = in.L; f.S = 2 * f.P + f.L;
   f.F = f.B * f.T; f.R = f.F * f.S;
   const int F = f.F, D = (int)c->tl.size();
   const bool have_mask = in.vis_mask != nullptr || in.text_mask != nullptr;
@@ -795,7 +832,9 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
   }
   run_temporal_sampling(f);
   select_pass1(c->logit_f[0], c->logit_f[1], 0.45f, in.force_choose1, c->att_seq, c->w1, c->K1, f.B, f.T, st);
-  f.count();
+  f.all_reduce_f32(c->K1, f.B);
+  select_finish(c->w1, c->K1, f.B, f.T, f.T_global(), st);
+  f.count(2);
   run_spatial_seed(f, c->w1, c->K1);
   run_decoders(f, have_mask, in.pos_frames);
   const float* wfinal = c->w1;
@@ -803,7 +842,9 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
     f.linear(c->t_inter + (size_t)(D - 1) * F * 256, 256, c->action_embed.l0, F, c->t_hs, 256, ACT_RELU);
     rowvec_head(c->t_hs, 256, c->action_embed.w1, c->action_embed.b1, c->act1, 1, F, 1, 1, st);  // sigmoid
     select_pass2(c->act1, in.force_choose2, c->w2, c->K2, f.B, f.T, st);
-    f.count(2);
+    f.all_reduce_f32(c->K2, f.B);
+    select_finish(c->w2, c->K2, f.B, f.T, f.T_global(), st);
+    f.count(3);
     run_spatial_seed(f, c->w2, c->K2);
     run_decoders(f, have_mask, in.pos_frames);
     wfinal = c->w2;
@@ -1003,7 +1044,7 @@ static void forward_async(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
   ensure_streams(c);
   select_slot(c, slot);
   vgqa_ctx::Boundary& b = c->bd[slot];
-  const bool eager = !c->cfg.use_cuda_graph || out.encoded_feature != nullptr || in.stop_after_encoder;
+  const bool eager = !c->cfg.use_cuda_graph || out.encoded_feature != nullptr || in.stop_after_encoder || c->sh_world > 1;
   VG_CUDA(cudaEventRecord(b.ev_in, st));
   VG_CUDA(cudaStreamWaitEvent(c->enc_stream, b.ev_in, 0));
   if (b.used) VG_CUDA(cudaStreamWaitEvent(c->enc_stream, b.dec_done, 0));  // phase 1 of the previous user of this slot
@@ -1116,6 +1157,15 @@ int vgqa_forward_host_wait(vgqa_ctx* c, int slot) {
 int vgqa_forward_host(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outputs* hout) {
   int rc = vgqa_forward_host_async(c, hin, hout, 0);
   return rc != 0 ? rc : vgqa_forward_host_wait(c, 0);
+}
+
+int vgqa_set_sharding(vgqa_ctx* c, int rank, int world, vgqa_exchange_fn fn, void* user) {
+  try {
+    VG_CHECK(c && world >= 1 && rank >= 0 && rank < world, "bad rank / world");
+    VG_CHECK(world == 1 || fn != nullptr, "a sharded context needs an exchange callback");
+    c->sh_rank = rank; c->sh_world = world; c->sh_fn = fn; c->sh_user = user;
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
 }
 
 int vgqa_postprocess(const float* boxes, const float* sted, const float* sizes_hw, float* boxes_px, int32_t* sted_idx,

@@ -151,23 +151,34 @@ void enc_finalize(const float* X, const float* w, const float* b, float eps, bf1
   VG_CUDA(cudaGetLastError());
 }
 
-// grounding_net.py:119 (f_text_cls) and :131 (f_text_cls[:, :1] as the SpatialActivation init query)
-__global__ void __launch_bounds__(256) text_mean_kernel(const bf16* __restrict__ Xf, bf16* __restrict__ ftext,
-                                                        bf16* __restrict__ q0, float* __restrict__ q0_32, int T, int S,
-                                                        int P, int L) {
+// grounding_net.py:119 (f_text_cls) and :131 (f_text_cls[:, :1] as the SpatialActivation init query).
+// Two steps so that a frame-sharded clip can all-reduce the fp32 sums in between (vgqa_set_sharding).
+__global__ void __launch_bounds__(256) text_sum_kernel(const bf16* __restrict__ Xf, float* __restrict__ sums, int T, int S,
+                                                       int P, int L) {
   const int b = blockIdx.x / L, l = blockIdx.x % L, c = threadIdx.x;
   float acc = 0.f;
   for (int t = 0; t < T; ++t) acc += __bfloat162float(Xf[(((size_t)b * T + t) * S + P + l) * 256 + c]);
-  const bf16 m = __float2bfloat16(acc / T);
+  sums[((size_t)b * L + l) * 256 + c] = acc;
+}
+void text_sum(const bf16* Xf, float* sums, int B, int T, int S, int P, int L, cudaStream_t st) {
+  text_sum_kernel<<<B * L, 256, 0, st>>>(Xf, sums, T, S, P, L);
+  VG_CUDA(cudaGetLastError());
+}
+__global__ void __launch_bounds__(256) text_finish_kernel(const float* __restrict__ sums, float inv_t, bf16* __restrict__ ftext,
+                                                          bf16* __restrict__ q0, float* __restrict__ q0_32, int T, int L) {
+  const int b = blockIdx.x / L, l = blockIdx.x % L, c = threadIdx.x;
+  const float m32 = sums[((size_t)b * L + l) * 256 + c] * inv_t;
+  const bf16 m = __float2bfloat16(m32);
   ftext[((size_t)b * L + l) * 256 + c] = m;
   if (l == 0)
     for (int t = 0; t < T; ++t) {
       q0[((size_t)b * T + t) * 256 + c] = m;
-      q0_32[((size_t)b * T + t) * 256 + c] = acc / T;
+      q0_32[((size_t)b * T + t) * 256 + c] = m32;
     }
 }
-void text_mean(const bf16* Xf, bf16* ftext, bf16* q0, float* q0_32, int B, int T, int S, int P, int L, cudaStream_t st) {
-  text_mean_kernel<<<B * L, 256, 0, st>>>(Xf, ftext, q0, q0_32, T, S, P, L);
+void text_finish(const float* sums, float inv_t_global, bf16* ftext, bf16* q0, float* q0_32, int B, int T, int L,
+                 cudaStream_t st) {
+  text_finish_kernel<<<B * L, 256, 0, st>>>(sums, inv_t_global, ftext, q0, q0_32, T, L);
   VG_CUDA(cudaGetLastError());
 }
 
@@ -218,11 +229,7 @@ __global__ void __launch_bounds__(256) select_pass1_kernel(const float* lfm, con
   float tot = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) tot += cnt[k];
-  if (tot == 0.f) {  // `choose_index or nonzero(att > 0)`: sigmoid average is always > 0 → every frame
-    for (int t = threadIdx.x; t < T; t += 256) w[(size_t)b * T + t] = 1.f;
-    tot = (float)T;
-  }
-  if (threadIdx.x == 0) K[b] = tot;
+  if (threadIdx.x == 0) K[b] = tot;   // local count; the fall-back is applied by select_finish
 }
 void select_pass1(const float* lfm, const float* lfa, float theta, const float* force_w, float* att, float* w, float* K,
                   int B, int T, cudaStream_t st) {
@@ -247,10 +254,6 @@ __global__ void __launch_bounds__(256) select_pass2_kernel(const float* act_sig,
   float tot = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) tot += cnt[k];
-  if (tot == 0.f) {
-    for (int t = threadIdx.x; t < T; t += 256) w[(size_t)b * T + t] = 1.f;
-    tot = (float)T;
-  }
   if (threadIdx.x == 0) K[b] = tot;
 }
 void select_pass2(const float* act_sig, const float* force_w, float* w, float* K, int B, int T, cudaStream_t st) {
@@ -258,21 +261,67 @@ void select_pass2(const float* act_sig, const float* force_w, float* w, float* K
   VG_CUDA(cudaGetLastError());
 }
 
-// classifier.py:80: head(query).mean(0) over the chosen frames
-__global__ void masked_mean_rows_kernel(const float* x, int ldx, const float* w, const float* K, float* out, int T, int N) {
-  const int b = blockIdx.x, j = threadIdx.x;
-  if (j >= N) return;
-  float acc = 0.f;
-  for (int t = 0; t < T; ++t) acc += w[(size_t)b * T + t] * x[((size_t)b * T + t) * ldx + j];
-  out[(size_t)b * N + j] = acc / K[b];
+// `choose_index or nonzero(att_sequences > 0)` (grounding_net.py:128,150): if no frame of the clip was selected
+// (K = count over ALL ranks of a sharded clip) every frame is used — the sigmoid average is always > 0.
+__global__ void __launch_bounds__(256) select_finish_kernel(float* w, float* K, int T, int T_global) {
+  const int b = blockIdx.x;
+  if (K[b] != 0.f) return;
+  for (int t = threadIdx.x; t < T; t += 256) w[(size_t)b * T + t] = 1.f;
+  __syncthreads();
+  if (threadIdx.x == 0) K[b] = (float)T_global;
 }
-void masked_mean_rows(const float* x, int ldx, const float* w, const float* K, float* out, int B, int T, int N,
-                      cudaStream_t st) {
-  masked_mean_rows_kernel<<<B, 64, 0, st>>>(x, ldx, w, K, out, T, N);
+void select_finish(float* w, float* K, int B, int T, int T_global, cudaStream_t st) {
+  select_finish_kernel<<<B, 256, 0, st>>>(w, K, T, T_global);
   VG_CUDA(cudaGetLastError());
 }
 
-// grounding_net.py:135-136 / 155-160: (enc[chosen] * att_map[..., None]).mean((0, 1))
+// classifier.py:80 `head(query).mean(0)` and grounding_net.py:135-136 `(enc[chosen] * att_map).mean((0, 1))` over the
+// chosen frames, as local fp32 sums (red[b] = [64 logit sums | 256 seed sums]) + a finishing step; a sharded clip
+// all-reduces `red` in between.
+__global__ void __launch_bounds__(320) masked_sums_kernel(const float* __restrict__ logit_rows, int ldx, int N,
+                                                          const float* __restrict__ part, const float* __restrict__ w,
+                                                          float* __restrict__ red, int T) {
+  const int b = blockIdx.x, j = threadIdx.x;
+  float acc = 0.f;
+  if (j < 64) {
+    if (j < N)
+      for (int t = 0; t < T; ++t) acc += w[(size_t)b * T + t] * logit_rows[((size_t)b * T + t) * ldx + j];
+  } else {
+    for (int t = 0; t < T; ++t) acc += part[((size_t)b * T + t) * 256 + (j - 64)];   // part is already weighted by w
+  }
+  red[(size_t)b * 320 + j] = acc;
+}
+void masked_sums(const float* logit_rows, int ldx, int N, const float* part, const float* w, float* red, int B, int T,
+                 cudaStream_t st) {
+  masked_sums_kernel<<<B, 320, 0, st>>>(logit_rows, ldx, N, part, w, red, T);
+  VG_CUDA(cudaGetLastError());
+}
+__global__ void __launch_bounds__(320) seed_finish_kernel(const float* __restrict__ red, const float* __restrict__ K,
+                                                          float* __restrict__ logits_r, int N, float* __restrict__ q,
+                                                          bf16* __restrict__ tgt, int ldt, float* __restrict__ tgt32, int T,
+                                                          int P) {
+  const int b = blockIdx.x, j = threadIdx.x;
+  const float v = red[(size_t)b * 320 + j];
+  if (j < 64) {
+    if (j < N) logits_r[(size_t)b * N + j] = v / K[b];
+    return;
+  }
+  const int c = j - 64;
+  const float acc = v / (K[b] * (float)P);
+  q[(size_t)b * 256 + c] = acc;
+  const bf16 h = __float2bfloat16(acc);
+  for (int t = 0; t < T; ++t) {  // query_decoder.py:102,114 expand
+    tgt[((size_t)b * T + t) * ldt + c] = h;
+    tgt32[((size_t)b * T + t) * 256 + c] = acc;
+  }
+}
+void seed_finish(const float* red, const float* K, float* logits_r, int N, float* q, bf16* tgt, int ldt, float* tgt32,
+                 int B, int T, int P, cudaStream_t st) {
+  seed_finish_kernel<<<B, 320, 0, st>>>(red, K, logits_r, N, q, tgt, ldt, tgt32, T, P);
+  VG_CUDA(cudaGetLastError());
+}
+
+// grounding_net.py:135-136 / 155-160: per-frame part of (enc[chosen] * att_map[..., None]).sum over tokens
 __global__ void __launch_bounds__(256) seed_partial_kernel(const bf16* __restrict__ Xf, const float* __restrict__ att,
                                                            const float* __restrict__ w, float* __restrict__ part, int S,
                                                            int tok0, int P) {
@@ -287,25 +336,6 @@ __global__ void __launch_bounds__(256) seed_partial_kernel(const bf16* __restric
 void seed_partial(const bf16* Xf, const float* att, const float* w, float* part, int F, int S, int tok0, int P,
                   cudaStream_t st) {
   seed_partial_kernel<<<F, 256, 0, st>>>(Xf, att, w, part, S, tok0, P);
-  VG_CUDA(cudaGetLastError());
-}
-__global__ void __launch_bounds__(256) seed_reduce_kernel(const float* __restrict__ part, const float* __restrict__ K,
-                                                          float* __restrict__ q, bf16* __restrict__ tgt, int ldt,
-                                                          float* __restrict__ tgt32, int T, int P) {
-  const int b = blockIdx.x, c = threadIdx.x;
-  float acc = 0.f;
-  for (int t = 0; t < T; ++t) acc += part[((size_t)b * T + t) * 256 + c];
-  acc /= (K[b] * (float)P);
-  q[(size_t)b * 256 + c] = acc;
-  const bf16 v = __float2bfloat16(acc);
-  for (int t = 0; t < T; ++t) {  // query_decoder.py:102,114 expand
-    tgt[((size_t)b * T + t) * ldt + c] = v;
-    tgt32[((size_t)b * T + t) * 256 + c] = acc;
-  }
-}
-void seed_reduce(const float* part, const float* K, float* q, bf16* tgt, int ldt, float* tgt32, int B, int T, int P,
-                 cudaStream_t st) {
-  seed_reduce_kernel<<<B, 256, 0, st>>>(part, K, q, tgt, ldt, tgt32, T, P);
   VG_CUDA(cudaGetLastError());
 }
 

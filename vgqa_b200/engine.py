@@ -65,6 +65,8 @@ def _declare(L):
     L.vgqa_last_launch_count.argtypes = [c_void_p]
     L.vgqa_postprocess.restype = c_int
     L.vgqa_postprocess.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+    L.vgqa_set_sharding.restype = c_int
+    L.vgqa_set_sharding.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
     L.vgqa_reference_flops.restype = ctypes.c_double
     L.vgqa_reference_flops.argtypes = [c_int] * 8
     L._vgqa_engine_declared = True
@@ -74,6 +76,9 @@ def reference_flops(T, H, W, L, enc_layers=6, dec_layers=6, ffn_dim=2048, passes
     L_ = _lib.lib()
     _declare(L_)
     return float(L_.vgqa_reference_flops(T, H, W, L, enc_layers, dec_layers, ffn_dim, passes))
+
+
+EXCHANGE_FN = ctypes.CFUNCTYPE(None, c_void_p, c_int, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p)
 
 
 class GroundingEngine:
@@ -111,6 +116,13 @@ class GroundingEngine:
             shape = (ctypes.c_int64 * max(a.ndim, 1))(*a.shape)
             _lib.check(self._L.vgqa_set_weight(self._ctx, name.encode(), a.ctypes.data_as(c_void_p), shape, a.ndim))
         _lib.check(self._L.vgqa_finalize_weights(self._ctx))
+
+    def set_sharding(self, rank: int, world: int, exchange_cb=None):
+        """Frame-shard one long clip over `world` ranks.  `exchange_cb` is a ctypes callback of type EXCHANGE_FN (see
+        vgqa_b200/parallel.py: nccl_exchange); keep it alive as long as the engine."""
+        self._exchange_cb = exchange_cb
+        fn = ctypes.cast(exchange_cb, c_void_p) if exchange_cb is not None else None
+        _lib.check(self._L.vgqa_set_sharding(self._ctx, rank, world, fn, None))
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
