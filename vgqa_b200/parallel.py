@@ -58,14 +58,14 @@ def nccl_exchange(group=None):
 
     def cb(user, op, send, recv, count, dtype, stream):
         try:
-            ts = "<f4" if dtype == 1 else "<i2"      # bf16 payloads travel as opaque 16-bit words
+            ts, nb = ("<f4", 1) if dtype == 1 else ("|u1", 2)      # bf16 payloads travel as opaque bytes
             with torch.cuda.stream(torch.cuda.ExternalStream(int(stream))):
                 if op == 1:
                     t = torch.as_tensor(_DevArray(recv, count, ts), device="cuda")
                     dist.all_reduce(t, group=group)
                 else:
-                    src = torch.as_tensor(_DevArray(send, count, ts), device="cuda")
-                    dst = torch.as_tensor(_DevArray(recv, count * world, ts), device="cuda")
+                    src = torch.as_tensor(_DevArray(send, count * nb, ts), device="cuda")
+                    dst = torch.as_tensor(_DevArray(recv, count * nb * world, ts), device="cuda")
                     dist.all_gather_into_tensor(dst, src, group=group)
         except BaseException as e:  # exceptions cannot cross the C frame
             errors.append(e)
