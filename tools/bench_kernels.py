@@ -63,6 +63,21 @@ def bench_xattn(F=4096, S=118, tok0=0, Mk=69, use_pos=False, use_kpos=False, nam
     print(f"xattn1 {name} F={F} Mk={Mk}: {t:8.1f} us  {byts / t / 1e3:7.1f} GB/s")
 
 
+def bench_ffn(M, F=2048, parts=4):
+    x32 = torch.randn(M, 256, device="cuda")
+    x = x32.bfloat16()
+    W1 = (torch.randn(F, 256, device="cuda") / 16).bfloat16()
+    W2 = (torch.randn(256, F, device="cuda") / F ** 0.5).bfloat16()
+    b1 = torch.zeros(F, device="cuda"); b2 = torch.zeros(256, device="cuda"); lw = torch.ones(256, device="cuda")
+    pos = torch.randn(118, 256, device="cuda").bfloat16()
+    C = torch.empty(M, 256, device="cuda", dtype=torch.bfloat16); C2 = torch.empty_like(C); C32 = torch.empty(M, 256, device="cuda")
+    t = timeit(lambda: _lib.check(L.vgqa_ffn_fused(_lib.ptr(x), _lib.ptr(W1), _lib.ptr(b1), _lib.ptr(W2), _lib.ptr(b2), M, F, _lib.ptr(x32),
+                                                   _lib.ptr(lw), _lib.ptr(b2), 1e-5, _lib.ptr(C), _lib.ptr(C32), _lib.ptr(C2), _lib.ptr(pos), 118, parts, st())))
+    flops = 4.0 * M * F * 256
+    byts = M * 3584.0
+    print(f"ffn_fused parts={parts} M={M} F={F}: {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s  {byts / t / 1e3:7.1f} GB/s")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["attn", "gemm"]
     if "attn" in which:
@@ -72,6 +87,10 @@ if __name__ == "__main__":
         bench_xattn(Mk=49, tok0=69, name="spatial")
         bench_xattn(Mk=69, tok0=0, use_kpos=True, name="pos-decoder")
         bench_xattn(Mk=69, tok0=49, use_pos=True, name="time-decoder")
+    if "ffn" in which:
+        for parts in (4, 2):
+            bench_ffn(64 * 64 * 118, parts=parts)
+            bench_ffn(16 * 64 * 118, parts=parts)
     if "gemm" in which:
         R = 64 * 64 * 118
         bench_gemm(R, 768, 256, name="qkv")

@@ -28,6 +28,9 @@ def _declare(L):
     L.vgqa_gemm_bf16.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                  c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                  c_void_p, c_float, c_void_p]
+    L.vgqa_ffn_fused.restype = c_int
+    L.vgqa_ffn_fused.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
     L.vgqa_mha32.restype = c_int
     L.vgqa_mha32.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p, c_float, c_void_p]

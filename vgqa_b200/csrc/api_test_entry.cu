@@ -32,6 +32,22 @@ int vgqa_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N,
   }
 }
 
+int vgqa_ffn_fused(const void* X, const void* W1, const float* b1, const void* W2, const float* b2, int M, int F,
+                    const float* res32, const float* ln_w, const float* ln_b, float eps, void* C, float* C32, void* C2,
+                    const void* add2, int add2_period, int epi_parts, void* stream) {
+  try {
+    vg::ffn_fused(static_cast<const vg::bf16*>(X), static_cast<const vg::bf16*>(W1), b1, static_cast<const vg::bf16*>(W2), b2,
+                  M, F, res32, ln_w, ln_b, eps, static_cast<vg::bf16*>(C), C32, static_cast<vg::bf16*>(C2),
+                  static_cast<const vg::bf16*>(add2), add2_period, epi_parts, static_cast<cudaStream_t>(stream));
+    return 0;
+  } catch (const std::exception& e) {
+    vg::set_last_error(e.what());
+    return 1;
+  }
+}
+
+void vgqa_ffn_prof_read(long long* dst) { vg::ffn_prof_read(dst); }
+
 int vgqa_mha32(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int groups,
                int Sq, int Sk, const uint8_t* kmask, float scale, void* stream) {
   try {

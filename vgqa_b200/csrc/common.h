@@ -71,6 +71,12 @@ void gemm_ws(const bf16* A, const bf16* A2, int a_switch_col, int lda, const bf1
 // Residual + LayerNorm epilogue variant (gemm_ln.cu), N = 256.
 bool gemm_ln_supported(int N, int K, const GemmEpi& e);
 void gemm_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, const GemmEpi& e, cudaStream_t stream);
+// Fused FFN block (ffn_fused.cu): y = LN(res32 + W2 relu(W1 x + b1) + b2) on CTA pairs; hidden activation stays on chip.
+bool ffn_fused_supported(int F);
+void ffn_fused(const bf16* X, const bf16* W1, const float* b1, const bf16* W2, const float* b2, int M, int F,
+               const float* res32, const float* ln_w, const float* ln_b, float eps, bf16* C, float* C32, bf16* C2,
+               const bf16* add2, int add2_period, int epi_parts, cudaStream_t stream);
+void ffn_prof_read(long long* dst);  // debug timeline of the fused FFN kernel (zeros unless built with -DVGQA_FFN_PROFILE)
 int gemm_launch_count();  // number of tcgen05 GEMM launches issued so far by this process
 
 }  // namespace vg

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <stdlib.h>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -113,6 +114,8 @@ struct vgqa_ctx {
   vgqa_config cfg;
   int device = 0;
   bool finalized = false;
+  // VGQA_FFN_FUSED=0 selects the two-kernel FFN (gemm_ws + gemm_ln) for A/B measurements; both are CUDA paths
+  bool use_ffn_fused = [] { const char* e = getenv("VGQA_FFN_FUSED"); return e == nullptr || e[0] != '0'; }();
   std::unordered_map<std::string, HostT> sd;
   Arena warena, ws;
   // ---- packed weights
@@ -625,11 +628,18 @@ static void run_encoder(Fwd& f, const vgqa_inputs& in, bool have_mask, int pos_r
       mha32(c->QKV, 768, c->QKV + 256, 768, c->QKV + 512, 768, c->AO, 256, F, S, S, km, 0.17677669529663687f, st);
     f.count();
     f.linear_res_ln(c->AO, 256, e.out, R, c->X32, e.ln1, 1e-5f, c->X1, 256, c->X1_32);
-    f.linear(c->X1, 256, e.ff1, R, c->HID, e.ff1.N, ACT_RELU);
-    {  // x = LN2(x1 + W2 relu(..) + b2); also emits x + pos for the next layer's Q/K projection
+    // x = LN2(x1 + W2 relu(W1 x1 + b1) + b2); also emits x + pos for the next layer's Q/K projection
+    const bool last = l + 1 == c->enc.size();
+    if (c->use_ffn_fused && ffn_fused_supported(e.ff1.N)) {
+      // one CTA-pair kernel, the [R, FFN_DIM] hidden activation never leaves the SMs (ffn_fused.cu)
+      ffn_fused(c->X1, e.ff1.W, e.ff1.b, e.ff2.W, e.ff2.b, R, e.ff1.N, c->X1_32, e.ln2.w, e.ln2.b, 1e-5f, c->X, c->X32,
+                last ? nullptr : c->XP, c->pos_enc, pos_rows, 0, st);
+      f.count();
+    } else {
+      f.linear(c->X1, 256, e.ff1, R, c->HID, e.ff1.N, ACT_RELU);
       GemmEpi ep; ep.C = c->X; ep.ldc = 256; ep.bias = e.ff2.b; ep.bias_ld = 256; ep.res32 = c->X1_32; ep.ldres32 = 256;
       ep.C32 = c->X32; ep.ldc32 = 256; ep.ln_w = e.ln2.w; ep.ln_b = e.ln2.b; ep.ln_eps = 1e-5f;
-      if (l + 1 < c->enc.size()) { ep.C2 = c->XP; ep.ldc2 = 256; ep.add2 = c->pos_enc; ep.add2_period = pos_rows; }
+      if (!last) { ep.C2 = c->XP; ep.ldc2 = 256; ep.add2 = c->pos_enc; ep.add2_period = pos_rows; }
       f.gemm(c->HID, e.ff2.K, e.ff2, R, ep);
     }
   }
