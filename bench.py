@@ -10,7 +10,7 @@ random-init (seeded synthetic) weights.  Prints ONE JSON line (rank 0).
   value        clips/s with the inputs already resident in HBM (device-timed with CUDA events, max over ranks)
   e2e          clips/s through the C-ABI host path (`vgqa_forward_host_async/_wait`, two slots) with pinned HOST buffers:
                every step uploads its inputs, computes, downloads and reads its results inside the timed region
-  roofline     the dominant kernel (tcgen05 FFN GEMM) timed alone with CUDA events: algorithmic FLOPs / duration
+  roofline     the dominant kernel (fused FFN block, tcgen05 cta_group::2) timed alone with CUDA events: algorithmic FLOPs / duration
   cpu_baseline the numpy oracle port timed on the host cores on a bounded sample (rank 0, N=1 only)
   --impl reference : the reference arm = the oracle port on the host cores (the reference itself is PyTorch
                      source under /root/reference which does not exist on the GPU box)
@@ -116,22 +116,35 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE ffn_fused_kernel launch at 64 clips (ncu, profiles/r01_ffn_fused_ncu.md):
+# 747.3 MB read + 941.3 MB written; the algorithmic bytes are 742 MB + 990 MB
+FFN_FUSED_DRAM_BYTES_AT_64_CLIPS = 747.30e6 + 941.25e6
+
+
 def time_dominant_kernel(B, pk):
-    """FFN linear1 GEMM of one encoder layer over the whole batch — gemm_ws_kernel<256>, M = B*T*S, N = 2048, K = 256."""
+    """The fused FFN block of one encoder layer over the whole batch — ffn_fused_kernel (CTA pairs, tcgen05 cta_group::2):
+    y = LN(x32 + W2 relu(W1 x + b1) + b2), M = B*T*S rows, 256 -> 2048 -> 256.  Algorithmic FLOPs = 2 * (2*M*256*2048)."""
     import torch
     from vgqa_b200 import _lib
     Lb = _lib.lib()
     S = 2 * H * W + L
-    M, N, K = B * T * S, 2048, 256
-    A = torch.randn(M, K, device="cuda").bfloat16()
-    Wt = (torch.randn(N, K, device="cuda") / 16).bfloat16()
-    bias = torch.zeros(N, device="cuda")
-    C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    M, F = B * T * S, 2048
+    x32 = torch.randn(M, 256, device="cuda")
+    x = x32.bfloat16()
+    W1 = (torch.randn(F, 256, device="cuda") / 16).bfloat16()
+    W2 = (torch.randn(256, F, device="cuda") / F ** 0.5).bfloat16()
+    b1 = torch.zeros(F, device="cuda")
+    b2 = torch.zeros(256, device="cuda")
+    lw = torch.ones(256, device="cuda")
+    pos = torch.randn(S, 256, device="cuda").bfloat16()
+    C = torch.empty(M, 256, device="cuda", dtype=torch.bfloat16)
+    C2 = torch.empty_like(C)
+    C32 = torch.empty(M, 256, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
 
     def launch():
-        _lib.check(Lb.vgqa_gemm_bf16(_lib.ptr(A), K, _lib.ptr(Wt), K, M, N, K, _lib.ptr(C), N, 0, _lib.ptr(bias), 1, N, 1,
-                                     None, 0, None, 0, None, None, 1e-5, st))
+        _lib.check(Lb.vgqa_ffn_fused(_lib.ptr(x), _lib.ptr(W1), _lib.ptr(b1), _lib.ptr(W2), _lib.ptr(b2), M, F, _lib.ptr(x32),
+                                     _lib.ptr(lw), _lib.ptr(b2), 1e-5, _lib.ptr(C), _lib.ptr(C32), _lib.ptr(C2), _lib.ptr(pos), S, 0, st))
     for _ in range(3):
         launch()
     torch.cuda.synchronize()
@@ -143,15 +156,16 @@ def time_dominant_kernel(B, pk):
     e1.record()
     torch.cuda.synchronize()
     dt = e0.elapsed_time(e1) / reps * 1e-3
-    flops = 2.0 * M * N * K
+    flops = 4.0 * M * F * 256
+    alg_bytes = M * (512 + 1024 + 512 + 1024 + 512) + 2 * F * 256 * 2     # x, residual in; bf16, fp32, bf16(x+pos) out; weights once
     ach = flops / dt / 1e12
-    return {"kernel": "gemm_ws_kernel<256> (encoder FFN linear1+ReLU, M=%d N=2048 K=256)" % M, "bound": "tensor",
-            "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
-            # (profiles/r01_gemm_ws_ncu.md), scaled to this batch size; algorithmic bytes are (M*K + M*N + N*K) * 2
-            "traffic": (248.6e6 + 1921.6e6) * (B / 64.0), "peak_source": pk["source"] + ", burst (kernel timed alone)",
-            "algorithmic_flops_per_launch": flops, "launch_ms": dt * 1e3,
-            "hbm_gbs_at_algorithmic_bytes": (M * K * 2 + M * N * 2 + N * K * 2) / dt / 1e9}
+    traffic = None if FFN_FUSED_DRAM_BYTES_AT_64_CLIPS is None else FFN_FUSED_DRAM_BYTES_AT_64_CLIPS * (B / 64.0)
+    return {"kernel": "ffn_fused_kernel (encoder FFN block linear1+ReLU+linear2+residual+LayerNorm, M=%d, 256->2048->256)" % M,
+            "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+            "traffic": traffic, "peak_source": pk["source"] + ", burst (kernel timed alone)",
+            "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dt * 1e3,
+            "frac_of_sustained_peak": ach / pk["bf16_tflops_sustained"],
+            "hbm_gbs_at_algorithmic_bytes": alg_bytes / dt / 1e9}
 
 
 def main():

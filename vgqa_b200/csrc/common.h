@@ -77,6 +77,7 @@ void ffn_fused(const bf16* X, const bf16* W1, const float* b1, const bf16* W2, c
                const float* res32, const float* ln_w, const float* ln_b, float eps, bf16* C, float* C32, bf16* C2,
                const bf16* add2, int add2_period, int epi_parts, cudaStream_t stream);
 void ffn_prof_read(long long* dst);  // debug timeline of the fused FFN kernel (zeros unless built with -DVGQA_FFN_PROFILE)
+void set_sm_budget(int n);  // cap (per host thread) on the grid of persistent kernels launched next; 0 = all SMs
 int gemm_launch_count();  // number of tcgen05 GEMM launches issued so far by this process
 
 }  // namespace vg

@@ -59,7 +59,7 @@ static constexpr int kFfnThreads = 512;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFfnThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w1,
-                 const __grid_constant__ CUtensorMap tma_w2, const __grid_constant__ CUtensorMap tma_res, const FfnParams p) {
+                 const __grid_constant__ CUtensorMap tma_w2, const FfnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sx = smem;
   uint8_t* sh = sx + kFfnXBytes;
@@ -137,13 +137,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
         load_w1(1);
         for (int it = 0; it < n_my; ++it) {
           for (int c = 0; c < nchunk; ++c) {
-            // warm L2 with the NEXT tile's x rows and fp32 residual rows, one 16 KB box per chunk so the prefetches
-            // never queue in front of a weight load at the TMA unit
-            if (it + 1 < n_my && c < 12) {
-              const int rown = (pair + (it + 1) * npairs) * 256 + (int)rank * 128;
-              if (c < 4) tma_prefetch_l2_2d(&tma_x, c * 64, rown);
-              else if (p.res32 != nullptr) tma_prefetch_l2_2d(&tma_res, (c - 4) * 32, rown);
-            }
             load_w2(c);
             if (c + 2 < nchunk) load_w1(c + 2);
             else if (c == nchunk - 1 && it + 1 < n_my) { load_w1(0); load_w1(1); }
@@ -307,8 +300,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(out_empty_remote);
       if (ew == 0) FFN_PROF(it * nchunk, 13);
-      {  // ---- v += residual + b2.  The residual rows come in coalesced 64-byte row segments (cp.async, L2-prefetched by
-         //      the producer warp) through the two halves of the slab.
+      {  // ---- v += residual + b2.  The residual rows come in coalesced 64-byte row segments (cp.async) through the two
+         //      halves of the slab.
         const bool has_res = p.res32 != nullptr;
         const int r4l = lane >> 2, u4 = lane & 3;
         auto issue = [&](int h) __attribute__((always_inline)) {   // h = 0..7: 16 fp32 columns [h*16, +16) of this warp's 128
@@ -432,7 +425,7 @@ void ffn_prof_read(long long* dst) { for (int i = 0; i < 32768; ++i) dst[i] = 0;
 
 bool ffn_fused_supported(int F) { return F % 128 == 0 && F >= 256; }
 
-static void launch_ffn(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tres, const FfnParams& p,
+static void launch_ffn(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2, const FfnParams& p,
                        cudaStream_t stream) {
   static int max_pairs = 0;
   if (max_pairs == 0) {
@@ -449,8 +442,9 @@ static void launch_ffn(const CUtensorMap& tx, const CUtensorMap& tw1, const CUte
     max_pairs = n < device_sm_count() / 2 ? n : device_sm_count() / 2;
   }
   const int tiles = (p.M + 255) / 256;
-  const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  ffn_fused_kernel<<<2 * pairs, kFfnThreads, kFfnSmem, stream>>>(tx, tw1, tw2, tres, p);
+  int pairs = tiles < max_pairs ? tiles : max_pairs;
+  if (pairs > device_sm_count() / 2) pairs = device_sm_count() / 2;   // honours the model's SM budget
+  ffn_fused_kernel<<<2 * pairs, kFfnThreads, kFfnSmem, stream>>>(tx, tw1, tw2, p);
   VG_CUDA(cudaGetLastError());
   count_gemm_launch();
 }
@@ -468,9 +462,8 @@ void ffn_fused(const bf16* X, const bf16* W1, const float* b1, const bf16* W2, c
   CUtensorMap tx = make_tmap_2d(X, M, 256, 256, 128, false);
   CUtensorMap tw1 = make_tmap_2d(W1, F, 256, 256, 64, false);
   CUtensorMap tw2 = make_tmap_2d(W2, 256, F, F, 128, false);
-  CUtensorMap tres = res32 ? make_tmap_2d(res32, M, 256, 256, 128, true) : tx;
   (void)epi_parts;
-  launch_ffn(tx, tw1, tw2, tres, p, stream);
+  launch_ffn(tx, tw1, tw2, p, stream);
 }
 
 }  // namespace vg

@@ -380,13 +380,17 @@ static int g_num_sms = 0;
 static int g_gemm_launches = 0;
 int gemm_launch_count() { return g_gemm_launches; }
 void count_gemm_launch() { ++g_gemm_launches; }
+// Persistent kernels size their grids with device_sm_count().  The model caps it (sm_budget) for the encoder phase so that
+// a few SMs stay free for the latency-bound decoder-phase launches of the previous batch running on the other stream.
+static thread_local int g_sm_budget = 0;
+void set_sm_budget(int n) { g_sm_budget = n; }
 int device_sm_count() {
   if (g_num_sms == 0) {
     int dev = 0;
     VG_CUDA(cudaGetDevice(&dev));
     VG_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  return g_num_sms;
+  return g_sm_budget > 0 && g_sm_budget < g_num_sms ? g_sm_budget : g_num_sms;
 }
 
 template <int BN>
@@ -402,7 +406,7 @@ static void launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, int M, i
   CUtensorMap tb = make_tmap_2d(W, N, K, ldw, BN, false);
   CUtensorMap tc = make_tmap_2d(ep.C, M, N, ep.ldc, 32, ep.c_f32 != 0);
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   gemm_tc_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, tb, tc, ep, M, N, K);
   VG_CUDA(cudaGetLastError());
   ++g_gemm_launches;

@@ -115,6 +115,8 @@ struct vgqa_ctx {
   int device = 0;
   bool finalized = false;
   // VGQA_FFN_FUSED=0 selects the two-kernel FFN (gemm_ws + gemm_ln) for A/B measurements; both are CUDA paths
+  // VGQA_ENC_SMS: SMs the encoder-phase persistent kernels may occupy (0 = all)
+  int enc_sm_budget = [] { const char* e = getenv("VGQA_ENC_SMS"); return e ? atoi(e) : 0; }();
   bool use_ffn_fused = [] { const char* e = getenv("VGQA_FFN_FUSED"); return e == nullptr || e[0] != '0'; }();
   std::unordered_map<std::string, HostT> sd;
   Arena warena, ws;
@@ -833,7 +835,12 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
   const int pos_rows = in.pos_frames * f.S;
   c->launches = 0;
   if (phase == 0) {
+    // Leave `dec_sms` SMs out of the encoder's persistent grids: the decoder phase of the previous batch (other stream,
+    // higher priority) is a chain of small latency-bound launches that then runs beside the encoder instead of between
+    // its kernels.
+    set_sm_budget(c->enc_sm_budget);
     run_encoder(f, in, have_mask, pos_rows);
+    set_sm_budget(0);
     return;
   }
   if (in.stop_after_encoder) {
