@@ -194,6 +194,8 @@ struct Xattn1Params {
   const bf16* q2;     // optional [F, 256]: per-head 32-d query for the kpos term
   const bf16* kpos;   // optional [*, Mk, ldkpos]; frame f uses kpos + f*kpos_fstride
   const uint8_t* kmask;  // optional [F, ldmask]
+  const float* sbias; // optional [F, 8, ldsb] additive score term (unscaled), e.g. q~·pos or the kpos term as a GEMM
+  int ldsb;
   bf16* ctx;          // [F, 8*256]
   float* att;         // optional [F, Mk]: minmax(sigmoid(sum_h p_h))  (classifier.py:75-78)
   long long frame_stride;  // in rows of 256
@@ -316,9 +318,12 @@ __global__ void __launch_bounds__(XNT) xattn1_kernel(const Xattn1Params p) {
     const int h = warp;
     float* s0 = sS + h * Mp;
     const float* s1 = sS + (8 + h) * Mp;
+    const float* sb = p.sbias ? p.sbias + ((size_t)f * 8 + h) * p.ldsb : nullptr;
     float mx = -INFINITY;
     for (int m = lane; m < Mk; m += 32) {
-      float v = (s0[m] + s1[m]) * p.scale_log2e;
+      float v = s0[m] + s1[m];
+      if (sb != nullptr) v += __ldg(sb + m);
+      v *= p.scale_log2e;
       if (km != nullptr && km[m] != 0) v = -INFINITY;
       s0[m] = v;
       mx = fmaxf(mx, v);
@@ -389,10 +394,12 @@ __global__ void __launch_bounds__(XNT) xattn1_kernel(const Xattn1Params p) {
 
 void xattn1(const bf16* qt, const bf16* mem, long long frame_stride_rows, int F, int Mk, const bf16* posk,
             long long posk_fstride, const bf16* q2, const bf16* kpos, int ldkpos, long long kpos_fstride,
-            const uint8_t* kmask, int ldmask, float scale, bf16* ctx, float* att, cudaStream_t stream) {
+            const uint8_t* kmask, int ldmask, float scale, bf16* ctx, float* att, cudaStream_t stream,
+            const float* sbias, int ldsb) {
   VG_CHECK(F > 0 && Mk > 0, "xattn1: empty problem");
   Xattn1Params p;
   p.qt = qt; p.mem = mem; p.posk = posk; p.q2 = q2; p.kpos = kpos; p.kmask = kmask; p.ctx = ctx; p.att = att;
+  p.sbias = sbias; p.ldsb = ldsb;
   p.frame_stride = frame_stride_rows; p.posk_fstride = posk_fstride; p.kpos_fstride = kpos_fstride;
   p.Mk = Mk; p.ldkpos = ldkpos; p.ldmask = ldmask; p.scale_log2e = scale * kLog2e;
   const int Mp = (Mk + 15) & ~15;

@@ -9,7 +9,12 @@ void mha32(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ld
            int Sq, int Sk, const uint8_t* kmask, float scale, cudaStream_t stream);
 void xattn1(const bf16* qt, const bf16* mem, long long frame_stride_rows, int F, int Mk, const bf16* posk,
             long long posk_fstride, const bf16* q2, const bf16* kpos, int ldkpos, long long kpos_fstride,
-            const uint8_t* kmask, int ldmask, float scale, bf16* ctx, float* att, cudaStream_t stream);
+            const uint8_t* kmask, int ldmask, float scale, bf16* ctx, float* att, cudaStream_t stream,
+            const float* sbias = nullptr, int ldsb = 0);
+// frame-invariant kpos table → block-diagonal GEMM operand: out[l][h*Mpad + m][h*32 + d] = kposb[m][l*256 + h*32 + d]
+void build_kpos_blockdiag(const bf16* kposb, int ldk, bf16* out, int layers, int Mk, int Mpad, cudaStream_t st);
+// dst[r, :] = r < rows ? src[r, :] : 0 for r < rows_pad (256 bf16 columns)
+void pad_rows_bf16(const bf16* src, bf16* dst, int rows, int rows_pad, cudaStream_t st);
 
 // ---- attn_tc.cu: tcgen05 per-frame self-attention over the packed QKV buffer (S <= 128)
 bool enc_attn_tc_supported(int S);

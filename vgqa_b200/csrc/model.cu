@@ -138,6 +138,9 @@ struct vgqa_ctx {
   float *pfc_ln0w, *pfc_ln0b, *pfc_W, *pfc_b, *pfc_ln4w, *pfc_ln4b;
   // ---- workspace (device)
   bf16 *X, *X1, *QKV, *AO, *HID, *Xf, *pos_enc, *kposb;
+  // positional score terms of the decoders' cross-attentions as GEMM outputs (frame-invariant pos only)
+  bf16 *pos_pad = nullptr, *kpos_bd = nullptr;
+  float *t_sb = nullptr, *p_sb = nullptr;
   float *X32, *X1_32;  // fp32 residual stream of the encoder
   bf16* XP;            // bf16(x + pos): A operand of the Q/K in-projection
   uint8_t* encmask;
@@ -503,6 +506,11 @@ static void carve_workspace(vgqa_ctx* c) {
   c->HID = a.get<bf16>(R * FF);
   c->X32 = a.get<float>(R * 256); c->X1_32 = a.get<float>(R * 256); c->XP = a.get<bf16>(R * 256);
   c->kposb = a.get<bf16>(R * 1536);
+  {
+    const size_t Mm = P + L, Npad = (Mm + 63) / 64 * 64, Mpad = (Mm + 7) / 8 * 8;
+    c->pos_pad = a.get<bf16>(Npad * 256); c->kpos_bd = a.get<bf16>(D * 8 * Mpad * 256);
+    c->t_sb = a.get<float>(F * 8 * Npad); c->p_sb = a.get<float>(F * 8 * Mpad);
+  }
   for (auto& b : c->bd) {
     b.Xf = a.get<bf16>(R * 256); b.pos_enc = a.get<bf16>(R * 256); b.encmask = a.get<uint8_t>(R);
     b.frames_cls = a.get<float>(F * 256); b.ftext = a.get<bf16>(B * L * 256); b.q0 = a.get<bf16>(F * 256);
@@ -727,6 +735,13 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames) {
   pos_fc_boxes(c->frames_cls, c->pfc_ln0w, c->pfc_ln0b, c->pfc_W, c->pfc_b, c->pfc_ln4w, c->pfc_ln4b, c->boxes0, F, st);
   f.count();
   f.fork();
+  // With a frame-invariant positional table the positional score terms are plain GEMMs over the absorbed queries:
+  //   TimeDecoder  q~_h·(mem_m + pos_m) = q~_h·mem_m + (q~ pos^T)[h, m]
+  //   PosDecoder   q2_h·kpos_h(m)       = (q2 · blockdiag(kpos)^T)[h, m]
+  // so the cross-attention kernel streams the memory tokens once and only adds a [8, M] fp32 table per frame.
+  const bool pos_gemm = pos_frames == 1;
+  const int Npad = (M + 63) / 64 * 64, Mpad = (M + 7) / 8 * 8;
+  if (pos_gemm) { pad_rows_bf16(c->pos_enc + (size_t)P * 256, c->pos_pad, M, Npad, st); f.count(); }
   // ---------------- TimeDecoder (query_decoder.py:379-486), memory = [text | vid] tokens
   for (int l = 0; l < D; ++l) {
     TimeLayer& t = c->tl[l];
@@ -740,8 +755,16 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames) {
     f.linear_res_ln(c->t_ao, 256, t.out, F, c->t_tgt32, t.ln1, 1e-5f, c->t_x, 256, c->t_x32);
     f.linear(c->t_x, 256, t.qabs, F, c->t_qabs, 2048);
     // keys = mem + pos_t (:474); mask = encoded_mask[:, :-P] applied positionally (:100,476)
-    xattn1(c->t_qabs, c->Xf + (size_t)P * 256, S, F, M, c->pos_enc + (size_t)P * 256, pos_fs, nullptr, nullptr, 0, 0,
-           have_mask ? c->encmask : nullptr, S, 0.17677669529663687f, c->t_ctx8, nullptr, st);
+    if (pos_gemm) {
+      GemmEpi ep; ep.C = c->t_sb; ep.ldc = Npad; ep.c_f32 = 1;
+      gemm_bf16_tn(c->t_qabs, 256, c->pos_pad, 256, F * 8, Npad, 256, ep, st);
+      f.count();
+      xattn1(c->t_qabs, c->Xf + (size_t)P * 256, S, F, M, nullptr, 0, nullptr, nullptr, 0, 0,
+             have_mask ? c->encmask : nullptr, S, 0.17677669529663687f, c->t_ctx8, nullptr, st, c->t_sb, Npad);
+    } else {
+      xattn1(c->t_qabs, c->Xf + (size_t)P * 256, S, F, M, c->pos_enc + (size_t)P * 256, pos_fs, nullptr, nullptr, 0, 0,
+             have_mask ? c->encmask : nullptr, S, 0.17677669529663687f, c->t_ctx8, nullptr, st);
+    }
     f.linear_res_ln(c->t_ctx8, 2048, t.vo, F, c->t_x32, t.ln3, 1e-5f, c->t_x2, 256, c->t_x2_32);
     f.linear(c->t_x2, 256, t.ff1, F, c->t_hid, t.ff1.N, ACT_RELU);
     f.linear_res_ln(c->t_hid, t.ff2.K, t.ff2, F, c->t_x2_32, t.ln4, 1e-5f, c->t_tgt, 256, c->t_tgt32);
@@ -753,6 +776,7 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames) {
   st = f.aux;
   { GemmEpi ep; ep.C = c->kposb; ep.ldc = 1536; ep.bias = c->kpos_all.b; ep.bias_ld = c->kpos_all.N;
     f.gemm(c->pos_enc, 256, c->kpos_all, pos_frames * S, ep); }  // ca_kpos_proj(pos_s) for all layers (:309)
+  if (pos_gemm) { build_kpos_blockdiag(c->kposb, 1536, c->kpos_bd, D, M, Mpad, st); f.count(); }
   const float* boxes = c->boxes0;
   for (int l = 0; l < D; ++l) {
     PosLayer& q = c->pl[l];
@@ -782,8 +806,16 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames) {
     { GemmEpi ep; ep.C = c->p_q2; ep.ldc = 256; ep.bias = q.sine.b; ep.bias_ld = 256; ep.res = q2res; ep.ldres = 256;
       f.gemm(s256, lds, q.sine, F, ep); }                                       // ca_qpos_sine_proj (:320)
     f.linear(qa, 768, q.qabs, F, c->p_qabs, 2048);
-    xattn1(c->p_qabs, c->Xf, S, F, M, nullptr, 0, c->p_q2, c->kposb + (size_t)l * 256, 1536, pos_frames > 1 ? (long long)S * 1536 : 0,
-           nullptr, 0, 0.125f, c->p_ctx8, nullptr, st);                         // (512/8)^-0.5 (attention.py:151)
+    if (pos_gemm) {
+      GemmEpi ep; ep.C = c->p_sb; ep.ldc = 8 * Mpad; ep.c_f32 = 1;
+      gemm_bf16_tn(c->p_q2, 256, c->kpos_bd + (size_t)l * 8 * Mpad * 256, 256, F, 8 * Mpad, 256, ep, st);
+      f.count();
+      xattn1(c->p_qabs, c->Xf, S, F, M, nullptr, 0, nullptr, nullptr, 0, 0, nullptr, 0, 0.125f, c->p_ctx8, nullptr, st,
+             c->p_sb, Mpad);                                                    // (512/8)^-0.5 (attention.py:151)
+    } else {
+      xattn1(c->p_qabs, c->Xf, S, F, M, nullptr, 0, c->p_q2, c->kposb + (size_t)l * 256, 1536, (long long)S * 1536,
+             nullptr, 0, 0.125f, c->p_ctx8, nullptr, st);
+    }
     f.linear_res_ln(c->p_ctx8, 2048, q.vo, F, c->p_x32, q.ln3, 1e-5f, c->p_x2, 256, c->p_x2_32);
     f.linear(c->p_x2, 256, q.ff1, F, c->p_hid, q.ff1.N, ACT_RELU);
     f.linear_res_ln(c->p_hid, q.ff2.K, q.ff2, F, c->p_x2_32, q.ln4, 1e-5f, c->p_cat, 768, c->p_tgt32);

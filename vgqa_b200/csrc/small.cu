@@ -499,4 +499,27 @@ void postprocess(const float* boxes, const float* sted, const float* sizes_hw, f
   VG_CUDA(cudaGetLastError());
 }
 
+// ---- operands of the "score bias as a GEMM" formulation of the decoders' positional terms (model.cu, run_decoders)
+__global__ void build_kpos_blockdiag_kernel(const bf16* __restrict__ kposb, int ldk, bf16* __restrict__ out, int Mk, int Mpad) {
+  // grid (8 * Mpad, layers), 32 threads x 8 bf16 = one 256-wide row
+  const int r = blockIdx.x, l = blockIdx.y, h = r / Mpad, m = r % Mpad, c = threadIdx.x;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (m < Mk && (c >> 2) == h) v = *reinterpret_cast<const uint4*>(kposb + (size_t)m * ldk + l * 256 + c * 8);
+  *reinterpret_cast<uint4*>(out + ((size_t)l * 8 * Mpad + r) * 256 + c * 8) = v;
+}
+void build_kpos_blockdiag(const bf16* kposb, int ldk, bf16* out, int layers, int Mk, int Mpad, cudaStream_t st) {
+  build_kpos_blockdiag_kernel<<<dim3(8 * Mpad, layers), 32, 0, st>>>(kposb, ldk, out, Mk, Mpad);
+  VG_CUDA(cudaGetLastError());
+}
+__global__ void pad_rows_bf16_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int rows) {
+  const int r = blockIdx.x, c = threadIdx.x;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (r < rows) v = *reinterpret_cast<const uint4*>(src + (size_t)r * 256 + c * 8);
+  *reinterpret_cast<uint4*>(dst + (size_t)r * 256 + c * 8) = v;
+}
+void pad_rows_bf16(const bf16* src, bf16* dst, int rows, int rows_pad, cudaStream_t st) {
+  pad_rows_bf16_kernel<<<rows_pad, 32, 0, st>>>(src, dst, rows);
+  VG_CUDA(cudaGetLastError());
+}
+
 }  // namespace vg
