@@ -162,6 +162,15 @@ int vgqa_enc_attn(const void* QKV, void* AO, int F, int S, const uint8_t* kmask,
 int vgqa_xattn1(const void* qt, const void* mem, long long frame_stride_rows, int F, int Mk, const void* posk,
                 long long posk_fstride, const void* q2, const void* kpos, int ldkpos, long long kpos_fstride,
                 const uint8_t* kmask, int ldmask, float scale, void* ctx_out, float* att_out, void* stream);
+/* Fused post-norm FFN block of one encoder layer (modal_encoder.py:175-177):
+ *   y = LayerNorm(res32 + W2 relu(W1 x + b1) + b2);  C = bf16(y), C32 = y (fp32, optional), C2 = bf16(y + add2[row % period]) (optional)
+ * x [M,256] bf16, W1 [F,256] bf16, W2 [256,F] bf16 (nn.Linear layouts), F % 128 == 0, all row strides 256.  One launch on
+ * CTA pairs (tcgen05 cta_group::2); the [M,F] hidden activation never reaches HBM.  `epi_parts` is reserved (pass 0). */
+int vgqa_ffn_fused(const void* X, const void* W1, const float* b1, const void* W2, const float* b2, int M, int F,
+                   const float* res32, const float* ln_w, const float* ln_b, float eps, void* C, float* C32, void* C2,
+                   const void* add2, int add2_period, int epi_parts, void* stream);
+/* Debug: in-kernel timeline of vgqa_ffn_fused (32768 int64 values; zeros unless built with -DVGQA_FFN_PROFILE). */
+void vgqa_ffn_prof_read(long long* dst);
 
 #ifdef __cplusplus
 }
