@@ -10,22 +10,29 @@
 //   warp 1      tcgen05.mma issuer:  S = Q K^T (128x128x32, 2 UMMAs, K-major SW64 operands) into TMEM, and
 //               O = P V (128x32x128, 8 UMMAs; P is a K-major SW128 smem operand written by the softmax warps,
 //               V is an MN-major SW64 operand straight from the TMA tile).
-//   warps 2..9  two softmax warpgroups ping-ponging on alternate units, one score row per thread (TMEM lane):
-//               row max / exp2 / row sum without any shuffle, P packed to bf16 in shared memory, then the
-//               O epilogue (1/sum scaling, bf16, TMA store).
-// S and O are double-buffered in TMEM (2 x 128 + 2 x 32 columns) so the tensor core works on unit u+1 while the
-// softmax of unit u runs.
+//   warps 2..17 FOUR softmax warpgroups taking units round-robin, one score row per thread (TMEM lane):
+//               row max / exp2 without any shuffle, P packed to bf16 in shared memory, then the O epilogue
+//               (1/sum scaling, bf16, TMA store).
+// The softmax of one unit is a ~4.5 k-cycle dependent chain (in-kernel timeline: max pass 1.25 k, exp pass 3.3 k) that neither
+// MUFU nor issue bandwidth explains, so throughput comes from units in flight: four S tiles live in TMEM (4 x 128 columns;
+// the O tile of a unit is written over the first 48 columns of its own S tile once the softmax has consumed it), Q|K and V
+// travel through separate rings (V must outlive the softmax), and the MMA warp issues P·V three units behind Q·K^T.
 #include "common.h"
 #include "ptx.cuh"
 
 namespace vg {
 
-static constexpr int kAtQkvBytes = 3 * 8192;      // Q, K, V: 128 rows x 64 B each
-static constexpr int kAtPBytes = 32768;           // P: 2 atoms of 128 rows x 128 B
-static constexpr int kAtOBytes = 8192;            // O staging: 128 rows x 64 B
-static constexpr int kAtStages = 4;                // Q/K/V ring depth (decoupled from the 2 TMEM buffers)
+static constexpr int kAtWgs = 4;                  // softmax warpgroups = units in flight
+static constexpr int kAtLag = kAtWgs - 1;         // P·V is issued this many units behind Q·K^T
+static constexpr int kAtQkBytes = 2 * 8192;       // Q, K: 128 rows x 64 B each
+static constexpr int kAtVBytes = 8192;            // V
+static constexpr int kAtQkStages = 3;
+static constexpr int kAtVStages = kAtWgs + 1;     // a V tile is held from its load until the unit's P·V has completed
+static constexpr int kAtPBytes = 32768;           // P: 2 atoms of 128 rows x 128 B (its first 8 KB double as the O staging tile)
 static constexpr int kAtOnesBytes = 8192;         // constant bf16 1.0 tile: extra V columns that make the MMA emit row sums
-static constexpr int kAtSmem = kAtStages * kAtQkvBytes + 2 * kAtPBytes + 2 * kAtOBytes + kAtOnesBytes + 1024 + 256;
+static constexpr int kAtThreads = 64 + kAtWgs * 128;
+static constexpr int kAtSmem = kAtQkStages * kAtQkBytes + kAtVStages * kAtVBytes + kAtWgs * kAtPBytes + kAtOnesBytes + 1024 + 256;
+static_assert(kAtSmem <= 232448, "attention smem");
 
 struct AttnTcParams {
   const uint8_t* kmask;  // [F, S] or nullptr
@@ -79,23 +86,25 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   return r;
 }
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(kAtThreads, 1)
 enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_o,
                    const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_qkv = smem;                               // [kAtStages][Q|K|V]
-  uint8_t* s_p = s_qkv + kAtStages * kAtQkvBytes;      // [2][2 atoms]
-  uint8_t* s_o = s_p + 2 * kAtPBytes;                  // [2]
-  uint8_t* s_ones = s_o + 2 * kAtOBytes;
+  uint8_t* s_qk = smem;                                  // [kAtQkStages][Q|K]
+  uint8_t* s_v = s_qk + kAtQkStages * kAtQkBytes;        // [kAtVStages]
+  uint8_t* s_p = s_v + kAtVStages * kAtVBytes;           // [kAtWgs][2 atoms]
+  uint8_t* s_ones = s_p + kAtWgs * kAtPBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + kAtOnesBytes);
-  uint64_t* qkv_full = bars;                    // [kAtStages]
-  uint64_t* qkv_empty = bars + kAtStages;       // [kAtStages]
-  uint64_t* s_full = bars + 2 * kAtStages;      // [2]
-  uint64_t* p_full = s_full + 2;                // [2]
-  uint64_t* o_full = s_full + 4;                // [2]
-  uint64_t* t_free = s_full + 6;                // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
+  uint64_t* qk_full = bars;                       // [kAtQkStages]
+  uint64_t* qk_empty = qk_full + kAtQkStages;     // [kAtQkStages]
+  uint64_t* v_full = qk_empty + kAtQkStages;      // [kAtVStages]
+  uint64_t* v_empty = v_full + kAtVStages;        // [kAtVStages]
+  uint64_t* s_full = v_empty + kAtVStages;        // [kAtWgs]
+  uint64_t* p_full = s_full + kAtWgs;             // [kAtWgs]
+  uint64_t* o_full = p_full + kAtWgs;             // [kAtWgs]
+  uint64_t* t_free = o_full + kAtWgs;             // [kAtWgs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_free + kAtWgs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.S;
@@ -106,11 +115,9 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_o);
-    for (int b = 0; b < kAtStages; ++b) {
-      mbar_init(&qkv_full[b], 1);
-      mbar_init(&qkv_empty[b], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kAtQkStages; ++b) { mbar_init(&qk_full[b], 1); mbar_init(&qk_empty[b], 1); }
+    for (int b = 0; b < kAtVStages; ++b) { mbar_init(&v_full[b], 1); mbar_init(&v_empty[b], 1); }
+    for (int b = 0; b < kAtWgs; ++b) {
       mbar_init(&s_full[b], 1);
       mbar_init(&p_full[b], 128);
       mbar_init(&o_full[b], 1);
@@ -120,7 +127,7 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   if (warp >= 2) {  // ones tile (bf16 1.0 = 0x3F80); uniform, so the swizzle pattern is irrelevant
-    for (int i = threadIdx.x - 64; i < kAtOnesBytes / 16; i += 256)
+    for (int i = threadIdx.x - 64; i < kAtOnesBytes / 16; i += kAtWgs * 128)
       reinterpret_cast<uint4*>(s_ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
   }
@@ -133,68 +140,70 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     // ===================== TMA producer =====================
     if (lane == 0) {
       for (int u = 0; u < num_units; ++u) {
-        const int st = u % kAtStages;
+        const int sq = u % kAtQkStages, sv = u % kAtVStages;
         const int f = blockIdx.x + (u >> 3) * gridDim.x, h = u & 7;
-        mbar_wait(&qkv_empty[st], ((u / kAtStages) & 1) ^ 1);
-        mbar_expect_tx(&qkv_full[st], kAtQkvBytes);
-        uint8_t* dst = s_qkv + st * kAtQkvBytes;
-        tma_load_3d(dst, &tm_qkv, &qkv_full[st], h * 32, 0, f);
-        tma_load_3d(dst + 8192, &tm_qkv, &qkv_full[st], 256 + h * 32, 0, f);
-        tma_load_3d(dst + 16384, &tm_qkv, &qkv_full[st], 512 + h * 32, 0, f);
+        mbar_wait(&qk_empty[sq], ((u / kAtQkStages) & 1) ^ 1);
+        mbar_expect_tx(&qk_full[sq], kAtQkBytes);
+        uint8_t* dst = s_qk + sq * kAtQkBytes;
+        tma_load_3d(dst, &tm_qkv, &qk_full[sq], h * 32, 0, f);
+        tma_load_3d(dst + 8192, &tm_qkv, &qk_full[sq], 256 + h * 32, 0, f);
+        mbar_wait(&v_empty[sv], ((u / kAtVStages) & 1) ^ 1);
+        mbar_expect_tx(&v_full[sv], kAtVBytes);
+        tma_load_3d(s_v + sv * kAtVBytes, &tm_qkv, &v_full[sv], 512 + h * 32, 0, f);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 48) | (1u << 16);  // B = [V | ones] is MN-major, N = 32 + 16
-    for (int u = 0; u <= num_units; ++u) {
+    for (int u = 0; u < num_units + kAtLag; ++u) {
       if (u < num_units) {
-        const int b = u & 1, st = u % kAtStages;
-        const uint32_t ph = (u >> 1) & 1;
-        mbar_wait(&qkv_full[st], (u / kAtStages) & 1);
-        mbar_wait(&t_free[b], ph ^ 1);
+        const int b = u % kAtWgs, sq = u % kAtQkStages;
+        mbar_wait(&qk_full[sq], (u / kAtQkStages) & 1);
+        mbar_wait(&t_free[b], ((u / kAtWgs) & 1) ^ 1);   // the O tile of unit u - kAtWgs (aliased on this S tile) has been read
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t q_addr = smem_u32(s_qkv + st * kAtQkvBytes);
+          const uint32_t q_addr = smem_u32(s_qk + sq * kAtQkBytes);
           const uint64_t qd = umma_desc_sw64_kmajor(q_addr), kd = umma_desc_sw64_kmajor(q_addr + 8192);
           umma_bf16(tmem_base + b * 128, qd, kd, idesc_s, 0u);
           umma_bf16(tmem_base + b * 128, qd + 2, kd + 2, idesc_s, 1u);
           umma_commit(&s_full[b]);
+          umma_commit(&qk_empty[sq]);
         }
         __syncwarp();
       }
-      if (u >= 1) {
-        const int v = u - 1, b = v & 1, st = v % kAtStages;
-        const uint32_t ph = (v >> 1) & 1;
-        mbar_wait(&p_full[b], ph);
+      if (u >= kAtLag) {
+        const int v = u - kAtLag, b = v % kAtWgs, sv = v % kAtVStages;
+        mbar_wait(&v_full[sv], (v / kAtVStages) & 1);
+        mbar_wait(&p_full[b], (v / kAtWgs) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t v_addr = smem_u32(s_qkv + st * kAtQkvBytes + 16384);
+          const uint32_t v_addr = smem_u32(s_v + sv * kAtVBytes);
           const uint32_t p_addr = smem_u32(s_p + b * kAtPBytes);
           const uint64_t vd = umma_desc_sw64_mnmajor(v_addr, smem_u32(s_ones) - v_addr);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {  // 8 x 16 keys
+          for (int k = 0; k < 8; ++k) {  // 8 x 16 keys; O lands on the first 48 columns of the (consumed) S tile
             const uint64_t pd = umma_desc_sw128_kmajor(p_addr + (k >> 2) * 16384) + 2 * (k & 3);
-            umma_bf16(tmem_base + 256 + b * 64, pd, vd + (uint64_t)((k * 1024) >> 4), idesc_o, k ? 1u : 0u);
+            umma_bf16(tmem_base + b * 128, pd, vd + (uint64_t)((k * 1024) >> 4), idesc_o, k ? 1u : 0u);
           }
           umma_commit(&o_full[b]);
-          umma_commit(&qkv_empty[st]);
+          umma_commit(&v_empty[sv]);
         }
         __syncwarp();
       }
     }
   } else {
     // ===================== softmax + output warpgroups =====================
-    const int wg = (warp - 2) >> 2;          // 0 or 1: handles units u with (u & 1) == wg
+    const int wg = (warp - 2) >> 2;          // handles units u with u % kAtWgs == wg
     const int quad = warp & 3;
     const int row = quad * 32 + lane;        // score row / token index within the frame
     const int wg_tid = (warp - 2 - wg * 4) * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     uint8_t* p_buf = s_p + wg * kAtPBytes;
-    uint8_t* o_buf = s_o + wg * kAtOBytes;
-    for (int u = wg; u < num_units; u += 2) {
+    uint8_t* o_buf = p_buf;                  // O staging reuses the head of this warpgroup's P tile (dead once P·V is done)
+    for (int u = wg; u < num_units; u += kAtWgs) {
       const int f = blockIdx.x + (u >> 3) * gridDim.x, h = u & 7;
-      const uint32_t ph = (u >> 1) & 1;
+      const uint32_t ph = (u / kAtWgs) & 1;
       const uint8_t* km = p.kmask ? p.kmask + (size_t)f * S : nullptr;
       mbar_wait(&s_full[wg], ph);
       tc_fence_after();
@@ -230,6 +239,8 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
       const float nbase = -(mx == -INFINITY ? 0.f : mx) * p.scale_log2e;
       const uint32_t sw = static_cast<uint32_t>(row & 7) << 4;
+      if (wg_tid == 0) tma_store_wait_read<0>();  // the previous unit's output store has drained the head of p_buf
+      named_bar_sync(1 + wg, 128);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
@@ -254,15 +265,13 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       // O epilogue
       mbar_wait(&o_full[wg], ph);
       tc_fence_after();
-      tmem_ld32(tmem_base + lane_base + 256 + wg * 64, raw);
-      const float sum = __uint_as_float(tmem_ld1(tmem_base + lane_base + 256 + wg * 64 + 32));  // P · ones
+      tmem_ld32(tmem_base + lane_base + wg * 128, raw);
+      const float sum = __uint_as_float(tmem_ld1(tmem_base + lane_base + wg * 128 + 32));  // P · ones
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&t_free[wg]);   // S[wg] and O[wg] may be overwritten by unit u+2
+      if (lane == 0) mbar_arrive(&t_free[wg]);   // this S/O tile may be overwritten by unit u + kAtWgs
       const float inv = 1.f / sum;
-      if (wg_tid == 0) tma_store_wait_read<0>();  // the previous store of this warpgroup has drained o_buf
-      named_bar_sync(1 + wg, 128);
       {
         uint8_t* rowp = o_buf + row * 64;
 #pragma unroll
@@ -327,7 +336,7 @@ void enc_attn_tc(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* kmask, 
   CUtensorMap to = make_tmap_frames(AO, F, S, 256, 256);
   AttnTcParams p{kmask, S, F, scale * 1.4426950408889634f};
   const int grid = F < device_sm_count() ? F : device_sm_count();
-  enc_attn_tc_kernel<<<grid, 320, kAtSmem, stream>>>(tq, to, p);
+  enc_attn_tc_kernel<<<grid, kAtThreads, kAtSmem, stream>>>(tq, to, p);
   VG_CUDA(cudaGetLastError());
 }
 
