@@ -146,6 +146,9 @@ int vgqa_postprocess(const float* boxes, const float* sted, const float* sizes_h
 
 /* Counters: kernels launched by the last vgqa_forward call (graph replays count the captured launches). */
 int vgqa_last_launch_count(const vgqa_ctx* ctx);
+/* Debug (VGQA_TIMELINE=1 in the environment at vgqa_create): device timestamps, in ms since the context's first call, of the
+ * last forward issued on `slot`: [encoder phase start, end, decoder phase start, end]. */
+int vgqa_debug_phase_times(vgqa_ctx* ctx, int slot, float* ms4);
 /* Algorithmic hot-path FLOPs per clip at (T,H,W,L) by the reference's op count (SURVEY.md §8d closed form). */
 double vgqa_reference_flops(int T, int H, int W, int L, int enc_layers, int dec_layers, int ffn_dim, int passes);
 
@@ -162,6 +165,10 @@ int vgqa_enc_attn(const void* QKV, void* AO, int F, int S, const uint8_t* kmask,
 int vgqa_xattn1(const void* qt, const void* mem, long long frame_stride_rows, int F, int Mk, const void* posk,
                 long long posk_fstride, const void* q2, const void* kpos, int ldkpos, long long kpos_fstride,
                 const uint8_t* kmask, int ldmask, float scale, void* ctx_out, float* att_out, void* stream);
+/* Same op with the positional score terms supplied as an additive table sbias[F, 8, ldsb] (fp32, unscaled) — the form the
+ * decoders use when `pos` is frame-invariant; runs the warp-per-frame streaming kernel (xattn_stream.cu). */
+int vgqa_xattn1_bias(const void* qt, const void* mem, long long frame_stride_rows, int F, int Mk, const float* sbias, int ldsb,
+                     const uint8_t* kmask, int ldmask, float scale, void* ctx_out, float* att_out, void* stream);
 /* Fused post-norm FFN block of one encoder layer (modal_encoder.py:175-177):
  *   y = LayerNorm(res32 + W2 relu(W1 x + b1) + b2);  C = bf16(y), C32 = y (fp32, optional), C2 = bf16(y + add2[row % period]) (optional)
  * x [M,256] bf16, W1 [F,256] bf16, W2 [256,F] bf16 (nn.Linear layouts), F % 128 == 0, all row strides 256.  One launch on

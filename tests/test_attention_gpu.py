@@ -91,6 +91,52 @@ def test_xattn1(F, S, tok0, Mk, use_pos, use_kpos, use_mask, want_att):
         assert (att - a).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("F,S,tok0,Mk,use_bias,use_mask,want_att",
+                         [(70, 118, 49, 69, True, False, False),      # decoders: positional terms as an additive table
+                          (700, 118, 0, 69, True, False, False),      # more frames than workers: the per-warp ring wraps
+                          (33, 118, 69, 49, False, False, True),      # SpatialActivation
+                          (9, 27, 12, 15, True, True, False),
+                          (5, 352, 208, 144, False, False, True),     # cfg-5 memory length
+                          (3, 412, 0, 208, True, True, True),
+                          (2, 9, 1, 3, True, False, True)])
+def test_xattn_stream(F, S, tok0, Mk, use_bias, use_mask, want_att):
+    """Warp-per-frame streaming kernel (TMA ring, register-resident softmax) vs torch fp32."""
+    from vgqa_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(F * 17 + Mk)
+    mem_all = torch.randn(F, S, 256, device="cuda", generator=g).bfloat16()
+    qt = (torch.randn(F, 8, 256, device="cuda", generator=g) / 4).bfloat16()
+    ldsb = (Mk + 7) // 8 * 8
+    sb = (torch.randn(F, 8, ldsb, device="cuda", generator=g) * 2) if use_bias else None
+    mask = None
+    if use_mask:
+        mask = torch.rand(F, S, device="cuda", generator=g) < 0.3
+        mask[:, 0] = False
+        mask_u8 = mask.to(torch.uint8).contiguous()
+    ctx = torch.zeros(F, 2048, device="cuda", dtype=torch.bfloat16)
+    att = torch.zeros(F, Mk, device="cuda") if want_att else None
+    scale = 0.125
+    mem = mem_all[:, tok0:tok0 + Mk]
+    _lib.check(L.vgqa_xattn1_bias(_lib.ptr(qt), _lib.ptr(mem), S, F, Mk, _lib.ptr(sb), ldsb,
+                                  _lib.ptr(mask_u8) if use_mask else None, S, scale, _lib.ptr(ctx), _lib.ptr(att), _stream()))
+    torch.cuda.synchronize()
+    memf = mem.float()
+    s = torch.einsum("fhc,fmc->fhm", qt.float(), memf)
+    if use_bias:
+        s = s + sb[:, :, :Mk]
+    s = s * scale
+    if use_mask:
+        s = s.masked_fill(mask[:, None, :Mk], float("-inf"))
+    p = s.softmax(-1)
+    ref = torch.einsum("fhm,fmc->fhc", p, memf).reshape(F, 2048)
+    err = (ctx.float() - ref).abs().max().item()
+    assert err < 3e-2, err
+    if want_att:
+        a = p.sum(1).sigmoid()
+        a = (a - a.min(1, keepdim=True)[0]) / (a.max(1, keepdim=True)[0] - a.min(1, keepdim=True)[0] + 1e-6)
+        assert (att - a).abs().max().item() < 2e-2
+
+
 @pytest.mark.parametrize("F,S,masked", [(5, 118, False), (300, 118, False), (3, 128, False), (7, 47, True), (2, 3, False),
                                         (4, 27, False), (9, 118, True)])
 def test_enc_attn_tcgen05(F, S, masked):

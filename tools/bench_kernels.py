@@ -63,6 +63,18 @@ def bench_xattn(F=4096, S=118, tok0=0, Mk=69, use_pos=False, use_kpos=False, nam
     print(f"xattn1 {name} F={F} Mk={Mk}: {t:8.1f} us  {byts / t / 1e3:7.1f} GB/s")
 
 
+def bench_xattn_stream(F=4096, S=118, tok0=0, Mk=69, bias=True, name=""):
+    mem_all = torch.randn(F, S, 256, device="cuda").bfloat16()
+    qt = (torch.randn(F, 8, 256, device="cuda") / 4).bfloat16()
+    sb = torch.randn(F, 8, 72, device="cuda") if bias else None
+    ctx = torch.zeros(F, 2048, device="cuda", dtype=torch.bfloat16)
+    mem = mem_all[:, tok0:tok0 + Mk]
+    t = timeit(lambda: _lib.check(L.vgqa_xattn1_bias(_lib.ptr(qt), _lib.ptr(mem), S, F, Mk, _lib.ptr(sb), 72, None, 0, 0.125,
+                                                     _lib.ptr(ctx), None, st())))
+    byts = F * (Mk * 512 + 4096 + 4096 + (8 * Mk * 4 if bias else 0))
+    print(f"xattn stream {name} F={F} Mk={Mk}: {t:8.1f} us  {byts / t / 1e3:7.1f} GB/s")
+
+
 def bench_ffn(M, F=2048, parts=4):
     x32 = torch.randn(M, 256, device="cuda")
     x = x32.bfloat16()
@@ -84,6 +96,8 @@ if __name__ == "__main__":
         bench_attn()
         bench_attn(F=1024, S=118)
     if "xattn" in which:
+        bench_xattn_stream(Mk=49, tok0=69, bias=False, name="spatial")
+        bench_xattn_stream(Mk=69, tok0=0, name="decoder")
         bench_xattn(Mk=49, tok0=69, name="spatial")
         bench_xattn(Mk=69, tok0=0, use_kpos=True, name="pos-decoder")
         bench_xattn(Mk=69, tok0=49, use_pos=True, name="time-decoder")

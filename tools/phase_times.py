@@ -55,3 +55,21 @@ def piped():
 t_pipe = timed(piped, n=8, drain=lambda: (eng.wait(0), eng.wait(1)))
 print(f"clips={B}: encoder phase alone (eager, + fp32 copy of the encoded features) {t_enc:.2f} ms | "
       f"full forward unpipelined {t_full:.2f} ms | pipelined {t_pipe:.2f} ms per step")
+
+if os.environ.get("VGQA_TIMELINE") == "1":
+    import ctypes
+    from vgqa_b200 import _lib
+    L = _lib.lib()
+    rows = []
+    for k in range(8):
+        piped()
+        s_ = (i[0] - 1) & 1
+        buf = (ctypes.c_float * 4)()
+        # read the PREVIOUS call on the other slot (complete by now or soon), keeping two calls in flight
+        if k >= 1:
+            _lib.check(L.vgqa_debug_phase_times(eng._ctx, s_ ^ 1, buf))
+            rows.append(list(buf))
+    t0 = rows[0][0]
+    print("step  enc_start  enc_end   dec_start  dec_end    (ms, relative)")
+    for r in rows:
+        print("      " + "  ".join(f"{x - t0:8.2f}" for x in r))

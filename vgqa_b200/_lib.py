@@ -42,6 +42,11 @@ def _declare(L):
                               c_void_p, c_void_p]
 
 
+    L.vgqa_xattn1_bias.restype = c_int
+    L.vgqa_xattn1_bias.argtypes = [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
+                                   c_float, c_void_p, c_void_p, c_void_p]
+
+
 def check(status: int):
     if status != 0:
         raise RuntimeError("vgqa_b200: " + lib().vgqa_last_error().decode())

@@ -75,6 +75,19 @@ int vgqa_xattn1(const void* qt, const void* mem, long long frame_stride_rows, in
   }
 }
 
+int vgqa_xattn1_bias(const void* qt, const void* mem, long long frame_stride_rows, int F, int Mk, const float* sbias, int ldsb,
+                     const uint8_t* kmask, int ldmask, float scale, void* ctx_out, float* att_out, void* stream) {
+  try {
+    vg::xattn1(static_cast<const vg::bf16*>(qt), static_cast<const vg::bf16*>(mem), frame_stride_rows, F, Mk, nullptr, 0,
+               nullptr, nullptr, 0, 0, kmask, ldmask, scale, static_cast<vg::bf16*>(ctx_out), att_out,
+               static_cast<cudaStream_t>(stream), sbias, ldsb);
+    return 0;
+  } catch (const std::exception& e) {
+    vg::set_last_error(e.what());
+    return 1;
+  }
+}
+
 int vgqa_enc_attn(const void* QKV, void* AO, int F, int S, const uint8_t* kmask, float scale, int use_tcgen05,
                   void* stream) {
   try {

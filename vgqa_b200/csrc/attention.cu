@@ -14,7 +14,10 @@
 //                  Linear layers (92% of the reference decoder FLOPs) are never executed: mem is read once
 //                  per layer at HBM speed.  Arithmetic intensity ~16 FLOP/B (HBM-bound), so warp-level
 //                  HMMA (mma.sync m16n8k16) is used rather than tcgen05.
+#include <stdlib.h>
+
 #include "common.h"
+#include "kernels.h"
 #include "ptx.cuh"
 
 namespace vg {
@@ -397,6 +400,14 @@ void xattn1(const bf16* qt, const bf16* mem, long long frame_stride_rows, int F,
             const uint8_t* kmask, int ldmask, float scale, bf16* ctx, float* att, cudaStream_t stream,
             const float* sbias, int ldsb) {
   VG_CHECK(F > 0 && Mk > 0, "xattn1: empty problem");
+  {  // frame-invariant positional terms arrive as `sbias`: the streaming kernel (xattn_stream.cu) handles everything else
+    static int use_stream = -1;
+    if (use_stream < 0) { const char* e = getenv("VGQA_XATTN_STREAM"); use_stream = (e == nullptr || e[0] != '0') ? 1 : 0; }
+    if (use_stream && posk == nullptr && q2 == nullptr && kpos == nullptr && xattn_stream_supported(Mk, frame_stride_rows)) {
+      xattn_stream(qt, mem, frame_stride_rows, F, Mk, sbias, ldsb, kmask, ldmask, scale, ctx, att, stream);
+      return;
+    }
+  }
   Xattn1Params p;
   p.qt = qt; p.mem = mem; p.posk = posk; p.q2 = q2; p.kpos = kpos; p.kmask = kmask; p.ctx = ctx; p.att = att;
   p.sbias = sbias; p.ldsb = ldsb;

@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <stdexcept>
+#include <utility>
 #include <string>
 
 namespace vg {
@@ -33,6 +34,20 @@ struct Error : std::runtime_error {
   } while (0)
 
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+bool pdl_enabled();   // VGQA_PDL=0 disables programmatic dependent launch (gemm_tc.cu)
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel must call pdl_wait() before it touches anything
+// its predecessor in the stream produced (or still reads).
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  VG_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
 
 // Epilogue of the tcgen05 GEMM:  v = acc + bias[(row % bias_period) * bias_ld + col];  v = act(v);
 // v *= mul[row, col];  v += res[row, col] + res32[row, col];  if (ln_w) v = LayerNorm_row(v) * ln_w + ln_b;  C[row, col] = v.

@@ -442,8 +442,9 @@ static void launch_ffn(const CUtensorMap& tx, const CUtensorMap& tw1, const CUte
     max_pairs = n < device_sm_count() / 2 ? n : device_sm_count() / 2;
   }
   const int tiles = (p.M + 255) / 256;
-  int pairs = tiles < max_pairs ? tiles : max_pairs;
-  if (pairs > device_sm_count() / 2) pairs = device_sm_count() / 2;   // honours the model's SM budget
+  int pairs = device_sm_count() / 2;   // honours the model's SM budget (which may exceed the SM count: several waves)
+  if (pairs > tiles) pairs = tiles;
+  (void)max_pairs;
   ffn_fused_kernel<<<2 * pairs, kFfnThreads, kFfnSmem, stream>>>(tx, tw1, tw2, p);
   VG_CUDA(cudaGetLastError());
   count_gemm_launch();

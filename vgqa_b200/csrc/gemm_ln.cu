@@ -81,16 +81,30 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
+      // PDL: the weight blocks of the first ring pass do not depend on the previous kernel — fetch them before waiting for it
+      const int pre = (int)blockIdx.x < num_m ? (num_k < kLnStages ? num_k : kLnStages) : 0;
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_expect_tx(&full_bar[kb], kLnStageBytes);
+        tma_load_2d(smem_b + kb * kLnBBytes, &tma_b, &full_bar[kb], kb * LBK, 0);
+      }
+      pdl_wait();
+      pdl_launch_dependents();
       int stage = 0;
       uint32_t phase = 0;
+      bool first = true;
       for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], kLnStageBytes);
-          tma_load_2d(smem_a + stage * kLnABytes, &tma_a, &full_bar[stage], kb * LBK, mt * LBM);
-          tma_load_2d(smem_b + stage * kLnBBytes, &tma_b, &full_bar[stage], kb * LBK, 0);
+          if (first && kb < pre) {
+            tma_load_2d(smem_a + stage * kLnABytes, &tma_a, &full_bar[stage], kb * LBK, mt * LBM);
+          } else {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], kLnStageBytes);
+            tma_load_2d(smem_a + stage * kLnABytes, &tma_a, &full_bar[stage], kb * LBK, mt * LBM);
+            tma_load_2d(smem_b + stage * kLnBBytes, &tma_b, &full_bar[stage], kb * LBK, 0);
+          }
           if (++stage == kLnStages) { stage = 0; phase ^= 1; }
         }
+        first = false;
       }
     }
   } else if (warp == 1) {
@@ -120,6 +134,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else {
     // ===================== epilogue (warps 2..5), thread = accumulator row =====================
+    pdl_wait();   // the residual rows and the output buffers belong to earlier kernels of the stream
     const int quad = warp & 3;
     uint8_t* stg = smem_stg + (warp - 2) * 16384;
     uint8_t* bufA = stg;            // residual chunk (even) / bf16 output slab
@@ -289,7 +304,7 @@ void gemm_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, const
   CUtensorMap tc2 = p.has_c2 ? make_tmap_2d(e.C2, M, 256, e.ldc2, 32, false) : tc;
   const int num_m = (M + LBM - 1) / LBM;
   const int grid = num_m < device_sm_count() ? num_m : device_sm_count();
-  gemm_ln_kernel<<<grid, 192, kLnSmem, stream>>>(ta, tb, tres, tc, tc32, tc2, p);
+  launch_pdl(gemm_ln_kernel, dim3(grid), dim3(192), kLnSmem, stream, ta, tb, tres, tc, tc32, tc2, p);
   VG_CUDA(cudaGetLastError());
   count_gemm_launch();
 }

@@ -19,6 +19,8 @@
 #include <mutex>
 #include <unordered_map>
 
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -169,18 +171,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      // PDL: the weight blocks of the first ring pass do not depend on the previous kernel — fetch them before waiting for it
+      const int pre = (int)blockIdx.x < num_tiles ? (num_k < Cfg::kStages ? num_k : Cfg::kStages) : 0;
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_expect_tx(&full_bar[kb], Cfg::kStageBytes);
+        tma_load_2d(smem_b + kb * Cfg::kBBytes, &tma_b, &full_bar[kb], kb * BK, ((int)blockIdx.x % num_n) * BN);
+      }
+      pdl_wait();
+      pdl_launch_dependents();
       int stage = 0;
       uint32_t phase = 0;
+      bool first = true;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / num_n) * BM;
         const int n0 = (tile % num_n) * BN;
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tma_b, &full_bar[stage], kb * BK, n0);
+          if (first && kb < pre) {
+            tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m0);
+          } else {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m0);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tma_b, &full_bar[stage], kb * BK, n0);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
+        first = false;
       }
     }
   } else if (warp == 1) {
@@ -213,6 +229,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    pdl_wait();   // mul / residual operands and the output buffer belong to earlier kernels of the stream
     const int quad = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -376,6 +393,12 @@ CUtensorMap make_tmap_2d(const void* ptr, int rows, int cols, int ld, int box_ro
   return m;
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VGQA_PDL"); v = (e == nullptr || e[0] != '0') ? 1 : 0; }
+  return v != 0;
+}
+
 static int g_num_sms = 0;
 static int g_gemm_launches = 0;
 int gemm_launch_count() { return g_gemm_launches; }
@@ -390,7 +413,7 @@ int device_sm_count() {
     VG_CUDA(cudaGetDevice(&dev));
     VG_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  return g_sm_budget > 0 && g_sm_budget < g_num_sms ? g_sm_budget : g_num_sms;
+  return g_sm_budget > 0 ? g_sm_budget : g_num_sms;   // a budget above the SM count = short-lived CTAs (several waves)
 }
 
 template <int BN>
@@ -407,7 +430,7 @@ static void launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, int M, i
   CUtensorMap tc = make_tmap_2d(ep.C, M, N, ep.ldc, 32, ep.c_f32 != 0);
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  gemm_tc_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, tb, tc, ep, M, N, K);
+  launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(192), Cfg::kSmemBytes, stream, ta, tb, tc, ep, M, N, K);
   VG_CUDA(cudaGetLastError());
   ++g_gemm_launches;
 }

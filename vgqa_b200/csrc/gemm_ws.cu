@@ -89,6 +89,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       mbar_expect_tx(w_bar, (uint32_t)(BN * p.K * 2));
       for (int kb = 0; kb < num_k; ++kb) tma_load_2d(smem_w + kb * (BN * 128), &tma_w, w_bar, kb * WBK, n0);
+      pdl_wait();                // PDL: the resident weight slice was fetched while the previous kernel was still running
+      pdl_launch_dependents();
       const CUtensorMap* ta = n_tile < p.a_switch ? &tma_a : &tma_a2;
       int stage = 0;
       uint32_t phase = 0;
@@ -130,6 +132,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else {
     // ===================== epilogue: warps 2..9 =====================
+    pdl_wait();   // the output buffer may still be read by the previous kernel of the stream
     const int quad = warp & 3;              // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;       // which half of the BN columns
     uint8_t* slab = smem_out + (warp - 2) * 4096;
@@ -214,7 +217,7 @@ static void launch_ws(const bf16* A, const bf16* A2, int lda, const bf16* W, int
   int per_n = device_sm_count() / num_n;
   if (per_n < 1) per_n = 1;
   if (per_n > num_m) per_n = num_m;
-  gemm_ws_kernel<BN><<<num_n * per_n, 320, Cfg::kSmem, stream>>>(ta, ta2, tw, tc, p);
+  launch_pdl(gemm_ws_kernel<BN>, dim3(num_n * per_n), dim3(320), Cfg::kSmem, stream, ta, ta2, tw, tc, p);
   VG_CUDA(cudaGetLastError());
   count_gemm_launch();
 }

@@ -11,6 +11,10 @@ void xattn1(const bf16* qt, const bf16* mem, long long frame_stride_rows, int F,
             long long posk_fstride, const bf16* q2, const bf16* kpos, int ldkpos, long long kpos_fstride,
             const uint8_t* kmask, int ldmask, float scale, bf16* ctx, float* att, cudaStream_t stream,
             const float* sbias = nullptr, int ldsb = 0);
+// ---- xattn_stream.cu: warp-per-frame streaming form of xattn1 (no in-kernel positional terms; they arrive as sbias)
+bool xattn_stream_supported(int Mk, long long frame_stride_rows);
+void xattn_stream(const bf16* qt, const bf16* mem, long long frame_stride_rows, int F, int Mk, const float* sbias, int ldsb,
+                  const uint8_t* kmask, int ldmask, float scale, bf16* ctx, float* att, cudaStream_t stream);
 // frame-invariant kpos table → block-diagonal GEMM operand: out[l][h*Mpad + m][h*32 + d] = kposb[m][l*256 + h*32 + d]
 void build_kpos_blockdiag(const bf16* kposb, int ldk, bf16* out, int layers, int Mk, int Mpad, cudaStream_t st);
 // dst[r, :] = r < rows ? src[r, :] : 0 for r < rows_pad (256 bf16 columns)

@@ -174,8 +174,11 @@ struct vgqa_ctx {
     float *frames_cls, *pool32[2], *q0_32;
     uint8_t* encmask;
     cudaEvent_t ev_in = nullptr, enc_done = nullptr, dec_done = nullptr;
+    cudaEvent_t t_enc0 = nullptr, t_enc1 = nullptr, t_dec0 = nullptr, t_dec1 = nullptr;   // VGQA_TIMELINE=1: phase timestamps
     bool used = false;
   } bd[2];
+  cudaEvent_t t_base = nullptr;
+  bool timeline = [] { const char* e = getenv("VGQA_TIMELINE"); return e != nullptr && e[0] == '1'; }();
   cudaStream_t enc_stream = nullptr, dec_stream = nullptr;
   cudaStream_t aux_stream = nullptr;   // second branch of the fork/join sections (classifier pairs, the two decoders)
   cudaEvent_t fj[32] = {};
@@ -1024,15 +1027,20 @@ static void ensure_streams(vgqa_ctx* c) {
   if (c->enc_stream) return;
   int prio_lo = 0, prio_hi = 0;
   VG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  VG_CUDA(cudaStreamCreateWithPriority(&c->enc_stream, cudaStreamNonBlocking, prio_lo));
   // phase 1 is a long chain of small kernels: give it priority so that its blocks are placed first whenever SMs free up
-  VG_CUDA(cudaStreamCreateWithPriority(&c->dec_stream, cudaStreamNonBlocking, prio_hi));
+  // (VGQA_DEC_PRIO: 1 = decoder high [default], 0 = equal, -1 = encoder high)
+  int mode = 1;
+  if (const char* e = getenv("VGQA_DEC_PRIO")) mode = atoi(e);
+  VG_CUDA(cudaStreamCreateWithPriority(&c->enc_stream, cudaStreamNonBlocking, mode < 0 ? prio_hi : prio_lo));
+  VG_CUDA(cudaStreamCreateWithPriority(&c->dec_stream, cudaStreamNonBlocking, mode > 0 ? prio_hi : prio_lo));
   VG_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
   for (auto& b : c->bd) {
     VG_CUDA(cudaEventCreateWithFlags(&b.ev_in, cudaEventDisableTiming));
     VG_CUDA(cudaEventCreateWithFlags(&b.enc_done, cudaEventDisableTiming));
     VG_CUDA(cudaEventCreateWithFlags(&b.dec_done, cudaEventDisableTiming));
+    if (c->timeline) for (cudaEvent_t* e : {&b.t_enc0, &b.t_enc1, &b.t_dec0, &b.t_dec1}) VG_CUDA(cudaEventCreate(e));
   }
+  if (c->timeline) { VG_CUDA(cudaEventCreate(&c->t_base)); VG_CUDA(cudaEventRecord(c->t_base, c->enc_stream)); }
   for (auto& h : c->hs) VG_CUDA(cudaEventCreateWithFlags(&h.done, cudaEventDisableTiming));
 }
 
@@ -1097,10 +1105,14 @@ static void forward_async(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
   VG_CUDA(cudaEventRecord(b.ev_in, st));
   VG_CUDA(cudaStreamWaitEvent(c->enc_stream, b.ev_in, 0));
   if (b.used) VG_CUDA(cudaStreamWaitEvent(c->enc_stream, b.dec_done, 0));  // phase 1 of the previous user of this slot
+  if (c->timeline) VG_CUDA(cudaEventRecord(b.t_enc0, c->enc_stream));
   int launches = run_phase(c, in, out, 0, slot, c->enc_stream, eager);
+  if (c->timeline) VG_CUDA(cudaEventRecord(b.t_enc1, c->enc_stream));
   VG_CUDA(cudaEventRecord(b.enc_done, c->enc_stream));
   VG_CUDA(cudaStreamWaitEvent(c->dec_stream, b.enc_done, 0));
+  if (c->timeline) VG_CUDA(cudaEventRecord(b.t_dec0, c->dec_stream));
   launches += run_phase(c, in, out, 1, slot, c->dec_stream, eager);
+  if (c->timeline) VG_CUDA(cudaEventRecord(b.t_dec1, c->dec_stream));
   if (out.encoded_feature) {
     const size_t n = (size_t)in.clips * in.T * (2 * in.H * in.W + in.L) * 256;
     bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->dec_stream>>>(c->Xf, out.encoded_feature, n);
@@ -1227,6 +1239,17 @@ int vgqa_postprocess(const float* boxes, const float* sted, const float* sizes_h
 }
 
 int vgqa_last_launch_count(const vgqa_ctx* c) { return c ? c->last_launches : 0; }
+
+int vgqa_debug_phase_times(vgqa_ctx* c, int slot, float* ms4) {
+  try {
+    VG_CHECK(c && ms4 && (slot == 0 || slot == 1) && c->timeline && c->bd[slot].used, "phase timeline is off (VGQA_TIMELINE=1)");
+    vgqa_ctx::Boundary& b = c->bd[slot];
+    VG_CUDA(cudaEventSynchronize(b.t_dec1));
+    cudaEvent_t ev[4] = {b.t_enc0, b.t_enc1, b.t_dec0, b.t_dec1};
+    for (int i = 0; i < 4; ++i) VG_CUDA(cudaEventElapsedTime(&ms4[i], c->t_base, ev[i]));
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
 
 double vgqa_reference_flops(int T, int H, int W, int L, int enc_layers, int dec_layers, int ffn, int passes) {
   // 2*MACs of the reference modules: encoder + TemporalSampling + passes*(SpatialActivation + decoders)

@@ -255,6 +255,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is
+// still running: everything before pdl_wait() (barrier init, TMEM allocation, descriptor prefetch, loads of constant weights)
+// overlaps the predecessor; pdl_wait() returns once the predecessor has completed and its writes are visible.  We trigger the
+// NEXT kernel only after our own wait, so a prologue never runs ahead of anything but its immediate predecessor.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ legacy warp MMA (HMMA) helpers
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
