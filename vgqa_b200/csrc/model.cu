@@ -694,7 +694,10 @@ static void run_temporal_sampling(Fwd& f) {
 }
 
 // SpatialActivation + query seeding (classifier.py:64-81; grounding_net.py:131-136)
-static void run_spatial_seed(Fwd& f, const float* w, const float* K) {
+// The per-frame part (two BertLayer_Cross blocks + head, attention map) does not depend on which frames were chosen —
+// every frame attends only to its own tokens — so the second pass reuses logit_rows / attmap of the first and only redoes the
+// masked means over the newly chosen frames.
+static void run_spatial_seed(Fwd& f, const float* w, const float* K, bool second_pass) {
   vgqa_ctx* c = f.c;
   const int F = f.F, P = f.P, S = f.S;
   f.fork();
@@ -703,7 +706,7 @@ static void run_spatial_seed(Fwd& f, const float* w, const float* K) {
     const int tok0 = k == 0 ? P + f.L : 0;  // t_* reads vid tokens, s_* reads vis tokens
     const bf16* q = c->q0;
     const float* q32 = c->q0_32;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2 && !second_pass; ++i) {
       SaLayer& s = c->sa[k][i];
       f.linear(q, 256, s.qabs, F, c->c_qabs[k], 2048);
       xattn1(c->c_qabs[k], c->Xf + (size_t)tok0 * 256, S, F, P, nullptr, 0, nullptr, nullptr, 0, 0, nullptr, 0,
@@ -715,28 +718,35 @@ static void run_spatial_seed(Fwd& f, const float* w, const float* K) {
       q = c->c_h[k]; q32 = c->c_h32[k];
     }
     Head& hd = c->sa_head[k];
-    f.linear_res_ln(q, 256, hd.t, F, nullptr, hd.ln, 1e-12f, c->c_a[k], 256, nullptr, ACT_GELU);
-    rowvec_head(c->c_a[k], 256, hd.dw, hd.db, c->logit_rows[k], 64, F, hd.vocab, 0, f.st);
+    if (!second_pass) {
+      f.linear_res_ln(q, 256, hd.t, F, nullptr, hd.ln, 1e-12f, c->c_a[k], 256, nullptr, ACT_GELU);
+      rowvec_head(c->c_a[k], 256, hd.dw, hd.db, c->logit_rows[k], 64, F, hd.vocab, 0, f.st);
+      f.count();
+    }
     seed_partial(c->Xf, c->attmap[k], w, c->part[k], F, S, tok0, P, f.st);
     masked_sums(c->logit_rows[k], 64, hd.vocab, c->part[k], w, c->red[k], f.B, f.T, f.st);
     f.all_reduce_f32(c->red[k], (size_t)f.B * 320);
     // k = 0: init temporal query → TimeDecoder tgt; k = 1: init spatial query → PosDecoder tgt (cat cols 0..255)
     seed_finish(c->red[k], K, c->logits_r[k], hd.vocab, c->seedq[k], k == 0 ? c->t_tgt : c->p_cat, k == 0 ? 256 : 768,
                 k == 0 ? c->t_tgt32 : c->p_tgt32, f.B, f.T, P, f.st);
-    f.count(4);
+    f.count(3);
   }
   f.join();
 }
 
-static void run_decoders(Fwd& f, bool have_mask, int pos_frames) {
+// second_pass: the anchors from frames_cls, the padded positional table, ca_kpos_proj(pos) and layer 0's query_pos are the
+// same as in the first pass (they do not depend on the seeded queries) and are not recomputed.
+static void run_decoders(Fwd& f, bool have_mask, int pos_frames, bool second_pass) {
   vgqa_ctx* c = f.c;
   cudaStream_t st = f.st;
   const int F = f.F, P = f.P, L = f.L, S = f.S, T = f.T, M = P + L;
   const int D = (int)c->tl.size();
   const long long pos_fs = pos_frames > 1 ? (long long)S * 256 : 0;
   // anchors from frames_cls (query_decoder.py:92-94)
-  pos_fc_boxes(c->frames_cls, c->pfc_ln0w, c->pfc_ln0b, c->pfc_W, c->pfc_b, c->pfc_ln4w, c->pfc_ln4b, c->boxes0, F, st);
-  f.count();
+  if (!second_pass) {
+    pos_fc_boxes(c->frames_cls, c->pfc_ln0w, c->pfc_ln0b, c->pfc_W, c->pfc_b, c->pfc_ln4w, c->pfc_ln4b, c->boxes0, F, st);
+    f.count();
+  }
   f.fork();
   // With a frame-invariant positional table the positional score terms are plain GEMMs over the absorbed queries:
   //   TimeDecoder  q~_h·(mem_m + pos_m) = q~_h·mem_m + (q~ pos^T)[h, m]
@@ -744,7 +754,7 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames) {
   // so the cross-attention kernel streams the memory tokens once and only adds a [8, M] fp32 table per frame.
   const bool pos_gemm = pos_frames == 1;
   const int Npad = (M + 63) / 64 * 64, Mpad = (M + 7) / 8 * 8;
-  if (pos_gemm) { pad_rows_bf16(c->pos_enc + (size_t)P * 256, c->pos_pad, M, Npad, st); f.count(); }
+  if (pos_gemm && !second_pass) { pad_rows_bf16(c->pos_enc + (size_t)P * 256, c->pos_pad, M, Npad, st); f.count(); }
   // ---------------- TimeDecoder (query_decoder.py:379-486), memory = [text | vid] tokens
   for (int l = 0; l < D; ++l) {
     TimeLayer& t = c->tl[l];
@@ -777,9 +787,11 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames) {
   // ---------------- PosDecoder (query_decoder.py:129-375), memory = [vis | text] tokens — second branch
   f.st = f.aux;
   st = f.aux;
-  { GemmEpi ep; ep.C = c->kposb; ep.ldc = 1536; ep.bias = c->kpos_all.b; ep.bias_ld = c->kpos_all.N;
-    f.gemm(c->pos_enc, 256, c->kpos_all, pos_frames * S, ep); }  // ca_kpos_proj(pos_s) for all layers (:309)
-  if (pos_gemm) { build_kpos_blockdiag(c->kposb, 1536, c->kpos_bd, D, M, Mpad, st); f.count(); }
+  if (!second_pass) {
+    GemmEpi ep; ep.C = c->kposb; ep.ldc = 1536; ep.bias = c->kpos_all.b; ep.bias_ld = c->kpos_all.N;
+    f.gemm(c->pos_enc, 256, c->kpos_all, pos_frames * S, ep);   // ca_kpos_proj(pos_s) for all layers (:309)
+    if (pos_gemm) { build_kpos_blockdiag(c->kposb, 1536, c->kpos_bd, D, M, Mpad, st); f.count(); }
+  }
   const float* boxes = c->boxes0;
   for (int l = 0; l < D; ++l) {
     PosLayer& q = c->pl[l];
@@ -887,8 +899,8 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
   f.all_reduce_f32(c->K1, f.B);
   select_finish(c->w1, c->K1, f.B, f.T, f.T_global(), st);
   f.count(2);
-  run_spatial_seed(f, c->w1, c->K1);
-  run_decoders(f, have_mask, in.pos_frames);
+  run_spatial_seed(f, c->w1, c->K1, false);
+  run_decoders(f, have_mask, in.pos_frames, false);
   const float* wfinal = c->w1;
   if (in.iteration_rate < 0) {  // grounding_net.py:143-163
     f.linear(c->t_inter + (size_t)(D - 1) * F * 256, 256, c->action_embed.l0, F, c->t_hs, 256, ACT_RELU);
@@ -897,8 +909,8 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
     f.all_reduce_f32(c->K2, f.B);
     select_finish(c->w2, c->K2, f.B, f.T, f.T_global(), st);
     f.count(3);
-    run_spatial_seed(f, c->w2, c->K2);
-    run_decoders(f, have_mask, in.pos_frames);
+    run_spatial_seed(f, c->w2, c->K2, true);
+    run_decoders(f, have_mask, in.pos_frames, true);
     wfinal = c->w2;
   }
   // heads over all decoder layers (grounding_net.py:177-181)
