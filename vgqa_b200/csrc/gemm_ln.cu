@@ -16,15 +16,26 @@
 //     pass 1  residual chunks arrive by TMA (32 rows x 128 B, double-buffered per warp) → v → shifted moments,
 //             v parked back in TMEM (tcgen05.st)
 //     pass 2  normalise, write fp32 / bf16 / bf16+pos slabs (128B-swizzled) → TMA stores.
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
 namespace vg {
 
-static constexpr int LBM = 128, LBN = 256, LBK = 64, kLnStages = 3;
-static constexpr int kLnABytes = LBM * LBK * 2, kLnBBytes = LBN * LBK * 2, kLnStageBytes = kLnABytes + kLnBBytes;
-static constexpr int kLnStaging = 4 * 16384;
-static constexpr int kLnSmem = kLnStages * kLnStageBytes + kLnStaging + 3 * LBN * 4 + 1024 + 256;
+// NSPLIT = 2: a CTA pair (cluster) shares one 128-row tile, each CTA owning 128 of the 256 output columns (half of W, so half
+// the bytes per CTA and twice the CTAs for the decoders' M = clips*T <= 4096-row GEMMs with K = 2048); the two halves of a
+// row exchange their LayerNorm moments through distributed shared memory.
+static constexpr int LBM = 128, LBK = 64;
+template <int NSPLIT>
+struct LnCfg {
+  static constexpr int LBN = 256 / NSPLIT;
+  static constexpr int kStages = NSPLIT == 1 ? 3 : 4;
+  static constexpr int kABytes = LBM * LBK * 2, kBBytes = LBN * LBK * 2, kStageBytes = kABytes + kBBytes;
+  static constexpr int kStaging = 4 * 16384;
+  static constexpr int kXch = NSPLIT == 1 ? 0 : 2 * 128 * 8;   // [2 tile parities][128 rows] (mean, M2) written by the peer CTA
+  static constexpr int kSmem = kStages * kStageBytes + kStaging + kXch + 3 * LBN * 4 + 1024 + 256;
+};
 
 struct LnParams {
   const float* bias; const float* ln_w; const float* ln_b;
@@ -35,16 +46,21 @@ struct LnParams {
 
 __device__ __forceinline__ float ln_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-__global__ void __launch_bounds__(192, 1)
+template <int NSPLIT>
+__global__ void __cluster_dims__(NSPLIT, 1, 1) __launch_bounds__(192, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_res, const __grid_constant__ CUtensorMap tma_c,
                const __grid_constant__ CUtensorMap tma_c32, const __grid_constant__ CUtensorMap tma_c2, const LnParams p) {
+  using Cfg = LnCfg<NSPLIT>;
+  constexpr int LBN = Cfg::LBN, kLnStages = Cfg::kStages, kLnABytes = Cfg::kABytes, kLnBBytes = Cfg::kBBytes;
+  constexpr int kLnStageBytes = Cfg::kStageBytes, kLnStaging = Cfg::kStaging;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kLnStages * kLnABytes;
   uint8_t* smem_stg = smem + kLnStages * kLnStageBytes;
-  float* sbias = reinterpret_cast<float*>(smem_stg + kLnStaging);
+  float2* xch = reinterpret_cast<float2*>(smem_stg + kLnStaging);
+  float* sbias = reinterpret_cast<float*>(smem_stg + kLnStaging + Cfg::kXch);
   float* slnw = sbias + LBN;
   float* slnb = slnw + LBN;
   uint64_t* bars = reinterpret_cast<uint64_t*>(slnb + LBN);
@@ -53,46 +69,52 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + kLnStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* res_bar = tempty_bar + 2;  // [4 warps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
+  uint64_t* xbar = res_bar + 8;        // NSPLIT = 2: the peer's 128 epilogue threads have delivered their moments
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (p.M + LBM - 1) / LBM;
   const int num_k = p.K / LBK;
+  const int rank = NSPLIT == 1 ? 0 : (int)cluster_ctarank();
+  const int col0 = rank * LBN;                              // first output column of this CTA
+  const int tile0 = (int)blockIdx.x / NSPLIT, tile_step = (int)gridDim.x / NSPLIT;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_b); tma_prefetch_desc(&tma_c);
     for (int s = 0; s < kLnStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     for (int i = 0; i < 8; ++i) mbar_init(&res_bar[i], 1);
+    mbar_init(xbar, 128);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * LBN);
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < LBN; i += 128) {
-      sbias[i] = p.bias ? p.bias[i] : 0.f;
-      slnw[i] = p.ln_w[i];
-      slnb[i] = p.ln_b[i];
+      sbias[i] = p.bias ? p.bias[col0 + i] : 0.f;
+      slnw[i] = p.ln_w[col0 + i];
+      slnb[i] = p.ln_b[col0 + i];
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (NSPLIT > 1) cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       // PDL: the weight blocks of the first ring pass do not depend on the previous kernel — fetch them before waiting for it
-      const int pre = (int)blockIdx.x < num_m ? (num_k < kLnStages ? num_k : kLnStages) : 0;
+      const int pre = tile0 < num_m ? (num_k < kLnStages ? num_k : kLnStages) : 0;
       for (int kb = 0; kb < pre; ++kb) {
         mbar_expect_tx(&full_bar[kb], kLnStageBytes);
-        tma_load_2d(smem_b + kb * kLnBBytes, &tma_b, &full_bar[kb], kb * LBK, 0);
+        tma_load_2d(smem_b + kb * kLnBBytes, &tma_b, &full_bar[kb], kb * LBK, col0);
       }
       pdl_wait();
       pdl_launch_dependents();
       int stage = 0;
       uint32_t phase = 0;
       bool first = true;
-      for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
+      for (int mt = tile0; mt < num_m; mt += tile_step) {
         for (int kb = 0; kb < num_k; ++kb) {
           if (first && kb < pre) {
             tma_load_2d(smem_a + stage * kLnABytes, &tma_a, &full_bar[stage], kb * LBK, mt * LBM);
@@ -100,7 +122,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], kLnStageBytes);
             tma_load_2d(smem_a + stage * kLnABytes, &tma_a, &full_bar[stage], kb * LBK, mt * LBM);
-            tma_load_2d(smem_b + stage * kLnBBytes, &tma_b, &full_bar[stage], kb * LBK, 0);
+            tma_load_2d(smem_b + stage * kLnBBytes, &tma_b, &full_bar[stage], kb * LBK, col0);
           }
           if (++stage == kLnStages) { stage = 0; phase ^= 1; }
         }
@@ -111,7 +133,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     constexpr uint32_t idesc = umma_idesc_bf16(LBM, LBN);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
+    for (int mt = tile0; mt < num_m; mt += tile_step) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * LBN;
@@ -146,15 +168,19 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     const int swz = lane & 7;
-    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
+    uint32_t xph = 0;
+    const uint32_t peer_xch = NSPLIT == 1 ? 0u : mapa_u32(smem_u32(xch), (uint32_t)(rank ^ 1));
+    const uint32_t peer_xbar = NSPLIT == 1 ? 0u : mapa_u32(smem_u32(xbar), (uint32_t)(rank ^ 1));
+    int tile_i = 0;
+    for (int mt = tile0; mt < num_m; mt += tile_step, ++tile_i) {
       const int row0 = mt * LBM + quad * 32;
       const int row = row0 + lane;
       const bool valid = row < p.M;
       if (lane == 0) tma_store_wait_read<0>();  // the previous tile's stores have drained this warp's slabs
       __syncwarp();
       if (p.has_res && lane == 0) {
-        mbar_expect_tx(&rbar[0], 4096); tma_load_2d(bufA, &tma_res, &rbar[0], 0, row0);
-        mbar_expect_tx(&rbar[1], 4096); tma_load_2d(bufB, &tma_res, &rbar[1], 32, row0);
+        mbar_expect_tx(&rbar[0], 4096); tma_load_2d(bufA, &tma_res, &rbar[0], col0, row0);
+        mbar_expect_tx(&rbar[1], 4096); tma_load_2d(bufB, &tma_res, &rbar[1], col0 + 32, row0);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -189,7 +215,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           __syncwarp();  // every lane has consumed this buffer
           if (c + 2 < LBN / 32 && lane == 0) {
             mbar_expect_tx(&rbar[c & 1], 4096);
-            tma_load_2d(rb, &tma_res, &rbar[c & 1], (c + 2) * 32, row0);
+            tma_load_2d(rb, &tma_res, &rbar[c & 1], col0 + (c + 2) * 32, row0);
           }
         }
         if (c == 0) shift = v[0];
@@ -204,8 +230,21 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       tmem_st_wait();
       const float dm = s1 * (1.0f / LBN);
-      const float mean = shift + dm;
-      const float var = fmaxf(s2 * (1.0f / LBN) - dm * dm, 0.f);
+      float mean = shift + dm;
+      float var = fmaxf(s2 * (1.0f / LBN) - dm * dm, 0.f);
+      if (NSPLIT > 1) {
+        // (mean, M2) of this CTA's 128 columns → the peer's exchange slot; combine with the peer's (parallel-variance formula)
+        const int slot = (tile_i & 1) * 128 + quad * 32 + lane;
+        const float m2 = var * (float)LBN;
+        asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(peer_xch + (uint32_t)slot * 8u), "f"(mean), "f"(m2) : "memory");
+        mbar_arrive_cluster(peer_xbar);
+        mbar_wait_cluster(xbar, xph);
+        xph ^= 1;
+        const float2 o = xch[slot];
+        const float d = mean - o.x;
+        var = (m2 + o.y + 0.5f * (float)LBN * d * d) * (1.0f / 256.0f);
+        mean = 0.5f * (mean + o.x);
+      }
       const float rstd = rsqrtf(var + p.eps);
       // ---------------- pass 2: normalise → slabs → TMA stores (units of 64 columns)
 #pragma unroll 1
@@ -237,7 +276,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           if (p.has_c2) {
             uint8_t* rowp = bufB + lane * 128;
-            const uint4* a4 = reinterpret_cast<const uint4*>(p.add2 + (size_t)((valid ? row : 0) % p.add2_period) * 256 + c * 32);
+            const uint4* a4 = reinterpret_cast<const uint4*>(p.add2 + (size_t)((valid ? row : 0) % p.add2_period) * 256 + col0 + c * 32);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint4 q = __ldg(a4 + i);
@@ -251,9 +290,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tma_c, bufA, u * 64, row0);
-          if (p.has_c32) { tma_store_2d(&tma_c32, bufC, u * 64, row0); tma_store_2d(&tma_c32, bufD, u * 64 + 32, row0); }
-          if (p.has_c2) tma_store_2d(&tma_c2, bufB, u * 64, row0);
+          tma_store_2d(&tma_c, bufA, col0 + u * 64, row0);
+          if (p.has_c32) { tma_store_2d(&tma_c32, bufC, col0 + u * 64, row0); tma_store_2d(&tma_c32, bufD, col0 + u * 64 + 32, row0); }
+          if (p.has_c2) tma_store_2d(&tma_c2, bufB, col0 + u * 64, row0);
           tma_store_commit();
         }
       }
@@ -267,6 +306,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (NSPLIT > 1) cluster_sync_all();   // no CTA exits while its peer may still write into its shared memory
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * LBN);
@@ -284,28 +324,41 @@ bool gemm_ln_supported(int N, int K, const GemmEpi& e) {
   return true;
 }
 
-void gemm_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, const GemmEpi& e, cudaStream_t stream) {
-  VG_CHECK(gemm_ln_supported(256, K, e), "gemm_ln: unsupported epilogue");
+template <int NSPLIT>
+static void launch_ln(const CUtensorMap& ta, const bf16* W, int ldw, int K, const CUtensorMap& tres, const CUtensorMap& tc,
+                      const CUtensorMap& tc32, const CUtensorMap& tc2, const LnParams& p, int num_m, cudaStream_t stream) {
+  using Cfg = LnCfg<NSPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
-    VG_CUDA(cudaFuncSetAttribute(gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnSmem));
+    VG_CUDA(cudaFuncSetAttribute(gemm_ln_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr_set = true;
   }
+  CUtensorMap tb = make_tmap_2d(W, 256, K, ldw, Cfg::LBN, false);
+  int groups = device_sm_count() / NSPLIT;
+  if (groups > num_m) groups = num_m;
+  launch_pdl(gemm_ln_kernel<NSPLIT>, dim3(groups * NSPLIT), dim3(192), Cfg::kSmem, stream, ta, tb, tres, tc, tc32, tc2, p);
+}
+
+void gemm_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, const GemmEpi& e, cudaStream_t stream) {
+  VG_CHECK(gemm_ln_supported(256, K, e), "gemm_ln: unsupported epilogue");
   LnParams p;
   p.bias = e.bias; p.ln_w = e.ln_w; p.ln_b = e.ln_b; p.add2 = e.add2; p.M = M; p.K = K; p.act = e.act;
   p.add2_period = e.add2_period > 0 ? e.add2_period : 1;
   p.has_res = e.res32 != nullptr; p.has_c32 = e.C32 != nullptr; p.has_c2 = e.C2 != nullptr; p.eps = e.ln_eps;
   VG_CHECK(!p.has_c2 || e.add2 != nullptr, "gemm_ln: C2 needs add2");
   CUtensorMap ta = make_tmap_2d(A, M, K, lda, LBM, false);
-  CUtensorMap tb = make_tmap_2d(W, 256, K, ldw, LBN, false);
   CUtensorMap tc = make_tmap_2d(e.C, M, 256, e.ldc, 32, false);
   CUtensorMap tres = p.has_res ? make_tmap_2d(e.res32, M, 256, e.ldres32, 32, true) : tc;
   CUtensorMap tc32 = p.has_c32 ? make_tmap_2d(e.C32, M, 256, e.ldc32, 32, true) : tc;
   CUtensorMap tc2 = p.has_c2 ? make_tmap_2d(e.C2, M, 256, e.ldc2, 32, false) : tc;
   const int num_m = (M + LBM - 1) / LBM;
-  const int grid = num_m < device_sm_count() ? num_m : device_sm_count();
-  launch_pdl(gemm_ln_kernel, dim3(grid), dim3(192), kLnSmem, stream, ta, tb, tres, tc, tc32, tc2, p);
-  VG_CUDA(cudaGetLastError());
+  // few row tiles and a long K (the decoders' 2048 -> 256 projections): split the columns over CTA pairs
+  static int split_ok = -1;
+  if (split_ok < 0) { const char* s = getenv("VGQA_LN_SPLIT"); split_ok = (s == nullptr || s[0] != '0') ? 1 : 0; }
+  if (split_ok && num_m * 2 <= device_sm_count() && K >= 512)
+    launch_ln<2>(ta, W, ldw, K, tres, tc, tc32, tc2, p, num_m, stream);
+  else
+    launch_ln<1>(ta, W, ldw, K, tres, tc, tc32, tc2, p, num_m, stream);
   count_gemm_launch();
 }
 
