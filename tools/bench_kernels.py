@@ -75,7 +75,7 @@ def bench_xattn_stream(F=4096, S=118, tok0=0, Mk=69, bias=True, name=""):
     print(f"xattn stream {name} F={F} Mk={Mk}: {t:8.1f} us  {byts / t / 1e3:7.1f} GB/s")
 
 
-def bench_ffn(M, F=2048, parts=4):
+def bench_ffn(M, F=2048, parts=0):
     x32 = torch.randn(M, 256, device="cuda")
     x = x32.bfloat16()
     W1 = (torch.randn(F, 256, device="cuda") / 16).bfloat16()
@@ -87,7 +87,7 @@ def bench_ffn(M, F=2048, parts=4):
                                                    _lib.ptr(lw), _lib.ptr(b2), 1e-5, _lib.ptr(C), _lib.ptr(C32), _lib.ptr(C2), _lib.ptr(pos), 118, parts, st())))
     flops = 4.0 * M * F * 256
     byts = M * 3584.0
-    print(f"ffn_fused parts={parts} M={M} F={F}: {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s  {byts / t / 1e3:7.1f} GB/s")
+    print(f"ffn_fused M={M} F={F}: {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s  {byts / t / 1e3:7.1f} GB/s")
 
 
 if __name__ == "__main__":
@@ -102,9 +102,8 @@ if __name__ == "__main__":
         bench_xattn(Mk=69, tok0=0, use_kpos=True, name="pos-decoder")
         bench_xattn(Mk=69, tok0=49, use_pos=True, name="time-decoder")
     if "ffn" in which:
-        for parts in (4, 2):
-            bench_ffn(64 * 64 * 118, parts=parts)
-            bench_ffn(16 * 64 * 118, parts=parts)
+        bench_ffn(64 * 64 * 118)
+        bench_ffn(16 * 64 * 118)
     if "gemm" in which:
         R = 64 * 64 * 118
         bench_gemm(R, 768, 256, name="qkv")

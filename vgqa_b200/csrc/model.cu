@@ -159,6 +159,7 @@ struct vgqa_ctx {
   float *logit_f[2], *att_seq, *w1, *w2, *K1, *K2, *attmap[2], *logit_rows[2], *logits_r[2], *part[2], *seedq[2];
   float *t_tgt32, *t_x32, *t_x2_32, *p_tgt32, *p_x32, *p_x2_32;
   bf16 *t_tgt, *t_qkv, *t_ao, *t_x, *t_qabs, *t_ctx8, *t_x2, *t_hid, *t_inter, *t_hs;
+  bf16 *p_h2 = nullptr;   // scratch of the query_scale MLP (runs beside the ref_point_head MLP, which owns p_h)
   bf16 *p_cat, *p_sine, *p_h, *p_s256, *p_qkv, *p_ao, *p_q, *p_q2, *p_qabs, *p_ctx8, *p_x2, *p_hid, *p_b1, *p_b2;
   float *boxes0, *anchors, *sted_all, *act_all, *act1, *boxes_px;
   int* sted_idx;
@@ -181,6 +182,7 @@ struct vgqa_ctx {
   bool timeline = [] { const char* e = getenv("VGQA_TIMELINE"); return e != nullptr && e[0] == '1'; }();
   cudaStream_t enc_stream = nullptr, dec_stream = nullptr;
   cudaStream_t aux_stream = nullptr;   // second branch of the fork/join sections (classifier pairs, the two decoders)
+  cudaStream_t aux2_stream = nullptr;  // side branch inside the PosDecoder chain
   cudaEvent_t fj[32] = {};
   // frame sharding of one long clip over `sh_world` ranks (vgqa_set_sharding); exchanges go through the callback
   int sh_rank = 0, sh_world = 1;
@@ -544,6 +546,7 @@ static void carve_workspace(vgqa_ctx* c) {
   c->t_qabs = a.get<bf16>(F * 2048); c->t_ctx8 = a.get<bf16>(F * 2048); c->t_x2 = a.get<bf16>(F * 256);
   c->t_hid = a.get<bf16>(F * FF); c->t_inter = a.get<bf16>(D * F * 256); c->t_hs = a.get<bf16>(D * F * 256);
   c->p_cat = a.get<bf16>(F * 768); c->p_sine = a.get<bf16>(F * 512); c->p_h = a.get<bf16>(F * 256); c->p_s256 = a.get<bf16>(F * 256);
+  c->p_h2 = a.get<bf16>(F * 256);
   c->p_qkv = a.get<bf16>(F * 768); c->p_ao = a.get<bf16>(F * 256); c->p_q = a.get<bf16>(F * 256); c->p_q2 = a.get<bf16>(F * 256);
   c->p_qabs = a.get<bf16>(F * 2048); c->p_ctx8 = a.get<bf16>(F * 2048); c->p_x2 = a.get<bf16>(F * 256);
   c->p_hid = a.get<bf16>(F * FF); c->p_b1 = a.get<bf16>(F * 256); c->p_b2 = a.get<bf16>(F * 256);
@@ -565,6 +568,7 @@ struct Fwd {
   vgqa_ctx* c;
   cudaStream_t st;          // stream the helpers below launch on (main or aux)
   cudaStream_t main, aux;
+  cudaStream_t aux2 = nullptr;   // side branch of the PosDecoder chain (query_scale MLP, absorbed-query GEMM)
   int ev_i = 0;
   int B, T, P, L, S, F, R;
   // independent sub-graphs (the two classifiers of a pair, TimeDecoder vs PosDecoder) run on two streams; under
@@ -581,6 +585,20 @@ struct Fwd {
     VG_CUDA(cudaStreamWaitEvent(main, c->fj[ev_i], 0));
     ev_i = (ev_i + 1) & 31;
     st = main;
+  }
+  // side branch off the current stream `from`: work enqueued on aux2 after side_fork(from) runs beside `from` until
+  // side_join(from) (no-ops when everything runs on one stream)
+  void side_fork(cudaStream_t from) {
+    if (aux2 == from) return;
+    VG_CUDA(cudaEventRecord(c->fj[ev_i], from));
+    VG_CUDA(cudaStreamWaitEvent(aux2, c->fj[ev_i], 0));
+    ev_i = (ev_i + 1) & 31;
+  }
+  void side_join(cudaStream_t into) {
+    if (aux2 == into) return;
+    VG_CUDA(cudaEventRecord(c->fj[ev_i], aux2));
+    VG_CUDA(cudaStreamWaitEvent(into, c->fj[ev_i], 0));
+    ev_i = (ev_i + 1) & 31;
   }
   void gemm(const bf16* A, int lda, const Lin& w, int M, const GemmEpi& ep) {
     gemm_bf16_tn(A, lda, w.W, w.K, M, w.N, w.K, ep, st);
@@ -795,18 +813,23 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames, bool second_pas
   const float* boxes = c->boxes0;
   for (int l = 0; l < D; ++l) {
     PosLayer& q = c->pl[l];
-    sine_embed(boxes, c->p_sine, F, st);                                        // :169
-    f.count();
-    f.linear(c->p_sine, 512, c->rph0, F, c->p_h, 256, ACT_RELU);                // ref_point_head (:170)
-    f.linear(c->p_h, 256, c->rph1, F, c->p_cat + 256, 768);
+    // query_scale(tgt) (:176-179) only needs the layer input: it runs on a side stream beside the sine / ref_point_head /
+    // self-attention chain and is joined where its product (the scaled sine embedding) is first used.
     const bf16* s256 = c->p_sine;
     int lds = 512;
-    if (l > 0) {                                                                // query_scale (:176-179)
-      f.linear(c->p_cat, 768, c->qs0, F, c->p_h, 256, ACT_RELU);
+    sine_embed(boxes, c->p_sine, F, st);                                        // :169
+    f.count();
+    if (l > 0) {
+      f.side_fork(st);
+      f.st = f.aux2;
+      f.linear(c->p_cat, 768, c->qs0, F, c->p_h2, 256, ACT_RELU);
       GemmEpi ep; ep.C = c->p_s256; ep.ldc = 256; ep.bias = c->qs1.b; ep.bias_ld = 256; ep.mul = c->p_sine; ep.ldmul = 512;
-      f.gemm(c->p_h, 256, c->qs1, F, ep);
+      f.gemm(c->p_h2, 256, c->qs1, F, ep);
+      f.st = st;
       s256 = c->p_s256; lds = 256;
     }
+    f.linear(c->p_sine, 512, c->rph0, F, c->p_h, 256, ACT_RELU);                // ref_point_head (:170)
+    f.linear(c->p_h, 256, c->rph1, F, c->p_cat + 256, 768);
     { GemmEpi ep; ep.C = c->p_qkv; ep.ldc = 768; ep.bias = q.tab_sa + (size_t)c->sh_rank * T * 768; ep.bias_period = T; ep.bias_ld = 768;
       f.gemm(c->p_cat, 768, q.sa, F, ep); }                                     // 7 sa_* projs ∘ in_proj (:282-294)
     {
@@ -815,22 +838,30 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames, bool second_pas
       mha32(c->p_qkv, 768, kv + 256, 768, kv + 512, 768, c->p_ao, 256, f.B, T, f.T_global(), nullptr, 0.17677669529663687f, st);
     }
     f.linear_res_ln(c->p_ao, 256, q.sa_out, F, c->p_tgt32, q.ln1, 1e-5f, c->p_cat + 512, 768, c->p_x32);  // x → cat[:,512:]
+    if (l > 0) f.side_join(st);
     const bf16* qa = l == 0 ? c->p_cat + 256 : c->p_cat + 512;                  // [qpos | x] or x
+    // the absorbed content query (qabs) and the positional score term (sine proj → block-diagonal GEMM) are independent
+    f.side_fork(st);
+    f.st = f.aux2;
+    f.linear(qa, 768, q.qabs, F, c->p_qabs, 2048);
+    f.st = st;
     const bf16* q2res = nullptr;
     if (l == 0) { f.linear(qa, 768, q.q, F, c->p_q, 256); q2res = c->p_q; }      // :305,311-313
     { GemmEpi ep; ep.C = c->p_q2; ep.ldc = 256; ep.bias = q.sine.b; ep.bias_ld = 256; ep.res = q2res; ep.ldres = 256;
       f.gemm(s256, lds, q.sine, F, ep); }                                       // ca_qpos_sine_proj (:320)
-    f.linear(qa, 768, q.qabs, F, c->p_qabs, 2048);
     if (pos_gemm) {
       GemmEpi ep; ep.C = c->p_sb; ep.ldc = 8 * Mpad; ep.c_f32 = 1;
       gemm_bf16_tn(c->p_q2, 256, c->kpos_bd + (size_t)l * 8 * Mpad * 256, 256, F, 8 * Mpad, 256, ep, st);
       f.count();
+      f.side_join(st);
       xattn1(c->p_qabs, c->Xf, S, F, M, nullptr, 0, nullptr, nullptr, 0, 0, nullptr, 0, 0.125f, c->p_ctx8, nullptr, st,
              c->p_sb, Mpad);                                                    // (512/8)^-0.5 (attention.py:151)
     } else {
+      f.side_join(st);
       xattn1(c->p_qabs, c->Xf, S, F, M, nullptr, 0, c->p_q2, c->kposb + (size_t)l * 256, 1536, (long long)S * 1536,
              nullptr, 0, 0.125f, c->p_ctx8, nullptr, st);
     }
+    f.count();
     f.linear_res_ln(c->p_ctx8, 2048, q.vo, F, c->p_x32, q.ln3, 1e-5f, c->p_x2, 256, c->p_x2_32);
     f.linear(c->p_x2, 256, q.ff1, F, c->p_hid, q.ff1.N, ACT_RELU);
     f.linear_res_ln(c->p_hid, q.ff2.K, q.ff2, F, c->p_x2_32, q.ln4, 1e-5f, c->p_cat, 768, c->p_tgt32);
@@ -873,9 +904,10 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
     int prio_lo = 0, prio_hi = 0;
     VG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     VG_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_hi));
+    VG_CUDA(cudaStreamCreateWithPriority(&c->aux2_stream, cudaStreamNonBlocking, prio_hi));
     for (auto& e : c->fj) VG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  f.c = c; f.st = st; f.main = st; f.aux = c->sh_world > 1 ? st : c->aux_stream; f.B = in.clips; f.T = in.T; f.P = in.H * in.W; f.L = in.L; f.S = 2 * f.P + f.L;
+  f.c = c; f.st = st; f.main = st; f.aux = c->sh_world > 1 ? st : c->aux_stream; f.aux2 = c->sh_world > 1 ? st : c->aux2_stream; f.B = in.clips; f.T = in.T; f.P = in.H * in.W; f.L = in.L; f.S = 2 * f.P + f.L;
   f.F = f.B * f.T; f.R = f.F * f.S;
   const int F = f.F, D = (int)c->tl.size();
   const bool have_mask = in.vis_mask != nullptr || in.text_mask != nullptr;
@@ -1001,6 +1033,7 @@ void vgqa_destroy(vgqa_ctx* c) {
     if (b.dec_done) cudaEventDestroy(b.dec_done);
   }
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->aux2_stream) cudaStreamDestroy(c->aux2_stream);
   for (auto& e : c->fj) if (e) cudaEventDestroy(e);
   c->warena.release();
   c->ws.release();
@@ -1082,6 +1115,7 @@ static int run_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out
     forward_phase(c, in, out, phase, ex);  // eager warm-up (sets function attributes, validates, produces valid data)
     VG_CUDA(cudaStreamSynchronize(ex));
     VG_CUDA(cudaStreamSynchronize(c->aux_stream));
+    VG_CUDA(cudaStreamSynchronize(c->aux2_stream));
     cudaGraph_t graph = nullptr;
     VG_CUDA(cudaStreamBeginCapture(ex, cudaStreamCaptureModeThreadLocal));
     try {
