@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 T, H, W, L = 64, 7, 7, 20
+METRIC = "grounding clips/sec (64f@224, bf16)"   # BASELINE.json's metric; both arms print the same string
 WORKLOAD = "cfg2 grounding_vidstg.yaml@224: T=64 frames, 7x7 feature map, L=20 text tokens, 6 enc + 6 dec layers, 2 decoder passes"
 
 
@@ -106,7 +107,7 @@ def run_reference_arm(args, rank):
         if i >= args.warmup:
             t_steps.append(time.perf_counter() - t0)
     v = len(t_steps) / sum(t_steps)
-    line = {"impl": "reference", "metric": "grounding clips/sec (64f@224)", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(t_steps) / len(t_steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clips_per_step": 1},
@@ -289,7 +290,7 @@ def main():
         flops_clip = reference_flops(T, H, W, L)
         roof = time_dominant_kernel(B, pk)
         line = {
-            "metric": "grounding clips/sec (64f@224, bf16)", "value": value, "unit": "clips/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clips_per_step_per_gpu": B, "T": T, "H": H, "W": W, "L": L,
