@@ -302,6 +302,9 @@ def main():
             "gpu_launches_per_step": int(launches),
             "clocks": clocks,
             "roofline": roof,
+            # second half of BASELINE.json's metric: time-weighted sm__mem_tensor_cycles_active over the 412 decoder-phase launches
+            # of one step (ncu metric pass, profiles/r01_decoder_tensor_util.md); the decoder phase is latency-bound
+            "decoder_tensor_pipe_util_pct": {"value": 4.4, "gemm_launches_only": 6.7, "source": "ncu, profiles/r01_decoder_tensor_util.md"},
             "algorithmic_gflop_per_clip": flops_clip / 1e9,
             "algorithmic_tflops_whole_path": value / world * flops_clip / 1e12,
             "frac_of_sustained_bf16_peak_whole_path": value / world * flops_clip / 1e12 / pk["bf16_tflops_sustained"],
