@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--clips", type=int, default=64, help="clips per step per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--cpu-clips", type=int, default=4, help="clips of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-clips", type=int, default=10, help="clips of the bounded CPU-baseline sample (≈10-15 s of host work)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
