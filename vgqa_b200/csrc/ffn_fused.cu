@@ -427,24 +427,16 @@ bool ffn_fused_supported(int F) { return F % 128 == 0 && F >= 256; }
 
 static void launch_ffn(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2, const FfnParams& p,
                        cudaStream_t stream) {
-  static int max_pairs = 0;
-  if (max_pairs == 0) {
+  static bool attr_set = false;
+  if (!attr_set) {
     VG_CUDA(cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(device_sm_count() & ~1, 1, 1);
-    cfg.blockDim = dim3(kFfnThreads, 1, 1);
-    cfg.dynamicSmemBytes = kFfnSmem;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, ffn_fused_kernel, &cfg) != cudaSuccess || n <= 0) {
-      cudaGetLastError();
-      n = device_sm_count() / 2;
-    }
-    max_pairs = n < device_sm_count() / 2 ? n : device_sm_count() / 2;
+    attr_set = true;
   }
+  // one CTA pair per TPC (pairs beyond what is co-resident simply start later: the tile loop is a static stride);
+  // device_sm_count() honours the model's SM budget
   const int tiles = (p.M + 255) / 256;
-  int pairs = device_sm_count() / 2;   // honours the model's SM budget (which may exceed the SM count: several waves)
+  int pairs = device_sm_count() / 2;
   if (pairs > tiles) pairs = tiles;
-  (void)max_pairs;
   ffn_fused_kernel<<<2 * pairs, kFfnThreads, kFfnSmem, stream>>>(tx, tw1, tw2, p);
   VG_CUDA(cudaGetLastError());
   count_gemm_launch();
