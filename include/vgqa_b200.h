@@ -139,6 +139,16 @@ int vgqa_forward_host_wait(vgqa_ctx* ctx, int slot);
 typedef void (*vgqa_exchange_fn)(void* user, int op, const void* send, void* recv, long long count, int dtype, void* stream);
 int vgqa_set_sharding(vgqa_ctx* ctx, int rank, int world, vgqa_exchange_fn fn, void* user);
 
+/* The same sharding with the exchanges done ON THE DEVICE over NVLink peer memory (vgqa_b200/csrc/p2p_exchange.cu) instead of the
+ * callback: every rank calls _export (allocates its peer-mappable exchange buffer, returns a 64-byte cudaIpcMemHandle), the
+ * ranks all-gather the handles by any host channel, every rank calls _import with the world x 64 bytes (rank-major).  From then
+ * on the forward of this context is a frame shard of a `world`-rank clip whose all-gathers / all-reduces are single kernels
+ * (push to every peer, release/acquire flags, local reduce) — no host callback, so it is captured into a CUDA graph like the
+ * unsharded forward.  All ranks must issue the same sequence of forwards.  _error returns 1 if a wait ever timed out (≈2 s). */
+int vgqa_shard_p2p_export(vgqa_ctx* ctx, int rank, int world, unsigned char* handle_out /* 64 bytes */);
+int vgqa_shard_p2p_import(vgqa_ctx* ctx, int rank, int world, const unsigned char* handles /* world * 64 bytes */);
+int vgqa_shard_p2p_error(vgqa_ctx* ctx);
+
 /* PostProcess.forward (vgqa/core/postprocessor.py:14-50) on device tensors: boxes [clips,T,4] cxcywh, sted [clips,T,2],
  * sizes_hw [clips,2] → boxes_px [clips,T,4] xyxy pixels (clamped at 0), sted_idx int32 [clips,2] = argmax (start,end), start < end. */
 int vgqa_postprocess(const float* boxes, const float* sted, const float* sizes_hw, float* boxes_px, int32_t* sted_idx,

@@ -24,7 +24,12 @@ T, H, W, L, seed = (int(g[k]) for k in ("T", "H", "W", "L", "seed"))
 sd = O.synth_state_dict(seed, max_video_len=int(g["max_video_len"]))
 vis, vid, pos, text = O.synth_inputs(seed, T, H, W, L)
 s, e = shard_frames(T, world, rank)
-eng = GroundingEngine(sd, max_clips=1, max_frames=e - s, max_hw=H * W, max_text=L, max_video_len=int(g["max_video_len"]))
+# VGQA_SHARD_P2P=1: exchanges on the device over NVLink peer memory (CUDA-graph forward) instead of the NCCL callback (eager)
+p2p = os.environ.get("VGQA_SHARD_P2P") == "1"
+eng = GroundingEngine(sd, max_clips=1, max_frames=e - s, max_hw=H * W, max_text=L, max_video_len=int(g["max_video_len"]),
+                      use_cuda_graph=p2p)
+if p2p:
+    eng.enable_p2p_sharding(rank, world)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 args = (t(vis[None, s:e]), t(vid[None, s:e]), t(text[None, :, 0]), t(pos[:1]))
 out = forward_sharded_clip(eng, *args, ori_size_hw=(int(g["ori_size"][0]), int(g["ori_size"][1])))
@@ -51,5 +56,5 @@ dt = (time.perf_counter() - t0) / n
 if rank == 0:
     ok = all(v <= 2e-2 for v in errs.values()) and sel_ok and sted_ok
     print(f"SHARDED world={world} T={T} ({e - s} frames/rank): max-abs errors {errs} selection_identical={sel_ok} "
-          f"sted_argmax_identical={sted_ok} -> {'PASS' if ok else 'FAIL'}; {dt * 1e3:.2f} ms per clip (eager, {world} GPUs)")
+          f"sted_argmax_identical={sted_ok} -> {'PASS' if ok else 'FAIL'}; {dt * 1e3:.2f} ms per clip ({'peer-memory exchange, CUDA graph' if p2p else 'NCCL callback, eager'}, {world} GPUs), p2p_error={eng.p2p_error()}")
 dist.destroy_process_group()

@@ -70,4 +70,12 @@ void copy_cols_bf16(const bf16* src, int lds, bf16* dst, int ldd, int rows, int 
 void postprocess(const float* boxes, const float* sted, const float* sizes_hw, float* boxes_px, int* sted_idx, int B,
                  int T, cudaStream_t st);
 
+// ---- p2p_exchange.cu: device-side all-gather / all-reduce of a frame-sharded clip over NVLink peer memory
+void p2p_export(void*& state, int rank, int world, long long slot_bytes, unsigned char handle_out[64]);
+void p2p_import(void*& state, const unsigned char* handles);   // world x 64 bytes, rank-major
+bool p2p_ready(void* state);
+void p2p_exchange(void* state, int op, const void* send, void* recv, long long bytes, cudaStream_t st);   // op 0 gather, 1 fp32 sum
+int p2p_error(void* state);
+void p2p_destroy(void*& state);
+
 }  // namespace vg

@@ -188,6 +188,7 @@ struct vgqa_ctx {
   int sh_rank = 0, sh_world = 1;
   vgqa_exchange_fn sh_fn = nullptr;
   void* sh_user = nullptr;
+  void* p2p = nullptr;   // device-side exchange over peer memory (p2p_exchange.cu); replaces the callback when set up
   float *text_sums, *red[2];
   bf16 *t_qkv_all, *p_qkv_all;   // all-gathered in-projection rows of the temporal self-attention
   // graph cache
@@ -621,10 +622,13 @@ struct Fwd {
   int T_global() const { return T * c->sh_world; }
   // in-place sum over ranks of `n` fp32 values (no-op for a single rank)
   void all_reduce_f32(float* buf, size_t n) {
-    if (sharded()) c->sh_fn(c->sh_user, 1, buf, buf, (long long)n, 1, st);
+    if (!sharded()) return;
+    if (p2p_ready(c->p2p)) { p2p_exchange(c->p2p, 1, buf, buf, (long long)n * 4, st); ++c->launches; return; }
+    c->sh_fn(c->sh_user, 1, buf, buf, (long long)n, 1, st);
   }
   // recv[world][rows_local * cols] <- every rank's send[rows_local * cols] (bf16)
   void all_gather_bf16(const bf16* send, bf16* recv, size_t elems_per_rank) {
+    if (p2p_ready(c->p2p)) { p2p_exchange(c->p2p, 0, send, recv, (long long)elems_per_rank * 2, st); ++c->launches; return; }
     c->sh_fn(c->sh_user, 0, send, recv, (long long)elems_per_rank, 0, st);
   }
 };
@@ -1034,6 +1038,7 @@ void vgqa_destroy(vgqa_ctx* c) {
   }
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   if (c->aux2_stream) cudaStreamDestroy(c->aux2_stream);
+  vg::p2p_destroy(c->p2p);
   for (auto& e : c->fj) if (e) cudaEventDestroy(e);
   c->warena.release();
   c->ws.release();
@@ -1147,7 +1152,9 @@ static void forward_async(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
   ensure_streams(c);
   select_slot(c, slot);
   vgqa_ctx::Boundary& b = c->bd[slot];
-  const bool eager = !c->cfg.use_cuda_graph || out.encoded_feature != nullptr || in.stop_after_encoder || c->sh_world > 1;
+  // a sharded forward that exchanges through the host callback (NCCL) cannot be captured; the peer-memory exchange can
+  const bool eager = !c->cfg.use_cuda_graph || out.encoded_feature != nullptr || in.stop_after_encoder ||
+                     (c->sh_world > 1 && !p2p_ready(c->p2p));
   VG_CUDA(cudaEventRecord(b.ev_in, st));
   VG_CUDA(cudaStreamWaitEvent(c->enc_stream, b.ev_in, 0));
   if (b.used) VG_CUDA(cudaStreamWaitEvent(c->enc_stream, b.dec_done, 0));  // phase 1 of the previous user of this slot
@@ -1273,6 +1280,31 @@ int vgqa_set_sharding(vgqa_ctx* c, int rank, int world, vgqa_exchange_fn fn, voi
     c->sh_rank = rank; c->sh_world = world; c->sh_fn = fn; c->sh_user = user;
     return 0;
   } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_shard_p2p_export(vgqa_ctx* c, int rank, int world, unsigned char* handle_out) {
+  try {
+    VG_CHECK(c && handle_out, "bad argument");
+    const vgqa_config& g = c->cfg;
+    long long slot = (long long)g.max_frames * 768 * 2;                                  // temporal-attention Q|K|V rows
+    slot = std::max(slot, (long long)g.max_clips * g.max_text * 256 * 4);                // text-token sums
+    slot = std::max(slot, (long long)g.max_clips * 320 * 4);                             // classifier / seed sums
+    vg::p2p_export(c->p2p, rank, world, slot, handle_out);
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_shard_p2p_import(vgqa_ctx* c, int rank, int world, const unsigned char* handles) {
+  try {
+    VG_CHECK(c && handles && world >= 2 && rank >= 0 && rank < world, "bad argument");
+    vg::p2p_import(c->p2p, handles);
+    c->sh_rank = rank; c->sh_world = world;
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_shard_p2p_error(vgqa_ctx* c) {
+  try { return c ? vg::p2p_error(c->p2p) : 0; } catch (const std::exception& e) { vg::set_last_error(e.what()); return -1; }
 }
 
 int vgqa_postprocess(const float* boxes, const float* sted, const float* sizes_hw, float* boxes_px, int32_t* sted_idx,

@@ -124,6 +124,33 @@ class GroundingEngine:
         fn = ctypes.cast(exchange_cb, c_void_p) if exchange_cb is not None else None
         _lib.check(self._L.vgqa_set_sharding(self._ctx, rank, world, fn, None))
 
+    def enable_p2p_sharding(self, rank: int, world: int, group=None):
+        """Frame-shard one long clip over `world` ranks with the exchanges done on the device over NVLink peer memory
+        (csrc/p2p_exchange.cu) — no NCCL call inside the forward, which is therefore captured into a CUDA graph.  The
+        64-byte IPC handles of the ranks' exchange buffers are all-gathered once through torch.distributed."""
+        import torch.distributed as dist
+        L = self._L
+        L.vgqa_shard_p2p_export.restype = c_int
+        L.vgqa_shard_p2p_export.argtypes = [c_void_p, c_int, c_int, c_void_p]
+        L.vgqa_shard_p2p_import.restype = c_int
+        L.vgqa_shard_p2p_import.argtypes = [c_void_p, c_int, c_int, c_void_p]
+        L.vgqa_shard_p2p_error.restype = c_int
+        L.vgqa_shard_p2p_error.argtypes = [c_void_p]
+        mine = (ctypes.c_ubyte * 64)()
+        _lib.check(L.vgqa_shard_p2p_export(self._ctx, rank, world, mine))
+        backend = dist.get_backend(group)
+        dev = self.device if backend == "nccl" else torch.device("cpu")
+        local = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        allh = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, local, group=group)
+        buf = (ctypes.c_ubyte * (world * 64))(*allh.cpu().tolist())
+        _lib.check(L.vgqa_shard_p2p_import(self._ctx, rank, world, buf))
+        dist.barrier(group=group)   # every rank has mapped every buffer before anyone pushes
+        self._shard_cfg, self._shard_errors, self._p2p = (rank, world), [], True
+
+    def p2p_error(self) -> int:
+        return int(self._L.vgqa_shard_p2p_error(self._ctx)) if getattr(self, "_p2p", False) else 0
+
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
             self._L.vgqa_destroy(self._ctx)

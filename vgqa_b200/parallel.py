@@ -81,7 +81,7 @@ def forward_sharded_clip(engine, vis, vid, text, pos, *, ori_size_hw, group=None
     from . import _lib
     from .engine import _declare
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    if getattr(engine, "_shard_cfg", None) != (rank, world):
+    if getattr(engine, "_shard_cfg", None) != (rank, world):   # not set up yet (engine.enable_p2p_sharding sets it, too)
         cb, errors = nccl_exchange(group)
         engine.set_sharding(rank, world, cb)
         engine._shard_cfg, engine._shard_errors = (rank, world), errors
