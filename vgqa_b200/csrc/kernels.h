@@ -74,7 +74,7 @@ void postprocess(const float* boxes, const float* sted, const float* sizes_hw, f
 void p2p_export(void*& state, int rank, int world, long long slot_bytes, unsigned char handle_out[64]);
 void p2p_import(void*& state, const unsigned char* handles);   // world x 64 bytes, rank-major
 bool p2p_ready(void* state);
-void p2p_exchange(void* state, int op, const void* send, void* recv, long long bytes, cudaStream_t st);   // op 0 gather, 1 fp32 sum
+void p2p_exchange(void* state, int op, const void* send, void* recv, long long bytes, int channel, cudaStream_t st);   // op 0 gather, 1 fp32 sum; channel 0..2
 int p2p_error(void* state);
 void p2p_destroy(void*& state);
 

@@ -619,16 +619,18 @@ struct Fwd {
   }
   void count(int n = 1) { c->launches += n; }
   bool sharded() const { return c->sh_world > 1; }
+  // exchange channel of the peer-memory exchange: one per graph branch, so that every channel sees one global order
+  int channel() const { return st == main ? 0 : (st == aux ? 1 : 2); }
   int T_global() const { return T * c->sh_world; }
   // in-place sum over ranks of `n` fp32 values (no-op for a single rank)
   void all_reduce_f32(float* buf, size_t n) {
     if (!sharded()) return;
-    if (p2p_ready(c->p2p)) { p2p_exchange(c->p2p, 1, buf, buf, (long long)n * 4, st); ++c->launches; return; }
+    if (p2p_ready(c->p2p)) { p2p_exchange(c->p2p, 1, buf, buf, (long long)n * 4, channel(), st); ++c->launches; return; }
     c->sh_fn(c->sh_user, 1, buf, buf, (long long)n, 1, st);
   }
   // recv[world][rows_local * cols] <- every rank's send[rows_local * cols] (bf16)
   void all_gather_bf16(const bf16* send, bf16* recv, size_t elems_per_rank) {
-    if (p2p_ready(c->p2p)) { p2p_exchange(c->p2p, 0, send, recv, (long long)elems_per_rank * 2, st); ++c->launches; return; }
+    if (p2p_ready(c->p2p)) { p2p_exchange(c->p2p, 0, send, recv, (long long)elems_per_rank * 2, channel(), st); ++c->launches; return; }
     c->sh_fn(c->sh_user, 0, send, recv, (long long)elems_per_rank, 0, st);
   }
 };
@@ -911,7 +913,8 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
     VG_CUDA(cudaStreamCreateWithPriority(&c->aux2_stream, cudaStreamNonBlocking, prio_hi));
     for (auto& e : c->fj) VG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  f.c = c; f.st = st; f.main = st; f.aux = c->sh_world > 1 ? st : c->aux_stream; f.aux2 = c->sh_world > 1 ? st : c->aux2_stream; f.B = in.clips; f.T = in.T; f.P = in.H * in.W; f.L = in.L; f.S = 2 * f.P + f.L;
+  f.c = c; f.st = st; f.main = st; const bool one_stream = c->sh_world > 1 && !p2p_ready(c->p2p);   // NCCL-callback sharding: collectives stay in program order
+  f.aux = one_stream ? st : c->aux_stream; f.aux2 = one_stream ? st : c->aux2_stream; f.B = in.clips; f.T = in.T; f.P = in.H * in.W; f.L = in.L; f.S = 2 * f.P + f.L;
   f.F = f.B * f.T; f.R = f.F * f.S;
   const int F = f.F, D = (int)c->tl.size();
   const bool have_mask = in.vis_mask != nullptr || in.text_mask != nullptr;

@@ -1,7 +1,9 @@
 // Device-side exchange for a frame-sharded clip: all-gather / all-reduce over NVLink peer memory, no NCCL, no
 // host callback — so the sharded forward is one capturable stream of kernels.
 //
-// Every rank owns one peer-mapped buffer (cudaMalloc + cudaIpc):   [ control block | recv[2 parities][world slots][slot bytes] ]
+// Every rank owns one peer-mapped buffer (cudaMalloc + cudaIpc) with kChannels independent channels (one per concurrent graph
+// branch of the forward; exchanges of one channel are totally ordered, different channels never interact):
+//   [ control block x kChannels | recv[kChannels][2 parities][world slots][slot bytes] ]
 // One exchange = ONE kernel per rank (all of them run at the same point of their streams):
 //   push    my `bytes` go into slot[my rank] of EVERY rank's recv buffer (16-byte stores over NVLink, parity = seq & 1);
 //           the last CTA to finish pushing publishes seq in flag[my rank] of every rank (st.release.sys)
@@ -31,6 +33,8 @@ struct P2pControl {            // at the start of every rank's exchange buffer
 };
 static_assert(sizeof(P2pControl) == 256, "control block");
 
+static constexpr int kP2pChannels = 3;
+
 struct P2pParams {
   unsigned char* peer[16];     // peer[q] = base of rank q's exchange buffer as mapped in THIS process
   int rank, world;
@@ -48,13 +52,13 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 
 // op 0: gather (recv gets world * bytes), op 1: fp32 sum (recv gets bytes); send may alias recv for op 1.
 __global__ void __launch_bounds__(512) p2p_exchange_kernel(const P2pParams p, const unsigned char* send, unsigned char* recv,
-                                                           long long bytes, int op) {
-  P2pControl* ctl = reinterpret_cast<P2pControl*>(p.peer[p.rank]);
+                                                           long long bytes, int op, int ch) {
+  P2pControl* ctl = reinterpret_cast<P2pControl*>(p.peer[p.rank]) + ch;
   __shared__ unsigned long long s_seq;
   if (threadIdx.x == 0) s_seq = *reinterpret_cast<volatile unsigned long long*>(&ctl->seq) + 1;
   __syncthreads();
   const unsigned long long seq = s_seq;
-  const long long par_off = 256 + (long long)(seq & 1) * p.world * p.slot_bytes;
+  const long long par_off = 256 * kP2pChannels + ((long long)ch * 2 + (long long)(seq & 1)) * p.world * p.slot_bytes;
   const long long n16 = bytes >> 4;
   const int tail = (int)((bytes & 15) >> 2);   // bytes is a multiple of 4 (checked on the host): up to 3 trailing words
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(512) p2p_exchange_kernel(const P2pParams p, co
       ctl->pushed = 0;
       __threadfence_system();
       for (int q = 0; q < p.world; ++q)
-        st_release_sys(&reinterpret_cast<P2pControl*>(p.peer[q])->flag[p.rank], seq);
+        st_release_sys(&(reinterpret_cast<P2pControl*>(p.peer[q]) + ch)->flag[p.rank], seq);
     }
     // ---- wait for every rank's push into my buffer (bounded)
     const long long t0 = clock64();
@@ -131,7 +135,7 @@ void p2p_export(void*& opaque, int rank, int world, long long slot_bytes, unsign
   P2pState* s = state(opaque);
   VG_CHECK(s->own == nullptr, "p2p exchange buffer already exported");
   slot_bytes = (slot_bytes + 255) / 256 * 256;
-  s->bytes = 256 + (size_t)2 * world * slot_bytes;
+  s->bytes = 256 * kP2pChannels + (size_t)kP2pChannels * 2 * world * slot_bytes;
   VG_CUDA(cudaMalloc(&s->own, s->bytes));
   VG_CUDA(cudaMemset(s->own, 0, s->bytes));
   VG_CUDA(cudaDeviceSynchronize());
@@ -160,25 +164,30 @@ void p2p_import(void*& opaque, const unsigned char* handles) {
 
 bool p2p_ready(void* opaque) { return opaque != nullptr && static_cast<P2pState*>(opaque)->imported; }
 
-void p2p_exchange(void* opaque, int op, const void* send, void* recv, long long bytes, cudaStream_t st) {
+void p2p_exchange(void* opaque, int op, const void* send, void* recv, long long bytes, int channel, cudaStream_t st) {
   P2pState* s = static_cast<P2pState*>(opaque);
   VG_CHECK(s && s->imported, "p2p exchange is not set up");
+  VG_CHECK(channel >= 0 && channel < kP2pChannels, "p2p exchange: bad channel");
   VG_CHECK(bytes > 0 && bytes % 4 == 0 && bytes <= s->prm.slot_bytes, "p2p exchange: payload must be a multiple of 4 bytes and fit a slot");
   VG_CHECK((reinterpret_cast<uintptr_t>(send) & 15) == 0 && (reinterpret_cast<uintptr_t>(recv) & 15) == 0, "p2p exchange: unaligned buffer");
   VG_CHECK(op == 1 || bytes % 16 == 0, "p2p exchange: gathered payloads must be multiples of 16 bytes");
   int grid = (int)((bytes / 16 + 511) / 512);
   if (grid < 1) grid = 1;
   if (grid > 16) grid = 16;   // all CTAs must be co-resident: they wait for one another's pushes
-  p2p_exchange_kernel<<<grid, 512, 0, st>>>(s->prm, static_cast<const unsigned char*>(send), static_cast<unsigned char*>(recv), bytes, op);
+  p2p_exchange_kernel<<<grid, 512, 0, st>>>(s->prm, static_cast<const unsigned char*>(send), static_cast<unsigned char*>(recv), bytes, op, channel);
   VG_CUDA(cudaGetLastError());
 }
 
 int p2p_error(void* opaque) {
   P2pState* s = static_cast<P2pState*>(opaque);
   if (!s || !s->own) return 0;
-  unsigned int e = 0;
-  VG_CUDA(cudaMemcpy(&e, s->own + offsetof(P2pControl, error), 4, cudaMemcpyDeviceToHost));
-  return (int)e;
+  unsigned int any = 0;
+  for (int ch = 0; ch < kP2pChannels; ++ch) {
+    unsigned int e = 0;
+    VG_CUDA(cudaMemcpy(&e, s->own + ch * sizeof(P2pControl) + offsetof(P2pControl, error), 4, cudaMemcpyDeviceToHost));
+    any |= e;
+  }
+  return (int)any;
 }
 
 void p2p_destroy(void*& opaque) {
