@@ -28,10 +28,24 @@ s, e = shard_frames(T, world, rank)
 p2p = os.environ.get("VGQA_SHARD_P2P") == "1"
 eng = GroundingEngine(sd, max_clips=1, max_frames=e - s, max_hw=H * W, max_text=L, max_video_len=int(g["max_video_len"]),
                       use_cuda_graph=p2p)
-if p2p:
+if p2p and world > 1:
     eng.enable_p2p_sharding(rank, world)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 args = (t(vis[None, s:e]), t(vid[None, s:e]), t(text[None, :, 0]), t(pos[:1]))
+if world == 1:
+    # reference point: the same clip unsharded on one GPU (CUDA graph when VGQA_SHARD_P2P=1, else eager)
+    sizes = torch.tensor([[360.0, 640.0]], device="cuda")
+    run = lambda: eng.forward(*args, ori_sizes_hw=sizes, want=["pred_boxes", "pred_sted", "boxes_px", "sted_idx"])
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        run()
+    torch.cuda.synchronize()
+    print(f"UNSHARDED T={T} on one GPU: {(time.perf_counter() - t0) / 10 * 1e3:.2f} ms per clip ({'CUDA graph' if p2p else 'eager'})")
+    dist.destroy_process_group()
+    sys.exit(0)
 out = forward_sharded_clip(eng, *args, ori_size_hw=(int(g["ori_size"][0]), int(g["ori_size"][1])))
 torch.cuda.synchronize()
 errs = {"pred_boxes": float(np.abs(out["pred_boxes"].cpu().numpy() - g["pred_boxes"]).max()),
