@@ -67,6 +67,18 @@ typedef struct {
   int iteration_rate; /* < 0 (inference): two decoder passes; >= 0: one pass (grounding_net.py:143) */
   int stop_after_encoder; /* 1: run CrossModalEncoder only (outputs encoded_feature / frames_cls) — the
                              `build_encoder(cfg)` seam (vgqa/core/decoder/__init__.py:6-8) */
+  /* Optional RAW extractor outputs.  A non-NULL pointer replaces vis / vid / text (which may then be
+   * NULL) and the library applies the reference's own projection on the way into the encoder's token rows:
+   *   vis_raw  [clips, T, vis_raw_ch, H, W]  ResNet101 layer-4 map   → input_proj  (Conv2d 1x1, grounding_net.py:62,101)
+   *   vid_raw  [clips, T, vid_raw_ch, H, W]  Video-Swin stage-3 map  → input_proj2 (Conv2d 1x1, grounding_net.py:71,105)
+   *   text_raw [clips, L, text_raw_ch]       RoBERTa last_hidden_state → text_encoder.resizer (Linear + LayerNorm 1e-12,
+   *                                          vgqa/core/language/bert.py:63-96)
+   * Channel counts must match the weights given to vgqa_set_weight ("input_proj.weight" [256,C,1,1], "input_proj2.weight",
+   * "text_encoder.resizer.fc.weight" [256,C]) and be multiples of 64; a raw input whose weights were not set is an error. */
+  const float* vis_raw;
+  const float* vid_raw;
+  const float* text_raw;
+  int vis_raw_ch, vid_raw_ch, text_raw_ch;
 } vgqa_inputs;
 
 /* Outputs (fp32 unless noted); any pointer may be NULL to skip that output.
@@ -175,6 +187,11 @@ int vgqa_enc_attn(const void* QKV, void* AO, int F, int S, const uint8_t* kmask,
 int vgqa_xattn1(const void* qt, const void* mem, long long frame_stride_rows, int F, int Mk, const void* posk,
                 long long posk_fstride, const void* q2, const void* kpos, int ldkpos, long long kpos_fstride,
                 const uint8_t* kmask, int ldmask, float scale, void* ctx_out, float* att_out, void* stream);
+/* input_proj / input_proj2 (1x1 Conv2d, grounding_net.py:62,71,101,105) fused with the token-major re-layout:
+ *   X[(f*S + tok0 + p), :] = W in[f, :, p] + bias  for f < F, p < P;   in [F, C, P] fp32 (NCHW), W [256, C] bf16, C % 64 == 0.
+ * X (bf16), X32 (fp32, optional), XP = bf16(x + pos row) (optional; pos [pos_frames*S, 256] bf16, pos_frames 1 or F). */
+int vgqa_input_proj(const float* in, int C, const void* W, const float* bias, const void* pos, int pos_frames, void* X,
+                    float* X32, void* XP, int F, int S, int tok0, int P, void* stream);
 /* Same op with the positional score terms supplied as an additive table sbias[F, 8, ldsb] (fp32, unscaled) — the form the
  * decoders use when `pos` is frame-invariant; runs the warp-per-frame streaming kernel (xattn_stream.cu). */
 int vgqa_xattn1_bias(const void* qt, const void* mem, long long frame_stride_rows, int F, int Mk, const float* sbias, int ldsb,

@@ -560,12 +560,31 @@ def input_proj(x: np.ndarray, w: np.ndarray, b: np.ndarray) -> np.ndarray:
     return y.reshape(T, H, W, -1).transpose(0, 3, 1, 2).astype(F32)
 
 
+def feature_resizer(x: np.ndarray, sd: Dict[str, np.ndarray], prefix: str = "text_encoder.resizer") -> np.ndarray:
+    """FeatureResizer — vgqa/core/language/bert.py:77-96: fc → nn.LayerNorm(eps=1e-12) → dropout (identity in eval)."""
+    y = linear(x, sd[prefix + ".fc.weight"], sd[prefix + ".fc.bias"])
+    return layer_norm(y, sd[prefix + ".layer_norm.weight"], sd[prefix + ".layer_norm.bias"], 1e-12)
+
+
+def front_end(sd, vis_raw: np.ndarray, vid_raw: np.ndarray, text_raw: np.ndarray):
+    """The step right before the hot path: grounding_net.py:101 `input_proj(vis_res_features)`,
+    :105 `input_proj2(vid_features_all['3'])`, bert.py:70,73 `resizer(last_hidden_state.transpose(0, 1))`.
+
+    vis_raw (T,Cv,H,W), vid_raw (T,Cd,H,W), text_raw (L,Ct) → vis (T,256,H,W), vid (T,256,H,W), text (L,1,256)."""
+    vis = input_proj(vis_raw, sd["input_proj.weight"], sd["input_proj.bias"])
+    vid = input_proj(vid_raw, sd["input_proj2.weight"], sd["input_proj2.bias"])
+    text = feature_resizer(text_raw, sd)[:, None, :]
+    return vis, vid, text
+
+
 # ----------------------------------------------------------------------------------------------
 # deterministic synthetic weights / inputs shared by golden maker, tests, bench and smoke
 # ----------------------------------------------------------------------------------------------
 def hot_path_param_shapes(enc_layers=6, dec_layers=6, d=256, ffn=2048, max_video_len=200,
-                          app_num=20, mot_num=34) -> Dict[str, Tuple[int, ...]]:
-    """Names/shapes of every state_dict entry the hot path READS (subset of SURVEY.md §8b)."""
+                          app_num=20, mot_num=34, front_end_ch: Optional[Tuple[int, int, int]] = None) -> Dict[str, Tuple[int, ...]]:
+    """Names/shapes of every state_dict entry the hot path READS (subset of SURVEY.md §8b).  `front_end_ch` =
+    (ResNet channels, Video-Swin channels, RoBERTa hidden) appends `input_proj`, `input_proj2` and
+    `text_encoder.resizer` AFTER every other entry (so the hot-path weights of a seed do not depend on it)."""
     s: Dict[str, Tuple[int, ...]] = {}
 
     def lin(name, o, i):
@@ -613,6 +632,11 @@ def hot_path_param_shapes(enc_layers=6, dec_layers=6, d=256, ffn=2048, max_video
     lin("bbox_embed.layers.0", d, d); lin("bbox_embed.layers.1", d, d); lin("bbox_embed.layers.2", 4, d)
     lin("temp_embed.layers.0", d, d); lin("temp_embed.layers.1", 2, d)
     lin("action_embed.layers.0", d, d); lin("action_embed.layers.1", 1, d)
+    if front_end_ch is not None:
+        cv, cd, ct = front_end_ch
+        s["input_proj.weight"] = (d, cv, 1, 1); s["input_proj.bias"] = (d,)
+        s["input_proj2.weight"] = (d, cd, 1, 1); s["input_proj2.bias"] = (d,)
+        lin("text_encoder.resizer.fc", d, ct); ln("text_encoder.resizer.layer_norm")
     return s
 
 
@@ -650,6 +674,16 @@ def synth_inputs(seed: int, T: int, H: int, W: int, L: int, d: int = 256):
     text = rng.standard_normal((L, 1, d), dtype=F32)
     pos = position_embedding_sine(np.zeros((T, H, W), bool))
     return vis, vid, pos, text
+
+
+def synth_raw_inputs(seed: int, T: int, H: int, W: int, L: int, ch: Tuple[int, int, int] = (2048, 768, 768)):
+    """Synthetic extractor outputs for the front end: a non-negative (post-ReLU, like ResNet layer 4) map, a
+    normal Video-Swin map and normal RoBERTa hidden states."""
+    rng = np.random.Generator(np.random.PCG64(5000 + seed))
+    vis_raw = np.maximum(rng.standard_normal((T, ch[0], H, W), dtype=F32), 0)
+    vid_raw = rng.standard_normal((T, ch[1], H, W), dtype=F32)
+    text_raw = rng.standard_normal((L, ch[2]), dtype=F32)
+    return vis_raw, vid_raw, text_raw
 
 
 def synth_masks(masked: bool, T: int, H: int, W: int, L: int):

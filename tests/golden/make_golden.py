@@ -130,13 +130,15 @@ def load_synth(model: torch.nn.Module, sd_np):
 masks_for = O.synth_masks
 
 
-def run_case(R, name, T, H, W, L, seed, max_len, masked, outdir):
+def run_case(R, name, T, H, W, L, seed, max_len, masked, outdir, inputs=None, extra=None):
+    """`inputs` = (vis, vid, text) overrides the synthetic hot-path-boundary inputs (make_golden_frontend.py feeds the
+    reference front end's outputs through here); `extra` entries are stored with the record."""
     cfg = make_cfg(max_video_len=max_len)
     torch.manual_seed(0)
     model = RefHotPath(R, cfg).eval()
     sd = O.synth_state_dict(seed, max_video_len=max_len)
     load_synth(model, sd)
-    vis, vid, _, text = O.synth_inputs(seed, T, H, W, L)
+    vis, vid, _, text = O.synth_inputs(seed, T, H, W, L) if inputs is None else (inputs[0], inputs[1], None, inputs[2])
     vis_mask, text_mask = masks_for(masked, T, H, W, L)
     pos_t = R.PositionEmbeddingSine(128, normalize=True)(R.NestedTensor(torch.from_numpy(vis), torch.from_numpy(vis_mask), [T]))
     out, dbg = model(torch.from_numpy(vis), torch.from_numpy(vid), pos_t, torch.from_numpy(text),
@@ -177,6 +179,7 @@ def run_case(R, name, T, H, W, L, seed, max_len, masked, outdir):
         margin_act=np.float32(np.abs(act1 - 0.5).min()),
         margin_sted_top2=np.float32(top2[-1] - top2[-2]),
     )
+    rec.update(extra or {})
     np.savez_compressed(os.path.join(outdir, name + ".npz"), **rec)
     print(f"{name}: K1={len(dbg['choose_pass1'])} K2={len(dbg['choose_pass2'])} sted={steds} "
           f"margins theta={rec['margin_theta']:.4g} act={rec['margin_act']:.4g} top2={rec['margin_sted_top2']:.4g}")

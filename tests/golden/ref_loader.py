@@ -92,6 +92,21 @@ def load_reference():
     return ns
 
 
+def load_feature_resizer():
+    """`FeatureResizer` of the text encoder (vgqa/core/language/bert.py:77-96).  bert.py imports
+    `pytorch_pretrained_bert` (absent here, import-time only) — stubbed; `transformers` is installed."""
+    load_reference()
+    if "pytorch_pretrained_bert" not in sys.modules:
+        ppb = types.ModuleType("pytorch_pretrained_bert")
+        ppb.__path__ = []
+        mod = types.ModuleType("pytorch_pretrained_bert.modeling")
+        mod.BertModel = object
+        ppb.modeling = mod
+        sys.modules["pytorch_pretrained_bert"] = ppb
+        sys.modules["pytorch_pretrained_bert.modeling"] = mod
+    return importlib.import_module("vgqa.core.language.bert").FeatureResizer
+
+
 def make_cfg(max_video_len: int = 200, hidden=256, heads=8, ffn=2048, enc_layers=6, dec_layers=6):
     """Attribute-tree stand-in for the yacs cfg: only the keys the hot path reads at construction
     (vgqa/config/defaults.py:7,63-72; SOLVER.USE_ATTN :153)."""

@@ -90,6 +90,25 @@ def bench_ffn(M, F=2048, parts=0):
     print(f"ffn_fused M={M} F={F}: {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s  {byts / t / 1e3:7.1f} GB/s")
 
 
+def bench_input_proj(F=4096, C=2048, H=7, W=7, Lt=20, second=False, name=""):
+    import ctypes
+    L.vgqa_input_proj.restype = ctypes.c_int
+    L.vgqa_input_proj.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int] + [ctypes.c_void_p] * 3 + \
+        [ctypes.c_int] * 4 + [ctypes.c_void_p]
+    P = H * W
+    S = 2 * P + Lt
+    x = torch.randn(F, C, H, W, device="cuda")
+    Wt = (torch.randn(256, C, device="cuda") / C ** 0.5).bfloat16()
+    b = torch.zeros(256, device="cuda")
+    pos = torch.randn(S, 256, device="cuda").bfloat16()
+    X = torch.empty(F * S, 256, device="cuda", dtype=torch.bfloat16); XP = torch.empty_like(X); X32 = torch.empty(F * S, 256, device="cuda")
+    t = timeit(lambda: _lib.check(L.vgqa_input_proj(_lib.ptr(x), C, _lib.ptr(Wt), _lib.ptr(b), _lib.ptr(pos), 1, _lib.ptr(X), _lib.ptr(X32),
+                                                    _lib.ptr(XP), F, S, (P + Lt) if second else 0, P, st())))
+    flops = 2.0 * F * P * 256 * C
+    byts = F * P * (C * 4.0 + 2048)
+    print(f"input_proj {name} F={F} C={C} P={P}: {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s  {byts / t / 1e3:7.1f} GB/s (algorithmic bytes)")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["attn", "gemm"]
     if "attn" in which:
@@ -101,6 +120,10 @@ if __name__ == "__main__":
         bench_xattn(Mk=49, tok0=69, name="spatial")
         bench_xattn(Mk=69, tok0=0, use_kpos=True, name="pos-decoder")
         bench_xattn(Mk=69, tok0=49, use_pos=True, name="time-decoder")
+    if "input_proj" in which:
+        bench_input_proj(C=2048, name="ResNet101 -> vis tokens")
+        bench_input_proj(C=768, second=True, name="Video-Swin -> vid tokens")
+        bench_input_proj(F=1024, C=2048, H=14, W=14, name="14x14")
     if "ffn" in which:
         bench_ffn(64 * 64 * 118)
         bench_ffn(16 * 64 * 118)

@@ -1,0 +1,297 @@
+// input_proj / input_proj2 of VSTGNet (grounding_net.py:62,71,101,105): the 1x1 Conv2d that maps the extractor feature maps
+// (ResNet101 layer4: 2048 channels, Video-Swin stage 3: 768 channels) to the 256-d tokens of the cross-modal encoder —
+// SURVEY.md §8(f) rank 2, the step immediately before the hot path.
+//
+//   X[(f*S + tok0 + p), n] = sum_c W[n, c] * in[f, c, p] + b[n]        in: [F, C, P] fp32 (NCHW), W: [256, C] bf16
+//
+// writes the three tensors the first encoder layer reads (bf16 x, fp32 residual stream, bf16 x + pos) straight into their
+// token-major rows, so the projected NCHW feature map never exists in HBM (the two-step path wrote 256·P fp32 per frame and
+// read it back through nchw_to_tokens).
+//
+// The op reads 4·C bytes per token and does 512·C FLOP on it: 128 FLOP/B, below the B200 ridge (≈210 FLOP/B), i.e. it is bound
+// by the HBM read of the fp32 features.  The features arrive channel-major ([c][p], p contiguous), the tensor core wants a
+// K-major bf16 operand ([p][c]) — the transpose + conversion happens on the way into shared memory:
+//
+//   warp 0       TMA producer of the W k-blocks (256 x 64 bf16, 128B swizzle), 4-stage ring
+//   warp 1       tcgen05.mma issuer (UMMA 128x256x16), two TMEM accumulators so the epilogue of tile i overlaps tile i+1
+//   warps 2-5    epilogue: TMEM → + bias → X32 / X / XP rows (one token row per thread, 16-byte stores)
+//   warps 6-13   A producers: thread = (token row, 32 of the 64 channels of the k-block); 32 coalesced 4-byte loads (a warp
+//                reads 32 consecutive tokens of one channel), register double-buffered one k-block ahead, packed to bf16 and
+//                written as four 16-byte stores into the 128B-swizzled K-major tile the UMMA descriptor expects
+//
+// A tile is 128 token rows: floor(128 / P) whole frames when a frame has P <= 128 tokens (7x7: two frames, 98 rows), or one
+// 128-row slice of a frame otherwise (14x14: two slices).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vg {
+
+static constexpr int kIpStages = 4;
+static constexpr int kIpABytes = 128 * 64 * 2;
+static constexpr int kIpBBytes = 256 * 64 * 2;
+static constexpr int kIpSmem = kIpStages * (kIpABytes + kIpBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+static constexpr int kIpThreads = 64 + 128 + 256;
+
+struct IpParams {
+  const float* in;     // [F, C, P]
+  const float* bias;   // [256]
+  const bf16* pos;     // token-major positional rows [pos_frames * S, 256] (XP = x + pos) or nullptr when XP is nullptr
+  bf16* X;             // [F*S, 256]
+  float* X32;          // [F*S, 256] or nullptr
+  bf16* XP;            // [F*S, 256] or nullptr
+  int F, C, P, S, tok0;
+  int pos_per_frame;   // 1: pos row = output row; 0: pos row = tok0 + p (one table shared by every frame)
+  int fpt;             // frames per tile (P <= 128), else 0
+  int tpf;             // 128-row slices per frame (P > 128)
+  int num_tiles;
+};
+
+// tile row r → (frame, token); false for the padding rows of a tile
+__device__ __forceinline__ bool ip_row(const IpParams& p, int tile, int r, int& frame, int& tok) {
+  if (p.fpt > 0) {
+    const int fl = r / p.P;
+    frame = tile * p.fpt + fl;
+    tok = r - fl * p.P;
+    return fl < p.fpt && frame < p.F;
+  }
+  frame = tile / p.tpf;
+  tok = (tile - frame * p.tpf) * 128 + r;
+  return tok < p.P;
+}
+
+__global__ void __launch_bounds__(kIpThreads, 1)
+input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kIpStages * kIpABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kIpStages * kIpBBytes);
+  uint64_t* w_full = bars;                     // [stages] TMA bytes of the W k-block
+  uint64_t* a_full = bars + kIpStages;         // [stages] 8 arrivals (one per producer warp)
+  uint64_t* empty_bar = bars + 2 * kIpStages;  // [stages] tcgen05.commit: both operands of the stage are consumed
+  uint64_t* tfull_bar = bars + 3 * kIpStages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2] 4 arrivals (epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = p.C / 64;
+  const int n_my = ((int)blockIdx.x < p.num_tiles) ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_w);
+    for (int s = 0; s < kIpStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&a_full[s], 8); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: W k-blocks =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_my; ++it) {
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&w_full[stage], kIpBBytes);
+          tma_load_2d(smem_b + stage * kIpBBytes, &tma_w, &w_full[stage], kb * 64, 0);
+          if (++stage == kIpStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int it = 0; it < n_my; ++it) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * 256;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&w_full[stage], phase);
+        mbar_wait(&a_full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem_a + stage * kIpABytes));
+          const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem_b + stage * kIpBBytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_k - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == kIpStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp < 6) {
+    // ===================== epilogue: one token row per thread =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int it = 0; it < n_my; ++it) {
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      int frame, tok;
+      const bool valid = ip_row(p, tile, r, frame, tok);
+      const size_t orow = (size_t)frame * p.S + p.tok0 + tok;
+      const size_t prow = p.pos_per_frame ? orow : (size_t)(p.tok0 + tok);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        uint32_t raw[32];
+        float v[32];
+        tmem_ld32(taddr + c * 32, raw);
+        tmem_ld_wait();
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = __ldg(b4 + i);
+          v[4 * i + 0] = __uint_as_float(raw[4 * i + 0]) + b.x; v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + b.y;
+          v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + b.z; v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + b.w;
+        }
+        if (valid) {
+          const size_t o = orow * 256 + c * 32;
+          if (p.X32 != nullptr) {
+            float4* d = reinterpret_cast<float4*>(p.X32 + o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          uint4* d = reinterpret_cast<uint4*>(p.X + o);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            d[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                              pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+          if (p.XP != nullptr) {
+            const uint4* a4 = reinterpret_cast<const uint4*>(p.pos + prow * 256 + c * 32);
+            uint4* d2 = reinterpret_cast<uint4*>(p.XP + o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = __ldg(a4 + i);
+              const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), dd = unpack_bf16(u.w);
+              d2[i] = make_uint4(pack_bf16(v[8 * i] + a.x, v[8 * i + 1] + a.y), pack_bf16(v[8 * i + 2] + b.x, v[8 * i + 3] + b.y),
+                                 pack_bf16(v[8 * i + 4] + cc.x, v[8 * i + 5] + cc.y), pack_bf16(v[8 * i + 6] + dd.x, v[8 * i + 7] + dd.y));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== A producers: fp32 [c][p] (global) → bf16 [p][c] swizzled (shared) =====================
+    const int pt = threadIdx.x - 192;
+    const int r = pt & 127, half = pt >> 7;
+    const size_t cstride = (size_t)p.P;
+    // row base pointer (channel 0 of this thread's token) of my it-th tile, nullptr for padding rows
+    auto row_base = [&](int it) -> const float* {
+      if (it >= n_my) return nullptr;
+      int frame, tok;
+      if (!ip_row(p, (int)blockIdx.x + it * (int)gridDim.x, r, frame, tok)) return nullptr;
+      return p.in + (size_t)frame * p.C * cstride + tok;
+    };
+    auto load = [&](float (&dst)[32], const float* base, int kb) __attribute__((always_inline)) {
+      if (base != nullptr) {
+        const float* src = base + (size_t)(kb * 64 + half * 32) * cstride;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dst[i] = __ldg(src + (size_t)i * cstride);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dst[i] = 0.f;
+      }
+    };
+    float cur[32], nxt[32];
+    const float* base = row_base(0);
+    if (n_my > 0) load(cur, base, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < n_my; ++it) {
+      const float* base_next = row_base(it + 1);
+      for (int kb = 0; kb < num_k; ++kb) {
+        // the loads of the NEXT k-block are in flight while this one is converted and while the ring slot is awaited
+        const bool last_kb = kb + 1 == num_k;
+        if (!last_kb) load(nxt, base, kb + 1);
+        else if (it + 1 < n_my) load(nxt, base_next, 0);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* rowp = smem_a + stage * kIpABytes + r * 128;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(rowp + (((half * 4 + u) ^ (r & 7)) << 4)) =
+              make_uint4(pack_bf16(cur[8 * u], cur[8 * u + 1]), pack_bf16(cur[8 * u + 2], cur[8 * u + 3]),
+                         pack_bf16(cur[8 * u + 4], cur[8 * u + 5]), pack_bf16(cur[8 * u + 6], cur[8 * u + 7]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[stage]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
+        if (++stage == kIpStages) { stage = 0; phase ^= 1; }
+      }
+      base = base_next;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+CUtensorMap make_tmap_2d(const void* ptr, int rows, int cols, int ld, int box_rows, bool f32);  // gemm_tc.cu
+int device_sm_count();
+void count_gemm_launch();
+
+bool input_proj_supported(int C) { return C >= 64 && C % 64 == 0; }
+
+// X / X32 / XP rows [f*S + tok0, +P) of every frame f < F  <-  W in[f] + b  (+ pos); see the header comment.
+void input_proj(const float* in, int C, const bf16* W, const float* bias, const bf16* pos, int pos_frames, bf16* X, float* X32,
+                bf16* XP, int F, int S, int tok0, int P, cudaStream_t stream) {
+  VG_CHECK(input_proj_supported(C), "input_proj: the channel count must be a multiple of 64");
+  VG_CHECK(in && W && bias && X && F > 0 && P > 0 && tok0 >= 0 && tok0 + P <= S, "input_proj: bad arguments");
+  VG_CHECK(XP == nullptr || pos != nullptr, "input_proj: XP needs the positional rows");
+  VG_CHECK(pos_frames == 1 || pos_frames == F, "input_proj: pos_frames must be 1 or F");
+  static bool attr_set = false;
+  if (!attr_set) {
+    VG_CUDA(cudaFuncSetAttribute(input_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpSmem));
+    attr_set = true;
+  }
+  IpParams p;
+  p.in = in; p.bias = bias; p.pos = pos; p.X = X; p.X32 = X32; p.XP = XP;
+  p.F = F; p.C = C; p.P = P; p.S = S; p.tok0 = tok0; p.pos_per_frame = pos_frames > 1 ? 1 : 0;
+  if (P <= 128) { p.fpt = 128 / P; p.tpf = 1; p.num_tiles = (F + p.fpt - 1) / p.fpt; }
+  else { p.fpt = 0; p.tpf = (P + 127) / 128; p.num_tiles = F * p.tpf; }
+  CUtensorMap tw = make_tmap_2d(W, 256, C, C, 256, false);
+  const int sms = device_sm_count();
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  input_proj_kernel<<<grid, kIpThreads, kIpSmem, stream>>>(tw, p);
+  VG_CUDA(cudaGetLastError());
+  count_gemm_launch();
+}
+
+// ------------------------------------------------------------------------------------------ fp32 → bf16 rows (text_raw)
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+void f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t st) {
+  VG_CHECK(n % 4 == 0, "f32_to_bf16: length must be a multiple of 4");
+  const size_t n4 = n / 4;
+  f32_to_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(in, out, n4);
+  VG_CUDA(cudaGetLastError());
+}
+
+}  // namespace vg

@@ -24,6 +24,12 @@ void pad_rows_bf16(const bf16* src, bf16* dst, int rows, int rows_pad, cudaStrea
 bool enc_attn_tc_supported(int S);
 void enc_attn_tc(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* kmask, float scale, cudaStream_t stream);
 
+// ---- input_proj.cu: 1x1-conv projection of the extractor feature maps straight into the encoder's token rows
+bool input_proj_supported(int C);
+void input_proj(const float* in, int C, const bf16* W, const float* bias, const bf16* pos, int pos_frames, bf16* X, float* X32,
+                bf16* XP, int F, int S, int tok0, int P, cudaStream_t stream);
+void f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t st);
+
 // ---- small.cu
 // NCHW fp32 features → token-major bf16 rows: X[(f*S + tok0 + p), c] = in[f, c, p]   (in may be broadcast: fstride 0)
 void nchw_to_tokens(const float* in, long long in_fstride, bf16* X, float* X32, const float* pos, long long pos_fstride,

@@ -136,6 +136,11 @@ struct vgqa_ctx {
   float *bb2w = nullptr, *bb2b = nullptr;
   Mlp2 temp_embed, action_embed;
   float *pfc_ln0w, *pfc_ln0b, *pfc_W, *pfc_b, *pfc_ln4w, *pfc_ln4b;
+  // optional front end: input_proj / input_proj2 (1x1 convs) and the text resizer; K == 0 → not loaded
+  Lin ip_vis, ip_vid, ip_text;
+  LNp ip_text_ln;
+  bf16 *traw = nullptr, *tproj = nullptr;   // text_raw as bf16 rows, resizer output (bf16 twin of tproj32)
+  float* tproj32 = nullptr;
   // ---- workspace (device)
   bf16 *X, *X1, *QKV, *AO, *HID, *Xf, *pos_enc, *kposb;
   // positional score terms of the decoders' cross-attentions as GEMM outputs (frame-invariant pos only)
@@ -147,6 +152,7 @@ struct vgqa_ctx {
   // host-path input staging, two slots so that the upload of call k+1 overlaps the compute of call k
   struct HostSlot {
     float *vis, *vid, *text, *pos, *sizes, *f1, *f2;
+    float *vis_raw = nullptr, *vid_raw = nullptr, *text_raw = nullptr;
     uint8_t *vmask, *tmask;
     cudaEvent_t done = nullptr;
     bool used = false;
@@ -492,6 +498,23 @@ static void pack_weights(vgqa_ctx* c) {
   c->pfc_b = P.f32(P.get(g + "pos_fc.2.bias", {4}).v);
   c->pfc_ln4w = P.f32(P.get(g + "pos_fc.4.weight", {4}).v);
   c->pfc_ln4b = P.f32(P.get(g + "pos_fc.4.bias", {4}).v);
+  // ---------------- optional front end: input_proj / input_proj2 (grounding_net.py:62,71), text resizer (bert.py:77-96)
+  auto conv1x1 = [&](const std::string& name) {
+    Lin l;
+    auto it = c->sd.find(name + ".weight");
+    if (it == c->sd.end()) return l;
+    const HostT& w = it->second;
+    VG_CHECK((w.shape.size() == 4 && w.shape[0] == 256 && w.shape[2] == 1 && w.shape[3] == 1) ||
+                 (w.shape.size() == 2 && w.shape[0] == 256),
+             "weight '" + name + ".weight' must be [256, C, 1, 1]");
+    const int C = (int)w.shape[1];
+    VG_CHECK(input_proj_supported(C), "'" + name + "': the input channel count must be a multiple of 64");
+    return P.lin(w.v.data(), P.get(name + ".bias", {256}).v.data(), 256, C);
+  };
+  c->ip_vis = conv1x1("input_proj");
+  c->ip_vid = conv1x1("input_proj2");
+  c->ip_text = conv1x1("text_encoder.resizer.fc");
+  if (c->ip_text.K > 0) c->ip_text_ln = P.ln("text_encoder.resizer.layer_norm");
 }
 
 // ------------------------------------------------------------------------------------------------ workspace
@@ -527,6 +550,12 @@ static void carve_workspace(vgqa_ctx* c) {
     h.vis = a.get<float>(F * 256 * P); h.vid = a.get<float>(F * 256 * P); h.text = a.get<float>(B * L * 256);
     h.pos = a.get<float>(F * 256 * P); h.sizes = a.get<float>(B * 2); h.f1 = a.get<float>(F); h.f2 = a.get<float>(F);
     h.vmask = a.get<uint8_t>(F * P); h.tmask = a.get<uint8_t>(B * L);
+    if (c->ip_vis.K > 0) h.vis_raw = a.get<float>(F * c->ip_vis.K * P);
+    if (c->ip_vid.K > 0) h.vid_raw = a.get<float>(F * c->ip_vid.K * P);
+    if (c->ip_text.K > 0) h.text_raw = a.get<float>(B * L * c->ip_text.K);
+  }
+  if (c->ip_text.K > 0) {
+    c->traw = a.get<bf16>(B * L * c->ip_text.K); c->tproj = a.get<bf16>(B * L * 256); c->tproj32 = a.get<float>(B * L * 256);
   }
   c->kv_ts = a.get<bf16>(B * L * 2048);
   c->text_sums = a.get<float>(B * L * 256);
@@ -641,15 +670,33 @@ static void run_encoder(Fwd& f, const vgqa_inputs& in, bool have_mask, int pos_r
   const int S = f.S, P = f.P, L = f.L, R = f.R, F = f.F;
   // tokens: [vis | text | vid] per frame (modal_encoder.py:64)
   const long long pos_fs = in.pos_frames > 1 ? (long long)256 * P : 0;
-  nchw_to_tokens(in.vis, (long long)256 * P, c->X, c->X32, in.pos, pos_fs, c->XP, F, S, 0, P, st);
-  text_to_tokens(in.text, c->X, c->X32, c->XP, F, f.T, S, P, L, st);
-  nchw_to_tokens(in.vid, (long long)256 * P, c->X, c->X32, in.pos, pos_fs, c->XP, F, S, P + L, P, st);
   // positional rows: [pos | 0 | pos] (modal_encoder.py:66)
   const int pf = in.pos_frames;
   nchw_to_tokens(in.pos, (long long)256 * P, c->pos_enc, nullptr, nullptr, 0, nullptr, pf, S, 0, P, st);
   text_to_tokens(nullptr, c->pos_enc, nullptr, nullptr, pf, 1, S, P, L, st);
   nchw_to_tokens(in.pos, (long long)256 * P, c->pos_enc, nullptr, nullptr, 0, nullptr, pf, S, P + L, P, st);
-  f.count(6);
+  f.count(3);
+  // visual tokens: already-projected maps, or the raw extractor maps through input_proj / input_proj2 (input_proj.cu)
+  if (in.vis_raw != nullptr)
+    input_proj(in.vis_raw, c->ip_vis.K, c->ip_vis.W, c->ip_vis.b, c->pos_enc, pf, c->X, c->X32, c->XP, F, S, 0, P, st);
+  else
+    nchw_to_tokens(in.vis, (long long)256 * P, c->X, c->X32, in.pos, pos_fs, c->XP, F, S, 0, P, st);
+  if (in.vid_raw != nullptr)
+    input_proj(in.vid_raw, c->ip_vid.K, c->ip_vid.W, c->ip_vid.b, c->pos_enc, pf, c->X, c->X32, c->XP, F, S, P + L, P, st);
+  else
+    nchw_to_tokens(in.vid, (long long)256 * P, c->X, c->X32, in.pos, pos_fs, c->XP, F, S, P + L, P, st);
+  f.count(2);
+  const float* text = in.text;
+  if (in.text_raw != nullptr) {  // FeatureResizer: LayerNorm_1e-12(fc(hidden states)) (bert.py:90-96), dropout = identity
+    f32_to_bf16(in.text_raw, c->traw, (size_t)f.B * L * c->ip_text.K, st);
+    GemmEpi ep; ep.C = c->tproj; ep.ldc = 256; ep.bias = c->ip_text.b; ep.bias_ld = 256; ep.C32 = c->tproj32; ep.ldc32 = 256;
+    ep.ln_w = c->ip_text_ln.w; ep.ln_b = c->ip_text_ln.b; ep.ln_eps = 1e-12f;
+    f.gemm(c->traw, c->ip_text.K, c->ip_text, f.B * L, ep);
+    f.count();
+    text = c->tproj32;
+  }
+  text_to_tokens(text, c->X, c->X32, c->XP, F, f.T, S, P, L, st);
+  f.count();
   if (have_mask) { build_encoded_mask(in.vis_mask, in.text_mask, c->encmask, F, f.T, P, L, st); f.count(); }
   const uint8_t* km = have_mask ? c->encmask : nullptr;
   for (size_t l = 0; l < c->enc.size(); ++l) {
@@ -894,7 +941,14 @@ static void check_inputs(vgqa_ctx* c, const vgqa_inputs& in) {
            "shape exceeds the context capacity: " + shape_str(in));
   VG_CHECK(in.T <= c->cfg.max_video_len + 1,
            "T exceeds INPUT.MAX_VIDEO_LEN+1 rows of the time embedding (reference raises RuntimeError too)");
-  VG_CHECK(in.vis && in.vid && in.text && in.pos, "vis/vid/text/pos must be non-null");
+  VG_CHECK((in.vis || in.vis_raw) && (in.vid || in.vid_raw) && (in.text || in.text_raw) && in.pos,
+           "vis/vid/text (or their *_raw forms) and pos must be non-null");
+  VG_CHECK(!in.vis_raw || (c->ip_vis.K > 0 && in.vis_raw_ch == c->ip_vis.K),
+           "vis_raw needs the 'input_proj' weights and vis_raw_ch equal to their input channels");
+  VG_CHECK(!in.vid_raw || (c->ip_vid.K > 0 && in.vid_raw_ch == c->ip_vid.K),
+           "vid_raw needs the 'input_proj2' weights and vid_raw_ch equal to their input channels");
+  VG_CHECK(!in.text_raw || (c->ip_text.K > 0 && in.text_raw_ch == c->ip_text.K),
+           "text_raw needs the 'text_encoder.resizer' weights and text_raw_ch equal to their input features");
   VG_CHECK(in.pos_frames == 1 || in.pos_frames == in.clips * in.T, "pos_frames must be 1 or clips*T");
   if (c->sh_world > 1) {
     VG_CHECK(in.clips == 1, "frame sharding handles one clip per call");
@@ -1108,7 +1162,8 @@ static int run_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out
                                (uint64_t)in.W, (uint64_t)in.L, (uint64_t)in.pos_frames, (uint64_t)(in.iteration_rate < 0)};
   for (const void* q : {(const void*)in.vis, (const void*)in.vid, (const void*)in.text, (const void*)in.pos,
                         (const void*)in.vis_mask, (const void*)in.text_mask, (const void*)in.ori_sizes_hw,
-                        (const void*)in.force_choose1, (const void*)in.force_choose2})
+                        (const void*)in.force_choose1, (const void*)in.force_choose2, (const void*)in.vis_raw,
+                        (const void*)in.vid_raw, (const void*)in.text_raw})
     key.push_back((uint64_t)(uintptr_t)q);
   if (phase == 1)
     for (const void* q : {(const void*)out.pred_boxes, (const void*)out.pred_sted, (const void*)out.pred_actioness,
@@ -1221,9 +1276,12 @@ int vgqa_forward_host_async(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outp
       VG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, up));
     };
     vgqa_inputs din = *hin;
-    h2d(h.vis, hin->vis, F * 256 * P * 4); din.vis = h.vis;
-    h2d(h.vid, hin->vid, F * 256 * P * 4); din.vid = h.vid;
-    h2d(h.text, hin->text, B * L * 256 * 4); din.text = h.text;
+    if (hin->vis_raw) { h2d(h.vis_raw, hin->vis_raw, F * c->ip_vis.K * P * 4); din.vis_raw = h.vis_raw; din.vis = nullptr; }
+    else { h2d(h.vis, hin->vis, F * 256 * P * 4); din.vis = h.vis; }
+    if (hin->vid_raw) { h2d(h.vid_raw, hin->vid_raw, F * c->ip_vid.K * P * 4); din.vid_raw = h.vid_raw; din.vid = nullptr; }
+    else { h2d(h.vid, hin->vid, F * 256 * P * 4); din.vid = h.vid; }
+    if (hin->text_raw) { h2d(h.text_raw, hin->text_raw, B * L * c->ip_text.K * 4); din.text_raw = h.text_raw; din.text = nullptr; }
+    else { h2d(h.text, hin->text, B * L * 256 * 4); din.text = h.text; }
     h2d(h.pos, hin->pos, (size_t)hin->pos_frames * 256 * P * 4); din.pos = h.pos;
     if (hin->vis_mask) { h2d(h.vmask, hin->vis_mask, F * P); din.vis_mask = h.vmask; }
     if (hin->text_mask) { h2d(h.tmask, hin->text_mask, B * L); din.text_mask = h.tmask; }

@@ -26,7 +26,9 @@ class VgqaInputs(ctypes.Structure):
                 ("vis", c_void_p), ("vid", c_void_p), ("text", c_void_p), ("pos", c_void_p), ("pos_frames", c_int),
                 ("vis_mask", c_void_p), ("text_mask", c_void_p), ("ori_sizes_hw", c_void_p),
                 ("force_choose1", c_void_p), ("force_choose2", c_void_p), ("iteration_rate", c_int),
-                ("stop_after_encoder", c_int)]
+                ("stop_after_encoder", c_int),
+                ("vis_raw", c_void_p), ("vid_raw", c_void_p), ("text_raw", c_void_p),
+                ("vis_raw_ch", c_int), ("vid_raw_ch", c_int), ("text_raw_ch", c_int)]
 
 
 OUTPUT_FIELDS = ("pred_boxes", "pred_sted", "pred_actioness", "logits_f_m", "logits_f_a", "logits_r_a", "logits_r_m",
@@ -188,31 +190,41 @@ class GroundingEngine:
         return None if t is None else c_void_p(t.data_ptr())
 
     def _pack_io(self, vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force1, force2, iteration_rate, outs,
-                 stop_after_encoder=0):
+                 stop_after_encoder=0, raw=False):
+        """raw=True: vis / vid / text are the extractor outputs ([clips,T,Cv,H,W], [clips,T,Cd,H,W], [clips,L,Ct]) and the
+        library applies input_proj / input_proj2 / text_encoder.resizer itself (their weights must be in the state_dict)."""
         B, T, d, H, W = vis.shape
-        assert d == 256 and tuple(vid.shape) == tuple(vis.shape), "vis/vid must be [clips, T, 256, H, W]"
+        if raw:
+            assert tuple(vid.shape[:2]) == (B, T) and tuple(vid.shape[3:]) == (H, W), "vid_raw must be [clips, T, C, H, W]"
+            assert text.dim() == 3 and text.shape[0] == B, "text_raw must be [clips, L, C]"
+        else:
+            assert d == 256 and tuple(vid.shape) == tuple(vis.shape), "vis/vid must be [clips, T, 256, H, W]"
+            assert tuple(text.shape) == (B, text.shape[1], 256), "text must be [clips, L, 256]"
         Lt = text.shape[1]
-        assert tuple(text.shape) == (B, Lt, 256), "text must be [clips, L, 256]"
         assert pos.shape[0] in (1, B * T) and tuple(pos.shape[1:]) == (256, H, W), "pos must be [1 or clips*T, 256, H, W]"
         for t in (vis, vid, text, pos):
             assert t.dtype == torch.float32 and t.is_contiguous()
-        inp = VgqaInputs(B, T, H, W, Lt, self._p(vis), self._p(vid), self._p(text), self._p(pos), pos.shape[0],
+        n = None
+        inp = VgqaInputs(B, T, H, W, Lt, n if raw else self._p(vis), n if raw else self._p(vid), n if raw else self._p(text),
+                         self._p(pos), pos.shape[0],
                          self._p(vis_mask), self._p(text_mask), self._p(ori_sizes_hw), self._p(force1), self._p(force2),
-                         iteration_rate, stop_after_encoder)
+                         iteration_rate, stop_after_encoder,
+                         self._p(vis) if raw else n, self._p(vid) if raw else n, self._p(text) if raw else n,
+                         vis.shape[2] if raw else 0, vid.shape[2] if raw else 0, text.shape[2] if raw else 0)
         out = VgqaOutputs(**{k: self._p(outs.get(k)) for k in OUTPUT_FIELDS})
         return inp, out
 
-    def encode(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None):
+    def encode(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, raw=False):
         """CrossModalEncoder only: returns encoded_feature [clips*T, S, 256] (frame-major) and frames_cls [clips*T, 256]."""
         B, T, _, H, W = vis.shape
         outs = self.alloc_outputs(B, T, H, W, text.shape[1], ["encoded_feature", "frames_cls"])
-        inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, None, None, None, -1, outs, 1)
+        inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, None, None, None, -1, outs, 1, raw=raw)
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(self._L.vgqa_forward(self._ctx, ctypes.byref(inp), ctypes.byref(out), c_void_p(st)))
         return outs
 
     def forward(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, ori_sizes_hw=None, force_choose1=None,
-                force_choose2=None, iteration_rate=-1, outs=None, want=None):
+                force_choose2=None, iteration_rate=-1, outs=None, want=None, raw=False):
         """Device-resident inputs (fp32 CUDA tensors, reference layouts); enqueues on the current stream."""
         B, T, _, H, W = vis.shape
         if outs is None:
@@ -220,16 +232,16 @@ class GroundingEngine:
             if ori_sizes_hw is None:
                 outs.pop("boxes_px", None), outs.pop("sted_idx", None)
         inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force_choose1, force_choose2,
-                                 iteration_rate, outs)
+                                 iteration_rate, outs, raw=raw)
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(self._L.vgqa_forward(self._ctx, ctypes.byref(inp), ctypes.byref(out), c_void_p(st)))
         return outs
 
     def forward_async(self, vis, vid, text, pos, *, outs, slot, vis_mask=None, text_mask=None, ori_sizes_hw=None,
-                      force_choose1=None, force_choose2=None, iteration_rate=-1):
+                      force_choose1=None, force_choose2=None, iteration_rate=-1, raw=False):
         """Pipelined device path: alternate slot 0/1 on consecutive calls; `outs` are complete after `wait(slot)`."""
         inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force_choose1, force_choose2,
-                                 iteration_rate, outs)
+                                 iteration_rate, outs, raw=raw)
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(self._L.vgqa_forward_async(self._ctx, ctypes.byref(inp), ctypes.byref(out), slot, c_void_p(st)))
         return outs
@@ -240,7 +252,7 @@ class GroundingEngine:
         _lib.check(self._L.vgqa_forward_wait(self._ctx, slot, c_void_p(st), 1 if host_sync else 0))
 
     def forward_host(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, ori_sizes_hw=None,
-                     force_choose1=None, force_choose2=None, iteration_rate=-1, outs=None, want=None):
+                     force_choose1=None, force_choose2=None, iteration_rate=-1, outs=None, want=None, raw=False):
         """Host buffers (CPU tensors, ideally pinned): H2D + forward + D2H inside the call (synchronous)."""
         B, T, _, H, W = vis.shape
         if outs is None:
@@ -248,15 +260,15 @@ class GroundingEngine:
             if ori_sizes_hw is None:
                 outs.pop("boxes_px", None), outs.pop("sted_idx", None)
         inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force_choose1, force_choose2,
-                                 iteration_rate, outs)
+                                 iteration_rate, outs, raw=raw)
         _lib.check(self._L.vgqa_forward_host(self._ctx, ctypes.byref(inp), ctypes.byref(out)))
         return outs
 
     def forward_host_async(self, vis, vid, text, pos, *, outs, slot, vis_mask=None, text_mask=None, ori_sizes_hw=None,
-                           force_choose1=None, force_choose2=None, iteration_rate=-1):
+                           force_choose1=None, force_choose2=None, iteration_rate=-1, raw=False):
         """Pipelined host path: returns immediately; `outs` (pinned host tensors) are valid after `wait_host(slot)`."""
         inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force_choose1, force_choose2,
-                                 iteration_rate, outs)
+                                 iteration_rate, outs, raw=raw)
         _lib.check(self._L.vgqa_forward_host_async(self._ctx, ctypes.byref(inp), ctypes.byref(out), slot))
         return outs
 
