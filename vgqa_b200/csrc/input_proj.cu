@@ -13,14 +13,22 @@
 // K-major bf16 operand ([p][c]) — the transpose + conversion happens on the way into shared memory:
 //
 //   warp 0       TMA producer of the W k-blocks (256 x 64 bf16, 128B swizzle), 4-stage ring
+//   warp 2       L2 prefetcher: cp.async.bulk.prefetch.L2 of the fp32 chunks 8 k-blocks ahead of the tensor core, so the
+//                producers' register loads hit L2 (a third of the HBM latency → three times the bytes per register in flight)
 //   warp 1       tcgen05.mma issuer (UMMA 128x256x16), two TMEM accumulators so the epilogue of tile i overlaps tile i+1
-//   warps 2-5    epilogue: TMEM → + bias → X32 / X / XP rows (one token row per thread, 16-byte stores)
-//   warps 6-13   A producers: thread = (token row, 32 of the 64 channels of the k-block); 32 coalesced 4-byte loads (a warp
-//                reads 32 consecutive tokens of one channel), register double-buffered one k-block ahead, packed to bf16 and
-//                written as four 16-byte stores into the 128B-swizzled K-major tile the UMMA descriptor expects
+//   warps 4-7    epilogue: TMEM row per thread → swizzled 4 KB slab per warp → + bias → X32 / X / XP with every store
+//                instruction covering four 128-byte (fp32) / 64-byte (bf16) row segments (row-per-thread stores cost 32 L1
+//                wavefronts each and made the LSU data pipe the limiter: ncu 78 % → profiles/r01_input_proj_ncu.md)
+//   warps 8-31   A producers, three groups of 8 warps; group g converts the k-blocks with (k-block index % 3) == g, so three
+//                k-blocks (96 KB of fp32) are in flight per SM — the kernel is bound by HBM latency x bytes in flight, not
+//                by issue.  Thread = (token row, 32 of the 64 channels of the k-block): 32 coalesced 4-byte loads (a warp
+//                reads 32 consecutive tokens of one channel), packed to bf16 and written as four 16-byte stores into the
+//                128B-swizzled K-major tile the UMMA descriptor expects.  Registers are re-balanced with setmaxnreg.
 //
 // A tile is 128 token rows: floor(128 / P) whole frames when a frame has P <= 128 tokens (7x7: two frames, 98 rows), or one
 // 128-row slice of a frame otherwise (14x14: two slices).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -29,8 +37,11 @@ namespace vg {
 static constexpr int kIpStages = 4;
 static constexpr int kIpABytes = 128 * 64 * 2;
 static constexpr int kIpBBytes = 256 * 64 * 2;
-static constexpr int kIpSmem = kIpStages * (kIpABytes + kIpBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
-static constexpr int kIpThreads = 64 + 128 + 256;
+static constexpr int kIpSlabBytes = 4 * 4096;               // epilogue staging: 32 rows x 128 B per warp
+static constexpr int kIpSmem = kIpStages * (kIpABytes + kIpBBytes) + kIpSlabBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+static constexpr int kIpPrefetchDist = 8;                  // k-blocks the L2 prefetcher runs ahead of the MMA issuer
+static constexpr int kIpGroups = 3;                        // producer groups (k-blocks in flight)
+static constexpr int kIpThreads = 256 + kIpGroups * 256;  // 4 control/idle warps + 4 epilogue warps + 8 warps per group
 
 struct IpParams {
   const float* in;     // [F, C, P]
@@ -44,6 +55,7 @@ struct IpParams {
   int fpt;             // frames per tile (P <= 128), else 0
   int tpf;             // 128-row slices per frame (P > 128)
   int num_tiles;
+  int l2_prefetch;     // 1: `in` is 16-byte aligned → bulk L2 prefetch of the chunks ahead
 };
 
 // tile row r → (frame, token); false for the padding rows of a tile
@@ -59,19 +71,25 @@ __device__ __forceinline__ bool ip_row(const IpParams& p, int tile, int r, int& 
   return tok < p.P;
 }
 
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {   // 16-byte aligned address and size
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 __global__ void __launch_bounds__(kIpThreads, 1)
 input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kIpStages * kIpABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kIpStages * kIpBBytes);
+  uint8_t* smem_slab = smem_b + kIpStages * kIpBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_slab + kIpSlabBytes);
   uint64_t* w_full = bars;                     // [stages] TMA bytes of the W k-block
   uint64_t* a_full = bars + kIpStages;         // [stages] 8 arrivals (one per producer warp)
   uint64_t* empty_bar = bars + 2 * kIpStages;  // [stages] tcgen05.commit: both operands of the stage are consumed
   uint64_t* tfull_bar = bars + 3 * kIpStages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2] 4 arrivals (epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  volatile int* consumed = reinterpret_cast<volatile int*>(tmem_slot + 1);   // k-blocks issued to the tensor core so far
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = p.C / 64;
@@ -81,6 +99,7 @@ input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
     tma_prefetch_desc(&tma_w);
     for (int s = 0; s < kIpStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&a_full[s], 8); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    *consumed = 0;
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -89,7 +108,9 @@ input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+   if (warp == 0) {
     // ===================== TMA producer: W k-blocks =====================
     if (lane == 0) {
       int stage = 0;
@@ -123,64 +144,94 @@ input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
           for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (kb == num_k - 1) umma_commit(&tfull_bar[acc]);
+          *consumed = it * num_k + kb + 1;
         }
         __syncwarp();
         if (++stage == kIpStages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp < 6) {
-    // ===================== epilogue: one token row per thread =====================
+   } else if (warp == 2) {
+    // ===================== L2 prefetcher =====================
+    if (lane == 0 && p.l2_prefetch) {
+      const int total = n_my * num_k;
+      const size_t chunk = (size_t)64 * p.P;   // floats of one frame's k-block: 64 channels x P tokens, contiguous
+      for (int g = 0; g < total; ++g) {
+        while (g > *consumed + kIpPrefetchDist) __nanosleep(100);
+        const int it = g / num_k, kb = g - it * num_k;
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        if (p.fpt > 0) {
+          for (int fl = 0; fl < p.fpt; ++fl) {
+            const int frame = tile * p.fpt + fl;
+            if (frame < p.F) bulk_prefetch_l2(p.in + ((size_t)frame * p.C + kb * 64) * p.P, (uint32_t)(chunk * 4));
+          }
+        } else if (tile % p.tpf == 0) {        // the first slice of a frame fetches the chunk for all of its slices
+          bulk_prefetch_l2(p.in + ((size_t)(tile / p.tpf) * p.C + kb * 64) * p.P, (uint32_t)(chunk * 4));
+        }
+      }
+    }
+   }
+  } else if (warp < 8) {
+    // ===================== epilogue: TMEM row per thread → swizzled slab → coalesced row-segment stores =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
+    uint8_t* slab = smem_slab + quad * 4096;   // 32 rows x 32 fp32
+    const int rl = lane >> 3, ul = lane & 7;   // read-back: row within a group of 4, 16-byte unit of the 128-byte slab row
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int it = 0; it < n_my; ++it) {
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       int frame, tok;
       const bool valid = ip_row(p, tile, r, frame, tok);
-      const size_t orow = (size_t)frame * p.S + p.tok0 + tok;
-      const size_t prow = p.pos_per_frame ? orow : (size_t)(p.tok0 + tok);
+      const int my_orow = valid ? frame * p.S + p.tok0 + tok : -1;          // output row of this lane's TMEM row
+      const int my_prow = !valid ? 0 : (p.pos_per_frame ? my_orow : p.tok0 + tok);
+      int orow8[8], prow8[8];   // output / positional rows of the 8 slab rows this lane stores (rows itr*4 + rl)
+#pragma unroll
+      for (int itr = 0; itr < 8; ++itr) {
+        orow8[itr] = __shfl_sync(0xffffffffu, my_orow, itr * 4 + rl);
+        prow8[itr] = __shfl_sync(0xffffffffu, my_prow, itr * 4 + rl);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         uint32_t raw[32];
-        float v[32];
         tmem_ld32(taddr + c * 32, raw);
         tmem_ld_wait();
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + c * 32);
+        {
+          uint8_t* rowp = slab + lane * 128;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = __ldg(b4 + i);
-          v[4 * i + 0] = __uint_as_float(raw[4 * i + 0]) + b.x; v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + b.y;
-          v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + b.z; v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + b.w;
+          for (int u = 0; u < 8; ++u)
+            *reinterpret_cast<uint4*>(rowp + ((u ^ (lane & 7)) << 4)) = make_uint4(raw[4 * u], raw[4 * u + 1], raw[4 * u + 2], raw[4 * u + 3]);
         }
-        if (valid) {
-          const size_t o = orow * 256 + c * 32;
-          if (p.X32 != nullptr) {
-            float4* d = reinterpret_cast<float4*>(p.X32 + o);
+        __syncwarp();
+        const int col = c * 32 + ul * 4;
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        // all positional loads of the chunk are issued before the first store (padding rows read row 0, unused)
+        uint2 posv[8];
+        if (p.XP != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-          uint4* d = reinterpret_cast<uint4*>(p.X + o);
+          for (int itr = 0; itr < 8; ++itr)
+            posv[itr] = __ldg(reinterpret_cast<const uint2*>(p.pos + (size_t)prow8[itr] * 256 + col));
+        }
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            d[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                              pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
-          if (p.XP != nullptr) {
-            const uint4* a4 = reinterpret_cast<const uint4*>(p.pos + prow * 256 + c * 32);
-            uint4* d2 = reinterpret_cast<uint4*>(p.XP + o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 u = __ldg(a4 + i);
-              const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), dd = unpack_bf16(u.w);
-              d2[i] = make_uint4(pack_bf16(v[8 * i] + a.x, v[8 * i + 1] + a.y), pack_bf16(v[8 * i + 2] + b.x, v[8 * i + 3] + b.y),
-                                 pack_bf16(v[8 * i + 4] + cc.x, v[8 * i + 5] + cc.y), pack_bf16(v[8 * i + 6] + dd.x, v[8 * i + 7] + dd.y));
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rr = itr * 4 + rl;
+          if (orow8[itr] >= 0) {
+            const float4 z = *reinterpret_cast<const float4*>(slab + rr * 128 + ((ul ^ (rr & 7)) << 4));
+            const float y0 = z.x + b4.x, y1 = z.y + b4.y, y2 = z.z + b4.z, y3 = z.w + b4.w;
+            const size_t o = (size_t)orow8[itr] * 256 + col;
+            if (p.X32 != nullptr) __stcs(reinterpret_cast<float4*>(p.X32 + o), make_float4(y0, y1, y2, y3));
+            __stcs(reinterpret_cast<uint2*>(p.X + o), make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3)));
+            if (p.XP != nullptr) {
+              const float2 pa = unpack_bf16(posv[itr].x), pb = unpack_bf16(posv[itr].y);
+              __stcs(reinterpret_cast<uint2*>(p.XP + o), make_uint2(pack_bf16(y0 + pa.x, y1 + pa.y), pack_bf16(y2 + pb.x, y3 + pb.y)));
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -189,53 +240,40 @@ input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
     }
   } else {
     // ===================== A producers: fp32 [c][p] (global) → bf16 [p][c] swizzled (shared) =====================
-    const int pt = threadIdx.x - 192;
-    const int r = pt & 127, half = pt >> 7;
+    const int pt = threadIdx.x - 256;
+    const int grp = pt >> 8;                  // this group owns the k-blocks with (running k-block index % kIpGroups) == grp
+    const int r = pt & 127, half = (pt >> 7) & 1;
     const size_t cstride = (size_t)p.P;
-    // row base pointer (channel 0 of this thread's token) of my it-th tile, nullptr for padding rows
-    auto row_base = [&](int it) -> const float* {
-      if (it >= n_my) return nullptr;
-      int frame, tok;
-      if (!ip_row(p, (int)blockIdx.x + it * (int)gridDim.x, r, frame, tok)) return nullptr;
-      return p.in + (size_t)frame * p.C * cstride + tok;
-    };
-    auto load = [&](float (&dst)[32], const float* base, int kb) __attribute__((always_inline)) {
+    const int total = n_my * num_k;           // k-blocks this CTA walks through, over all of its tiles
+    int it_cached = -1;
+    const float* base = nullptr;              // channel 0 of this thread's token in tile `it_cached`; nullptr for padding rows
+    for (int g = grp; g < total; g += kIpGroups) {
+      const int it = g / num_k, kb = g - it * num_k;
+      if (it != it_cached) {
+        int frame, tok;
+        base = ip_row(p, (int)blockIdx.x + it * (int)gridDim.x, r, frame, tok) ? p.in + (size_t)frame * p.C * cstride + tok : nullptr;
+        it_cached = it;
+      }
+      float v[32];
       if (base != nullptr) {
         const float* src = base + (size_t)(kb * 64 + half * 32) * cstride;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dst[i] = __ldg(src + (size_t)i * cstride);
+        for (int i = 0; i < 32; ++i) v[i] = __ldg(src + (size_t)i * cstride);
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dst[i] = 0.f;
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
       }
-    };
-    float cur[32], nxt[32];
-    const float* base = row_base(0);
-    if (n_my > 0) load(cur, base, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int it = 0; it < n_my; ++it) {
-      const float* base_next = row_base(it + 1);
-      for (int kb = 0; kb < num_k; ++kb) {
-        // the loads of the NEXT k-block are in flight while this one is converted and while the ring slot is awaited
-        const bool last_kb = kb + 1 == num_k;
-        if (!last_kb) load(nxt, base, kb + 1);
-        else if (it + 1 < n_my) load(nxt, base_next, 0);
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* rowp = smem_a + stage * kIpABytes + r * 128;
+      const int stage = g % kIpStages;
+      mbar_wait(&empty_bar[stage], ((g / kIpStages) & 1) ^ 1);
+      uint8_t* rowp = smem_a + stage * kIpABytes + r * 128;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<uint4*>(rowp + (((half * 4 + u) ^ (r & 7)) << 4)) =
-              make_uint4(pack_bf16(cur[8 * u], cur[8 * u + 1]), pack_bf16(cur[8 * u + 2], cur[8 * u + 3]),
-                         pack_bf16(cur[8 * u + 4], cur[8 * u + 5]), pack_bf16(cur[8 * u + 6], cur[8 * u + 7]));
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[stage]);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
-        if (++stage == kIpStages) { stage = 0; phase ^= 1; }
-      }
-      base = base_next;
+      for (int u = 0; u < 4; ++u)
+        *reinterpret_cast<uint4*>(rowp + (((half * 4 + u) ^ (r & 7)) << 4)) =
+            make_uint4(pack_bf16(v[8 * u], v[8 * u + 1]), pack_bf16(v[8 * u + 2], v[8 * u + 3]),
+                       pack_bf16(v[8 * u + 4], v[8 * u + 5]), pack_bf16(v[8 * u + 6], v[8 * u + 7]));
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[stage]);
     }
   }
 
@@ -271,6 +309,8 @@ void input_proj(const float* in, int C, const bf16* W, const float* bias, const 
   p.F = F; p.C = C; p.P = P; p.S = S; p.tok0 = tok0; p.pos_per_frame = pos_frames > 1 ? 1 : 0;
   if (P <= 128) { p.fpt = 128 / P; p.tpf = 1; p.num_tiles = (F + p.fpt - 1) / p.fpt; }
   else { p.fpt = 0; p.tpf = (P + 127) / 128; p.num_tiles = F * p.tpf; }
+  p.l2_prefetch = (reinterpret_cast<uintptr_t>(in) & 15) == 0 ? 1 : 0;
+  if (const char* e = getenv("VGQA_IP_PREFETCH")) p.l2_prefetch = p.l2_prefetch && e[0] != '0';
   CUtensorMap tw = make_tmap_2d(W, 256, C, C, 256, false);
   const int sms = device_sm_count();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
