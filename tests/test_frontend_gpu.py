@@ -178,3 +178,41 @@ def test_raw_inputs_need_their_weights():
     with pytest.raises(RuntimeError, match="vis_raw_ch"):
         eng.forward(z(1, 4, 192, 3, 3), z(1, 4, 64, 3, 3), z(1, 4, 64), z(1, 256, 3, 3), raw=True)
     eng.close()
+
+
+def test_vstgnet_dropin_and_predictor_with_fused_front_end():
+    """The Python seam with raw extractor outputs: B200VSTGNet skips the torch input_proj modules (they are never called) and
+    GroundingPredictor(raw_inputs=True) serves the even/odd passes from raw maps; both against the reference golden."""
+    from make_golden import make_cfg
+    from vgqa_b200 import modules as M
+    from vgqa_b200.predict import GroundingPredictor
+    g = np.load(golden_path("fe_cfg1_T32_7x7_L20_s0"))
+    T, H, W, L, seed = (int(g[k]) for k in ("T", "H", "W", "L", "seed"))
+    ch = tuple(int(x) for x in g["front_end_ch"])
+    sd = O.synth_state_dict(seed, front_end_ch=ch)
+    vis_raw, vid_raw, text_raw = (torch.from_numpy(a).cuda() for a in O.synth_raw_inputs(seed, T, H, W, L, ch))
+    pos = torch.from_numpy(O.position_embedding_sine(np.zeros((T, H, W), bool))).cuda()
+
+    class Boom(torch.nn.Module):
+        def forward(self, x):
+            raise AssertionError("the torch input_proj must not run when the front end is fused")
+
+    vis_encoder = lambda videos: (M.NestedTensor(vis_raw, videos.mask[:, :H, :W], videos.durations), pos)
+    vid_model = lambda tensors, n: {"3": vid_raw}
+    text_encoder = lambda texts, device: ((torch.zeros(1, L, dtype=torch.bool, device=device), None, text_raw[:, None, :]), None)
+    model = M.B200VSTGNet(make_cfg(), vis_encoder, vid_model, text_encoder, Boom(), Boom(), sd, verb_label2={"0": {"sub": ""}},
+                          max_frames=64, max_hw=49, max_text=20).eval()
+    assert model.fused_front_end
+    videos = M.NestedTensor(torch.zeros(T, 3, 224, 224, device="cuda"), torch.zeros(T, 224, 224, dtype=torch.bool, device="cuda"), [T])
+    out = model(videos, ["a person jumping"], [{"item_id": 0, "actioness": torch.ones(T, device="cuda")}])
+    for k in ("pred_boxes", "pred_sted", "logits_f_m", "logits_f_a", "att_sequences"):
+        assert float(np.abs(out[k].cpu().numpy() - g[k]).max()) <= TOL, k
+    # predictor: 2T sampled frames whose even pass is the golden clip
+    pred = GroundingPredictor(sd, sample_num=T, max_hw=H * W, max_text=L, raw_inputs=True)
+    il = lambda a: torch.stack([a, a.flip(0)], 1).reshape(2 * T, *a.shape[1:]).contiguous()   # even frames = the clip
+    fids = list(range(2 * T))
+    res = pred.predict(il(vis_raw), il(vid_raw), text_raw, pos[:1], fids, (360, 640), fps=25.0)
+    even = {t["frame"]: t["bbox"] for t in res["tube"] if t["frame"] % 2 == 0}
+    got = np.asarray([even[f] for f in range(0, 2 * T, 2)])
+    np.testing.assert_allclose(got, g["post_boxes"], atol=TOL * 640)
+    pred.close()

@@ -71,9 +71,12 @@ class HotPath(torch.nn.Module):
                                        max_hw=max_hw, max_text=max_text, use_cuda_graph=use_cuda_graph)
 
     @torch.no_grad()
-    def forward(self, vis_features, vis_mask, vis_pos, text_mask, text_features, vid_features, iteration_rate=-1):
+    def forward(self, vis_features, vis_mask, vis_pos, text_mask, text_features, vid_features, iteration_rate=-1, raw=False):
         """vis/vid_features [T,256,H,W], vis_mask [T,H,W] bool, vis_pos [T,256,H,W], text_features [L,1,256],
-        text_mask [1,L] bool → the reference's output dict entries that depend on the hot path."""
+        text_mask [1,L] bool → the reference's output dict entries that depend on the hot path.
+        raw=True: the features are the extractor outputs (ResNet map [T,Cv,H,W], Video-Swin map [T,Cd,H,W], RoBERTa states
+        [L,1,Ct]) and input_proj / input_proj2 / text_encoder.resizer run fused inside the library (grounding_net.py:101,105;
+        bert.py:73) — their weights must be in the state_dict."""
         T, d, H, W = vis_features.shape
         assert vis_pos.shape[0] == T, "{} != {}".format(vis_pos.shape[0], T)          # modal_encoder.py:44
         f32 = lambda t: t.detach().to(torch.float32).contiguous()
@@ -86,7 +89,7 @@ class HotPath(torch.nn.Module):
         else:
             pos = f32(vis_pos[:1])   # PositionEmbeddingSine of an all-False mask is identical on every frame
         o = self.engine.forward(f32(vis_features)[None], f32(vid_features)[None], f32(text_features[:, 0])[None], pos,
-                                iteration_rate=iteration_rate, **kw)
+                                iteration_rate=iteration_rate, raw=raw, **kw)
         out = {"pred_boxes": o["pred_boxes"][0], "logits_f_m": o["logits_f_m"][0], "logits_f_a": o["logits_f_a"][0],
                "logits_r_a": o["logits_r_a"], "logits_r_m": o["logits_r_m"], "pred_sted": o["pred_sted"],
                "pred_actioness": o["pred_actioness"][..., None], "att_sequences": o["att_sequences"]}
@@ -144,10 +147,15 @@ class B200VSTGNet(torch.nn.Module):
     text_encoder(texts, device) -> ((mask, text, raw), cls); input_proj / input_proj2 are 1x1 convs."""
 
     def __init__(self, cfg, vis_encoder, vid, text_encoder, input_proj, input_proj2, state_dict, verb_label=None,
-                 verb_label2=None, **cap):
+                 verb_label2=None, fused_front_end=None, **cap):
         super().__init__()
         self.vis_encoder, self.vid, self.text_encoder = vis_encoder, vid, text_encoder
         self.input_proj, self.input_proj2 = input_proj, input_proj2
+        # fused front end (csrc/input_proj.cu): the 1x1 convs and the text resizer run inside the library when their weights
+        # are in the state_dict; `input_proj` / `input_proj2` modules are then not called
+        has = all(k in state_dict for k in ("input_proj.weight", "input_proj2.weight", "text_encoder.resizer.fc.weight"))
+        self.fused_front_end = has if fused_front_end is None else bool(fused_front_end)
+        assert has or not self.fused_front_end, "fused_front_end needs input_proj / input_proj2 / text_encoder.resizer weights"
         self.hot = HotPath(cfg, state_dict, **cap)
         self.verb_label = verb_label or {}
         self.verb_label2 = verb_label2 or {}
@@ -162,15 +170,18 @@ class B200VSTGNet(torch.nn.Module):
     def forward(self, videos, texts, targets, iteration_rate: int = -1):
         vis_outputs, vis_pos = self.vis_encoder(videos)
         vis_res, vis_mask, vis_durations = vis_outputs.decompose()
-        vis_features = self.input_proj(vis_res)
-        vid_features = self.input_proj2(self.vid(videos.tensors, len(videos.tensors))["3"])
+        vid_res = self.vid(videos.tensors, len(videos.tensors))["3"]
+        fused = self.fused_front_end
+        vis_features = vis_res if fused else self.input_proj(vis_res)
+        vid_features = vid_res if fused else self.input_proj2(vid_res)
         info_key = str(targets[0]["item_id"])
         labels = self.verb_label if self.training else self.verb_label2
         texts = [labels[info_key]["sub"] + " " + texts[0]]
-        (text_mask, text_features, _), _ = self.text_encoder(texts, vis_features.device)
+        (text_mask, text_features, text_memory), _ = self.text_encoder(texts, vis_features.device)
         vm = vis_mask.clone()
         vm[:, 0, 0] = False
-        out = self.hot(vis_features, vm, vis_pos, text_mask, text_features, vid_features, iteration_rate)
+        out = self.hot(vis_features, vm, vis_pos, text_mask, text_memory if fused else text_features, vid_features,
+                       iteration_rate, raw=fused)
         choose_index = out.pop("_choose_index").tolist()
         out["verb_labels"] = labels.get(info_key, {}).get("verb_index_list", [])
         out["attr_labels"] = labels.get(info_key, {}).get("adj_index_list", [])

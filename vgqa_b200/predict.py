@@ -23,8 +23,11 @@ class GroundingPredictor:
     """One engine, many predict() calls.  `max_queries` bounds the number of (clip, query) pairs per call."""
 
     def __init__(self, state_dict: Mapping[str, Any], *, sample_num=64, max_hw=49, max_text=64, max_queries=1,
-                 max_video_len=200, use_cuda_graph=True, **engine_kw):
+                 max_video_len=200, use_cuda_graph=True, raw_inputs=False, **engine_kw):
+        """raw_inputs=True: items carry the extractor outputs ("vis" [2T,Cv,H,W] ResNet map, "vid" [2T,Cd,H,W] Video-Swin map,
+        "text" [L,Ct] RoBERTa states) and input_proj / input_proj2 / the text resizer run fused inside the library."""
         self.sample_num = int(sample_num)
+        self.raw_inputs = bool(raw_inputs)
         self.engine = GroundingEngine(state_dict, max_clips=2 * int(max_queries), max_frames=self.sample_num, max_hw=max_hw,
                                       max_text=max_text, max_video_len=max_video_len, use_cuda_graph=use_cuda_graph,
                                       **engine_kw)
@@ -34,6 +37,7 @@ class GroundingPredictor:
     def predict_many(self, items: Sequence[Mapping[str, Any]]) -> List[Dict[str, Any]]:
         """items[q]: {"vis": [2T,256,H,W], "vid": [2T,256,H,W], "text": [L,256], "pos": [1,256,H,W], "frame_ids": 2T ints
         (ascending, as sampled by predict()), "ori_size": (h, w), "fps": float}.  All items share T, H, W, L.
+        With raw_inputs=True the channel counts are those of the extractors (see __init__).
         Returns one {"temporal": {...}, "tube": [...]} dict per item (grounding.py:227-244)."""
         Q = len(items)
         if Q == 0:
@@ -57,7 +61,7 @@ class GroundingPredictor:
         vis, vid, text = torch.stack(vis).contiguous(), torch.stack(vid).contiguous(), torch.stack(text).contiguous()
         pos = f32(items[0]["pos"])[:1].contiguous()
         o = self.engine.forward(vis, vid, text, pos, ori_sizes_hw=torch.tensor(sizes, device=dev),
-                                want=["att_sequences", "boxes_px", "sted_idx"])
+                                want=["att_sequences", "boxes_px", "sted_idx"], raw=self.raw_inputs)
         boxes = o["boxes_px"].reshape(2 * Q, T, 4).cpu().tolist()     # one D2H copy per output
         att = o["att_sequences"].reshape(2 * Q, T).cpu().tolist()
         idx = o["sted_idx"].reshape(2 * Q, 2).cpu().tolist()
