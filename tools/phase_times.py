@@ -1,5 +1,5 @@
 """Wall-clock split of one step: encoder phase alone, full forward unpipelined (encoder + decoder back to back),
-and the two-slot pipelined path bench.py measures.  usage: phase_times.py [clips]"""
+and the two-slot pipelined path bench.py measures.  usage: phase_times.py [clips [T H W L]]"""
 import os
 import sys
 
@@ -12,7 +12,7 @@ from oracle import vgqa_oracle as O  # synthetic weights / inputs only
 from vgqa_b200.engine import GroundingEngine
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-T, H, W, L = 64, 7, 7, 20
+T, H, W, L = (int(a) for a in sys.argv[2:6]) if len(sys.argv) >= 6 else (64, 7, 7, 20)
 eng = GroundingEngine(O.synth_state_dict(0), max_clips=B, max_frames=T, max_hw=H * W, max_text=L, use_cuda_graph=True)
 base = [O.synth_inputs(i, T, H, W, L) for i in range(4)]
 vis = torch.from_numpy(np.stack([base[i % 4][0] for i in range(B)])).cuda()
@@ -53,6 +53,9 @@ def piped():
 
 
 t_pipe = timed(piped, n=8, drain=lambda: (eng.wait(0), eng.wait(1)))
+from vgqa_b200.engine import reference_flops
+gf = reference_flops(T, H, W, L) / 1e9
+print(f"T={T} {H}x{W} L={L}: {B / t_pipe * 1e3:.1f} clips/s = {B / t_pipe * gf:.0f} algorithmic TFLOP/s ({gf:.1f} GF per clip)")
 print(f"clips={B}: encoder phase alone (eager, + fp32 copy of the encoded features) {t_enc:.2f} ms | "
       f"full forward unpipelined {t_full:.2f} ms | pipelined {t_pipe:.2f} ms per step")
 
