@@ -138,7 +138,10 @@ def test_xattn_stream(F, S, tok0, Mk, use_bias, use_mask, want_att):
 
 
 @pytest.mark.parametrize("F,S,masked", [(5, 118, False), (300, 118, False), (3, 128, False), (7, 47, True), (2, 3, False),
-                                        (4, 27, False), (9, 118, True)])
+                                        (4, 27, False), (9, 118, True),
+                                        # more than 128 tokens per frame: online-softmax variant (attn_tc_long.cu)
+                                        (3, 129, False), (5, 352, False), (2, 412, True), (1, 256, False), (160, 200, True),
+                                        (2, 700, False)])
 def test_enc_attn_tcgen05(F, S, masked):
     """tcgen05/TMEM per-frame attention vs torch fp32, and vs the warp-MMA kernel on the same data."""
     from vgqa_b200 import _lib

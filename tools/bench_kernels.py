@@ -30,6 +30,8 @@ def bench_attn(F=4096, S=118):
     qkv = torch.randn(F * S, 768, device="cuda").bfloat16()
     O = torch.empty(F * S, 256, device="cuda", dtype=torch.bfloat16)
     for use_tc in (1, 0):
+        if use_tc and L.vgqa_enc_attn(_lib.ptr(qkv), _lib.ptr(O), F, S, None, 1 / math.sqrt(32), 1, st()) != 0:
+            print(f"enc_attn tcgen05 F={F} S={S}: not supported"); continue
         t = timeit(lambda: _lib.check(L.vgqa_enc_attn(_lib.ptr(qkv), _lib.ptr(O), F, S, None, 1 / math.sqrt(32), use_tc, st())))
         flops = 4.0 * S * S * 32 * 8 * F
         byts = F * S * (768 + 256) * 2
@@ -114,6 +116,10 @@ if __name__ == "__main__":
     if "attn" in which:
         bench_attn()
         bench_attn(F=1024, S=118)
+    if "attn_long" in which:
+        bench_attn(F=1024, S=352)
+        bench_attn(F=1024, S=412)
+        bench_attn(F=1024, S=256)
     if "xattn" in which:
         bench_xattn_stream(Mk=49, tok0=69, bias=False, name="spatial")
         bench_xattn_stream(Mk=69, tok0=0, name="decoder")

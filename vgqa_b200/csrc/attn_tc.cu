@@ -17,74 +17,9 @@
 // MUFU nor issue bandwidth explains, so throughput comes from units in flight: four S tiles live in TMEM (4 x 128 columns;
 // the O tile of a unit is written over the first 48 columns of its own S tile once the softmax has consumed it), Q|K and V
 // travel through separate rings (V must outlive the softmax), and the MMA warp issues P·V three units behind Q·K^T.
-#include "common.h"
-#include "ptx.cuh"
+#include "attn_tc.cuh"
 
 namespace vg {
-
-static constexpr int kAtWgs = 4;                  // softmax warpgroups = units in flight
-static constexpr int kAtLag = kAtWgs - 1;         // P·V is issued this many units behind Q·K^T
-static constexpr int kAtQkBytes = 2 * 8192;       // Q, K: 128 rows x 64 B each
-static constexpr int kAtVBytes = 8192;            // V
-static constexpr int kAtQkStages = 3;
-static constexpr int kAtVStages = kAtWgs + 1;     // a V tile is held from its load until the unit's P·V has completed
-static constexpr int kAtPBytes = 32768;           // P: 2 atoms of 128 rows x 128 B (its first 8 KB double as the O staging tile)
-static constexpr int kAtOnesBytes = 8192;         // constant bf16 1.0 tile: extra V columns that make the MMA emit row sums
-static constexpr int kAtThreads = 64 + kAtWgs * 128;
-static constexpr int kAtSmem = kAtQkStages * kAtQkBytes + kAtVStages * kAtVBytes + kAtWgs * kAtPBytes + kAtOnesBytes + 1024 + 256;
-static_assert(kAtSmem <= 232448, "attention smem");
-
-struct AttnTcParams {
-  const uint8_t* kmask;  // [F, S] or nullptr
-  int S, F;
-  float scale_log2e;
-};
-
-// K-major operand, rows of 64 B (32 bf16), 64B swizzle: 8-row groups 512 B apart.
-__device__ __forceinline__ uint64_t umma_desc_sw64_kmajor(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(512 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(4) << 61;  // SWIZZLE_64B
-  return d;
-}
-// MN-major operand (N contiguous): rows = K index, 64 B (32 bf16 of N) per row, 64B swizzle; 8-row K groups 512 B apart
-// (SBO); the second MN block (columns 32..47 = the constant ones tile → row sums of P) sits LBO bytes after the first.
-__device__ __forceinline__ uint64_t umma_desc_sw64_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;   // next 32-wide MN block (the ones tile)
-  d |= static_cast<uint64_t>(512 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(4) << 61;
-  return d;
-}
-
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-// two 2^x per MUFU op on packed bf16 (ex2(-inf) = +0); the result is directly the bf16x2 word stored into P
-__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
-  uint32_t y;
-  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
-}
-__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
-  uint32_t r;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-  return r;
-}
 
 __global__ void __launch_bounds__(kAtThreads, 1)
 enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_o,
@@ -308,7 +243,7 @@ void* tensor_map_encode_fn();  // gemm_tc.cu
 int device_sm_count();
 
 // [F frames][S tokens][cols] bf16 with row stride ld; box = 32 cols x 128 tokens x 1 frame, 64B swizzle.
-static CUtensorMap make_tmap_frames(const bf16* ptr, int F, int S, int cols, int ld) {
+CUtensorMap make_tmap_frames(const bf16* ptr, int F, int S, int cols, int ld) {
   CUtensorMap m;
   cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)S, (cuuint64_t)F};
   cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)S * ld * 2};
@@ -322,11 +257,17 @@ static CUtensorMap make_tmap_frames(const bf16* ptr, int F, int S, int cols, int
   return m;
 }
 
-bool enc_attn_tc_supported(int S) { return S >= 1 && S <= 128; }
+void enc_attn_tc_long(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* kmask, float scale, cudaStream_t stream);  // attn_tc_long.cu
+
+bool enc_attn_tc_supported(int S) { return S >= 1 && S <= 4096; }
 
 // AO[f*S + s, h*32 + d] = softmax_s'(scale * q·k) v  over the S tokens of frame f; QKV is [F*S, 768] (q | k | v).
 void enc_attn_tc(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* kmask, float scale, cudaStream_t stream) {
-  VG_CHECK(enc_attn_tc_supported(S) && F > 0, "enc_attn_tc: S must be in [1,128]");
+  VG_CHECK(enc_attn_tc_supported(S) && F > 0, "enc_attn_tc: S must be in [1,4096]");
+  if (S > 128) {   // several 128-key tiles per frame: online-softmax variant
+    enc_attn_tc_long(QKV, AO, F, S, kmask, scale, stream);
+    return;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     VG_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));

@@ -117,6 +117,8 @@ struct vgqa_ctx {
   // VGQA_FFN_FUSED=0 selects the two-kernel FFN (gemm_ws + gemm_ln) for A/B measurements; both are CUDA paths
   // VGQA_ENC_SMS: SMs the encoder-phase persistent kernels may occupy (0 = all)
   int enc_sm_budget = [] { const char* e = getenv("VGQA_ENC_SMS"); return e ? atoi(e) : 0; }();
+  // VGQA_ATTN_TC=0 selects the warp-MMA flash kernel for the encoder attention (A/B measurements)
+  bool use_attn_tc = [] { const char* e = getenv("VGQA_ATTN_TC"); return e == nullptr || e[0] != '0'; }();
   bool use_ffn_fused = [] { const char* e = getenv("VGQA_FFN_FUSED"); return e == nullptr || e[0] != '0'; }();
   std::unordered_map<std::string, HostT> sd;
   Arena warena, ws;
@@ -706,7 +708,7 @@ static void run_encoder(Fwd& f, const vgqa_inputs& in, bool have_mask, int pos_r
       gemm_ws(c->XP, c->X, 512, 256, e.qkv.W, 256, R, 768, 256, ep, st);
       f.count();
     }
-    if (enc_attn_tc_supported(S))   // tcgen05/TMEM kernel (7x7 .. 8x8 feature maps); larger frames use the warp-MMA flash kernel
+    if (c->use_attn_tc && enc_attn_tc_supported(S))   // tcgen05/TMEM kernels: attn_tc.cu (S <= 128), attn_tc_long.cu (key tiles, online softmax)
       enc_attn_tc(c->QKV, c->AO, F, S, km, 0.17677669529663687f, st);
     else
       mha32(c->QKV, 768, c->QKV + 256, 768, c->QKV + 512, 768, c->AO, 256, F, S, S, km, 0.17677669529663687f, st);
