@@ -110,67 +110,67 @@ input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-   if (warp == 0) {
-    // ===================== TMA producer: W k-blocks =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+    if (warp == 0) {
+      // ===================== TMA producer: W k-blocks =====================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < n_my; ++it) {
+          for (int kb = 0; kb < num_k; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&w_full[stage], kIpBBytes);
+            tma_load_2d(smem_b + stage * kIpBBytes, &tma_w, &w_full[stage], kb * 64, 0);
+            if (++stage == kIpStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
       for (int it = 0; it < n_my; ++it) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 256;
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&w_full[stage], kIpBBytes);
-          tma_load_2d(smem_b + stage * kIpBBytes, &tma_w, &w_full[stage], kb * 64, 0);
+          mbar_wait(&w_full[stage], phase);
+          mbar_wait(&a_full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem_a + stage * kIpABytes));
+            const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem_b + stage * kIpBBytes));
+  #pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_k - 1) umma_commit(&tfull_bar[acc]);
+            *consumed = it * num_k + kb + 1;
+          }
+          __syncwarp();
           if (++stage == kIpStages) { stage = 0; phase ^= 1; }
         }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
-    int stage = 0, acc = 0;
-    uint32_t phase = 0, acc_phase = 0;
-    for (int it = 0; it < n_my; ++it) {
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * 256;
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(&w_full[stage], phase);
-        mbar_wait(&a_full[stage], phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem_a + stage * kIpABytes));
-          const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem_b + stage * kIpBBytes));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          if (kb == num_k - 1) umma_commit(&tfull_bar[acc]);
-          *consumed = it * num_k + kb + 1;
-        }
-        __syncwarp();
-        if (++stage == kIpStages) { stage = 0; phase ^= 1; }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-   } else if (warp == 2) {
-    // ===================== L2 prefetcher =====================
-    if (lane == 0 && p.l2_prefetch) {
-      const int total = n_my * num_k;
-      const size_t chunk = (size_t)64 * p.P;   // floats of one frame's k-block: 64 channels x P tokens, contiguous
-      for (int g = 0; g < total; ++g) {
-        while (g > *consumed + kIpPrefetchDist) __nanosleep(100);
-        const int it = g / num_k, kb = g - it * num_k;
-        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-        if (p.fpt > 0) {
-          for (int fl = 0; fl < p.fpt; ++fl) {
-            const int frame = tile * p.fpt + fl;
-            if (frame < p.F) bulk_prefetch_l2(p.in + ((size_t)frame * p.C + kb * 64) * p.P, (uint32_t)(chunk * 4));
+    } else if (warp == 2) {
+      // ===================== L2 prefetcher =====================
+      if (lane == 0 && p.l2_prefetch) {
+        const int total = n_my * num_k;
+        const size_t chunk = (size_t)64 * p.P;   // floats of one frame's k-block: 64 channels x P tokens, contiguous
+        for (int g = 0; g < total; ++g) {
+          while (g > *consumed + kIpPrefetchDist) __nanosleep(100);
+          const int it = g / num_k, kb = g - it * num_k;
+          const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+          if (p.fpt > 0) {
+            for (int fl = 0; fl < p.fpt; ++fl) {
+              const int frame = tile * p.fpt + fl;
+              if (frame < p.F) bulk_prefetch_l2(p.in + ((size_t)frame * p.C + kb * 64) * p.P, (uint32_t)(chunk * 4));
+            }
+          } else if (tile % p.tpf == 0) {        // the first slice of a frame fetches the chunk for all of its slices
+            bulk_prefetch_l2(p.in + ((size_t)(tile / p.tpf) * p.C + kb * 64) * p.P, (uint32_t)(chunk * 4));
           }
-        } else if (tile % p.tpf == 0) {        // the first slice of a frame fetches the chunk for all of its slices
-          bulk_prefetch_l2(p.in + ((size_t)(tile / p.tpf) * p.C + kb * 64) * p.P, (uint32_t)(chunk * 4));
         }
       }
     }
-   }
   } else if (warp < 8) {
     // ===================== epilogue: TMEM row per thread → swizzled slab → coalesced row-segment stores =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
