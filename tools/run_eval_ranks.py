@@ -31,7 +31,7 @@ t0 = time.perf_counter()
 out = E.do_eval(eng, items, ev, clips_per_call=8, rank=rank, world=world)
 dt = time.perf_counter() - t0
 if rank == 0:
-    ref_ev = E.VidSTGEvaluator(gt, [0.3, 0.5])
+    ref_ev = E.VidSTGEvaluator(gt, [0.3, 0.5], distributed=False)
     ref = E.do_eval(eng, items, ref_ev, clips_per_call=8) if world > 1 else out
     same = all(abs(out[k] - ref[k]) < 1e-9 for k in ref) and ev.video_predictions == ref_ev.video_predictions if world > 1 else True
     print(f"do_eval world={world}: {n} items ({2 * n} clips of {T2 // 2} frames) in {dt * 1e3:.1f} ms; merged == single-rank: {same}; "

@@ -87,13 +87,14 @@ class VidSTGiouEvaluator:
 class VidSTGEvaluator:
     """Accumulates the per-rank prediction dicts, merges them across ranks and averages the metrics per question type."""
 
-    def __init__(self, gt_data, iou_thresholds: Sequence[float] = (0.3, 0.5), logger=None, group=None):
+    def __init__(self, gt_data, iou_thresholds: Sequence[float] = (0.3, 0.5), logger=None, group=None, distributed: bool = True):
         self.evaluator = VidSTGiouEvaluator(gt_data, list(iou_thresholds))
         self.iou_thresholds = list(iou_thresholds)
         self.predictions, self.att_predictions, self.confs, self.video_predictions, self.kf_pred = {}, {}, {}, {}, {}
         self.results = None
         self.logger = logger or logging.getLogger("vgqa_b200.evaluate")
         self.group = group
+        self.distributed = distributed   # False: a process-local evaluator (synchronize_between_processes is a no-op)
 
     def update(self, predictions): self.predictions.update(predictions)
     def update_att(self, predictions): self.att_predictions.update(predictions)
@@ -102,6 +103,8 @@ class VidSTGEvaluator:
     def video_update(self, video_predictions): self.video_predictions.update(video_predictions)
 
     def synchronize_between_processes(self):
+        if not self.distributed:
+            return
         for name in ("predictions", "att_predictions", "confs", "kf_pred", "video_predictions"):
             setattr(self, name, gather_predictions(getattr(self, name), self.group))
 
