@@ -79,6 +79,11 @@ typedef struct {
   const float* vid_raw;
   const float* text_raw;
   int vis_raw_ch, vid_raw_ch, text_raw_ch;
+  /* Optional RoBERTa token ids [clips, L] (int32, <s> ... </s>, pad id 1; L <= 64): replaces text / text_raw — the library runs
+   * the text tower itself (`self.body(**tokenized).last_hidden_state`, vgqa/core/language/bert.py:49,66-69: transformers
+   * RobertaModel embeddings + encoder layers, weights "text_encoder.body.*") and then text_encoder.resizer.  Padded positions
+   * are given by text_mask (1 = padded = `attention_mask.ne(1)`, bert.py:70), which also masks them in the cross-modal encoder. */
+  const int32_t* text_ids;
 } vgqa_inputs;
 
 /* Outputs (fp32 unless noted); any pointer may be NULL to skip that output.
@@ -165,6 +170,14 @@ int vgqa_shard_p2p_error(vgqa_ctx* ctx);
  * sizes_hw [clips,2] → boxes_px [clips,T,4] xyxy pixels (clamped at 0), sted_idx int32 [clips,2] = argmax (start,end), start < end. */
 int vgqa_postprocess(const float* boxes, const float* sted, const float* sizes_hw, float* boxes_px, int32_t* sted_idx,
                      int clips, int T, void* stream);
+
+/* The RoBERTa text tower + resizer alone (tests / serving a query once for many clips): ids [clips, L] int32 device pointer,
+ * text_mask [clips, L] uint8 (1 = padded) or NULL → hidden [clips, L, Hd] fp32 (= last_hidden_state, bf16-rounded: the rows the
+ * resizer reads) and text [clips, L, 256] fp32 (= the `text` input of vgqa_forward); either output may be NULL.
+ * vgqa_text_tower_hidden returns Hd (0 when the tower's weights were not given). */
+int vgqa_text_tower(vgqa_ctx* ctx, const int32_t* ids, const uint8_t* text_mask, int clips, int L, float* hidden, float* text,
+                    void* stream);
+int vgqa_text_tower_hidden(const vgqa_ctx* ctx);
 
 /* Counters: kernels launched by the last vgqa_forward call (graph replays count the captured launches). */
 int vgqa_last_launch_count(const vgqa_ctx* ctx);

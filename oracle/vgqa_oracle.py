@@ -566,6 +566,46 @@ def feature_resizer(x: np.ndarray, sd: Dict[str, np.ndarray], prefix: str = "tex
     return layer_norm(y, sd[prefix + ".layer_norm.weight"], sd[prefix + ".layer_norm.bias"], 1e-12)
 
 
+def roberta_encoder(sd, input_ids: np.ndarray, attention_pad: Optional[np.ndarray] = None, prefix: str = "text_encoder.body.",
+                    pad_id: int = 1, eps: float = 1e-5) -> np.ndarray:
+    """RoBERTa-base encoder → `last_hidden_state` (bert.py:66,69: `self.body(**tokenized).last_hidden_state`).
+
+    The arithmetic lives in a third-party dependency that is NOT vendored in the reference: `transformers` (pinned 4.37.2 in
+    the reference's requirements.txt:2; 5.5.0 in this image) `RobertaModel` = `RobertaEmbeddings` + 12 x `RobertaLayer`.
+    Restated from its published algorithm: position ids = cumsum(ids != pad) * (ids != pad) + pad; embeddings = word +
+    token_type[0] + position → LayerNorm(eps 1e-5 in roberta-base's config) ; per layer: q/k/v Linear, heads of 64,
+    softmax(q k^T / 8 + key padding mask) v, dense + LayerNorm(x + ·), dense 3072 erf-GELU, dense + LayerNorm(x + ·).
+    Pinned by tests/golden/make_golden_text.py against transformers' own RobertaModel run in this container.
+
+    input_ids (B, L) int; attention_pad (B, L) bool, True = padded (the reference's `attention_mask.ne(1)`, bert.py:70)."""
+    ids = np.asarray(input_ids)
+    B, L = ids.shape
+    keep = ids != pad_id
+    pos_ids = np.cumsum(keep, axis=1) * keep + pad_id
+    e = prefix + "embeddings."
+    x = sd[e + "word_embeddings.weight"][ids] + sd[e + "position_embeddings.weight"][pos_ids] + sd[e + "token_type_embeddings.weight"][0]
+    x = layer_norm(x, sd[e + "LayerNorm.weight"], sd[e + "LayerNorm.bias"], eps)
+    d = x.shape[-1]
+    nh, dh = d // 64, 64
+    i = 0
+    while f"{prefix}encoder.layer.{i}.attention.self.query.weight" in sd:
+        p = f"{prefix}encoder.layer.{i}."
+        lin = lambda t, n: linear(t, sd[p + n + ".weight"], sd[p + n + ".bias"])
+        q = lin(x, "attention.self.query").reshape(B, L, nh, dh).transpose(0, 2, 1, 3)
+        k = lin(x, "attention.self.key").reshape(B, L, nh, dh).transpose(0, 2, 1, 3)
+        v = lin(x, "attention.self.value").reshape(B, L, nh, dh).transpose(0, 2, 1, 3)
+        sc = (q @ k.transpose(0, 1, 3, 2)) / F32(math.sqrt(dh))
+        if attention_pad is not None:
+            sc = np.where(np.asarray(attention_pad, bool)[:, None, None, :], -np.inf, sc)
+        ctx = (softmax(sc, -1) @ v).transpose(0, 2, 1, 3).reshape(B, L, d)
+        a = layer_norm(lin(ctx, "attention.output.dense") + x, sd[p + "attention.output.LayerNorm.weight"],
+                       sd[p + "attention.output.LayerNorm.bias"], eps)
+        h = gelu_erf(lin(a, "intermediate.dense"))
+        x = layer_norm(lin(h, "output.dense") + a, sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"], eps)
+        i += 1
+    return x.astype(F32)
+
+
 def front_end(sd, vis_raw: np.ndarray, vid_raw: np.ndarray, text_raw: np.ndarray):
     """The step right before the hot path: grounding_net.py:101 `input_proj(vis_res_features)`,
     :105 `input_proj2(vid_features_all['3'])`, bert.py:70,73 `resizer(last_hidden_state.transpose(0, 1))`.
@@ -581,10 +621,12 @@ def front_end(sd, vis_raw: np.ndarray, vid_raw: np.ndarray, text_raw: np.ndarray
 # deterministic synthetic weights / inputs shared by golden maker, tests, bench and smoke
 # ----------------------------------------------------------------------------------------------
 def hot_path_param_shapes(enc_layers=6, dec_layers=6, d=256, ffn=2048, max_video_len=200,
-                          app_num=20, mot_num=34, front_end_ch: Optional[Tuple[int, int, int]] = None) -> Dict[str, Tuple[int, ...]]:
+                          app_num=20, mot_num=34, front_end_ch: Optional[Tuple[int, int, int]] = None,
+                          text_tower: Optional[Tuple[int, int]] = None) -> Dict[str, Tuple[int, ...]]:
     """Names/shapes of every state_dict entry the hot path READS (subset of SURVEY.md §8b).  `front_end_ch` =
     (ResNet channels, Video-Swin channels, RoBERTa hidden) appends `input_proj`, `input_proj2` and
-    `text_encoder.resizer` AFTER every other entry (so the hot-path weights of a seed do not depend on it)."""
+    `text_encoder.resizer` AFTER every other entry (so the hot-path weights of a seed do not depend on it).
+    `text_tower` = (layers, vocab) appends the RoBERTa encoder `text_encoder.body.*` (hidden = front_end_ch[2]) after those."""
     s: Dict[str, Tuple[int, ...]] = {}
 
     def lin(name, o, i):
@@ -637,6 +679,20 @@ def hot_path_param_shapes(enc_layers=6, dec_layers=6, d=256, ffn=2048, max_video
         s["input_proj.weight"] = (d, cv, 1, 1); s["input_proj.bias"] = (d,)
         s["input_proj2.weight"] = (d, cd, 1, 1); s["input_proj2.bias"] = (d,)
         lin("text_encoder.resizer.fc", d, ct); ln("text_encoder.resizer.layer_norm")
+    if text_tower is not None:
+        layers, vocab = text_tower
+        hd = front_end_ch[2]
+        b = "text_encoder.body."
+        s[b + "embeddings.word_embeddings.weight"] = (vocab, hd)
+        s[b + "embeddings.position_embeddings.weight"] = (514, hd)
+        s[b + "embeddings.token_type_embeddings.weight"] = (1, hd)
+        ln(b + "embeddings.LayerNorm", hd)
+        for i in range(layers):
+            p = f"{b}encoder.layer.{i}."
+            for n in ("query", "key", "value"):
+                lin(p + "attention.self." + n, hd, hd)
+            lin(p + "attention.output.dense", hd, hd); ln(p + "attention.output.LayerNorm", hd)
+            lin(p + "intermediate.dense", 4 * hd, hd); lin(p + "output.dense", hd, 4 * hd); ln(p + "output.LayerNorm", hd)
     return s
 
 
@@ -653,6 +709,11 @@ def synth_state_dict(seed: int = 0, **kw) -> Dict[str, np.ndarray]:
     for name, shp in hot_path_param_shapes(**kw).items():
         if name.endswith("time_embed.te"):
             sd[name] = seq_embedding_sine(shp[0], shp[2])
+        elif name.startswith("text_encoder.body.") and len(shp) >= 2:
+            # transformers init: N(0, 0.02) for Linear / Embedding weights → uniform of the same std; a larger scale (x4) on the
+            # Linear weights keeps the random-init tower away from the LayerNorm-only regime so that every matmul matters
+            bound = 0.02 * math.sqrt(3.0) * (1.0 if "embeddings" in name else 4.0)
+            sd[name] = rng.uniform(-bound, bound, size=shp).astype(F32)
         elif len(shp) >= 2:
             if name.startswith(("ground_encoder.", "ground_decoder.")):
                 bound = math.sqrt(6.0 / (shp[0] + shp[1]))
@@ -684,6 +745,21 @@ def synth_raw_inputs(seed: int, T: int, H: int, W: int, L: int, ch: Tuple[int, i
     vid_raw = rng.standard_normal((T, ch[1], H, W), dtype=F32)
     text_raw = rng.standard_normal((L, ch[2]), dtype=F32)
     return vis_raw, vid_raw, text_raw
+
+
+def synth_text_ids(seed: int, B: int, L: int, vocab: int, pad_tail: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """Token ids as RobertaTokenizer emits them: <s>=0 ... </s>=2, pad=1 on the last `pad_tail` positions of the odd rows.
+    Returns (ids (B, L) int32, pad mask (B, L) bool, True = padded)."""
+    rng = np.random.Generator(np.random.PCG64(7000 + seed))
+    ids = rng.integers(3, vocab, size=(B, L)).astype(np.int32)
+    ids[:, 0] = 0
+    pad = np.zeros((B, L), bool)
+    for b in range(B):
+        n = L - (pad_tail if b % 2 == 1 else 0)
+        ids[b, n - 1] = 2
+        ids[b, n:] = 1
+        pad[b, n:] = True
+    return ids, pad
 
 
 def synth_masks(masked: bool, T: int, H: int, W: int, L: int):

@@ -42,3 +42,20 @@ def test_front_end_then_hot_path_matches_reference(name):
         np.testing.assert_allclose(out[k], g[k], atol=2e-4, err_msg=k)
     assert out["debug"]["choose_pass1"] == g["choose_pass1"].tolist()
     assert out["debug"]["choose_pass2"] == g["choose_pass2"].tolist()
+
+
+TEXT_CASES = ["text_tiny_L5_2layers", "text_base_L20_12layers", "text_base_L64_12layers"]
+
+
+@pytest.mark.parametrize("name", TEXT_CASES)
+def test_roberta_oracle_matches_transformers(name):
+    """oracle.roberta_encoder + feature_resizer vs transformers' RobertaModel + the reference FeatureResizer (make_golden_text.py)."""
+    g = np.load(golden_path(name))
+    seed, B, L, layers, vocab, pad_tail = (int(g[k]) for k in ("seed", "B", "L", "layers", "vocab", "pad_tail"))
+    sd = O.synth_state_dict(seed, front_end_ch=tuple(int(x) for x in g["front_end_ch"]), text_tower=(layers, vocab))
+    ids, pad = O.synth_text_ids(seed, B, L, vocab, pad_tail)
+    hid = O.roberta_encoder(sd, ids, pad)
+    keep = ~pad
+    assert float(np.abs(hid - g["last_hidden_state"])[keep].max()) <= 5e-5
+    text = O.feature_resizer(hid, sd).transpose(1, 0, 2)          # (L, B, 256) as bert.py:69,73
+    assert float(np.abs(text - g["text_resized"])[keep.T].max()) <= 5e-5

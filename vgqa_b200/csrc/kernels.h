@@ -30,6 +30,12 @@ void input_proj(const float* in, int C, const bf16* W, const float* bias, const 
                 bf16* XP, int F, int S, int tok0, int P, cudaStream_t stream);
 void f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t st);
 
+// ---- text_tower.cu: SIMT pieces of the RoBERTa text tower (the Linear layers are tcgen05 GEMMs)
+void roberta_embed_ln(const int* ids, const float* word, const float* pos, const float* type0, const float* w, const float* b,
+                      float eps, float* x32, bf16* x, int rows, int L, int Hd, int vocab, int max_pos, int pad_id, cudaStream_t st);
+void ln_rows_wide(const float* x, const float* w, const float* b, float eps, float* y32, bf16* y, int rows, int Hd, cudaStream_t st);
+void text_attn(const bf16* QKV, const uint8_t* pad, bf16* ctx, int Q, int L, int Hd, cudaStream_t st);
+
 // ---- small.cu
 // NCHW fp32 features → token-major bf16 rows: X[(f*S + tok0 + p), c] = in[f, c, p]   (in may be broadcast: fstride 0)
 void nchw_to_tokens(const float* in, long long in_fstride, bf16* X, float* X32, const float* pos, long long pos_fstride,

@@ -105,6 +105,7 @@ struct Head { Lin t; LNp ln; float* dw = nullptr; float* db = nullptr; int vocab
 struct TimeLayer { Lin qkv, out, qabs, vo, ff1, ff2; LNp ln1, ln3, ln4; float* tab = nullptr; };
 struct PosLayer { Lin sa, sa_out, q, sine, qabs, vo, ff1, ff2; LNp ln1, ln3, ln4; float* tab_sa = nullptr; };
 struct Mlp2 { Lin l0; float* w1 = nullptr; float* b1 = nullptr; int n1 = 0; };
+struct TextLayer { Lin qkv, out, ff1, ff2; LNp ln1, ln2; };   // one RobertaLayer (q;k;v packed into one [3*Hd, Hd] Linear)
 
 }  // namespace vg
 
@@ -143,6 +144,13 @@ struct vgqa_ctx {
   LNp ip_text_ln;
   bf16 *traw = nullptr, *tproj = nullptr;   // text_raw as bf16 rows, resizer output (bf16 twin of tproj32)
   float* tproj32 = nullptr;
+  // optional RoBERTa text tower (text_encoder.body.*): token ids → last_hidden_state → resizer
+  std::vector<TextLayer> tt;
+  float *tt_word = nullptr, *tt_pos = nullptr, *tt_type = nullptr;
+  LNp tt_emb_ln;
+  int tt_vocab = 0, tt_maxpos = 0, tt_hd = 0;
+  float *tx32 = nullptr, *ta32 = nullptr;
+  bf16 *tx = nullptr, *ta = nullptr, *tqkv = nullptr, *tctx = nullptr, *th = nullptr;
   // ---- workspace (device)
   bf16 *X, *X1, *QKV, *AO, *HID, *Xf, *pos_enc, *kposb;
   // positional score terms of the decoders' cross-attentions as GEMM outputs (frame-invariant pos only)
@@ -155,6 +163,7 @@ struct vgqa_ctx {
   struct HostSlot {
     float *vis, *vid, *text, *pos, *sizes, *f1, *f2;
     float *vis_raw = nullptr, *vid_raw = nullptr, *text_raw = nullptr;
+    int* ids = nullptr;
     uint8_t *vmask, *tmask;
     cudaEvent_t done = nullptr;
     bool used = false;
@@ -288,7 +297,10 @@ static void pack_weights(vgqa_ctx* c) {
   Packer P{c};
   const vgqa_config& cfg = c->cfg;
   const int F = cfg.ffn_dim, Tm = cfg.max_video_len + 1;
-  c->warena.init((size_t)320 << 20);
+  size_t tower_bytes = 0;   // the optional text tower brings ≈330 MB of its own (fp32 embeddings + bf16 layers)
+  for (const auto& kv : c->sd)
+    if (kv.first.rfind("text_encoder.body.", 0) == 0) tower_bytes += (size_t)kv.second.numel() * 4 + 512;
+  c->warena.init(((size_t)320 << 20) + tower_bytes);
   // ---------------- encoder (modal_encoder.py:143-178)
   c->enc.resize(cfg.enc_layers);
   for (int l = 0; l < cfg.enc_layers; ++l) {
@@ -517,6 +529,43 @@ static void pack_weights(vgqa_ctx* c) {
   c->ip_vid = conv1x1("input_proj2");
   c->ip_text = conv1x1("text_encoder.resizer.fc");
   if (c->ip_text.K > 0) c->ip_text_ln = P.ln("text_encoder.resizer.layer_norm");
+  // ---------------- optional RoBERTa tower (transformers RobertaModel under `text_encoder.body`, bert.py:49)
+  const std::string tb = "text_encoder.body.";
+  auto wit = c->sd.find(tb + "embeddings.word_embeddings.weight");
+  if (wit != c->sd.end()) {
+    VG_CHECK(wit->second.shape.size() == 2, "word_embeddings.weight must be [vocab, hidden]");
+    const int Hd = (int)wit->second.shape[1];
+    VG_CHECK(Hd % 64 == 0, "text tower: the hidden size must be a multiple of 64");
+    VG_CHECK(c->ip_text.K == Hd, "text tower: 'text_encoder.resizer.fc' must take the tower's hidden size");
+    c->tt_hd = Hd; c->tt_vocab = (int)wit->second.shape[0];
+    c->tt_word = P.f32(wit->second.v);
+    const HostT& pe = P.get(tb + "embeddings.position_embeddings.weight");
+    VG_CHECK(pe.shape.size() == 2 && pe.shape[1] == Hd, "position_embeddings.weight must be [max_pos, hidden]");
+    c->tt_maxpos = (int)pe.shape[0];
+    c->tt_pos = P.f32(pe.v);
+    c->tt_type = P.f32(P.get(tb + "embeddings.token_type_embeddings.weight").v.data(), Hd);   // row 0 (type ids are all zero)
+    c->tt_emb_ln = P.ln(tb + "embeddings.LayerNorm", Hd);
+    for (int l = 0; c->sd.count(tb + "encoder.layer." + std::to_string(l) + ".attention.self.query.weight"); ++l) {
+      const std::string p = tb + "encoder.layer." + std::to_string(l) + ".";
+      TextLayer t;
+      std::vector<float> W((size_t)3 * Hd * Hd), b((size_t)3 * Hd);
+      const char* qkv[3] = {"query", "key", "value"};
+      for (int k = 0; k < 3; ++k) {
+        const HostT& w = P.get(p + "attention.self." + qkv[k] + ".weight", {Hd, Hd});
+        const HostT& bb = P.get(p + "attention.self." + qkv[k] + ".bias", {Hd});
+        std::copy(w.v.begin(), w.v.end(), W.begin() + (size_t)k * Hd * Hd);
+        std::copy(bb.v.begin(), bb.v.end(), b.begin() + (size_t)k * Hd);
+      }
+      t.qkv = P.lin(W.data(), b.data(), 3 * Hd, Hd);
+      t.out = P.lin(p + "attention.output.dense", Hd, Hd);
+      t.ln1 = P.ln(p + "attention.output.LayerNorm", Hd);
+      t.ff1 = P.lin(p + "intermediate.dense", 4 * Hd, Hd);
+      t.ff2 = P.lin(p + "output.dense", Hd, 4 * Hd);
+      t.ln2 = P.ln(p + "output.LayerNorm", Hd);
+      c->tt.push_back(t);
+    }
+    VG_CHECK(!c->tt.empty(), "text tower: no encoder layers found under text_encoder.body.encoder.layer.*");
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ workspace
@@ -555,6 +604,12 @@ static void carve_workspace(vgqa_ctx* c) {
     if (c->ip_vis.K > 0) h.vis_raw = a.get<float>(F * c->ip_vis.K * P);
     if (c->ip_vid.K > 0) h.vid_raw = a.get<float>(F * c->ip_vid.K * P);
     if (c->ip_text.K > 0) h.text_raw = a.get<float>(B * L * c->ip_text.K);
+  }
+  if (!c->tt.empty()) {
+    const size_t Hd = c->tt_hd, Rt = B * L;
+    c->tx32 = a.get<float>(Rt * Hd); c->ta32 = a.get<float>(Rt * Hd); c->tx = a.get<bf16>(Rt * Hd); c->ta = a.get<bf16>(Rt * Hd);
+    c->tqkv = a.get<bf16>(Rt * 3 * Hd); c->tctx = a.get<bf16>(Rt * Hd); c->th = a.get<bf16>(Rt * 4 * Hd);
+    for (auto& h : c->hs) h.ids = a.get<int>(Rt);
   }
   if (c->ip_text.K > 0) {
     c->traw = a.get<bf16>(B * L * c->ip_text.K); c->tproj = a.get<bf16>(B * L * 256); c->tproj32 = a.get<float>(B * L * 256);
@@ -666,6 +721,35 @@ struct Fwd {
   }
 };
 
+// RoBERTa encoder (transformers RobertaModel: embeddings + N x RobertaLayer, post-LayerNorm, eps 1e-5 as in roberta-base's
+// config) over clips x L token ids → bf16 last_hidden_state rows in c->traw (the resizer's A operand).  bert.py:66-69.
+static void run_text_tower(Fwd& f, const int* ids, const uint8_t* pad) {
+  vgqa_ctx* c = f.c;
+  cudaStream_t st = f.st;
+  const int Hd = c->tt_hd, R = f.B * f.L;
+  const float eps = 1e-5f;
+  roberta_embed_ln(ids, c->tt_word, c->tt_pos, c->tt_type, c->tt_emb_ln.w, c->tt_emb_ln.b, eps, c->tx32, c->tx, R, f.L, Hd,
+                   c->tt_vocab, c->tt_maxpos, /*pad_id=*/1, st);
+  f.count();
+  for (size_t l = 0; l < c->tt.size(); ++l) {
+    TextLayer& t = c->tt[l];
+    f.linear(c->tx, Hd, t.qkv, R, c->tqkv, 3 * Hd);
+    text_attn(c->tqkv, pad, c->tctx, f.B, f.L, Hd, st);
+    {  // attention.output: LayerNorm(dense(ctx) + x)
+      GemmEpi ep; ep.C = c->ta32; ep.ldc = Hd; ep.c_f32 = 1; ep.bias = t.out.b; ep.bias_ld = Hd; ep.res32 = c->tx32; ep.ldres32 = Hd;
+      f.gemm(c->tctx, Hd, t.out, R, ep);
+    }
+    ln_rows_wide(c->ta32, t.ln1.w, t.ln1.b, eps, c->ta32, c->ta, R, Hd, st);
+    f.linear(c->ta, Hd, t.ff1, R, c->th, 4 * Hd, ACT_GELU);
+    {  // output: LayerNorm(dense(gelu(...)) + attention_output)
+      GemmEpi ep; ep.C = c->tx32; ep.ldc = Hd; ep.c_f32 = 1; ep.bias = t.ff2.b; ep.bias_ld = Hd; ep.res32 = c->ta32; ep.ldres32 = Hd;
+      f.gemm(c->th, 4 * Hd, t.ff2, R, ep);
+    }
+    ln_rows_wide(c->tx32, t.ln2.w, t.ln2.b, eps, c->tx32, l + 1 == c->tt.size() ? c->traw : c->tx, R, Hd, st);
+    f.count(3);
+  }
+}
+
 static void run_encoder(Fwd& f, const vgqa_inputs& in, bool have_mask, int pos_rows) {
   vgqa_ctx* c = f.c;
   cudaStream_t st = f.st;
@@ -689,12 +773,12 @@ static void run_encoder(Fwd& f, const vgqa_inputs& in, bool have_mask, int pos_r
     nchw_to_tokens(in.vid, (long long)256 * P, c->X, c->X32, in.pos, pos_fs, c->XP, F, S, P + L, P, st);
   f.count(2);
   const float* text = in.text;
-  if (in.text_raw != nullptr) {  // FeatureResizer: LayerNorm_1e-12(fc(hidden states)) (bert.py:90-96), dropout = identity
-    f32_to_bf16(in.text_raw, c->traw, (size_t)f.B * L * c->ip_text.K, st);
+  if (in.text_ids != nullptr) run_text_tower(f, in.text_ids, in.text_mask);   // → c->traw (bf16 last_hidden_state rows)
+  if (in.text_raw != nullptr || in.text_ids != nullptr) {  // FeatureResizer: LayerNorm_1e-12(fc(hidden states)) (bert.py:90-96)
+    if (in.text_ids == nullptr) { f32_to_bf16(in.text_raw, c->traw, (size_t)f.B * L * c->ip_text.K, st); f.count(); }
     GemmEpi ep; ep.C = c->tproj; ep.ldc = 256; ep.bias = c->ip_text.b; ep.bias_ld = 256; ep.C32 = c->tproj32; ep.ldc32 = 256;
     ep.ln_w = c->ip_text_ln.w; ep.ln_b = c->ip_text_ln.b; ep.ln_eps = 1e-12f;
     f.gemm(c->traw, c->ip_text.K, c->ip_text, f.B * L, ep);
-    f.count();
     text = c->tproj32;
   }
   text_to_tokens(text, c->X, c->X32, c->XP, F, f.T, S, P, L, st);
@@ -943,8 +1027,11 @@ static void check_inputs(vgqa_ctx* c, const vgqa_inputs& in) {
            "shape exceeds the context capacity: " + shape_str(in));
   VG_CHECK(in.T <= c->cfg.max_video_len + 1,
            "T exceeds INPUT.MAX_VIDEO_LEN+1 rows of the time embedding (reference raises RuntimeError too)");
-  VG_CHECK((in.vis || in.vis_raw) && (in.vid || in.vid_raw) && (in.text || in.text_raw) && in.pos,
-           "vis/vid/text (or their *_raw forms) and pos must be non-null");
+  VG_CHECK((in.vis || in.vis_raw) && (in.vid || in.vid_raw) && (in.text || in.text_raw || in.text_ids) && in.pos,
+           "vis/vid/text (or their *_raw / text_ids forms) and pos must be non-null");
+  VG_CHECK(!in.text_ids || (!c->tt.empty() && c->ip_text.K > 0),
+           "text_ids needs the 'text_encoder.body' (RoBERTa) and 'text_encoder.resizer' weights");
+  VG_CHECK(!in.text_ids || in.L <= 64, "text_ids: a query has at most 64 tokens");
   VG_CHECK(!in.vis_raw || (c->ip_vis.K > 0 && in.vis_raw_ch == c->ip_vis.K),
            "vis_raw needs the 'input_proj' weights and vis_raw_ch equal to their input channels");
   VG_CHECK(!in.vid_raw || (c->ip_vid.K > 0 && in.vid_raw_ch == c->ip_vid.K),
@@ -1165,7 +1252,7 @@ static int run_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out
   for (const void* q : {(const void*)in.vis, (const void*)in.vid, (const void*)in.text, (const void*)in.pos,
                         (const void*)in.vis_mask, (const void*)in.text_mask, (const void*)in.ori_sizes_hw,
                         (const void*)in.force_choose1, (const void*)in.force_choose2, (const void*)in.vis_raw,
-                        (const void*)in.vid_raw, (const void*)in.text_raw})
+                        (const void*)in.vid_raw, (const void*)in.text_raw, (const void*)in.text_ids})
     key.push_back((uint64_t)(uintptr_t)q);
   if (phase == 1)
     for (const void* q : {(const void*)out.pred_boxes, (const void*)out.pred_sted, (const void*)out.pred_actioness,
@@ -1282,7 +1369,8 @@ int vgqa_forward_host_async(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outp
     else { h2d(h.vis, hin->vis, F * 256 * P * 4); din.vis = h.vis; }
     if (hin->vid_raw) { h2d(h.vid_raw, hin->vid_raw, F * c->ip_vid.K * P * 4); din.vid_raw = h.vid_raw; din.vid = nullptr; }
     else { h2d(h.vid, hin->vid, F * 256 * P * 4); din.vid = h.vid; }
-    if (hin->text_raw) { h2d(h.text_raw, hin->text_raw, B * L * c->ip_text.K * 4); din.text_raw = h.text_raw; din.text = nullptr; }
+    if (hin->text_ids) { h2d(h.ids, hin->text_ids, B * L * 4); din.text_ids = h.ids; din.text = nullptr; din.text_raw = nullptr; }
+    else if (hin->text_raw) { h2d(h.text_raw, hin->text_raw, B * L * c->ip_text.K * 4); din.text_raw = h.text_raw; din.text = nullptr; }
     else { h2d(h.text, hin->text, B * L * 256 * 4); din.text = h.text; }
     h2d(h.pos, hin->pos, (size_t)hin->pos_frames * 256 * P * 4); din.pos = h.pos;
     if (hin->vis_mask) { h2d(h.vmask, hin->vis_mask, F * P); din.vis_mask = h.vmask; }
@@ -1375,6 +1463,28 @@ int vgqa_postprocess(const float* boxes, const float* sted, const float* sizes_h
   try {
     VG_CHECK(boxes && sted && sizes_hw && boxes_px && sted_idx && clips >= 1 && T >= 2, "vgqa_postprocess: bad argument");
     vg::postprocess(boxes, sted, sizes_hw, boxes_px, sted_idx, clips, T, static_cast<cudaStream_t>(stream));
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_text_tower_hidden(const vgqa_ctx* c) { return c ? c->tt_hd : 0; }
+
+int vgqa_text_tower(vgqa_ctx* c, const int32_t* ids, const uint8_t* text_mask, int clips, int L, float* hidden, float* text,
+                    void* stream) {
+  try {
+    VG_CHECK(c && c->finalized && ids && clips >= 1 && L >= 1, "vgqa_text_tower: bad argument");
+    VG_CHECK(!c->tt.empty() && c->ip_text.K > 0, "vgqa_text_tower needs the 'text_encoder.body' and 'text_encoder.resizer' weights");
+    VG_CHECK(clips <= c->cfg.max_clips && L <= c->cfg.max_text && L <= 64, "vgqa_text_tower: shape exceeds the context capacity");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    vg::Fwd f;
+    f.c = c; f.st = st; f.main = st; f.aux = st; f.aux2 = st; f.B = clips; f.L = L;
+    vg::run_text_tower(f, ids, text_mask);
+    vg::GemmEpi ep; ep.C = c->tproj; ep.ldc = 256; ep.bias = c->ip_text.b; ep.bias_ld = 256; ep.C32 = c->tproj32; ep.ldc32 = 256;
+    ep.ln_w = c->ip_text_ln.w; ep.ln_b = c->ip_text_ln.b; ep.ln_eps = 1e-12f;
+    f.gemm(c->traw, c->ip_text.K, c->ip_text, clips * L, ep);
+    const size_t n = (size_t)clips * L * c->tt_hd;
+    if (hidden) bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->traw, hidden, n);
+    if (text) VG_CUDA(cudaMemcpyAsync(text, c->tproj32, (size_t)clips * L * 256 * 4, cudaMemcpyDeviceToDevice, st));
     return 0;
   } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
 }

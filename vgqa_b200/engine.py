@@ -28,7 +28,7 @@ class VgqaInputs(ctypes.Structure):
                 ("force_choose1", c_void_p), ("force_choose2", c_void_p), ("iteration_rate", c_int),
                 ("stop_after_encoder", c_int),
                 ("vis_raw", c_void_p), ("vid_raw", c_void_p), ("text_raw", c_void_p),
-                ("vis_raw_ch", c_int), ("vid_raw_ch", c_int), ("text_raw_ch", c_int)]
+                ("vis_raw_ch", c_int), ("vid_raw_ch", c_int), ("text_raw_ch", c_int), ("text_ids", c_void_p)]
 
 
 OUTPUT_FIELDS = ("pred_boxes", "pred_sted", "pred_actioness", "logits_f_m", "logits_f_a", "logits_r_a", "logits_r_m",
@@ -190,10 +190,13 @@ class GroundingEngine:
         return None if t is None else c_void_p(t.data_ptr())
 
     def _pack_io(self, vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force1, force2, iteration_rate, outs,
-                 stop_after_encoder=0, raw=False):
+                 stop_after_encoder=0, raw=False, text_ids=None):
         """raw=True: vis / vid / text are the extractor outputs ([clips,T,Cv,H,W], [clips,T,Cd,H,W], [clips,L,Ct]) and the
         library applies input_proj / input_proj2 / text_encoder.resizer itself (their weights must be in the state_dict)."""
         B, T, d, H, W = vis.shape
+        if text_ids is not None:   # RoBERTa token ids [clips, L] int32: the library runs the text tower + resizer (raw=True only)
+            assert raw and text_ids.dtype == torch.int32 and text_ids.dim() == 2 and text_ids.shape[0] == B and text_ids.is_contiguous()
+            text = torch.empty(B, text_ids.shape[1], 0, dtype=torch.float32, device=text_ids.device)   # placeholder (shape only)
         if raw:
             assert tuple(vid.shape[:2]) == (B, T) and tuple(vid.shape[3:]) == (H, W), "vid_raw must be [clips, T, C, H, W]"
             assert text.dim() == 3 and text.shape[0] == B, "text_raw must be [clips, L, C]"
@@ -209,39 +212,40 @@ class GroundingEngine:
                          self._p(pos), pos.shape[0],
                          self._p(vis_mask), self._p(text_mask), self._p(ori_sizes_hw), self._p(force1), self._p(force2),
                          iteration_rate, stop_after_encoder,
-                         self._p(vis) if raw else n, self._p(vid) if raw else n, self._p(text) if raw else n,
-                         vis.shape[2] if raw else 0, vid.shape[2] if raw else 0, text.shape[2] if raw else 0)
+                         self._p(vis) if raw else n, self._p(vid) if raw else n,
+                         self._p(text) if (raw and text_ids is None) else n,
+                         vis.shape[2] if raw else 0, vid.shape[2] if raw else 0, text.shape[2] if raw else 0, self._p(text_ids))
         out = VgqaOutputs(**{k: self._p(outs.get(k)) for k in OUTPUT_FIELDS})
         return inp, out
 
-    def encode(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, raw=False):
+    def encode(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, raw=False, text_ids=None):
         """CrossModalEncoder only: returns encoded_feature [clips*T, S, 256] (frame-major) and frames_cls [clips*T, 256]."""
         B, T, _, H, W = vis.shape
-        outs = self.alloc_outputs(B, T, H, W, text.shape[1], ["encoded_feature", "frames_cls"])
-        inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, None, None, None, -1, outs, 1, raw=raw)
+        outs = self.alloc_outputs(B, T, H, W, (text_ids if text_ids is not None else text).shape[1], ["encoded_feature", "frames_cls"])
+        inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, None, None, None, -1, outs, 1, raw=raw, text_ids=text_ids)
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(self._L.vgqa_forward(self._ctx, ctypes.byref(inp), ctypes.byref(out), c_void_p(st)))
         return outs
 
     def forward(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, ori_sizes_hw=None, force_choose1=None,
-                force_choose2=None, iteration_rate=-1, outs=None, want=None, raw=False):
+                force_choose2=None, iteration_rate=-1, outs=None, want=None, raw=False, text_ids=None):
         """Device-resident inputs (fp32 CUDA tensors, reference layouts); enqueues on the current stream."""
         B, T, _, H, W = vis.shape
         if outs is None:
-            outs = self.alloc_outputs(B, T, H, W, text.shape[1], want)
+            outs = self.alloc_outputs(B, T, H, W, (text_ids if text_ids is not None else text).shape[1], want)
             if ori_sizes_hw is None:
                 outs.pop("boxes_px", None), outs.pop("sted_idx", None)
         inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force_choose1, force_choose2,
-                                 iteration_rate, outs, raw=raw)
+                                 iteration_rate, outs, raw=raw, text_ids=text_ids)
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(self._L.vgqa_forward(self._ctx, ctypes.byref(inp), ctypes.byref(out), c_void_p(st)))
         return outs
 
     def forward_async(self, vis, vid, text, pos, *, outs, slot, vis_mask=None, text_mask=None, ori_sizes_hw=None,
-                      force_choose1=None, force_choose2=None, iteration_rate=-1, raw=False):
+                      force_choose1=None, force_choose2=None, iteration_rate=-1, raw=False, text_ids=None):
         """Pipelined device path: alternate slot 0/1 on consecutive calls; `outs` are complete after `wait(slot)`."""
         inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force_choose1, force_choose2,
-                                 iteration_rate, outs, raw=raw)
+                                 iteration_rate, outs, raw=raw, text_ids=text_ids)
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(self._L.vgqa_forward_async(self._ctx, ctypes.byref(inp), ctypes.byref(out), slot, c_void_p(st)))
         return outs
@@ -252,28 +256,45 @@ class GroundingEngine:
         _lib.check(self._L.vgqa_forward_wait(self._ctx, slot, c_void_p(st), 1 if host_sync else 0))
 
     def forward_host(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, ori_sizes_hw=None,
-                     force_choose1=None, force_choose2=None, iteration_rate=-1, outs=None, want=None, raw=False):
+                     force_choose1=None, force_choose2=None, iteration_rate=-1, outs=None, want=None, raw=False, text_ids=None):
         """Host buffers (CPU tensors, ideally pinned): H2D + forward + D2H inside the call (synchronous)."""
         B, T, _, H, W = vis.shape
         if outs is None:
-            outs = self.alloc_outputs(B, T, H, W, text.shape[1], want, host=True)
+            outs = self.alloc_outputs(B, T, H, W, (text_ids if text_ids is not None else text).shape[1], want, host=True)
             if ori_sizes_hw is None:
                 outs.pop("boxes_px", None), outs.pop("sted_idx", None)
         inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force_choose1, force_choose2,
-                                 iteration_rate, outs, raw=raw)
+                                 iteration_rate, outs, raw=raw, text_ids=text_ids)
         _lib.check(self._L.vgqa_forward_host(self._ctx, ctypes.byref(inp), ctypes.byref(out)))
         return outs
 
     def forward_host_async(self, vis, vid, text, pos, *, outs, slot, vis_mask=None, text_mask=None, ori_sizes_hw=None,
-                           force_choose1=None, force_choose2=None, iteration_rate=-1, raw=False):
+                           force_choose1=None, force_choose2=None, iteration_rate=-1, raw=False, text_ids=None):
         """Pipelined host path: returns immediately; `outs` (pinned host tensors) are valid after `wait_host(slot)`."""
         inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, ori_sizes_hw, force_choose1, force_choose2,
-                                 iteration_rate, outs, raw=raw)
+                                 iteration_rate, outs, raw=raw, text_ids=text_ids)
         _lib.check(self._L.vgqa_forward_host_async(self._ctx, ctypes.byref(inp), ctypes.byref(out), slot))
         return outs
 
     def wait_host(self, slot: int):
         _lib.check(self._L.vgqa_forward_host_wait(self._ctx, slot))
+
+    def text_tower(self, text_ids, text_mask=None):
+        """RoBERTa tower + resizer alone (parity tests): ids [clips, L] int32 (device) → (last_hidden_state [clips, L, Hd] fp32 of
+        the bf16 rows the resizer reads, resized text [clips, L, 256] fp32)."""
+        B, L = text_ids.shape
+        self._L.vgqa_text_tower.restype = c_int
+        self._L.vgqa_text_tower.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+        hd = torch.empty(1, dtype=torch.int32)
+        self._L.vgqa_text_tower_hidden.restype = c_int
+        self._L.vgqa_text_tower_hidden.argtypes = [c_void_p]
+        Hd = int(self._L.vgqa_text_tower_hidden(self._ctx))
+        hidden = torch.zeros(B, L, Hd, device=self.device)
+        text = torch.zeros(B, L, 256, device=self.device)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self._L.vgqa_text_tower(self._ctx, self._p(text_ids), self._p(text_mask), B, L, self._p(hidden), self._p(text),
+                                           c_void_p(st)))
+        return hidden, text
 
     @property
     def last_launch_count(self) -> int:
