@@ -33,6 +33,7 @@ METRIC = "grounding clips/sec (64f@224, bf16)"   # BASELINE.json's metric; both 
 WORKLOAD = "cfg2 grounding_vidstg.yaml@224: T=64 frames, 7x7 feature map, L=20 text tokens, 6 enc + 6 dec layers, 2 decoder passes"
 
 
+TEXT_TOWER = (12, 50265)          # RoBERTa-base: encoder layers, vocabulary (bert.py:49)
 FRONT_END_CH = (2048, 768, 768)   # ResNet101 layer-4, Video-Swin stage-3, RoBERTa-base channels (grounding_net.py:62,71; bert.py:77)
 
 
@@ -204,7 +205,7 @@ def main():
     pk = peaks()
     # hot-path weights of seed 0 + the front-end weights (input_proj / input_proj2 / text resizer) for the secondary
     # `front_end` measurement; the hot-path tensors of a seed do not depend on front_end_ch
-    eng = GroundingEngine(O.synth_state_dict(0, front_end_ch=FRONT_END_CH), max_clips=B, max_frames=T, max_hw=H * W, max_text=L,
+    eng = GroundingEngine(O.synth_state_dict(0, front_end_ch=FRONT_END_CH, text_tower=TEXT_TOWER), max_clips=B, max_frames=T, max_hw=H * W, max_text=L,
                           use_cuda_graph=not args.no_graph)
     # synthetic inputs: 8 distinct seeded clips tiled to B (per-rank offset), fp32 reference layouts
     base = [O.synth_inputs(rank * 8 + i, T, H, W, L) for i in range(8)]
@@ -299,6 +300,15 @@ def main():
         raw_i[0] += 1
 
     sec_raw = timed(step_raw, args.steps, drain=drain_dev)
+    # ... and from RoBERTa token ids: the 12-layer text tower (csrc/text_tower.cu + tcgen05 GEMMs) runs inside the forward too
+    r_ids = torch.from_numpy(O.synth_text_ids(rank, B, L, TEXT_TOWER[1])[0]).cuda()
+
+    def step_ids():
+        slot = raw_i[0] & 1
+        eng.forward_async(r_vis, r_vid, None, d_pos, ori_sizes_hw=d_sizes, outs=d_outs2[slot], slot=slot, raw=True, text_ids=r_ids)
+        raw_i[0] += 1
+
+    sec_ids = timed(step_ids, args.steps, drain=drain_dev)
     raw_bytes = int((r_vis.numel() + r_vid.numel() + r_text.numel()) * 4)
     del r_vis, r_vid, r_text
     total_clips = B * world * args.steps
@@ -323,7 +333,10 @@ def main():
                           "what": "same step from RAW extractor maps resident in HBM: input_proj (2048->256) + input_proj2 (768->256) "
                                   "+ text resizer fused into the forward (SURVEY 8f rank 2); adds 4.5 GFLOP and "
                                   f"{raw_bytes / B / 1e6:.1f} MB of fp32 reads per clip",
-                          "raw_input_bytes_per_step": raw_bytes},
+                          "raw_input_bytes_per_step": raw_bytes,
+                          "from_token_ids": {"value": total_clips / sec_ids, "unit": "clips/s", "ms_per_step": 1e3 * sec_ids / args.steps,
+                                             "what": f"as above, text from RoBERTa token ids: the {TEXT_TOWER[0]}-layer RoBERTa-base tower "
+                                                     f"({B} queries x {L} tokens per step) also runs inside the forward"}},
             "gpu_launches": int(launches) * args.steps,
             "gpu_launches_per_step": int(launches),
             "clocks": clocks,
