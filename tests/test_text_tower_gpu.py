@@ -64,3 +64,35 @@ def test_forward_from_token_ids_matches_oracle_chain():
         e2 = GroundingEngine(O.synth_state_dict(seed, front_end_ch=ch), max_clips=1, max_frames=T, max_hw=H * W, max_text=L)
         e2.forward(t(vis_raw[None]), t(vid_raw[None]), None, t(pos[:1]), raw=True, text_ids=t(ids))
     eng.close()
+
+
+def test_vstgnet_dropin_with_fused_text_tower():
+    """B200VSTGNet with a text encoder that only has a tokenizer: RoBERTa + resizer + input_proj* run inside the library."""
+    from make_golden import make_cfg
+    from vgqa_b200 import modules as M
+    seed, T, H, W, L, layers, vocab = 4, 8, 3, 3, 12, 3, 500
+    ch = (128, 64, 768)
+    sd = O.synth_state_dict(seed, front_end_ch=ch, text_tower=(layers, vocab))
+    vis_raw, vid_raw, _ = O.synth_raw_inputs(seed, T, H, W, L, ch)
+    ids, _ = O.synth_text_ids(seed, 1, L, vocab, 0)
+    vis, vid, text = O.front_end(sd, vis_raw, vid_raw, O.roberta_encoder(sd, ids)[0])
+    pos = O.position_embedding_sine(np.zeros((T, H, W), bool))
+    ref = O.hot_path_forward(sd, vis, vid, pos, text)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+    class TextEncoder:            # the reference's RoBERTa wrapper reduced to what the drop-in calls: the tokenizer (bert.py:50,65)
+        @staticmethod
+        def tokenizer(texts, padding, return_tensors):
+            assert padding == "longest" and return_tensors == "pt" and len(texts) == 1
+            return {"input_ids": torch.from_numpy(ids).long(), "attention_mask": torch.ones(1, L, dtype=torch.long)}
+
+    tvis, tvid, tpos = t(vis_raw), t(vid_raw), t(pos)
+    model = M.B200VSTGNet(make_cfg(), lambda videos: (M.NestedTensor(tvis, videos.mask[:, :H, :W], videos.durations), tpos),
+                          lambda tensors, n: {"3": tvid}, TextEncoder(), None, None, sd, verb_label2={"0": {"sub": ""}},
+                          max_frames=T, max_hw=H * W, max_text=L).eval()
+    assert model.fused_front_end and model.fused_text_tower
+    videos = M.NestedTensor(torch.zeros(T, 3, 96, 96, device="cuda"), torch.zeros(T, 96, 96, dtype=torch.bool, device="cuda"), [T])
+    out = model(videos, ["a person jumping"], [{"item_id": 0, "actioness": torch.ones(T, device="cuda")}])
+    # free-running decisions here: compare what does not depend on the frame selection, and the rest when selections agree
+    for k in ("logits_f_m", "logits_f_a", "att_sequences"):
+        assert float(np.abs(out[k].cpu().numpy() - ref[k]).max()) <= 2e-2, k

@@ -71,12 +71,14 @@ class HotPath(torch.nn.Module):
                                        max_hw=max_hw, max_text=max_text, use_cuda_graph=use_cuda_graph)
 
     @torch.no_grad()
-    def forward(self, vis_features, vis_mask, vis_pos, text_mask, text_features, vid_features, iteration_rate=-1, raw=False):
+    def forward(self, vis_features, vis_mask, vis_pos, text_mask, text_features, vid_features, iteration_rate=-1, raw=False,
+                text_ids=None):
         """vis/vid_features [T,256,H,W], vis_mask [T,H,W] bool, vis_pos [T,256,H,W], text_features [L,1,256],
         text_mask [1,L] bool → the reference's output dict entries that depend on the hot path.
         raw=True: the features are the extractor outputs (ResNet map [T,Cv,H,W], Video-Swin map [T,Cd,H,W], RoBERTa states
         [L,1,Ct]) and input_proj / input_proj2 / text_encoder.resizer run fused inside the library (grounding_net.py:101,105;
-        bert.py:73) — their weights must be in the state_dict."""
+        bert.py:73) — their weights must be in the state_dict.  text_ids [1, L] int32 (raw=True): RoBERTa token ids instead of
+        text_features; the text tower (`text_encoder.body.*`) then runs inside the library too."""
         T, d, H, W = vis_features.shape
         assert vis_pos.shape[0] == T, "{} != {}".format(vis_pos.shape[0], T)          # modal_encoder.py:44
         f32 = lambda t: t.detach().to(torch.float32).contiguous()
@@ -88,7 +90,10 @@ class HotPath(torch.nn.Module):
             pos = f32(vis_pos)
         else:
             pos = f32(vis_pos[:1])   # PositionEmbeddingSine of an all-False mask is identical on every frame
-        o = self.engine.forward(f32(vis_features)[None], f32(vid_features)[None], f32(text_features[:, 0])[None], pos,
+        if text_ids is not None:
+            kw["text_ids"] = text_ids.reshape(1, -1).to(torch.int32).contiguous()
+        o = self.engine.forward(f32(vis_features)[None], f32(vid_features)[None],
+                                None if text_ids is not None else f32(text_features[:, 0])[None], pos,
                                 iteration_rate=iteration_rate, raw=raw, **kw)
         out = {"pred_boxes": o["pred_boxes"][0], "logits_f_m": o["logits_f_m"][0], "logits_f_a": o["logits_f_a"][0],
                "logits_r_a": o["logits_r_a"], "logits_r_m": o["logits_r_m"], "pred_sted": o["pred_sted"],
@@ -156,6 +161,9 @@ class B200VSTGNet(torch.nn.Module):
         has = all(k in state_dict for k in ("input_proj.weight", "input_proj2.weight", "text_encoder.resizer.fc.weight"))
         self.fused_front_end = has if fused_front_end is None else bool(fused_front_end)
         assert has or not self.fused_front_end, "fused_front_end needs input_proj / input_proj2 / text_encoder.resizer weights"
+        # fused text tower: only the TOKENIZER of the text encoder is called (bert.py:65), RoBERTa itself runs inside the library
+        self.fused_text_tower = self.fused_front_end and hasattr(text_encoder, "tokenizer") and \
+            "text_encoder.body.embeddings.word_embeddings.weight" in state_dict
         self.hot = HotPath(cfg, state_dict, **cap)
         self.verb_label = verb_label or {}
         self.verb_label2 = verb_label2 or {}
@@ -177,11 +185,17 @@ class B200VSTGNet(torch.nn.Module):
         info_key = str(targets[0]["item_id"])
         labels = self.verb_label if self.training else self.verb_label2
         texts = [labels[info_key]["sub"] + " " + texts[0]]
-        (text_mask, text_features, text_memory), _ = self.text_encoder(texts, vis_features.device)
         vm = vis_mask.clone()
         vm[:, 0, 0] = False
-        out = self.hot(vis_features, vm, vis_pos, text_mask, text_memory if fused else text_features, vid_features,
-                       iteration_rate, raw=fused)
+        if self.fused_text_tower:
+            tok = self.text_encoder.tokenizer(texts, padding="longest", return_tensors="pt")      # bert.py:65
+            ids = tok["input_ids"].to(vis_features.device)
+            text_mask = tok["attention_mask"].to(vis_features.device).ne(1)                       # bert.py:70
+            out = self.hot(vis_features, vm, vis_pos, text_mask, None, vid_features, iteration_rate, raw=True, text_ids=ids)
+        else:
+            (text_mask, text_features, text_memory), _ = self.text_encoder(texts, vis_features.device)
+            out = self.hot(vis_features, vm, vis_pos, text_mask, text_memory if fused else text_features, vid_features,
+                           iteration_rate, raw=fused)
         choose_index = out.pop("_choose_index").tolist()
         out["verb_labels"] = labels.get(info_key, {}).get("verb_index_list", [])
         out["attr_labels"] = labels.get(info_key, {}).get("adj_index_list", [])
