@@ -12,18 +12,23 @@
 // by the HBM read of the fp32 features.  The features arrive channel-major ([c][p], p contiguous), the tensor core wants a
 // K-major bf16 operand ([p][c]) — the transpose + conversion happens on the way into shared memory:
 //
-//   warp 0       TMA producer of the W k-blocks (256 x 64 bf16, 128B swizzle), 4-stage ring
-//   warp 2       L2 prefetcher: cp.async.bulk.prefetch.L2 of the fp32 chunks 8 k-blocks ahead of the tensor core, so the
-//                producers' register loads hit L2 (a third of the HBM latency → three times the bytes per register in flight)
+//   warp 0       TMA producer of the W k-blocks (256 x 64 bf16, 128B swizzle)
+//   warp 2       feature producer.  kBulk (whole frames per tile, i.e. P <= 128, 16-byte aligned input): cp.async.bulk of each
+//                frame's [64 channels x P tokens] fp32 chunk — ONE contiguous 256·P-byte range — into a 3-stage shared-memory
+//                staging ring, so the features reach the SM through the TMA engine (no LSU wavefronts, no sector over-fetch
+//                of the unaligned 49-float rows).  Measured: 218 us vs 232 us (768 channels), 449 us vs 444 us (2048 channels)
+//                against the LDG form below — both forms sit at ≈4.6 TB/s (profiles/r01_input_proj_ncu.md).
+//                Otherwise (frames sliced into 128-row tiles): an L2 prefetcher (cp.async.bulk.prefetch.L2, 8 k-blocks ahead)
+//                and the converter warps read global memory with coalesced 4-byte loads.
 //   warp 1       tcgen05.mma issuer (UMMA 128x256x16), two TMEM accumulators so the epilogue of tile i overlaps tile i+1
 //   warps 4-7    epilogue: TMEM row per thread → swizzled 4 KB slab per warp → + bias → X32 / X / XP with every store
 //                instruction covering four 128-byte (fp32) / 64-byte (bf16) row segments (row-per-thread stores cost 32 L1
 //                wavefronts each and made the LSU data pipe the limiter: ncu 78 % → profiles/r01_input_proj_ncu.md)
-//   warps 8-31   A producers, three groups of 8 warps; group g converts the k-blocks with (k-block index % 3) == g, so three
-//                k-blocks (96 KB of fp32) are in flight per SM — the kernel is bound by HBM latency x bytes in flight, not
-//                by issue.  Thread = (token row, 32 of the 64 channels of the k-block): 32 coalesced 4-byte loads (a warp
-//                reads 32 consecutive tokens of one channel), packed to bf16 and written as four 16-byte stores into the
-//                128B-swizzled K-major tile the UMMA descriptor expects.  Registers are re-balanced with setmaxnreg.
+//   warps 8-31   converters, three groups of 8 warps; group g owns the k-blocks with (k-block index % 3) == g (= staging stage g),
+//                so three k-blocks are in flight per SM.  Thread = (token row, 32 of the 64 channels of the k-block): 32
+//                conflict-free 4-byte reads (a warp reads 32 consecutive tokens of one channel) from the staging stage — or from
+//                global memory in the fallback —, packed to bf16 and written as four 16-byte stores into the 128B-swizzled
+//                K-major tile the UMMA descriptor expects.  Registers are re-balanced with setmaxnreg.
 //
 // A tile is 128 token rows: floor(128 / P) whole frames when a frame has P <= 128 tokens (7x7: two frames, 98 rows), or one
 // 128-row slice of a frame otherwise (14x14: two slices).
@@ -34,14 +39,23 @@
 
 namespace vg {
 
-static constexpr int kIpStages = 4;
 static constexpr int kIpABytes = 128 * 64 * 2;
 static constexpr int kIpBBytes = 256 * 64 * 2;
+static constexpr int kIpStgBytes = 128 * 64 * 4;           // fp32 staging stage: up to 128 token rows x 64 channels
 static constexpr int kIpSlabBytes = 4 * 4096;               // epilogue staging: 32 rows x 128 B per warp
-static constexpr int kIpSmem = kIpStages * (kIpABytes + kIpBBytes) + kIpSlabBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 static constexpr int kIpPrefetchDist = 8;                  // k-blocks the L2 prefetcher runs ahead of the MMA issuer
-static constexpr int kIpGroups = 3;                        // producer groups (k-blocks in flight)
-static constexpr int kIpThreads = 256 + kIpGroups * 256;  // 4 control/idle warps + 4 epilogue warps + 8 warps per group
+static constexpr int kIpGroups = 3;                        // converter groups (k-blocks in flight)
+static constexpr int kIpThreads = 256 + kIpGroups * 256;  // 4 control warps + 4 epilogue warps + 8 warps per group
+
+template <bool kBulk>
+struct IpCfg {
+  static constexpr int kWStages = kBulk ? 2 : 4;
+  static constexpr int kAStages = kBulk ? 3 : 4;
+  static constexpr int kStgStages = kBulk ? kIpGroups : 0;   // one staging stage per converter group
+  static constexpr int kSmem = kWStages * kIpBBytes + kAStages * kIpABytes + kStgStages * kIpStgBytes + kIpSlabBytes +
+                               1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kSmem <= 232448, "input_proj shared memory");
+};
 
 struct IpParams {
   const float* in;     // [F, C, P]
@@ -55,7 +69,7 @@ struct IpParams {
   int fpt;             // frames per tile (P <= 128), else 0
   int tpf;             // 128-row slices per frame (P > 128)
   int num_tiles;
-  int l2_prefetch;     // 1: `in` is 16-byte aligned → bulk L2 prefetch of the chunks ahead
+  int l2_prefetch;     // LDG form: `in` is 16-byte aligned → bulk L2 prefetch of the chunks ahead
 };
 
 // tile row r → (frame, token); false for the padding rows of a tile
@@ -74,30 +88,45 @@ __device__ __forceinline__ bool ip_row(const IpParams& p, int tile, int r, int& 
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {   // 16-byte aligned address and size
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
+// contiguous global → shared copy through the TMA engine; completion bytes are posted to `bar` (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gptr, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gptr), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
+template <bool kBulk>
 __global__ void __launch_bounds__(kIpThreads, 1)
 input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
+  using Cfg = IpCfg<kBulk>;
+  constexpr int kWS = Cfg::kWStages, kAS = Cfg::kAStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kIpStages * kIpABytes;
-  uint8_t* smem_slab = smem_b + kIpStages * kIpBBytes;
+  uint8_t* smem_b = smem_a + kAS * kIpABytes;
+  uint8_t* smem_stg = smem_b + kWS * kIpBBytes;
+  uint8_t* smem_slab = smem_stg + Cfg::kStgStages * kIpStgBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_slab + kIpSlabBytes);
-  uint64_t* w_full = bars;                     // [stages] TMA bytes of the W k-block
-  uint64_t* a_full = bars + kIpStages;         // [stages] 8 arrivals (one per producer warp)
-  uint64_t* empty_bar = bars + 2 * kIpStages;  // [stages] tcgen05.commit: both operands of the stage are consumed
-  uint64_t* tfull_bar = bars + 3 * kIpStages;  // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;        // [2] 4 arrivals (epilogue warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* w_full = bars;              // [4] TMA bytes of the W k-block
+  uint64_t* w_empty = bars + 4;         // [4] tcgen05.commit
+  uint64_t* a_full = bars + 8;          // [4] 8 arrivals (the converter warps of one group)
+  uint64_t* a_empty = bars + 12;        // [4] tcgen05.commit
+  uint64_t* stg_full = bars + 16;       // [3] bulk-copy bytes of the fp32 chunk(s)
+  uint64_t* stg_empty = bars + 19;      // [3] 8 arrivals (the group has read the stage)
+  uint64_t* tfull_bar = bars + 22;      // [2]
+  uint64_t* tempty_bar = bars + 24;     // [2] 4 arrivals (epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
   volatile int* consumed = reinterpret_cast<volatile int*>(tmem_slot + 1);   // k-blocks issued to the tensor core so far
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = p.C / 64;
   const int n_my = ((int)blockIdx.x < p.num_tiles) ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total = n_my * num_k;           // k-blocks this CTA walks through, over all of its tiles
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_w);
-    for (int s = 0; s < kIpStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&a_full[s], 8); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); mbar_init(&a_full[s], 8); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 3; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_empty[s], 8); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     *consumed = 0;
     fence_mbar_init();
@@ -113,60 +142,72 @@ input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
     if (warp == 0) {
       // ===================== TMA producer: W k-blocks =====================
       if (lane == 0) {
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int it = 0; it < n_my; ++it) {
-          for (int kb = 0; kb < num_k; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&w_full[stage], kIpBBytes);
-            tma_load_2d(smem_b + stage * kIpBBytes, &tma_w, &w_full[stage], kb * 64, 0);
-            if (++stage == kIpStages) { stage = 0; phase ^= 1; }
-          }
+        for (int g = 0; g < total; ++g) {
+          const int sw = g % kWS, kb = g % num_k;
+          mbar_wait(&w_empty[sw], ((g / kWS) & 1) ^ 1);
+          mbar_expect_tx(&w_full[sw], kIpBBytes);
+          tma_load_2d(smem_b + sw * kIpBBytes, &tma_w, &w_full[sw], kb * 64, 0);
         }
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      int acc = 0, g = 0;
+      uint32_t acc_phase = 0;
       for (int it = 0; it < n_my; ++it) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * 256;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&w_full[stage], phase);
-          mbar_wait(&a_full[stage], phase);
+        for (int kb = 0; kb < num_k; ++kb, ++g) {
+          const int sw = g % kWS, sa = g % kAS;
+          mbar_wait(&w_full[sw], (g / kWS) & 1);
+          mbar_wait(&a_full[sa], (g / kAS) & 1);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem_a + stage * kIpABytes));
-            const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem_b + stage * kIpBBytes));
-  #pragma unroll
+            const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem_a + sa * kIpABytes));
+            const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem_b + sw * kIpBBytes));
+#pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit(&empty_bar[stage]);
+            umma_commit(&w_empty[sw]);
+            umma_commit(&a_empty[sa]);
             if (kb == num_k - 1) umma_commit(&tfull_bar[acc]);
-            *consumed = it * num_k + kb + 1;
+            *consumed = g + 1;
           }
           __syncwarp();
-          if (++stage == kIpStages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     } else if (warp == 2) {
-      // ===================== L2 prefetcher =====================
-      if (lane == 0 && p.l2_prefetch) {
-        const int total = n_my * num_k;
+      if (lane == 0) {
         const size_t chunk = (size_t)64 * p.P;   // floats of one frame's k-block: 64 channels x P tokens, contiguous
-        for (int g = 0; g < total; ++g) {
-          while (g > *consumed + kIpPrefetchDist) __nanosleep(100);
-          const int it = g / num_k, kb = g - it * num_k;
-          const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-          if (p.fpt > 0) {
-            for (int fl = 0; fl < p.fpt; ++fl) {
-              const int frame = tile * p.fpt + fl;
-              if (frame < p.F) bulk_prefetch_l2(p.in + ((size_t)frame * p.C + kb * 64) * p.P, (uint32_t)(chunk * 4));
+        if constexpr (kBulk) {
+          // ===================== feature producer: bulk copies of the fp32 chunks into the staging ring =====================
+          // (an additional L2 prefetch of the chunks ahead was measured and dropped: 469 us vs 449 us)
+          for (int g = 0; g < total; ++g) {
+            const int it = g / num_k, kb = g - it * num_k, s = g % kIpGroups;
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int f0 = tile * p.fpt;
+            const int nf = p.F - f0 < p.fpt ? p.F - f0 : p.fpt;
+            mbar_wait(&stg_empty[s], ((g / kIpGroups) & 1) ^ 1);
+            mbar_expect_tx(&stg_full[s], (uint32_t)(nf * chunk * 4));
+            for (int fl = 0; fl < nf; ++fl)
+              bulk_copy_g2s(smem_stg + s * kIpStgBytes + fl * chunk * 4, p.in + ((size_t)(f0 + fl) * p.C + kb * 64) * p.P,
+                            (uint32_t)(chunk * 4), &stg_full[s]);
+          }
+        } else if (p.l2_prefetch) {
+          // ===================== L2 prefetcher (LDG form) =====================
+          for (int g = 0; g < total; ++g) {
+            while (g > *consumed + kIpPrefetchDist) __nanosleep(100);
+            const int it = g / num_k, kb = g - it * num_k;
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            if (p.fpt > 0) {
+              for (int fl = 0; fl < p.fpt; ++fl) {
+                const int frame = tile * p.fpt + fl;
+                if (frame < p.F) bulk_prefetch_l2(p.in + ((size_t)frame * p.C + kb * 64) * p.P, (uint32_t)(chunk * 4));
+              }
+            } else if (tile % p.tpf == 0) {        // the first slice of a frame fetches the chunk for all of its slices
+              bulk_prefetch_l2(p.in + ((size_t)(tile / p.tpf) * p.C + kb * 64) * p.P, (uint32_t)(chunk * 4));
             }
-          } else if (tile % p.tpf == 0) {        // the first slice of a frame fetches the chunk for all of its slices
-            bulk_prefetch_l2(p.in + ((size_t)(tile / p.tpf) * p.C + kb * 64) * p.P, (uint32_t)(chunk * 4));
           }
         }
       }
@@ -239,33 +280,49 @@ input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== A producers: fp32 [c][p] (global) → bf16 [p][c] swizzled (shared) =====================
+    // ===================== converters: fp32 [c][p] (staging stage or global) → bf16 [p][c] swizzled (shared) =====================
     const int pt = threadIdx.x - 256;
     const int grp = pt >> 8;                  // this group owns the k-blocks with (running k-block index % kIpGroups) == grp
     const int r = pt & 127, half = (pt >> 7) & 1;
     const size_t cstride = (size_t)p.P;
-    const int total = n_my * num_k;           // k-blocks this CTA walks through, over all of its tiles
     int it_cached = -1;
-    const float* base = nullptr;              // channel 0 of this thread's token in tile `it_cached`; nullptr for padding rows
+    const float* base = nullptr;              // LDG form: channel 0 of this thread's token in tile `it_cached`; nullptr = padding row
+    int stg_off = -1;                         // bulk form: float offset of (frame-in-tile, channel 0, token) in a staging stage
     for (int g = grp; g < total; g += kIpGroups) {
       const int it = g / num_k, kb = g - it * num_k;
       if (it != it_cached) {
         int frame, tok;
-        base = ip_row(p, (int)blockIdx.x + it * (int)gridDim.x, r, frame, tok) ? p.in + (size_t)frame * p.C * cstride + tok : nullptr;
+        const bool valid = ip_row(p, (int)blockIdx.x + it * (int)gridDim.x, r, frame, tok);
+        base = valid ? p.in + (size_t)frame * p.C * cstride + tok : nullptr;
+        stg_off = valid ? (r / p.P) * 64 * p.P + tok : -1;
         it_cached = it;
       }
       float v[32];
-      if (base != nullptr) {
-        const float* src = base + (size_t)(kb * 64 + half * 32) * cstride;
+      if constexpr (kBulk) {
+        mbar_wait(&stg_full[grp], ((g / kIpGroups) & 1));
+        if (stg_off >= 0) {
+          const float* src = reinterpret_cast<const float*>(smem_stg + grp * kIpStgBytes) + stg_off + half * 32 * p.P;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __ldg(src + (size_t)i * cstride);
+          for (int i = 0; i < 32; ++i) v[i] = src[i * p.P];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stg_empty[grp]);   // the stage can be refilled while this k-block is converted
       } else {
+        if (base != nullptr) {
+          const float* src = base + (size_t)(kb * 64 + half * 32) * cstride;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          for (int i = 0; i < 32; ++i) v[i] = __ldg(src + (size_t)i * cstride);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
       }
-      const int stage = g % kIpStages;
-      mbar_wait(&empty_bar[stage], ((g / kIpStages) & 1) ^ 1);
-      uint8_t* rowp = smem_a + stage * kIpABytes + r * 128;
+      const int sa = g % kAS;
+      mbar_wait(&a_empty[sa], ((g / kAS) & 1) ^ 1);
+      uint8_t* rowp = smem_a + sa * kIpABytes + r * 128;
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         *reinterpret_cast<uint4*>(rowp + (((half * 4 + u) ^ (r & 7)) << 4)) =
@@ -273,7 +330,7 @@ input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
                        pack_bf16(v[8 * u + 4], v[8 * u + 5]), pack_bf16(v[8 * u + 6], v[8 * u + 7]));
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[stage]);
+      if (lane == 0) mbar_arrive(&a_full[sa]);
     }
   }
 
@@ -292,6 +349,19 @@ void count_gemm_launch();
 
 bool input_proj_supported(int C) { return C >= 64 && C % 64 == 0; }
 
+template <bool kBulk>
+static void launch_ip(const CUtensorMap& tw, const IpParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VG_CUDA(cudaFuncSetAttribute(input_proj_kernel<kBulk>, cudaFuncAttributeMaxDynamicSharedMemorySize, IpCfg<kBulk>::kSmem));
+    attr_set = true;
+  }
+  const int sms = device_sm_count();
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  input_proj_kernel<kBulk><<<grid, kIpThreads, IpCfg<kBulk>::kSmem, stream>>>(tw, p);
+  VG_CUDA(cudaGetLastError());
+}
+
 // X / X32 / XP rows [f*S + tok0, +P) of every frame f < F  <-  W in[f] + b  (+ pos); see the header comment.
 void input_proj(const float* in, int C, const bf16* W, const float* bias, const bf16* pos, int pos_frames, bf16* X, float* X32,
                 bf16* XP, int F, int S, int tok0, int P, cudaStream_t stream) {
@@ -299,23 +369,20 @@ void input_proj(const float* in, int C, const bf16* W, const float* bias, const 
   VG_CHECK(in && W && bias && X && F > 0 && P > 0 && tok0 >= 0 && tok0 + P <= S, "input_proj: bad arguments");
   VG_CHECK(XP == nullptr || pos != nullptr, "input_proj: XP needs the positional rows");
   VG_CHECK(pos_frames == 1 || pos_frames == F, "input_proj: pos_frames must be 1 or F");
-  static bool attr_set = false;
-  if (!attr_set) {
-    VG_CUDA(cudaFuncSetAttribute(input_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpSmem));
-    attr_set = true;
-  }
   IpParams p;
   p.in = in; p.bias = bias; p.pos = pos; p.X = X; p.X32 = X32; p.XP = XP;
   p.F = F; p.C = C; p.P = P; p.S = S; p.tok0 = tok0; p.pos_per_frame = pos_frames > 1 ? 1 : 0;
   if (P <= 128) { p.fpt = 128 / P; p.tpf = 1; p.num_tiles = (F + p.fpt - 1) / p.fpt; }
   else { p.fpt = 0; p.tpf = (P + 127) / 128; p.num_tiles = F * p.tpf; }
-  p.l2_prefetch = (reinterpret_cast<uintptr_t>(in) & 15) == 0 ? 1 : 0;
+  const bool aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  p.l2_prefetch = aligned ? 1 : 0;
   if (const char* e = getenv("VGQA_IP_PREFETCH")) p.l2_prefetch = p.l2_prefetch && e[0] != '0';
+  // whole frames per tile + aligned input → the TMA-engine (bulk copy) form; VGQA_IP_BULK=0 forces the LDG form (A/B runs)
+  bool bulk = aligned && P <= 128;
+  if (const char* e = getenv("VGQA_IP_BULK")) bulk = bulk && e[0] != '0';
   CUtensorMap tw = make_tmap_2d(W, 256, C, C, 256, false);
-  const int sms = device_sm_count();
-  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  input_proj_kernel<<<grid, kIpThreads, kIpSmem, stream>>>(tw, p);
-  VG_CUDA(cudaGetLastError());
+  if (bulk) launch_ip<true>(tw, p, stream);
+  else launch_ip<false>(tw, p, stream);
   count_gemm_launch();
 }
 

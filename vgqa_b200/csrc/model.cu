@@ -535,7 +535,7 @@ static void pack_weights(vgqa_ctx* c) {
   if (wit != c->sd.end()) {
     VG_CHECK(wit->second.shape.size() == 2, "word_embeddings.weight must be [vocab, hidden]");
     const int Hd = (int)wit->second.shape[1];
-    VG_CHECK(Hd % 64 == 0, "text tower: the hidden size must be a multiple of 64");
+    VG_CHECK(Hd % 64 == 0 && Hd <= 1024, "text tower: the hidden size must be a multiple of 64, at most 1024");
     VG_CHECK(c->ip_text.K == Hd, "text tower: 'text_encoder.resizer.fc' must take the tower's hidden size");
     c->tt_hd = Hd; c->tt_vocab = (int)wit->second.shape[0];
     c->tt_word = P.f32(wit->second.v);

@@ -45,26 +45,41 @@ void roberta_embed_ln(const int* ids, const float* word, const float* pos, const
   VG_CUDA(cudaGetLastError());
 }
 
-// y = LN(x) * w + b over rows of Hd fp32 values; writes fp32 (may alias x) and bf16
+// y = LN(x) * w + b over rows of Hd <= 1024 fp32 values (one warp per row, the row held in registers: one global read);
+// writes fp32 (may alias x) and bf16
 __global__ void __launch_bounds__(256) ln_rows_wide_kernel(const float* x, const float* __restrict__ w, const float* __restrict__ b,
                                                            float eps, float* y32, bf16* __restrict__ y, int rows, int Hd) {
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= rows) return;
   const float* xr = x + (size_t)r * Hd;
+  float v[32];
   float s = 0.f;
-  for (int c = lane; c < Hd; c += 32) s += xr[c];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < Hd ? xr[c] : 0.f;
+    s += v[i];
+  }
   const float mean = warp_sum(s) / (float)Hd;
   float m2 = 0.f;
-  for (int c = lane; c < Hd; c += 32) { const float d = xr[c] - mean; m2 = fmaf(d, d, m2); }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float d = lane + 32 * i < Hd ? v[i] - mean : 0.f;
+    m2 = fmaf(d, d, m2);
+  }
   const float rstd = rsqrtf(warp_sum(m2) / (float)Hd + eps);
-  for (int c = lane; c < Hd; c += 32) {
-    const float v = (xr[c] - mean) * rstd * w[c] + b[c];
-    y32[(size_t)r * Hd + c] = v;
-    y[(size_t)r * Hd + c] = __float2bfloat16(v);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + 32 * i;
+    if (c < Hd) {
+      const float o = (v[i] - mean) * rstd * w[c] + b[c];
+      y32[(size_t)r * Hd + c] = o;
+      y[(size_t)r * Hd + c] = __float2bfloat16(o);
+    }
   }
 }
 void ln_rows_wide(const float* x, const float* w, const float* b, float eps, float* y32, bf16* y, int rows, int Hd, cudaStream_t st) {
-  VG_CHECK(Hd % 32 == 0, "ln_rows_wide: the row width must be a multiple of 32");
+  VG_CHECK(Hd % 32 == 0 && Hd <= 1024, "ln_rows_wide: the row width must be a multiple of 32, at most 1024");
   ln_rows_wide_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, w, b, eps, y32, y, rows, Hd);
   VG_CUDA(cudaGetLastError());
 }

@@ -17,6 +17,7 @@
 //   phase 2   ctx^T[channel, head] = mem^T · P: channels are the M index (A = mem via ldmatrix.trans), B = Ps via ldmatrix;
 //             results staged over the consumed query tile → one TMA store.
 // 16 MT + 16 MT mma per frame (MT = 16-key tiles), none of them padded.
+#include <stdlib.h>
 #include <string>
 
 #include "common.h"
@@ -340,6 +341,12 @@ void xattn_stream(const bf16* qt, const bf16* mem, long long frame_stride_rows, 
   CUtensorMap tm = make_tmap_mem(mem, F, Mk, frame_stride_rows, MT * 16);
   CUtensorMap tq = make_tmap_2d(qt, F * 8, 256, 256, 8, false);
   CUtensorMap tc = make_tmap_2d(ctx, F * 8, 256, 256, 8, false);
+  // Four single-stage worker pairs per SM (default) instead of two double-buffered ones: the kernel is bound by the per-frame
+  // dependent chain, not by any unit (profiles/r01_xattn_stream_ncu.md), so frames in flight per SM are what counts:
+  // 40.3 us vs 49.1 us at the decoder shape.  VGQA_XS_PAIRS=2 selects the double-buffered form (A/B runs).
+  static const int pairs4 = [] { const char* e = getenv("VGQA_XS_PAIRS"); return e == nullptr || e[0] != '2' ? 1 : 0; }();
+  if (pairs4 && MT == 4) { launch_xs<4, 4, 1>(tm, tq, tc, p, stream); return; }
+  if (pairs4 && MT == 5) { launch_xs<5, 4, 1>(tm, tq, tc, p, stream); return; }
   switch (MT) {
     case 4: launch_xs<4, 2, 2>(tm, tq, tc, p, stream); break;
     case 5: launch_xs<5, 2, 2>(tm, tq, tc, p, stream); break;
