@@ -96,3 +96,23 @@ def test_vstgnet_dropin_with_fused_text_tower():
     # free-running decisions here: compare what does not depend on the frame selection, and the rest when selections agree
     for k in ("logits_f_m", "logits_f_a", "att_sequences"):
         assert float(np.abs(out[k].cpu().numpy() - ref[k]).max()) <= 2e-2, k
+
+
+def test_predictor_from_raw_maps_and_token_ids():
+    """GroundingPredictor(raw_inputs=True) with "text_ids": identical to feeding the tower's own hidden states as "text"."""
+    from vgqa_b200.engine import GroundingEngine
+    from vgqa_b200.predict import GroundingPredictor
+    seed, T, H, W, L, layers, vocab = 6, 8, 3, 3, 10, 2, 300
+    ch = (128, 64, 768)
+    sd = O.synth_state_dict(seed, front_end_ch=ch, text_tower=(layers, vocab))
+    vis_raw, vid_raw, _ = O.synth_raw_inputs(seed, 2 * T, H, W, L, ch)
+    ids, _ = O.synth_text_ids(seed, 1, L, vocab, 0)
+    pos = O.position_embedding_sine(np.zeros((1, H, W), bool))
+    pred = GroundingPredictor(sd, sample_num=T, max_hw=H * W, max_text=L, raw_inputs=True, use_cuda_graph=False)
+    fids = list(range(2 * T))
+    a = pred.predict_many([{"vis": vis_raw, "vid": vid_raw, "text_ids": ids[0], "pos": pos, "frame_ids": fids, "ori_size": (360, 640)}])[0]
+    hidden, _ = pred.engine.text_tower(torch.from_numpy(ids).cuda())
+    b = pred.predict_many([{"vis": vis_raw, "vid": vid_raw, "text": hidden[0], "pos": pos, "frame_ids": fids, "ori_size": (360, 640)}])[0]
+    assert a["temporal"] == b["temporal"] and [t["frame"] for t in a["tube"]] == [t["frame"] for t in b["tube"]]
+    np.testing.assert_allclose(np.asarray([t["bbox"] for t in a["tube"]]), np.asarray([t["bbox"] for t in b["tube"]]), atol=1e-3)
+    pred.close()

@@ -37,7 +37,8 @@ class GroundingPredictor:
     def predict_many(self, items: Sequence[Mapping[str, Any]]) -> List[Dict[str, Any]]:
         """items[q]: {"vis": [2T,256,H,W], "vid": [2T,256,H,W], "text": [L,256], "pos": [1,256,H,W], "frame_ids": 2T ints
         (ascending, as sampled by predict()), "ori_size": (h, w), "fps": float}.  All items share T, H, W, L.
-        With raw_inputs=True the channel counts are those of the extractors (see __init__).
+        With raw_inputs=True the channel counts are those of the extractors (see __init__); an item may then carry
+        "text_ids" ([L] RoBERTa token ids) instead of "text" — the text tower runs inside the library too (all items or none).
         Returns one {"temporal": {...}, "tube": [...]} dict per item (grounding.py:227-244)."""
         Q = len(items)
         if Q == 0:
@@ -47,6 +48,7 @@ class GroundingPredictor:
         dev = self.engine.device
         f32 = lambda t: torch.as_tensor(t, dtype=torch.float32, device=dev)
         vis, vid, text, sizes = [], [], [], []
+        use_ids = self.raw_inputs and all("text_ids" in it for it in items)
         for it in items:
             v, w = f32(it["vis"]), f32(it["vid"])
             n = v.shape[0]
@@ -54,14 +56,16 @@ class GroundingPredictor:
                 raise ValueError("predict() samples an even number of frames, at most 2*sample_num")   # grounding.py:137-138,157
             assert len(it["frame_ids"]) == n, "one frame id per sampled frame"
             for par in (0, 1):                       # even pass, odd pass (grounding.py:163-168)
-                vis.append(v[par::2]); vid.append(w[par::2]); text.append(f32(it["text"]))
+                vis.append(v[par::2]); vid.append(w[par::2])
+                text.append(torch.as_tensor(it["text_ids"], dtype=torch.int32, device=dev) if use_ids else f32(it["text"]))
                 sizes.append([float(it["ori_size"][0]), float(it["ori_size"][1])])
         T = vis[0].shape[0]
         assert all(x.shape[0] == T for x in vis), "all queries of a call must sample the same number of frames"
         vis, vid, text = torch.stack(vis).contiguous(), torch.stack(vid).contiguous(), torch.stack(text).contiguous()
         pos = f32(items[0]["pos"])[:1].contiguous()
-        o = self.engine.forward(vis, vid, text, pos, ori_sizes_hw=torch.tensor(sizes, device=dev),
-                                want=["att_sequences", "boxes_px", "sted_idx"], raw=self.raw_inputs)
+        o = self.engine.forward(vis, vid, None if use_ids else text, pos, ori_sizes_hw=torch.tensor(sizes, device=dev),
+                                want=["att_sequences", "boxes_px", "sted_idx"], raw=self.raw_inputs,
+                                text_ids=text if use_ids else None)
         boxes = o["boxes_px"].reshape(2 * Q, T, 4).cpu().tolist()     # one D2H copy per output
         att = o["att_sequences"].reshape(2 * Q, T).cpu().tolist()
         idx = o["sted_idx"].reshape(2 * Q, 2).cpu().tolist()
