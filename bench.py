@@ -173,6 +173,55 @@ def time_dominant_kernel(B, pk):
             "hbm_gbs_at_algorithmic_bytes": alg_bytes / dt / 1e9}
 
 
+def measure_with_backbone(eng, torch, d_pos, r_vid_small=None, rank=0, clips=8, steps=5):
+    """SURVEY §8d secondary number: clips/s with a PyTorch bf16 backbone in front of the library — torchvision ResNet101 (random
+    init, eval, bf16, channels_last: cuDNN/cuBLAS LIBRARY code, not part of this repo's kernels) on `clips` x 64 frames of 3x224x224,
+    its layer-4 map fed to the raw-input forward.  The Video-Swin map and the RoBERTa states stay synthetic (the reference's
+    Video-Swin implementation lives in /root/reference, which does not exist on the GPU box).  Returns None if torchvision is absent."""
+    try:
+        import torchvision
+    except Exception:
+        return None
+    net = torchvision.models.resnet101(weights=None)
+    body = torch.nn.Sequential(net.conv1, net.bn1, net.relu, net.maxpool, net.layer1, net.layer2, net.layer3, net.layer4)
+    body = body.eval().cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+    g = torch.Generator(device="cuda").manual_seed(99 + rank)
+    frames = torch.randn(clips * T, 3, 224, 224, device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    vid = torch.randn(clips, T, FRONT_END_CH[1], H, W, device="cuda", generator=g)
+    text = torch.randn(clips, L, FRONT_END_CH[2], device="cuda", generator=g)
+    sizes = torch.tensor([[360.0, 640.0]] * clips, device="cuda")
+    want = ["pred_boxes", "pred_sted", "boxes_px", "sted_idx"]
+    outs = eng.alloc_outputs(clips, T, H, W, L, want)
+
+    def step(backbone_only=False):
+        with torch.no_grad():
+            fmap = body(frames)                                            # [clips*T, 2048, 7, 7] bf16
+        if backbone_only:
+            return
+        vis = fmap.float().contiguous().view(clips, T, FRONT_END_CH[0], H, W)   # the C-ABI takes the reference's fp32 NCHW map
+        eng.forward(vis, vid, text, d_pos, ori_sizes_hw=sizes, outs=outs, raw=True)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / steps
+
+    sec, sec_bb = timed(step), timed(lambda: step(True))
+    del body, frames
+    torch.cuda.empty_cache()
+    return {"value": clips / sec, "unit": "clips/s", "ms_per_step": 1e3 * sec, "clips_per_step": clips,
+            "backbone_only_ms_per_step": 1e3 * sec_bb,
+            "what": "torchvision ResNet101 (random init, bf16, channels_last; PyTorch/cuDNN library code) on 64 x 3x224x224 frames per clip "
+                    "→ layer-4 map → this library's raw-input forward; Video-Swin map and RoBERTa states synthetic"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -330,6 +379,7 @@ def main():
         torch.cuda.synchronize()
 
     sec_one_sync = timed(step_one_sync, n_one, device_events=False)
+    with_bb = measure_with_backbone(eng, torch, d_pos, r_vid_small=None, rank=rank) if rank == 0 else None
     total_clips = B * world * args.steps
     value = total_clips / sec
     e2e = total_clips / sec_e2e
@@ -360,6 +410,7 @@ def main():
                        "ms_per_clip_synchronous": 1e3 * sec_one_sync / n_one,
                        "what": "ONE clip per forward call (the reference's batch 1, BASELINE configs[1] read literally): CUDA-graph replay "
                                "of the same ≈455 launches, latency-bound; pipelined = two calls in flight, synchronous = host waits per clip"},
+            "with_backbone": with_bb,
             "gpu_launches": int(launches) * args.steps,
             "gpu_launches_per_step": int(launches),
             "clocks": clocks,
