@@ -84,6 +84,10 @@ typedef struct {
    * RobertaModel embeddings + encoder layers, weights "text_encoder.body.*") and then text_encoder.resizer.  Padded positions
    * are given by text_mask (1 = padded = `attention_mask.ne(1)`, bert.py:70), which also masks them in the cross-modal encoder. */
   const int32_t* text_ids;
+  /* Layout of vis_raw / vid_raw: 0 = the reference's NCHW fp32 ([clips, T, C, H, W]); 1 = channels-last bf16
+   * ([clips, T, H, W, C] bf16 behind the same pointers — what a bf16 channels_last backbone emits on B200): the map is then the
+   * K-major GEMM operand itself and is read by TMA at half the bytes, with no conversion pass. */
+  int raw_layout;
 } vgqa_inputs;
 
 /* Outputs (fp32 unless noted); any pointer may be NULL to skip that output.
@@ -205,6 +209,9 @@ int vgqa_xattn1(const void* qt, const void* mem, long long frame_stride_rows, in
  * X (bf16), X32 (fp32, optional), XP = bf16(x + pos row) (optional; pos [pos_frames*S, 256] bf16, pos_frames 1 or F). */
 int vgqa_input_proj(const float* in, int C, const void* W, const float* bias, const void* pos, int pos_frames, void* X,
                     float* X32, void* XP, int F, int S, int tok0, int P, void* stream);
+/* The same projection from a channels-last bf16 map in [F, P, C] (raw_layout = 1). */
+int vgqa_input_proj_nhwc(const void* in_bf16, int C, const void* W, const float* bias, const void* pos, int pos_frames, void* X,
+                         float* X32, void* XP, int F, int S, int tok0, int P, void* stream);
 /* Same op with the positional score terms supplied as an additive table sbias[F, 8, ldsb] (fp32, unscaled) — the form the
  * decoders use when `pos` is frame-invariant; runs the warp-per-frame streaming kernel (xattn_stream.cu). */
 int vgqa_xattn1_bias(const void* qt, const void* mem, long long frame_stride_rows, int F, int Mk, const float* sbias, int ldsb,

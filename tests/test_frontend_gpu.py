@@ -216,3 +216,58 @@ def test_vstgnet_dropin_and_predictor_with_fused_front_end():
     got = np.asarray([even[f] for f in range(0, 2 * T, 2)])
     np.testing.assert_allclose(got, g["post_boxes"], atol=TOL * 640)
     pred.close()
+
+
+@pytest.mark.parametrize("F,C,H,W,L,second,pos_frames", [(1, 64, 1, 1, 1, False, 1), (64, 2048, 7, 7, 20, False, 1),
+                                                          (37, 768, 7, 7, 20, True, 37), (5, 768, 12, 12, 64, True, 1),
+                                                          (301, 192, 7, 7, 20, True, 1)])
+def test_input_proj_nhwc_bf16_kernel(F, C, H, W, L, second, pos_frames):
+    """Channels-last bf16 maps (raw_layout = 1): the rows are the TMA-fed A operand; vs an fp64 product of the same bf16 values."""
+    Lb, _lib = _load()
+    Lb.vgqa_input_proj_nhwc.restype = ctypes.c_int
+    Lb.vgqa_input_proj_nhwc.argtypes = Lb.vgqa_input_proj.argtypes
+    P = H * W
+    S = 2 * P + L
+    tok0 = (P + L) if second else 0
+    g = torch.Generator(device="cuda").manual_seed(F * 31 + C)
+    x = torch.randn(F, P, C, device="cuda", generator=g).relu_().to(torch.bfloat16)
+    w = (torch.randn(256, C, device="cuda", generator=g) / C ** 0.5).to(torch.bfloat16)
+    b = torch.randn(256, device="cuda", generator=g) * 0.05
+    pos = torch.randn(pos_frames * S, 256, device="cuda", generator=g).to(torch.bfloat16)
+    X = torch.full((F * S, 256), 768.0, dtype=torch.bfloat16, device="cuda")
+    X32 = torch.full((F * S, 256), 768.0, dtype=torch.float32, device="cuda")
+    XP = torch.full((F * S, 256), 768.0, dtype=torch.bfloat16, device="cuda")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(Lb.vgqa_input_proj_nhwc(p(x), C, p(w), p(b), p(pos), pos_frames, p(X), p(X32), p(XP), F, S, tok0, P,
+                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    ref = (x.double() @ w.double().T + b.double()).cpu().numpy()                    # [F, P, 256]
+    rows = slice(tok0, tok0 + P)
+    X32n = X32.cpu().numpy().reshape(F, S, 256)
+    assert float(np.abs(X32n[:, rows] - ref).max()) <= 2e-3
+    posr = pos.double().cpu().numpy().reshape(pos_frames, S, 256)[:, rows]
+    want = ref + (posr if pos_frames > 1 else posr[:1])
+    XPn = XP.float().cpu().numpy().reshape(F, S, 256)
+    assert float(np.abs(XPn[:, rows] - want).max()) <= 2e-3 + 2 ** -8 * float(np.abs(want).max())
+    other = np.ones(S, bool); other[rows] = False
+    assert (X32n[:, other] == 768.0).all() and (XPn[:, other] == 768.0).all()
+    assert (X.float().cpu().numpy().reshape(F, S, 256)[:, other] == 768.0).all()
+
+
+def test_forward_channels_last_bf16_equals_nchw_fp32():
+    """vgqa_forward with channels-last bf16 maps vs the same (bf16-rounded) values given as the reference's NCHW fp32 maps."""
+    g, sd, eng, raw, pos, rep = _engine_and_inputs("fe_cfg1_T32_7x7_L20_s0", clips=2)
+    tpos = torch.from_numpy(pos[:1].copy()).cuda()
+    want = ["pred_boxes", "pred_sted", "logits_f_m", "frames_cls"]
+    vis16, vid16 = rep(raw[0]).to(torch.bfloat16), rep(raw[1]).to(torch.bfloat16)       # [2, T, C, H, W]
+    a = eng.forward(vis16.float(), vid16.float(), rep(raw[2]), tpos, raw=True, want=want)
+    b = eng.forward(vis16.permute(0, 1, 3, 4, 2).contiguous(), vid16.permute(0, 1, 3, 4, 2).contiguous(), rep(raw[2]), tpos,
+                    raw=True, want=want)
+    torch.cuda.synchronize()
+    for k in want:
+        assert float((a[k] - b[k]).abs().max()) <= 5e-3, k
+    h = eng.forward_host(vis16.permute(0, 1, 3, 4, 2).contiguous().cpu(), vid16.permute(0, 1, 3, 4, 2).contiguous().cpu(),
+                         rep(raw[2]).cpu(), tpos.cpu(), raw=True, want=want)
+    for k in want:
+        np.testing.assert_allclose(h[k].numpy(), b[k].cpu().numpy(), atol=1e-6)
+    eng.close()

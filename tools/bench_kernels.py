@@ -109,6 +109,13 @@ def bench_input_proj(F=4096, C=2048, H=7, W=7, Lt=20, second=False, name=""):
     flops = 2.0 * F * P * 256 * C
     byts = F * P * (C * 4.0 + 2048)
     print(f"input_proj {name} F={F} C={C} P={P}: {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s  {byts / t / 1e3:7.1f} GB/s (algorithmic bytes)")
+    L.vgqa_input_proj_nhwc.restype = ctypes.c_int
+    L.vgqa_input_proj_nhwc.argtypes = L.vgqa_input_proj.argtypes
+    x16 = x.permute(0, 2, 3, 1).contiguous().bfloat16()
+    t = timeit(lambda: _lib.check(L.vgqa_input_proj_nhwc(_lib.ptr(x16), C, _lib.ptr(Wt), _lib.ptr(b), _lib.ptr(pos), 1, _lib.ptr(X),
+                                                         _lib.ptr(X32), _lib.ptr(XP), F, S, (P + Lt) if second else 0, P, st())))
+    byts = F * P * (C * 2.0 + 2048)
+    print(f"input_proj {name} channels-last bf16 F={F} C={C} P={P}: {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s  {byts / t / 1e3:7.1f} GB/s (algorithmic bytes)")
 
 
 if __name__ == "__main__":

@@ -100,6 +100,19 @@ int vgqa_input_proj(const float* in, int C, const void* W, const float* bias, co
   }
 }
 
+int vgqa_input_proj_nhwc(const void* in, int C, const void* W, const float* bias, const void* pos, int pos_frames, void* X,
+                         float* X32, void* XP, int F, int S, int tok0, int P, void* stream) {
+  try {
+    vg::input_proj_nhwc(static_cast<const vg::bf16*>(in), C, static_cast<const vg::bf16*>(W), bias, static_cast<const vg::bf16*>(pos),
+                        pos_frames, static_cast<vg::bf16*>(X), X32, static_cast<vg::bf16*>(XP), F, S, tok0, P,
+                        static_cast<cudaStream_t>(stream));
+    return 0;
+  } catch (const std::exception& e) {
+    vg::set_last_error(e.what());
+    return 1;
+  }
+}
+
 int vgqa_enc_attn(const void* QKV, void* AO, int F, int S, const uint8_t* kmask, float scale, int use_tcgen05,
                   void* stream) {
   try {

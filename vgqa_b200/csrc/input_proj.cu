@@ -47,11 +47,16 @@ static constexpr int kIpPrefetchDist = 8;                  // k-blocks the L2 pr
 static constexpr int kIpGroups = 3;                        // converter groups (k-blocks in flight)
 static constexpr int kIpThreads = 256 + kIpGroups * 256;  // 4 control warps + 4 epilogue warps + 8 warps per group
 
-template <bool kBulk>
+// kMode 0: NCHW fp32 input, converters read global memory (LDG form);  1: NCHW fp32 input through the bulk-copy staging ring;
+// 2: NHWC bf16 input (channels-last, what a bf16 channels_last backbone emits): the map IS the K-major A operand → plain TMA tiles
+enum { kIpLdg = 0, kIpBulk = 1, kIpNhwc = 2 };
+template <int kMode>
 struct IpCfg {
+  static constexpr bool kBulk = kMode == kIpBulk;
   static constexpr int kWStages = kBulk ? 2 : 4;
   static constexpr int kAStages = kBulk ? 3 : 4;
   static constexpr int kStgStages = kBulk ? kIpGroups : 0;   // one staging stage per converter group
+  static constexpr int kThreads = kMode == kIpNhwc ? 256 : kIpThreads;   // no converter warps when the input is already bf16 rows
   static constexpr int kSmem = kWStages * kIpBBytes + kAStages * kIpABytes + kStgStages * kIpStgBytes + kIpSlabBytes +
                                1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(kSmem <= 232448, "input_proj shared memory");
@@ -67,7 +72,7 @@ struct IpParams {
   int F, C, P, S, tok0;
   int pos_per_frame;   // 1: pos row = output row; 0: pos row = tok0 + p (one table shared by every frame)
   int fpt;             // frames per tile (P <= 128), else 0
-  int tpf;             // 128-row slices per frame (P > 128)
+  int tpf;             // 128-row slices per frame (P > 128); 0 in the NHWC form: a tile is 128 consecutive rows of [F*P, C]
   int num_tiles;
   int l2_prefetch;     // LDG form: `in` is 16-byte aligned → bulk L2 prefetch of the chunks ahead
 };
@@ -79,6 +84,12 @@ __device__ __forceinline__ bool ip_row(const IpParams& p, int tile, int r, int& 
     frame = tile * p.fpt + fl;
     tok = r - fl * p.P;
     return fl < p.fpt && frame < p.F;
+  }
+  if (p.tpf == 0) {   // flat rows (NHWC input)
+    const int m = tile * 128 + r;
+    frame = m / p.P;
+    tok = m - frame * p.P;
+    return frame < p.F;
   }
   frame = tile / p.tpf;
   tok = (tile - frame * p.tpf) * 128 + r;
@@ -95,10 +106,11 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gptr, 
                : "memory");
 }
 
-template <bool kBulk>
+template <int kMode>
 __global__ void __launch_bounds__(kIpThreads, 1)
-input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
-  using Cfg = IpCfg<kBulk>;
+input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_a, const IpParams p) {
+  using Cfg = IpCfg<kMode>;
+  constexpr bool kBulk = kMode == kIpBulk;
   constexpr int kWS = Cfg::kWStages, kAS = Cfg::kAStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -125,7 +137,10 @@ input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_w);
-    for (int s = 0; s < 4; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); mbar_init(&a_full[s], 8); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); mbar_init(&a_empty[s], 1);
+      mbar_init(&a_full[s], kMode == kIpNhwc ? 1 : 8);   // TMA bytes, or one arrival per converter warp of a group
+    }
     for (int s = 0; s < 3; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_empty[s], 8); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     *consumed = 0;
@@ -180,7 +195,16 @@ input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
     } else if (warp == 2) {
       if (lane == 0) {
         const size_t chunk = (size_t)64 * p.P;   // floats of one frame's k-block: 64 channels x P tokens, contiguous
-        if constexpr (kBulk) {
+        if constexpr (kMode == kIpNhwc) {
+          // ===================== feature producer: the bf16 rows are the A operand — TMA tiles straight into the A ring =====================
+          tma_prefetch_desc(&tma_a);
+          for (int g = 0; g < total; ++g) {
+            const int it = g / num_k, kb = g - it * num_k, sa = g % kAS;
+            mbar_wait(&a_empty[sa], ((g / kAS) & 1) ^ 1);
+            mbar_expect_tx(&a_full[sa], kIpABytes);
+            tma_load_2d(smem_a + sa * kIpABytes, &tma_a, &a_full[sa], kb * 64, ((int)blockIdx.x + it * (int)gridDim.x) * 128);
+          }
+        } else if constexpr (kBulk) {
           // ===================== feature producer: bulk copies of the fp32 chunks into the staging ring =====================
           // (an additional L2 prefetch of the chunks ahead was measured and dropped: 469 us vs 449 us)
           for (int g = 0; g < total; ++g) {
@@ -279,7 +303,7 @@ input_proj_kernel(const __grid_constant__ CUtensorMap tma_w, const IpParams p) {
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else {
+  } else if constexpr (kMode != kIpNhwc) {
     // ===================== converters: fp32 [c][p] (staging stage or global) → bf16 [p][c] swizzled (shared) =====================
     const int pt = threadIdx.x - 256;
     const int grp = pt >> 8;                  // this group owns the k-blocks with (running k-block index % kIpGroups) == grp
@@ -349,16 +373,16 @@ void count_gemm_launch();
 
 bool input_proj_supported(int C) { return C >= 64 && C % 64 == 0; }
 
-template <bool kBulk>
-static void launch_ip(const CUtensorMap& tw, const IpParams& p, cudaStream_t stream) {
+template <int kMode>
+static void launch_ip(const CUtensorMap& tw, const CUtensorMap& ta, const IpParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    VG_CUDA(cudaFuncSetAttribute(input_proj_kernel<kBulk>, cudaFuncAttributeMaxDynamicSharedMemorySize, IpCfg<kBulk>::kSmem));
+    VG_CUDA(cudaFuncSetAttribute(input_proj_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, IpCfg<kMode>::kSmem));
     attr_set = true;
   }
   const int sms = device_sm_count();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  input_proj_kernel<kBulk><<<grid, kIpThreads, IpCfg<kBulk>::kSmem, stream>>>(tw, p);
+  input_proj_kernel<kMode><<<grid, IpCfg<kMode>::kThreads, IpCfg<kMode>::kSmem, stream>>>(tw, ta, p);
   VG_CUDA(cudaGetLastError());
 }
 
@@ -381,8 +405,27 @@ void input_proj(const float* in, int C, const bf16* W, const float* bias, const 
   bool bulk = aligned && P <= 128;
   if (const char* e = getenv("VGQA_IP_BULK")) bulk = bulk && e[0] != '0';
   CUtensorMap tw = make_tmap_2d(W, 256, C, C, 256, false);
-  if (bulk) launch_ip<true>(tw, p, stream);
-  else launch_ip<false>(tw, p, stream);
+  if (bulk) launch_ip<kIpBulk>(tw, tw, p, stream);
+  else launch_ip<kIpLdg>(tw, tw, p, stream);
+  count_gemm_launch();
+}
+
+// The same projection from a channels-last bf16 map  in[f, p, c]  ([F*P, C] rows — what a bf16 channels_last backbone emits):
+// the rows are the K-major A operand, so they go from HBM into the UMMA tile by TMA with no conversion at half the bytes.
+void input_proj_nhwc(const bf16* in, int C, const bf16* W, const float* bias, const bf16* pos, int pos_frames, bf16* X, float* X32,
+                     bf16* XP, int F, int S, int tok0, int P, cudaStream_t stream) {
+  VG_CHECK(input_proj_supported(C), "input_proj: the channel count must be a multiple of 64");
+  VG_CHECK(in && W && bias && X && F > 0 && P > 0 && tok0 >= 0 && tok0 + P <= S, "input_proj: bad arguments");
+  VG_CHECK(XP == nullptr || pos != nullptr, "input_proj: XP needs the positional rows");
+  VG_CHECK(pos_frames == 1 || pos_frames == F, "input_proj: pos_frames must be 1 or F");
+  VG_CHECK((long long)F * P < (1ll << 31), "input_proj: too many rows");
+  IpParams p;
+  p.in = nullptr; p.bias = bias; p.pos = pos; p.X = X; p.X32 = X32; p.XP = XP;
+  p.F = F; p.C = C; p.P = P; p.S = S; p.tok0 = tok0; p.pos_per_frame = pos_frames > 1 ? 1 : 0;
+  p.fpt = 0; p.tpf = 0; p.num_tiles = (F * P + 127) / 128; p.l2_prefetch = 0;
+  CUtensorMap tw = make_tmap_2d(W, 256, C, C, 256, false);
+  CUtensorMap ta = make_tmap_2d(in, F * P, C, C, 128, false);
+  launch_ip<kIpNhwc>(tw, ta, p, stream);
   count_gemm_launch();
 }
 

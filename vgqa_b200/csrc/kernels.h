@@ -28,6 +28,8 @@ void enc_attn_tc(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* kmask, 
 bool input_proj_supported(int C);
 void input_proj(const float* in, int C, const bf16* W, const float* bias, const bf16* pos, int pos_frames, bf16* X, float* X32,
                 bf16* XP, int F, int S, int tok0, int P, cudaStream_t stream);
+void input_proj_nhwc(const bf16* in, int C, const bf16* W, const float* bias, const bf16* pos, int pos_frames, bf16* X, float* X32,
+                     bf16* XP, int F, int S, int tok0, int P, cudaStream_t stream);
 void f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t st);
 
 // ---- text_tower.cu: SIMT pieces of the RoBERTa text tower (the Linear layers are tcgen05 GEMMs)

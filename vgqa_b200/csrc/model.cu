@@ -763,11 +763,17 @@ static void run_encoder(Fwd& f, const vgqa_inputs& in, bool have_mask, int pos_r
   nchw_to_tokens(in.pos, (long long)256 * P, c->pos_enc, nullptr, nullptr, 0, nullptr, pf, S, P + L, P, st);
   f.count(3);
   // visual tokens: already-projected maps, or the raw extractor maps through input_proj / input_proj2 (input_proj.cu)
-  if (in.vis_raw != nullptr)
+  if (in.vis_raw != nullptr && in.raw_layout == 1)
+    input_proj_nhwc(reinterpret_cast<const bf16*>(in.vis_raw), c->ip_vis.K, c->ip_vis.W, c->ip_vis.b, c->pos_enc, pf, c->X, c->X32,
+                    c->XP, F, S, 0, P, st);
+  else if (in.vis_raw != nullptr)
     input_proj(in.vis_raw, c->ip_vis.K, c->ip_vis.W, c->ip_vis.b, c->pos_enc, pf, c->X, c->X32, c->XP, F, S, 0, P, st);
   else
     nchw_to_tokens(in.vis, (long long)256 * P, c->X, c->X32, in.pos, pos_fs, c->XP, F, S, 0, P, st);
-  if (in.vid_raw != nullptr)
+  if (in.vid_raw != nullptr && in.raw_layout == 1)
+    input_proj_nhwc(reinterpret_cast<const bf16*>(in.vid_raw), c->ip_vid.K, c->ip_vid.W, c->ip_vid.b, c->pos_enc, pf, c->X, c->X32,
+                    c->XP, F, S, P + L, P, st);
+  else if (in.vid_raw != nullptr)
     input_proj(in.vid_raw, c->ip_vid.K, c->ip_vid.W, c->ip_vid.b, c->pos_enc, pf, c->X, c->X32, c->XP, F, S, P + L, P, st);
   else
     nchw_to_tokens(in.vid, (long long)256 * P, c->X, c->X32, in.pos, pos_fs, c->XP, F, S, P + L, P, st);
@@ -1032,6 +1038,7 @@ static void check_inputs(vgqa_ctx* c, const vgqa_inputs& in) {
   VG_CHECK(!in.text_ids || (!c->tt.empty() && c->ip_text.K > 0),
            "text_ids needs the 'text_encoder.body' (RoBERTa) and 'text_encoder.resizer' weights");
   VG_CHECK(!in.text_ids || in.L <= 64, "text_ids: a query has at most 64 tokens");
+  VG_CHECK(in.raw_layout == 0 || in.raw_layout == 1, "raw_layout must be 0 (NCHW fp32) or 1 (channels-last bf16)");
   VG_CHECK(!in.vis_raw || (c->ip_vis.K > 0 && in.vis_raw_ch == c->ip_vis.K),
            "vis_raw needs the 'input_proj' weights and vis_raw_ch equal to their input channels");
   VG_CHECK(!in.vid_raw || (c->ip_vid.K > 0 && in.vid_raw_ch == c->ip_vid.K),
@@ -1248,7 +1255,8 @@ static int run_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out
     return c->launches;
   }
   std::vector<uint64_t> key = {(uint64_t)phase, (uint64_t)slot, (uint64_t)in.clips, (uint64_t)in.T, (uint64_t)in.H,
-                               (uint64_t)in.W, (uint64_t)in.L, (uint64_t)in.pos_frames, (uint64_t)(in.iteration_rate < 0)};
+                               (uint64_t)in.W, (uint64_t)in.L, (uint64_t)in.pos_frames, (uint64_t)(in.iteration_rate < 0),
+                               (uint64_t)in.raw_layout};
   for (const void* q : {(const void*)in.vis, (const void*)in.vid, (const void*)in.text, (const void*)in.pos,
                         (const void*)in.vis_mask, (const void*)in.text_mask, (const void*)in.ori_sizes_hw,
                         (const void*)in.force_choose1, (const void*)in.force_choose2, (const void*)in.vis_raw,
@@ -1365,9 +1373,10 @@ int vgqa_forward_host_async(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outp
       VG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, up));
     };
     vgqa_inputs din = *hin;
-    if (hin->vis_raw) { h2d(h.vis_raw, hin->vis_raw, F * c->ip_vis.K * P * 4); din.vis_raw = h.vis_raw; din.vis = nullptr; }
+    const size_t raw_es = hin->raw_layout == 1 ? 2 : 4;   // channels-last bf16 or NCHW fp32 maps
+    if (hin->vis_raw) { h2d(h.vis_raw, hin->vis_raw, F * c->ip_vis.K * P * raw_es); din.vis_raw = h.vis_raw; din.vis = nullptr; }
     else { h2d(h.vis, hin->vis, F * 256 * P * 4); din.vis = h.vis; }
-    if (hin->vid_raw) { h2d(h.vid_raw, hin->vid_raw, F * c->ip_vid.K * P * 4); din.vid_raw = h.vid_raw; din.vid = nullptr; }
+    if (hin->vid_raw) { h2d(h.vid_raw, hin->vid_raw, F * c->ip_vid.K * P * raw_es); din.vid_raw = h.vid_raw; din.vid = nullptr; }
     else { h2d(h.vid, hin->vid, F * 256 * P * 4); din.vid = h.vid; }
     if (hin->text_ids) { h2d(h.ids, hin->text_ids, B * L * 4); din.text_ids = h.ids; din.text = nullptr; din.text_raw = nullptr; }
     else if (hin->text_raw) { h2d(h.text_raw, hin->text_raw, B * L * c->ip_text.K * 4); din.text_raw = h.text_raw; din.text = nullptr; }

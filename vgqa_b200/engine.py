@@ -28,7 +28,8 @@ class VgqaInputs(ctypes.Structure):
                 ("force_choose1", c_void_p), ("force_choose2", c_void_p), ("iteration_rate", c_int),
                 ("stop_after_encoder", c_int),
                 ("vis_raw", c_void_p), ("vid_raw", c_void_p), ("text_raw", c_void_p),
-                ("vis_raw_ch", c_int), ("vid_raw_ch", c_int), ("text_raw_ch", c_int), ("text_ids", c_void_p)]
+                ("vis_raw_ch", c_int), ("vid_raw_ch", c_int), ("text_raw_ch", c_int), ("text_ids", c_void_p),
+                ("raw_layout", c_int)]
 
 
 OUTPUT_FIELDS = ("pred_boxes", "pred_sted", "pred_actioness", "logits_f_m", "logits_f_a", "logits_r_a", "logits_r_m",
@@ -186,6 +187,13 @@ class GroundingEngine:
         return outs
 
     @staticmethod
+    def _dims(vis, raw):
+        """(clips, T, H, W) of a feature tensor: [clips,T,C,H,W] fp32, or channels-last bf16 [clips,T,H,W,C] (raw only)."""
+        if raw and vis.dtype == torch.bfloat16:
+            return vis.shape[0], vis.shape[1], vis.shape[2], vis.shape[3]
+        return vis.shape[0], vis.shape[1], vis.shape[3], vis.shape[4]
+
+    @staticmethod
     def _p(t):
         return None if t is None else c_void_p(t.data_ptr())
 
@@ -193,11 +201,17 @@ class GroundingEngine:
                  stop_after_encoder=0, raw=False, text_ids=None):
         """raw=True: vis / vid / text are the extractor outputs ([clips,T,Cv,H,W], [clips,T,Cd,H,W], [clips,L,Ct]) and the
         library applies input_proj / input_proj2 / text_encoder.resizer itself (their weights must be in the state_dict)."""
-        B, T, d, H, W = vis.shape
+        nhwc = bool(raw and vis.dtype == torch.bfloat16)   # channels-last bf16 maps [clips, T, H, W, C] (raw_layout = 1)
+        if nhwc:
+            B, T, H, W, d = vis.shape
+        else:
+            B, T, d, H, W = vis.shape
         if text_ids is not None:   # RoBERTa token ids [clips, L] int32: the library runs the text tower + resizer (raw=True only)
             assert raw and text_ids.dtype == torch.int32 and text_ids.dim() == 2 and text_ids.shape[0] == B and text_ids.is_contiguous()
             text = torch.empty(B, text_ids.shape[1], 0, dtype=torch.float32, device=text_ids.device)   # placeholder (shape only)
-        if raw:
+        if nhwc:
+            assert vid.dtype == torch.bfloat16 and tuple(vid.shape[:4]) == (B, T, H, W), "vid_raw must be bf16 [clips, T, H, W, C] too"
+        elif raw:
             assert tuple(vid.shape[:2]) == (B, T) and tuple(vid.shape[3:]) == (H, W), "vid_raw must be [clips, T, C, H, W]"
             assert text.dim() == 3 and text.shape[0] == B, "text_raw must be [clips, L, C]"
         else:
@@ -206,7 +220,7 @@ class GroundingEngine:
         Lt = text.shape[1]
         assert pos.shape[0] in (1, B * T) and tuple(pos.shape[1:]) == (256, H, W), "pos must be [1 or clips*T, 256, H, W]"
         for t in (vis, vid, text, pos):
-            assert t.dtype == torch.float32 and t.is_contiguous()
+            assert (t.dtype == torch.float32 or (nhwc and (t is vis or t is vid))) and t.is_contiguous()
         n = None
         inp = VgqaInputs(B, T, H, W, Lt, n if raw else self._p(vis), n if raw else self._p(vid), n if raw else self._p(text),
                          self._p(pos), pos.shape[0],
@@ -214,13 +228,14 @@ class GroundingEngine:
                          iteration_rate, stop_after_encoder,
                          self._p(vis) if raw else n, self._p(vid) if raw else n,
                          self._p(text) if (raw and text_ids is None) else n,
-                         vis.shape[2] if raw else 0, vid.shape[2] if raw else 0, text.shape[2] if raw else 0, self._p(text_ids))
+                         (vis.shape[4] if nhwc else vis.shape[2]) if raw else 0, (vid.shape[4] if nhwc else vid.shape[2]) if raw else 0,
+                         text.shape[2] if raw else 0, self._p(text_ids), 1 if nhwc else 0)
         out = VgqaOutputs(**{k: self._p(outs.get(k)) for k in OUTPUT_FIELDS})
         return inp, out
 
     def encode(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, raw=False, text_ids=None):
         """CrossModalEncoder only: returns encoded_feature [clips*T, S, 256] (frame-major) and frames_cls [clips*T, 256]."""
-        B, T, _, H, W = vis.shape
+        B, T, H, W = self._dims(vis, raw)
         outs = self.alloc_outputs(B, T, H, W, (text_ids if text_ids is not None else text).shape[1], ["encoded_feature", "frames_cls"])
         inp, out = self._pack_io(vis, vid, text, pos, vis_mask, text_mask, None, None, None, -1, outs, 1, raw=raw, text_ids=text_ids)
         st = torch.cuda.current_stream().cuda_stream
@@ -230,7 +245,7 @@ class GroundingEngine:
     def forward(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, ori_sizes_hw=None, force_choose1=None,
                 force_choose2=None, iteration_rate=-1, outs=None, want=None, raw=False, text_ids=None):
         """Device-resident inputs (fp32 CUDA tensors, reference layouts); enqueues on the current stream."""
-        B, T, _, H, W = vis.shape
+        B, T, H, W = self._dims(vis, raw)
         if outs is None:
             outs = self.alloc_outputs(B, T, H, W, (text_ids if text_ids is not None else text).shape[1], want)
             if ori_sizes_hw is None:
@@ -258,7 +273,7 @@ class GroundingEngine:
     def forward_host(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, ori_sizes_hw=None,
                      force_choose1=None, force_choose2=None, iteration_rate=-1, outs=None, want=None, raw=False, text_ids=None):
         """Host buffers (CPU tensors, ideally pinned): H2D + forward + D2H inside the call (synchronous)."""
-        B, T, _, H, W = vis.shape
+        B, T, H, W = self._dims(vis, raw)
         if outs is None:
             outs = self.alloc_outputs(B, T, H, W, (text_ids if text_ids is not None else text).shape[1], want, host=True)
             if ori_sizes_hw is None:
