@@ -216,6 +216,12 @@ int vgqa_input_proj_nhwc(const void* in_bf16, int C, const void* W, const float*
  * decoders use when `pos` is frame-invariant; runs the warp-per-frame streaming kernel (xattn_stream.cu). */
 int vgqa_xattn1_bias(const void* qt, const void* mem, long long frame_stride_rows, int F, int Mk, const float* sbias, int ldsb,
                      const uint8_t* kmask, int ldmask, float scale, void* ctx_out, float* att_out, void* stream);
+/* norm(x + sublayer(x)) as ONE GEMM:  y = LayerNorm_256(act(A W^T + bias) + res32) * ln_w + ln_b;  C = bf16(y), C32 = y (optional),
+ * C2 = bf16(y + add2[row % period]) (optional).  A [M,K] bf16 (row stride lda), W [256,K] bf16, all output / residual row strides
+ * 256.  Dispatches like the forward does (gemm_ln.cu: one CTA per 128-row tile, or CTA pairs for few rows and a long K). */
+int vgqa_gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int K, const float* bias, int act, const float* res32,
+                 const float* ln_w, const float* ln_b, float eps, void* C, float* C32, void* C2, const void* add2, int add2_period,
+                 void* stream);
 /* Fused post-norm FFN block of one encoder layer (modal_encoder.py:175-177):
  *   y = LayerNorm(res32 + W2 relu(W1 x + b1) + b2);  C = bf16(y), C32 = y (fp32, optional), C2 = bf16(y + add2[row % period]) (optional)
  * x [M,256] bf16, W1 [F,256] bf16, W2 [256,F] bf16 (nn.Linear layouts), F % 128 == 0, all row strides 256.  One launch on

@@ -100,3 +100,49 @@ def test_gemm_gelu_mul_strided():
     _gemm(A, W, C, bias=b, act=2, mul=mul)
     _close(C, _ref(A, W, b, act=2, mul=mul))
     assert float(Cbig[:, :512].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,K,res,c32,c2,act", [(1000, 256, True, True, True, 0),
+                                                (80000, 256, True, True, True, 0),      # several tiles per SM: the persistent loop wraps
+                                                (80000 + 77, 256, True, True, False, 0),  # ragged last tile
+                                                (3000, 2048, True, True, False, 0),     # few rows, long K: the CTA-pair (column-split) form
+                                                (76000, 512, False, False, False, 1),   # no residual, ReLU, bf16 output only
+                                                (77000, 64, True, False, True, 0)])
+def test_gemm_residual_layernorm_all_outputs(M, K, res, c32, c2, act):
+    """vgqa_gemm_ln (the `norm(x + sublayer(x))` launches of the forward) vs torch fp32: bf16 / fp32 / bf16(x+pos) outputs."""
+    import ctypes
+    from vgqa_b200 import _lib
+    L = _lib.lib()
+    L.vgqa_gemm_ln.restype = ctypes.c_int
+    v = ctypes.c_void_p
+    L.vgqa_gemm_ln.argtypes = [v, ctypes.c_int, v, ctypes.c_int, ctypes.c_int, ctypes.c_int, v, ctypes.c_int, v, v, v, ctypes.c_float,
+                               v, v, v, v, ctypes.c_int, v]
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(256, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(256, device="cuda", generator=g) * 0.1
+    r = torch.randn(M, 256, device="cuda", generator=g) if res else None
+    lw = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
+    lb = 0.1 * torch.randn(256, device="cuda", generator=g)
+    period = 118
+    add2 = torch.randn(period, 256, device="cuda", generator=g).bfloat16()
+    C = torch.full((M + 4, 256), 9.0, device="cuda", dtype=torch.bfloat16)      # canary rows behind the end
+    C32 = torch.full((M + 4, 256), 9.0, device="cuda") if c32 else None
+    C2 = torch.full((M + 4, 256), 9.0, device="cuda", dtype=torch.bfloat16) if c2 else None
+    _lib.check(L.vgqa_gemm_ln(_lib.ptr(A), K, _lib.ptr(W), K, M, K, _lib.ptr(b), act, _lib.ptr(r), _lib.ptr(lw), _lib.ptr(lb), 1e-5,
+                              _lib.ptr(C), _lib.ptr(C32), _lib.ptr(C2), _lib.ptr(add2), period, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    y = A.float() @ W.float().t() + b
+    if act == 1:
+        y = torch.relu(y)
+    if res:
+        y = y + r
+    ref = torch.nn.functional.layer_norm(y, (256,), lw, lb, 1e-5)
+    _close(C[:M], ref)
+    assert float((C[M:].float() - 9.0).abs().max()) == 0.0
+    if c32:
+        assert float((C32[:M] - ref).abs().max()) <= 2e-2 and float((C32[M:] - 9.0).abs().max()) == 0.0
+    if c2:
+        idx = torch.arange(M, device="cuda") % period
+        _close(C2[:M], ref + add2.float()[idx])
+        assert float((C2[M:].float() - 9.0).abs().max()) == 0.0

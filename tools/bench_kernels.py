@@ -118,6 +118,23 @@ def bench_input_proj(F=4096, C=2048, H=7, W=7, Lt=20, second=False, name=""):
     print(f"input_proj {name} channels-last bf16 F={F} C={C} P={P}: {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s  {byts / t / 1e3:7.1f} GB/s (algorithmic bytes)")
 
 
+def bench_gemm_ln(M, K=256, name=""):
+    import ctypes
+    v = ctypes.c_void_p
+    L.vgqa_gemm_ln.restype = ctypes.c_int
+    L.vgqa_gemm_ln.argtypes = [v, ctypes.c_int, v, ctypes.c_int, ctypes.c_int, ctypes.c_int, v, ctypes.c_int, v, v, v, ctypes.c_float,
+                               v, v, v, v, ctypes.c_int, v]
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    W = (torch.randn(256, K, device="cuda") / K ** 0.5).bfloat16()
+    b = torch.zeros(256, device="cuda"); lw = torch.ones(256, device="cuda")
+    r = torch.randn(M, 256, device="cuda")
+    C = torch.empty(M, 256, device="cuda", dtype=torch.bfloat16); C32 = torch.empty(M, 256, device="cuda")
+    t = timeit(lambda: _lib.check(L.vgqa_gemm_ln(_lib.ptr(A), K, _lib.ptr(W), K, M, K, _lib.ptr(b), 0, _lib.ptr(r), _lib.ptr(lw), _lib.ptr(b),
+                                                 1e-5, _lib.ptr(C), _lib.ptr(C32), None, None, 1, st())))
+    byts = M * (K * 2 + 1024 + 512 + 1024.0)
+    print(f"gemm_ln {name} M={M} K={K} (residual in, bf16 + fp32 out): {t:8.1f} us  {2.0 * M * 256 * K / t / 1e6:7.1f} TFLOP/s  {byts / t / 1e3:7.1f} GB/s")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["attn", "gemm"]
     if "attn" in which:
@@ -137,6 +154,8 @@ if __name__ == "__main__":
         bench_input_proj(C=2048, name="ResNet101 -> vis tokens")
         bench_input_proj(C=768, second=True, name="Video-Swin -> vid tokens")
         bench_input_proj(F=1024, C=2048, H=14, W=14, name="14x14")
+    if "gemm_ln" in which:
+        bench_gemm_ln(64 * 64 * 118, name="encoder out-proj + LN1")
     if "ffn" in which:
         bench_ffn(64 * 64 * 118)
         bench_ffn(16 * 64 * 118)

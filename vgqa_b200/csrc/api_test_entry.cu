@@ -32,6 +32,23 @@ int vgqa_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N,
   }
 }
 
+int vgqa_gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int K, const float* bias, int act, const float* res32,
+                 const float* ln_w, const float* ln_b, float eps, void* C, float* C32, void* C2, const void* add2, int add2_period,
+                 void* stream) {
+  try {
+    vg::GemmEpi ep;
+    ep.C = C; ep.ldc = 256; ep.bias = bias; ep.bias_ld = 256; ep.act = act; ep.res32 = res32; ep.ldres32 = 256; ep.C32 = C32; ep.ldc32 = 256;
+    ep.C2 = static_cast<vg::bf16*>(C2); ep.ldc2 = 256; ep.add2 = static_cast<const vg::bf16*>(add2); ep.add2_period = add2_period;
+    ep.ln_w = ln_w; ep.ln_b = ln_b; ep.ln_eps = eps;
+    vg::gemm_bf16_tn(static_cast<const vg::bf16*>(A), lda, static_cast<const vg::bf16*>(W), ldw, M, 256, K, ep,
+                     static_cast<cudaStream_t>(stream));
+    return 0;
+  } catch (const std::exception& e) {
+    vg::set_last_error(e.what());
+    return 1;
+  }
+}
+
 int vgqa_ffn_fused(const void* X, const void* W1, const float* b1, const void* W2, const float* b2, int M, int F,
                     const float* res32, const float* ln_w, const float* ln_b, float eps, void* C, float* C32, void* C2,
                     const void* add2, int add2_period, int epi_parts, void* stream) {
