@@ -271,3 +271,26 @@ def test_forward_channels_last_bf16_equals_nchw_fp32():
     for k in want:
         np.testing.assert_allclose(h[k].numpy(), b[k].cpu().numpy(), atol=1e-6)
     eng.close()
+
+
+def test_hot_path_module_takes_bf16_channels_last_maps_zero_copy():
+    """HotPath.forward(raw=True) with bf16 channels_last backbone outputs: same result as the fp32 NCHW form of the same values."""
+    from make_golden import make_cfg
+    from vgqa_b200 import modules as M
+    g = np.load(golden_path("fe_cfg1_T32_7x7_L20_s0"))
+    T, H, W, L, seed = (int(g[k]) for k in ("T", "H", "W", "L", "seed"))
+    ch = tuple(int(x) for x in g["front_end_ch"])
+    sd = O.synth_state_dict(seed, front_end_ch=ch)
+    vis_raw, vid_raw, text_raw = (torch.from_numpy(a).cuda() for a in O.synth_raw_inputs(seed, T, H, W, L, ch))
+    pos = torch.from_numpy(O.position_embedding_sine(np.zeros((T, H, W), bool))).cuda()
+    hot = M.build_hot_path(make_cfg(), sd, max_frames=64, max_hw=49, max_text=20)
+    vm = torch.zeros(T, H, W, dtype=torch.bool, device="cuda")
+    tm = torch.zeros(1, L, dtype=torch.bool, device="cuda")
+    v16 = vis_raw.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    d16 = vid_raw.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    assert v16.permute(0, 2, 3, 1).is_contiguous()                 # the view the module hands to the library
+    a = hot(v16, vm, pos, tm, text_raw[:, None, :], d16, raw=True)
+    b = hot(v16.float().contiguous(), vm, pos, tm, text_raw[:, None, :], d16.float().contiguous(), raw=True)
+    for k in ("pred_boxes", "pred_sted", "logits_f_m", "att_sequences"):
+        assert float((a[k] - b[k]).abs().max()) <= 5e-3, k
+        assert float(np.abs(a[k].cpu().numpy() - g[k]).max()) <= 3e-2, k       # bf16-rounded extractor maps vs the fp32 golden

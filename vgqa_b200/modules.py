@@ -92,7 +92,12 @@ class HotPath(torch.nn.Module):
             pos = f32(vis_pos[:1])   # PositionEmbeddingSine of an all-False mask is identical on every frame
         if text_ids is not None:
             kw["text_ids"] = text_ids.reshape(1, -1).to(torch.int32).contiguous()
-        o = self.engine.forward(f32(vis_features)[None], f32(vid_features)[None],
+        fmap = f32
+        if raw and vis_features.dtype == torch.bfloat16 and vid_features.dtype == torch.bfloat16:
+            # bf16 backbones: hand the maps over as channels-last bf16 (raw_layout = 1).  A channels_last tensor already IS
+            # [T, H, W, C] in memory, so this is a zero-copy view; a plain NCHW bf16 tensor is permuted once.
+            fmap = lambda t: t.detach().permute(0, 2, 3, 1).contiguous()
+        o = self.engine.forward(fmap(vis_features)[None], fmap(vid_features)[None],
                                 None if text_ids is not None else f32(text_features[:, 0])[None], pos,
                                 iteration_rate=iteration_rate, raw=raw, **kw)
         out = {"pred_boxes": o["pred_boxes"][0], "logits_f_m": o["logits_f_m"][0], "logits_f_a": o["logits_f_a"][0],
