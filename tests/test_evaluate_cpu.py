@@ -83,3 +83,58 @@ def test_cross_rank_merge_gloo_world2():
     assert res[1][0] is None and res[0][1] == res[1][1] == len(g["predictions"])
     for k, v in g["summary"].items():
         assert res[0][0][k] == pytest.approx(v, abs=1e-12), k
+
+
+class _FakeEngine:
+    """Deterministic stand-in for GroundingEngine.forward (CPU): lets `do_eval`'s batching / partition / gather logic run under
+    gloo without a GPU.  Outputs depend only on each clip's own inputs, like the real engine's."""
+    device = "cpu"
+
+    def forward(self, vis, vid, text, pos, ori_sizes_hw=None, want=None, raw=False):
+        import torch
+        B, T = vis.shape[:2]
+        m = vis.reshape(B, T, -1).mean(-1) + vid.reshape(B, T, -1).mean(-1)                    # [B, T]
+        box = torch.stack([100 + 50 * m, 80 + 40 * m, 300 + 50 * m, 260 + 40 * m], -1)
+        idx = torch.stack([m.argmin(1).clamp(max=T - 2), torch.full((B,), T - 1)], 1).to(torch.int32)
+        return {"boxes_px": box, "att_sequences": torch.sigmoid(m), "sted_idx": idx, "choose2": (m > 0).float()}
+
+
+def _fake_items(n=7, T2=8):
+    rng = np.random.Generator(np.random.PCG64(3))
+    items, gt = [], []
+    for i in range(n):
+        fids = list(range(2 * i, 2 * i + T2))
+        items.append({"item_id": 500 + i, "vis": rng.standard_normal((T2, 4, 2, 2)).astype(np.float32),
+                      "vid": rng.standard_normal((T2, 4, 2, 2)).astype(np.float32), "text": np.zeros((3, 4), np.float32),
+                      "pos": np.zeros((1, 256, 2, 2), np.float32), "frame_ids": fids, "ori_size": (360, 640),
+                      "qtype": ["declar", "inter"][i % 2], "actioness": (np.arange(T2) % 3 == 0).astype(np.float32)})
+        gt.append({"item_id": 500 + i, "gt_temp_bound": [fids[1], fids[-2]], "bboxs": {f: [110.0, 90.0, 310.0, 270.0] for f in fids[1:-2]}})
+    return items, gt
+
+
+def _eval_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    items, gt = _fake_items()
+    ev = E.VidSTGEvaluator(gt, [0.3, 0.5])
+    out = E.do_eval(_FakeEngine(), items, ev, clips_per_call=2, rank=rank, world=world)
+    q.put((rank, out, ev.video_predictions))
+    dist.destroy_process_group()
+
+
+def test_do_eval_two_ranks_equals_one_rank_gloo():
+    items, gt = _fake_items()
+    ref_ev = E.VidSTGEvaluator(gt, [0.3, 0.5], distributed=False)
+    ref = E.do_eval(_FakeEngine(), items, ref_ev, clips_per_call=3)
+    assert len(ref_ev.video_predictions) == len(items) and set(k.split("_")[0] for k in ref) == {"declar", "inter"}
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + os.getpid() % 100
+    ps = [ctx.Process(target=_eval_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = dict((r, (o, vp)) for r, o, vp in (q.get(timeout=120) for _ in ps))
+    [p.join(60) for p in ps]
+    assert res[1][0] is None                                    # only rank 0 summarizes
+    assert res[0][1] == res[1][1] == ref_ev.video_predictions    # every rank holds the merged predictions
+    for k, v in ref.items():
+        assert res[0][0][k] == pytest.approx(v, abs=1e-12), k
