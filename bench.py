@@ -173,7 +173,7 @@ def time_dominant_kernel(B, pk):
             "hbm_gbs_at_algorithmic_bytes": alg_bytes / dt / 1e9}
 
 
-def measure_with_backbone(eng, torch, d_pos, r_vid_small=None, rank=0, clips=8, steps=5):
+def measure_with_backbone(eng, torch, d_pos, rank=0, clips=8, steps=5):
     """SURVEY §8d secondary number: clips/s with a PyTorch bf16 backbone in front of the library — torchvision ResNet101 (random
     init, eval, bf16, channels_last: cuDNN/cuBLAS LIBRARY code, not part of this repo's kernels) on `clips` x 64 frames of 3x224x224,
     its layer-4 map fed to the raw-input forward.  The Video-Swin map and the RoBERTa states stay synthetic (the reference's
@@ -338,63 +338,90 @@ def main():
     # e2e: pinned host buffers through the C-ABI (vgqa_forward_host_async/_wait, two slots); timed by wall clock
     # around enqueue + final drain (every step's H2D, compute and D2H are inside)
     sec_e2e = timed(step_host, args.steps, device_events=False, drain=drain_host)
-    # secondary: the same step fed with the RAW extractor maps resident in HBM (ResNet101 2048-ch + Video-Swin 768-ch fp32
-    # NCHW, RoBERTa 768-d states): input_proj / input_proj2 / resizer run inside the forward (csrc/input_proj.cu)
-    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    r_vis = torch.randn(B, T, FRONT_END_CH[0], H, W, device="cuda", generator=g).relu_()
-    r_vid = torch.randn(B, T, FRONT_END_CH[1], H, W, device="cuda", generator=g)
-    r_text = torch.randn(B, L, FRONT_END_CH[2], device="cuda", generator=g)
-    raw_i = [0]
-
-    def step_raw():
-        slot = raw_i[0] & 1
-        eng.forward_async(r_vis, r_vid, r_text, d_pos, ori_sizes_hw=d_sizes, outs=d_outs2[slot], slot=slot, raw=True)
-        raw_i[0] += 1
-
-    sec_raw = timed(step_raw, args.steps, drain=drain_dev)
-    # ... and from RoBERTa token ids: the 12-layer text tower (csrc/text_tower.cu + tcgen05 GEMMs) runs inside the forward too
-    r_ids = torch.from_numpy(O.synth_text_ids(rank, B, L, TEXT_TOWER[1])[0]).cuda()
-
-    def step_ids():
-        slot = raw_i[0] & 1
-        eng.forward_async(r_vis, r_vid, None, d_pos, ori_sizes_hw=d_sizes, outs=d_outs2[slot], slot=slot, raw=True, text_ids=r_ids)
-        raw_i[0] += 1
-
-    sec_ids = timed(step_ids, args.steps, drain=drain_dev)
-    # ... and with the maps in the B200-native layout (raw_layout = 1): channels-last bf16, read by TMA as the GEMM operand itself
-    c_vis = r_vis.permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16)
-    c_vid = r_vid.permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16)
-
-    def step_cl():
-        slot = raw_i[0] & 1
-        eng.forward_async(c_vis, c_vid, r_text, d_pos, ori_sizes_hw=d_sizes, outs=d_outs2[slot], slot=slot, raw=True)
-        raw_i[0] += 1
-
-    sec_cl = timed(step_cl, args.steps, drain=drain_dev)
-    del c_vis, c_vid
-    raw_bytes = int((r_vis.numel() + r_vid.numel() + r_text.numel()) * 4)
-    del r_vis, r_vid, r_text
-    # the literal configs[1] setting — ONE clip per forward call (the reference's batch 1): latency-bound, reported beside the
-    # throughput headline.  Same engine, same two-slot pipelined API, clip 0 of the batch.
-    one = [eng.alloc_outputs(1, T, H, W, L, want) for _ in range(2)]
-    v1, w1, t1, s1 = d_vis[:1].contiguous(), d_vid[:1].contiguous(), d_text[:1].contiguous(), d_sizes[:1].contiguous()
-    one_i = [0]
-
-    def step_one():
-        slot = one_i[0] & 1
-        eng.forward_async(v1, w1, t1, d_pos, ori_sizes_hw=s1, outs=one[slot], slot=slot)
-        one_i[0] += 1
-
-    n_one = 50
-    sec_one = timed(step_one, n_one, drain=drain_dev)
-
-    def step_one_sync():
-        eng.forward(v1, w1, t1, d_pos, ori_sizes_hw=s1, outs=one[0])
-        torch.cuda.synchronize()
-
-    sec_one_sync = timed(step_one_sync, n_one, device_events=False)
-    with_bb = measure_with_backbone(eng, torch, d_pos, r_vid_small=None, rank=rank) if rank == 0 else None
     total_clips = B * world * args.steps
+
+    def secondary():
+        """Secondary lines (front end, batch 1): same collectives on every rank; a failure here must not lose the headline."""
+        # secondary: the same step fed with the RAW extractor maps resident in HBM (ResNet101 2048-ch + Video-Swin 768-ch fp32
+        # NCHW, RoBERTa 768-d states): input_proj / input_proj2 / resizer run inside the forward (csrc/input_proj.cu)
+        g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+        r_vis = torch.randn(B, T, FRONT_END_CH[0], H, W, device="cuda", generator=g).relu_()
+        r_vid = torch.randn(B, T, FRONT_END_CH[1], H, W, device="cuda", generator=g)
+        r_text = torch.randn(B, L, FRONT_END_CH[2], device="cuda", generator=g)
+        raw_i = [0]
+
+        def step_raw():
+            slot = raw_i[0] & 1
+            eng.forward_async(r_vis, r_vid, r_text, d_pos, ori_sizes_hw=d_sizes, outs=d_outs2[slot], slot=slot, raw=True)
+            raw_i[0] += 1
+
+        sec_raw = timed(step_raw, args.steps, drain=drain_dev)
+        # ... and from RoBERTa token ids: the 12-layer text tower (csrc/text_tower.cu + tcgen05 GEMMs) runs inside the forward too
+        r_ids = torch.from_numpy(O.synth_text_ids(rank, B, L, TEXT_TOWER[1])[0]).cuda()
+
+        def step_ids():
+            slot = raw_i[0] & 1
+            eng.forward_async(r_vis, r_vid, None, d_pos, ori_sizes_hw=d_sizes, outs=d_outs2[slot], slot=slot, raw=True, text_ids=r_ids)
+            raw_i[0] += 1
+
+        sec_ids = timed(step_ids, args.steps, drain=drain_dev)
+        # ... and with the maps in the B200-native layout (raw_layout = 1): channels-last bf16, read by TMA as the GEMM operand itself
+        c_vis = r_vis.permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16)
+        c_vid = r_vid.permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16)
+
+        def step_cl():
+            slot = raw_i[0] & 1
+            eng.forward_async(c_vis, c_vid, r_text, d_pos, ori_sizes_hw=d_sizes, outs=d_outs2[slot], slot=slot, raw=True)
+            raw_i[0] += 1
+
+        sec_cl = timed(step_cl, args.steps, drain=drain_dev)
+        del c_vis, c_vid
+        raw_bytes = int((r_vis.numel() + r_vid.numel() + r_text.numel()) * 4)
+        del r_vis, r_vid, r_text
+        # the literal configs[1] setting — ONE clip per forward call (the reference's batch 1): latency-bound, reported beside the
+        # throughput headline.  Same engine, same two-slot pipelined API, clip 0 of the batch.
+        one = [eng.alloc_outputs(1, T, H, W, L, want) for _ in range(2)]
+        v1, w1, t1, s1 = d_vis[:1].contiguous(), d_vid[:1].contiguous(), d_text[:1].contiguous(), d_sizes[:1].contiguous()
+        one_i = [0]
+
+        def step_one():
+            slot = one_i[0] & 1
+            eng.forward_async(v1, w1, t1, d_pos, ori_sizes_hw=s1, outs=one[slot], slot=slot)
+            one_i[0] += 1
+
+        n_one = 50
+        sec_one = timed(step_one, n_one, drain=drain_dev)
+
+        def step_one_sync():
+            eng.forward(v1, w1, t1, d_pos, ori_sizes_hw=s1, outs=one[0])
+            torch.cuda.synchronize()
+
+        sec_one_sync = timed(step_one_sync, n_one, device_events=False)
+        front_end = {"value": total_clips / sec_raw, "unit": "clips/s", "ms_per_step": 1e3 * sec_raw / args.steps,
+                     "what": "same step from RAW extractor maps resident in HBM: input_proj (2048->256) + input_proj2 (768->256) "
+                             "+ text resizer fused into the forward (SURVEY 8f rank 2); adds 4.5 GFLOP and "
+                             f"{raw_bytes / B / 1e6:.1f} MB of fp32 reads per clip",
+                     "raw_input_bytes_per_step": raw_bytes,
+                     "channels_last_bf16": {"value": total_clips / sec_cl, "unit": "clips/s", "ms_per_step": 1e3 * sec_cl / args.steps,
+                                            "what": "same, maps given as channels-last bf16 [clips,T,H,W,C] (raw_layout = 1): half the bytes, "
+                                                    "TMA-fed with no conversion pass"},
+                     "from_token_ids": {"value": total_clips / sec_ids, "unit": "clips/s", "ms_per_step": 1e3 * sec_ids / args.steps,
+                                        "what": f"as above, text from RoBERTa token ids: the {TEXT_TOWER[0]}-layer RoBERTa-base tower "
+                                                f"({B} queries x {L} tokens per step) also runs inside the forward"}}
+        batch1 = {"value": n_one * world / sec_one, "unit": "clips/s", "ms_per_clip_pipelined": 1e3 * sec_one / n_one,
+                  "ms_per_clip_synchronous": 1e3 * sec_one_sync / n_one,
+                  "what": "ONE clip per forward call (the reference's batch 1, BASELINE configs[1] read literally): CUDA-graph replay "
+                          "of the same ≈455 launches, latency-bound; pipelined = two calls in flight, synchronous = host waits per clip"}
+        return front_end, batch1
+
+    try:
+        front_end, batch1 = secondary()
+    except Exception as ex:   # noqa: BLE001 — reported in the line
+        front_end = batch1 = {"error": f"{type(ex).__name__}: {ex}"}
+    try:
+        with_bb = measure_with_backbone(eng, torch, d_pos, rank=rank) if rank == 0 else None
+    except Exception as ex:   # noqa: BLE001
+        with_bb = {"error": f"{type(ex).__name__}: {ex}"}
     value = total_clips / sec
     e2e = total_clips / sec_e2e
     h2d = int(h_vis.numel() * 4 * 2 + h_text.numel() * 4 + h_pos.numel() * 4 + h_sizes.numel() * 4)
@@ -412,21 +439,8 @@ def main():
                        "cuda_graph": not args.no_graph, "parallelism": f"clips partitioned over {world} GPU(s), no data-path collective"},
             "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * sec_e2e / args.steps},
-            "front_end": {"value": total_clips / sec_raw, "unit": "clips/s", "ms_per_step": 1e3 * sec_raw / args.steps,
-                          "what": "same step from RAW extractor maps resident in HBM: input_proj (2048->256) + input_proj2 (768->256) "
-                                  "+ text resizer fused into the forward (SURVEY 8f rank 2); adds 4.5 GFLOP and "
-                                  f"{raw_bytes / B / 1e6:.1f} MB of fp32 reads per clip",
-                          "raw_input_bytes_per_step": raw_bytes,
-                          "channels_last_bf16": {"value": total_clips / sec_cl, "unit": "clips/s", "ms_per_step": 1e3 * sec_cl / args.steps,
-                                                 "what": "same, maps given as channels-last bf16 [clips,T,H,W,C] (raw_layout = 1): half the bytes, "
-                                                         "TMA-fed with no conversion pass"},
-                          "from_token_ids": {"value": total_clips / sec_ids, "unit": "clips/s", "ms_per_step": 1e3 * sec_ids / args.steps,
-                                             "what": f"as above, text from RoBERTa token ids: the {TEXT_TOWER[0]}-layer RoBERTa-base tower "
-                                                     f"({B} queries x {L} tokens per step) also runs inside the forward"}},
-            "batch1": {"value": n_one * world / sec_one, "unit": "clips/s", "ms_per_clip_pipelined": 1e3 * sec_one / n_one,
-                       "ms_per_clip_synchronous": 1e3 * sec_one_sync / n_one,
-                       "what": "ONE clip per forward call (the reference's batch 1, BASELINE configs[1] read literally): CUDA-graph replay "
-                               "of the same ≈455 launches, latency-bound; pipelined = two calls in flight, synchronous = host waits per clip"},
+            "front_end": front_end,
+            "batch1": batch1,
             "with_backbone": with_bb,
             "gpu_launches": int(launches) * args.steps,
             "gpu_launches_per_step": int(launches),
