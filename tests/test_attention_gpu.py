@@ -96,6 +96,7 @@ def test_xattn1(F, S, tok0, Mk, use_pos, use_kpos, use_mask, want_att):
                           (700, 118, 0, 69, True, False, False),      # more frames than workers: the per-warp ring wraps
                           (33, 118, 69, 49, False, False, True),      # SpatialActivation
                           (9, 27, 12, 15, True, True, False),
+                          (300, 250, 20, 100, True, True, True),      # 65..128 memory tokens (8x8 .. 10x10 maps)
                           (5, 352, 208, 144, False, False, True),     # cfg-5 memory length
                           (3, 412, 0, 208, True, True, True),
                           (2, 9, 1, 3, True, False, True)])

@@ -347,6 +347,7 @@ void xattn_stream(const bf16* qt, const bf16* mem, long long frame_stride_rows, 
   static const int pairs4 = [] { const char* e = getenv("VGQA_XS_PAIRS"); return e == nullptr || e[0] != '2' ? 1 : 0; }();
   if (pairs4 && MT == 4) { launch_xs<4, 4, 1>(tm, tq, tc, p, stream); return; }
   if (pairs4 && MT == 5) { launch_xs<5, 4, 1>(tm, tq, tc, p, stream); return; }
+  if (pairs4 && MT == 8) { launch_xs<8, 2, 1>(tm, tq, tc, p, stream); return; }   // 65..128 memory tokens: two single-stage pairs
   switch (MT) {
     case 4: launch_xs<4, 2, 2>(tm, tq, tc, p, stream); break;
     case 5: launch_xs<5, 2, 2>(tm, tq, tc, p, stream); break;
