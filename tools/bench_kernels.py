@@ -68,10 +68,11 @@ def bench_xattn(F=4096, S=118, tok0=0, Mk=69, use_pos=False, use_kpos=False, nam
 def bench_xattn_stream(F=4096, S=118, tok0=0, Mk=69, bias=True, name=""):
     mem_all = torch.randn(F, S, 256, device="cuda").bfloat16()
     qt = (torch.randn(F, 8, 256, device="cuda") / 4).bfloat16()
-    sb = torch.randn(F, 8, 72, device="cuda") if bias else None
+    ldsb = (Mk + 7) // 8 * 8
+    sb = torch.randn(F, 8, ldsb, device="cuda") if bias else None
     ctx = torch.zeros(F, 2048, device="cuda", dtype=torch.bfloat16)
     mem = mem_all[:, tok0:tok0 + Mk]
-    t = timeit(lambda: _lib.check(L.vgqa_xattn1_bias(_lib.ptr(qt), _lib.ptr(mem), S, F, Mk, _lib.ptr(sb), 72, None, 0, 0.125,
+    t = timeit(lambda: _lib.check(L.vgqa_xattn1_bias(_lib.ptr(qt), _lib.ptr(mem), S, F, Mk, _lib.ptr(sb), ldsb, None, 0, 0.125,
                                                      _lib.ptr(ctx), None, st())))
     byts = F * (Mk * 512 + 4096 + 4096 + (8 * Mk * 4 if bias else 0))
     print(f"xattn stream {name} F={F} Mk={Mk}: {t:8.1f} us  {byts / t / 1e3:7.1f} GB/s")
@@ -144,6 +145,11 @@ if __name__ == "__main__":
         bench_attn(F=1024, S=352)
         bench_attn(F=1024, S=412)
         bench_attn(F=1024, S=256)
+    if "xattn_long" in which:
+        bench_xattn_stream(F=1024, S=352, Mk=208, tok0=0, name="cfg-5 decoder (stream)")
+        bench_xattn(F=1024, S=352, Mk=208, tok0=0, name="cfg-5 decoder (CTA per frame, no positional terms)")
+        bench_xattn_stream(F=1024, S=352, Mk=144, tok0=208, bias=False, name="cfg-5 spatial (stream)")
+        bench_xattn(F=1024, S=352, Mk=144, tok0=208, name="cfg-5 spatial (CTA per frame)")
     if "xattn" in which:
         bench_xattn_stream(Mk=49, tok0=69, bias=False, name="spatial")
         bench_xattn_stream(Mk=69, tok0=0, name="decoder")

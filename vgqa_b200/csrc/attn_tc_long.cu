@@ -15,12 +15,16 @@
 
 namespace vg {
 
+// one control warpgroup (TMA, MMA, two idle warps: registers released) + the four softmax warpgroups (setmaxnreg 112: the running
+// 32-wide O row, two 32-wide chunk buffers and the packed probabilities stay in registers)
+static constexpr int kAtLongThreads = 128 + kAtWgs * 128;
+
 struct LongUnit {
   int f, h, qt, j;   // frame, head, query tile, key tile
   bool valid;
 };
 
-__global__ void __launch_bounds__(kAtThreads, 1)
+__global__ void __launch_bounds__(kAtLongThreads, 1)
 enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_o,
                         const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -75,8 +79,8 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < kAtOnesBytes / 16; i += kAtWgs * 128)
+  if (warp >= 4) {
+    for (int i = threadIdx.x - 128; i < kAtOnesBytes / 16; i += kAtWgs * 128)
       reinterpret_cast<uint4*>(s_ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
   }
@@ -85,6 +89,7 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -148,12 +153,13 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         ++n_pv;
       }
     }
-  } else {
+  } else if (warp >= 4) {
     // ===================== softmax + output warpgroups: one item stream each =====================
-    const int wg = (warp - 2) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int wg = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;        // query row within the tile
-    const int wg_tid = (warp - 2 - wg * 4) * 32 + lane;
+    const int wg_tid = (warp - 4 - wg * 4) * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     uint8_t* p_buf = s_p + wg * kAtPBytes;
     uint8_t* o_buf = p_buf;                  // O staging reuses the head of this warpgroup's P tile
@@ -283,7 +289,7 @@ void enc_attn_tc_long(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* km
   CUtensorMap to = make_tmap_frames(AO, F, S, 256, 256);
   AttnTcParams p{kmask, S, F, scale * 1.4426950408889634f};
   const int grid = F < device_sm_count() ? F : device_sm_count();
-  enc_attn_tc_long_kernel<<<grid, kAtThreads, kAtSmem, stream>>>(tq, to, p);
+  enc_attn_tc_long_kernel<<<grid, kAtLongThreads, kAtSmem, stream>>>(tq, to, p);
   VG_CUDA(cudaGetLastError());
 }
 
