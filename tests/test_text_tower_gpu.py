@@ -116,3 +116,35 @@ def test_predictor_from_raw_maps_and_token_ids():
     assert a["temporal"] == b["temporal"] and [t["frame"] for t in a["tube"]] == [t["frame"] for t in b["tube"]]
     np.testing.assert_allclose(np.asarray([t["bbox"] for t in a["tube"]]), np.asarray([t["bbox"] for t in b["tube"]]), atol=1e-3)
     pred.close()
+
+
+def test_forward_from_padded_token_ids_with_text_mask():
+    """Two queries of different length in one batch: pad id 1 + text_mask on the shorter one.  The mask must act both in the text
+    tower (keys) and in the cross-modal encoder (text tokens); each clip is checked against the oracle chain run on its own."""
+    from vgqa_b200.engine import GroundingEngine
+    seed, T, H, W, L, layers, vocab = 9, 6, 3, 3, 10, 2, 300
+    ch = (128, 64, 768)
+    sd = O.synth_state_dict(seed, front_end_ch=ch, text_tower=(layers, vocab))
+    vis_raw, vid_raw, _ = O.synth_raw_inputs(seed, T, H, W, L, ch)
+    ids, pad = O.synth_text_ids(seed, 2, L, vocab, pad_tail=3)          # row 1 has 3 padded positions
+    assert pad[1].sum() == 3 and not pad[0].any()
+    pos = O.position_embedding_sine(np.zeros((T, H, W), bool))
+    hid = O.roberta_encoder(sd, ids, pad)
+    refs = []
+    for b in range(2):
+        vis, vid, text = O.front_end(sd, vis_raw, vid_raw, hid[b])
+        refs.append(O.hot_path_forward(sd, vis, vid, pos, text, np.zeros((T, H, W), bool), pad[b:b + 1], return_debug=True))
+    eng = GroundingEngine(sd, max_clips=2, max_frames=T, max_hw=H * W, max_text=L)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    rep = lambda a: t(np.stack([a, a]))
+    force = lambda key: t(np.stack([np.isin(np.arange(T), r["debug"][key]).astype(np.float32) for r in refs]))
+    o = eng.forward(rep(vis_raw), rep(vid_raw), None, t(pos[:1]), raw=True, text_ids=t(ids), text_mask=t(pad.astype(np.uint8)),
+                    vis_mask=t(np.zeros((2 * T, H * W), np.uint8)), force_choose1=force("choose_pass1"),
+                    force_choose2=force("choose_pass2"), want=["pred_boxes", "pred_sted", "logits_f_m", "logits_f_a"])
+    torch.cuda.synchronize()
+    for b in range(2):
+        for k, r in (("pred_boxes", refs[b]["pred_boxes"]), ("pred_sted", refs[b]["pred_sted"][0]),
+                     ("logits_f_m", refs[b]["logits_f_m"]), ("logits_f_a", refs[b]["logits_f_a"])):
+            assert float(np.abs(o[k][b].cpu().numpy() - r).max()) <= 2e-2, (b, k)
+    assert float((o["logits_f_m"][0] - o["logits_f_m"][1]).abs().max()) > 1e-4      # the padded query really differs
+    eng.close()
