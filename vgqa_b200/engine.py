@@ -300,7 +300,6 @@ class GroundingEngine:
         B, L = text_ids.shape
         self._L.vgqa_text_tower.restype = c_int
         self._L.vgqa_text_tower.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
-        hd = torch.empty(1, dtype=torch.int32)
         self._L.vgqa_text_tower_hidden.restype = c_int
         self._L.vgqa_text_tower_hidden.argtypes = [c_void_p]
         Hd = int(self._L.vgqa_text_tower_hidden(self._ctx))
