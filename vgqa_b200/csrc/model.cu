@@ -1367,8 +1367,10 @@ int vgqa_forward_host_async(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outp
     cudaStream_t up = c->h2d_stream;
     const size_t B = hin->clips, T = hin->T, P = (size_t)hin->H * hin->W, L = hin->L, F = B * T;
     const size_t D = c->tl.size();
-    // uploads wait until the previous forward that read this slot's staging buffers has finished
-    if (c->bd[slot].used) VG_CUDA(cudaStreamWaitEvent(up, c->bd[slot].dec_done, 0));
+    // The feature / text / mask staging buffers of this slot are read by phase 0 (run_encoder) only: their upload may start as
+    // soon as the ENCODER phase of the previous call on this slot is done, i.e. it overlaps that call's decoder phase and the
+    // other slot's encoder phase.  (Waiting for dec_done here delayed the next encoder phase by most of the 8 ms upload.)
+    if (c->bd[slot].used) VG_CUDA(cudaStreamWaitEvent(up, c->bd[slot].enc_done, 0));
     auto h2d = [&](void* dst, const void* src, size_t bytes) {
       VG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, up));
     };
@@ -1384,6 +1386,8 @@ int vgqa_forward_host_async(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outp
     h2d(h.pos, hin->pos, (size_t)hin->pos_frames * 256 * P * 4); din.pos = h.pos;
     if (hin->vis_mask) { h2d(h.vmask, hin->vis_mask, F * P); din.vis_mask = h.vmask; }
     if (hin->text_mask) { h2d(h.tmask, hin->text_mask, B * L); din.text_mask = h.tmask; }
+    // sizes / forced selections are read by phase 1: wait for the previous call's decoder phase (and result downloads)
+    if (c->bd[slot].used) VG_CUDA(cudaStreamWaitEvent(up, c->bd[slot].dec_done, 0));
     if (hin->ori_sizes_hw) { h2d(h.sizes, hin->ori_sizes_hw, B * 2 * 4); din.ori_sizes_hw = h.sizes; }
     if (hin->force_choose1) { h2d(h.f1, hin->force_choose1, F * 4); din.force_choose1 = h.f1; }
     if (hin->force_choose2) { h2d(h.f2, hin->force_choose2, F * 4); din.force_choose2 = h.f2; }
