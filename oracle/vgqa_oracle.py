@@ -618,157 +618,8 @@ def front_end(sd, vis_raw: np.ndarray, vid_raw: np.ndarray, text_raw: np.ndarray
 
 
 # ----------------------------------------------------------------------------------------------
-# deterministic synthetic weights / inputs shared by golden maker, tests, bench and smoke
+# deterministic synthetic weights / inputs: they live in the product package (pure numpy, vgqa_b200/synth.py) so that the
+# GPU arm of bench.py imports nothing from oracle/; re-exported here for the tests and fixture makers
 # ----------------------------------------------------------------------------------------------
-def hot_path_param_shapes(enc_layers=6, dec_layers=6, d=256, ffn=2048, max_video_len=200,
-                          app_num=20, mot_num=34, front_end_ch: Optional[Tuple[int, int, int]] = None,
-                          text_tower: Optional[Tuple[int, int]] = None) -> Dict[str, Tuple[int, ...]]:
-    """Names/shapes of every state_dict entry the hot path READS (subset of SURVEY.md §8b).  `front_end_ch` =
-    (ResNet channels, Video-Swin channels, RoBERTa hidden) appends `input_proj`, `input_proj2` and
-    `text_encoder.resizer` AFTER every other entry (so the hot-path weights of a seed do not depend on it).
-    `text_tower` = (layers, vocab) appends the RoBERTa encoder `text_encoder.body.*` (hidden = front_end_ch[2]) after those."""
-    s: Dict[str, Tuple[int, ...]] = {}
-
-    def lin(name, o, i):
-        s[name + ".weight"] = (o, i); s[name + ".bias"] = (o,)
-
-    def ln(name, n=d):
-        s[name + ".weight"] = (n,); s[name + ".bias"] = (n,)
-
-    def mha(name):
-        s[name + ".in_proj_weight"] = (3 * d, d); s[name + ".in_proj_bias"] = (3 * d,)
-        lin(name + ".out_proj", d, d)
-
-    for i in range(enc_layers):
-        p = f"ground_encoder.encoder.spatial_layers.{i}."
-        mha(p + "self_attn"); lin(p + "linear1", ffn, d); lin(p + "linear2", d, ffn); ln(p + "norm1"); ln(p + "norm2")
-    ln("ground_encoder.encoder.norm")
-    for c, vocab in (("t_temporal_clas", 1), ("s_temporal_clas", 1), ("t_spatial_clas", mot_num), ("s_spatial_clas", app_num)):
-        for i in range(2):
-            p = f"{c}.layer_ca.{i}."
-            for n in ("query", "key", "value"):
-                lin(p + "attention.self." + n, d, d)
-            lin(p + "attention.output.dense", d, d); ln(p + "attention.output.LayerNorm")
-            lin(p + "hidden_intermediate.dense", d, d); lin(p + "output.dense", d, d); ln(p + "output.LayerNorm")
-        lin(c + ".head.transform.dense", d, d); ln(c + ".head.transform.LayerNorm")
-        s[c + ".head.decoder.weight"] = (vocab, d); s[c + ".head.bias"] = (vocab,)
-    g = "ground_decoder."
-    ln(g + "pos_fc.0"); lin(g + "pos_fc.2", 4, d); ln(g + "pos_fc.4", 4)
-    s[g + "time_embed.te"] = (max_video_len + 1, 1, d)
-    for i in range(dec_layers):
-        p = f"{g}time_decoder.layers.{i}."
-        mha(p + "self_attn"); mha(p + "cross_attn_image"); lin(p + "linear1", ffn, d); lin(p + "linear2", d, ffn)
-        ln(p + "norm1"); ln(p + "norm3"); ln(p + "norm4")
-        p = f"{g}decoder.layers.{i}."
-        for n in ("sa_qcontent_proj", "sa_qpos_proj", "sa_qtime_proj", "sa_kcontent_proj", "sa_kpos_proj",
-                  "sa_ktime_proj", "sa_v_proj", "ca_qcontent_proj", "ca_kcontent_proj", "ca_kpos_proj",
-                  "ca_v_proj", "ca_qpos_sine_proj"):
-            lin(p + n, d, d)
-        if i == 0:
-            lin(p + "ca_qpos_proj", d, d)
-        mha(p + "self_attn"); lin(p + "cross_attn.out_proj", d, d)
-        lin(p + "linear1", ffn, d); lin(p + "linear2", d, ffn); ln(p + "norm1"); ln(p + "norm3"); ln(p + "norm4")
-    ln(g + "time_decoder.norm")
-    lin(g + "decoder.query_scale.layers.0", d, d); lin(g + "decoder.query_scale.layers.1", d, d)
-    lin(g + "decoder.ref_point_head.layers.0", d, 2 * d); lin(g + "decoder.ref_point_head.layers.1", d, d)
-    lin("bbox_embed.layers.0", d, d); lin("bbox_embed.layers.1", d, d); lin("bbox_embed.layers.2", 4, d)
-    lin("temp_embed.layers.0", d, d); lin("temp_embed.layers.1", 2, d)
-    lin("action_embed.layers.0", d, d); lin("action_embed.layers.1", 1, d)
-    if front_end_ch is not None:
-        cv, cd, ct = front_end_ch
-        s["input_proj.weight"] = (d, cv, 1, 1); s["input_proj.bias"] = (d,)
-        s["input_proj2.weight"] = (d, cd, 1, 1); s["input_proj2.bias"] = (d,)
-        lin("text_encoder.resizer.fc", d, ct); ln("text_encoder.resizer.layer_norm")
-    if text_tower is not None:
-        layers, vocab = text_tower
-        hd = front_end_ch[2]
-        b = "text_encoder.body."
-        s[b + "embeddings.word_embeddings.weight"] = (vocab, hd)
-        s[b + "embeddings.position_embeddings.weight"] = (514, hd)
-        s[b + "embeddings.token_type_embeddings.weight"] = (1, hd)
-        ln(b + "embeddings.LayerNorm", hd)
-        for i in range(layers):
-            p = f"{b}encoder.layer.{i}."
-            for n in ("query", "key", "value"):
-                lin(p + "attention.self." + n, hd, hd)
-            lin(p + "attention.output.dense", hd, hd); ln(p + "attention.output.LayerNorm", hd)
-            lin(p + "intermediate.dense", 4 * hd, hd); lin(p + "output.dense", hd, 4 * hd); ln(p + "output.LayerNorm", hd)
-    return s
-
-
-def synth_state_dict(seed: int = 0, **kw) -> Dict[str, np.ndarray]:
-    """Deterministic synthetic weights (numpy PCG64 — identical on every machine, no torch RNG) with the SCALES of
-    the reference's own random init: encoder / decoder matrices ~ xavier_uniform (modal_encoder.py:36-39,
-    query_decoder.py:71-74); classifier, bbox/temp/action-head matrices ~ nn.Linear default U(±1/sqrt(fan_in))
-    (they are built outside / attached after the xavier reset, grounding_net.py:55-82).  Unlike the reference init,
-    biases are non-zero U(±0.05) and LayerNorm gains are 1+U(±0.1) so that every parameter is exercised.
-    `time_embed.te` is the real sine table.  Used instead of the reference's torch init so that golden fixtures
-    stay small (the 36 M weights are regenerated from the seed, never stored)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    sd: Dict[str, np.ndarray] = {}
-    for name, shp in hot_path_param_shapes(**kw).items():
-        if name.endswith("time_embed.te"):
-            sd[name] = seq_embedding_sine(shp[0], shp[2])
-        elif name.startswith("text_encoder.body.") and len(shp) >= 2:
-            # transformers init: N(0, 0.02) for Linear / Embedding weights → uniform of the same std; a larger scale (x4) on the
-            # Linear weights keeps the random-init tower away from the LayerNorm-only regime so that every matmul matters
-            bound = 0.02 * math.sqrt(3.0) * (1.0 if "embeddings" in name else 4.0)
-            sd[name] = rng.uniform(-bound, bound, size=shp).astype(F32)
-        elif len(shp) >= 2:
-            if name.startswith(("ground_encoder.", "ground_decoder.")):
-                bound = math.sqrt(6.0 / (shp[0] + shp[1]))
-            else:
-                bound = 1.0 / math.sqrt(shp[1])
-            sd[name] = rng.uniform(-bound, bound, size=shp).astype(F32)
-        elif ("norm" in name.lower() and name.endswith(".weight")) or name.endswith(("pos_fc.0.weight", "pos_fc.4.weight")):
-            sd[name] = (1.0 + rng.uniform(-0.1, 0.1, size=shp)).astype(F32)
-        else:
-            sd[name] = rng.uniform(-0.05, 0.05, size=shp).astype(F32)
-    return sd
-
-
-def synth_inputs(seed: int, T: int, H: int, W: int, L: int, d: int = 256):
-    """Synthetic hot-path-boundary inputs: randn features, all-False masks, sine pos."""
-    rng = np.random.Generator(np.random.PCG64(1000 + seed))
-    vis = rng.standard_normal((T, d, H, W), dtype=F32)
-    vid = rng.standard_normal((T, d, H, W), dtype=F32)
-    text = rng.standard_normal((L, 1, d), dtype=F32)
-    pos = position_embedding_sine(np.zeros((T, H, W), bool))
-    return vis, vid, pos, text
-
-
-def synth_raw_inputs(seed: int, T: int, H: int, W: int, L: int, ch: Tuple[int, int, int] = (2048, 768, 768)):
-    """Synthetic extractor outputs for the front end: a non-negative (post-ReLU, like ResNet layer 4) map, a
-    normal Video-Swin map and normal RoBERTa hidden states."""
-    rng = np.random.Generator(np.random.PCG64(5000 + seed))
-    vis_raw = np.maximum(rng.standard_normal((T, ch[0], H, W), dtype=F32), 0)
-    vid_raw = rng.standard_normal((T, ch[1], H, W), dtype=F32)
-    text_raw = rng.standard_normal((L, ch[2]), dtype=F32)
-    return vis_raw, vid_raw, text_raw
-
-
-def synth_text_ids(seed: int, B: int, L: int, vocab: int, pad_tail: int = 0) -> Tuple[np.ndarray, np.ndarray]:
-    """Token ids as RobertaTokenizer emits them: <s>=0 ... </s>=2, pad=1 on the last `pad_tail` positions of the odd rows.
-    Returns (ids (B, L) int32, pad mask (B, L) bool, True = padded)."""
-    rng = np.random.Generator(np.random.PCG64(7000 + seed))
-    ids = rng.integers(3, vocab, size=(B, L)).astype(np.int32)
-    ids[:, 0] = 0
-    pad = np.zeros((B, L), bool)
-    for b in range(B):
-        n = L - (pad_tail if b % 2 == 1 else 0)
-        ids[b, n - 1] = 2
-        ids[b, n:] = 1
-        pad[b, n:] = True
-    return ids, pad
-
-
-def synth_masks(masked: bool, T: int, H: int, W: int, L: int):
-    """Padding masks for the masked golden case: right column on every frame, bottom row on the second
-    half of the clip, two trailing text tokens (True = padded)."""
-    vis_mask = np.zeros((T, H, W), bool)
-    text_mask = np.zeros((1, L), bool)
-    if masked:
-        vis_mask[:, :, W - 1] = True
-        vis_mask[T // 2:, H - 1, :] = True
-        text_mask[0, L - 2:] = True
-    return vis_mask, text_mask
+from vgqa_b200.synth import (CALIB_PREFIX, apply_calibration, hot_path_param_shapes, synth_event_inputs, synth_inputs,  # noqa: E402,F401
+                             synth_masks, synth_raw_inputs, synth_state_dict, synth_text_ids)

@@ -2,9 +2,20 @@
 own PyTorch modules (tests/golden/*.npz) and against the numpy oracle on the same seeded inputs.
 
 Bar (BASELINE.json north_star): start/end argmax frames and tube frame indices identical; boxes and logits within
-2e-2 max-abs under bf16.  Discrete decisions (theta = 0.45 frame selection, sigmoid(actioness) > 0.5) are compared
-only where the reference margin exceeds the bf16 error bound (SURVEY.md §7 hard parts); continuous outputs are
-always compared with the reference's own decisions forced through `force_choose1/2`."""
+2e-2 max-abs under bf16.
+
+Two families of fixtures (tests/golden/make_golden.py):
+  * `ev_*` — "decisive" cases: event-structured inputs and re-designed last-layer heads, so that the reference's own decisions
+    are PARTIAL in both decoder passes (0 < K1 < T, 0 < K2 < T) and sit far from their thresholds (|att - 0.45| >= 0.02,
+    |sigmoid(actioness) - 0.5| >= 0.02, top-2 gap of the start/end score map >= 0.05).  For these the free-running forward
+    (nothing forced) must reproduce both frame selections, the start/end argmax, the tube frame ids and every continuous
+    output — unconditional asserts.
+  * the iid-random cases of round 1 (every frame chosen, or a fallback): continuous outputs with the reference's decisions
+    forced through `force_choose1/2`; their free-running decisions are compared where the stored margin allows and the
+    test SKIPS (never passes silently) where it does not."""
+import glob
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -19,17 +30,27 @@ CASES = ["tiny_T3_3x4_L3", "ragged_T6_4x5_L7_masked", "cfg1_T32_7x7_L20_s0", "cf
          "cfg2_T64_7x7_L20_s0", "cfg2_T64_7x7_L20_s2", "yaml_T16_14x14_L20_s0", "cfg4_T256_7x7_L20_s0",
          "cfg5_T128_12x12_L64_s0"]
 
+from conftest import GOLDEN  # noqa: E402
+
+EV_CASES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "ev_*.npz")))
+MIN_THETA, MIN_ACT, MIN_TOP2 = 0.02, 0.02, 0.05   # the bounds make_golden.py builds the ev_* fixtures to
+
 _engines = {}
 
 
-def engine_for(seed, max_len, T, P, L):
+def engine_for(g, name, T, P, L):
+    """One engine per (weights, capacity).  Fixtures with `w:*` overrides (ev_*) get their own weights."""
     from vgqa_b200.engine import GroundingEngine
-    key = (seed, max_len)
+    seed, max_len = int(g["seed"]), int(g["max_video_len"])
+    calibrated = any(k.startswith(O.CALIB_PREFIX) for k in g.files)
+    key = (seed, max_len, name if calibrated else None)
     cap = _engines.get(key)
     if cap is None or cap[1] < T or cap[2] < P or cap[3] < L:
         if cap is not None:
             cap[0].close()
-        sd = O.synth_state_dict(seed, max_video_len=max_len)
+        for k in [k for k in _engines if k[2] is not None and k != key]:   # calibrated engines are single-use: free them
+            _engines.pop(k)[0].close()
+        sd = O.apply_calibration(O.synth_state_dict(seed, max_video_len=max_len), g)
         eng = GroundingEngine(sd, max_clips=2, max_frames=max(T, 64), max_hw=max(P, 49), max_text=max(L, 20),
                               max_video_len=max_len)
         cap = (eng, max(T, 64), max(P, 49), max(L, 20))
@@ -37,12 +58,21 @@ def engine_for(seed, max_len, T, P, L):
     return cap[0]
 
 
+def case_inputs(g):
+    T, H, W, L, seed = (int(g[k]) for k in ("T", "H", "W", "L", "seed"))
+    amp = float(g["event_amp"]) if "event_amp" in g.files else 0.0
+    if amp > 0:
+        return O.synth_event_inputs(seed, T, H, W, L, amp=amp)
+    return O.synth_inputs(seed, T, H, W, L)
+
+
 def run_case(name, force, clips=1):
     g = np.load(golden_path(name))
     T, H, W, L, seed = (int(g[k]) for k in ("T", "H", "W", "L", "seed"))
     masked = bool(g["masked"])
-    eng = engine_for(seed, int(g["max_video_len"]), T, H * W, L)
-    vis, vid, _, text = O.synth_inputs(seed, T, H, W, L)
+    eng = engine_for(g, name, T, H * W, L)
+    vis, vid, _, text = case_inputs(g)
+    itr = int(g["iteration_rate"]) if "iteration_rate" in g.files else -1
     vm, tm = O.synth_masks(masked, T, H, W, L)
     pos = O.position_embedding_sine(vm)
     dev = "cuda"
@@ -62,15 +92,12 @@ def run_case(name, force, clips=1):
         w2 = np.zeros(T, np.float32); w2[g["choose_pass2"]] = 1
         f1, f2 = rep(w1), rep(w2)
     outs = eng.forward(tvis, tvid, ttext, tpos, vis_mask=tvm, text_mask=ttm, ori_sizes_hw=sizes, force_choose1=f1,
-                       force_choose2=f2, want=None)
+                       force_choose2=f2, iteration_rate=itr, want=None)
     torch.cuda.synchronize()
     return g, {k: v.cpu().numpy() for k, v in outs.items()}
 
 
-@pytest.mark.parametrize("name", CASES)
-def test_continuous_outputs_with_reference_decisions(name):
-    g, o = run_case(name, force=True)
-    T = int(g["T"])
+def continuous_errors(g, o):
     cmp = {"pred_boxes": g["pred_boxes"], "pred_sted": g["pred_sted"][0], "pred_actioness": g["pred_actioness"][0, :, 0],
            "logits_f_m": g["logits_f_m"], "logits_f_a": g["logits_f_a"], "logits_r_a": g["logits_r_a"][0],
            "logits_r_m": g["logits_r_m"][0], "att_sequences": g["att_sequences"][0],
@@ -83,6 +110,14 @@ def test_continuous_outputs_with_reference_decisions(name):
         if k.startswith("aux_"):
             got = o[k][:, 0]
         worst[k] = float(np.abs(got.reshape(ref.shape) - ref).max())
+    return worst
+
+
+@pytest.mark.parametrize("name", CASES + EV_CASES)
+def test_continuous_outputs_with_reference_decisions(name):
+    g, o = run_case(name, force=True)
+    T = int(g["T"])
+    worst = continuous_errors(g, o)
     bad = {k: v for k, v in worst.items() if not v <= TOL}
     assert not bad, f"{name}: max-abs errors over {TOL}: {bad} (all: {worst})"
     # PostProcess (postprocessor.py:36-48): the (start,end) argmax must be the reference's whenever the reference's
@@ -94,29 +129,84 @@ def test_continuous_outputs_with_reference_decisions(name):
     s, e = (int(x) for x in o["sted_idx"][0])
     assert s < e
     assert score[s, e] >= score.max() - 4 * max(worst["pred_sted"], 1e-3)
-    if float(g["margin_sted_top2"]) > 4 * worst["pred_sted"]:
+    if float(g["margin_sted_top2"]) >= MIN_TOP2 or float(g["margin_sted_top2"]) > 4 * worst["pred_sted"]:
         fid = g["frame_ids"]
         assert [int(fid[s]), int(fid[e]) + 1] == g["post_sted"][0].tolist()
     np.testing.assert_allclose(o["boxes_px"][0], g["post_boxes"], atol=TOL * 640)
 
 
-@pytest.mark.parametrize("name", CASES)
-def test_free_running_decisions(name):
+def _ref_sel(g, key):
+    w = np.zeros(int(g["T"]))
+    w[g[key]] = 1
+    return w
+
+
+def test_decisive_fixtures_clear_the_bounds():
+    """At least 8 of the 9 two-pass `ev_*` fixtures (+ the single-pass one) are partial in both passes with wide margins."""
+    two_pass = [n for n in EV_CASES if int(np.load(golden_path(n))["iteration_rate"]) < 0]
+    assert len(two_pass) >= 8 and len(EV_CASES) > len(two_pass), EV_CASES
+    clear = 0
+    for n in two_pass:
+        g = np.load(golden_path(n))
+        T = int(g["T"])
+        clear += (0 < len(g["choose_pass1"]) < T and 0 < len(g["choose_pass2"]) < T and float(g["margin_theta"]) >= MIN_THETA and
+                  float(g["margin_act"]) >= MIN_ACT and float(g["margin_sted_top2"]) >= MIN_TOP2)
+    assert clear >= 8, f"only {clear} of {len(two_pass)} decisive fixtures clear the margin bounds"
+
+
+@pytest.mark.parametrize("name", EV_CASES)
+def test_free_running_decisions_identical(name):
+    """Nothing forced: both frame selections, the start/end argmax, the tube frame ids and all continuous outputs must be
+    the reference's (grounding_net.py:125-128,143-163; postprocessor.py:36-48).  Unconditional."""
     g, o = run_case(name, force=False)
     T = int(g["T"])
+    two_pass = int(g["iteration_rate"]) < 0
+    assert float(g["margin_theta"]) >= MIN_THETA and float(g["margin_sted_top2"]) >= MIN_TOP2, "fixture is not decisive"
+    assert 0 < len(g["choose_pass1"]) < T
+    np.testing.assert_array_equal(o["choose1"][0], _ref_sel(g, "choose_pass1"), "pass-1 frame selection")
+    if two_pass:
+        assert float(g["margin_act"]) >= MIN_ACT and 0 < len(g["choose_pass2"]) < T
+        np.testing.assert_array_equal(o["choose2"][0], _ref_sel(g, "choose_pass2"), "pass-2 frame selection")
+    worst = continuous_errors(g, o)
+    bad = {k: v for k, v in worst.items() if not v <= TOL}
+    assert not bad, f"{name} (free-running): max-abs errors over {TOL}: {bad} (all: {worst})"
+    s, e = (int(x) for x in o["sted_idx"][0])
+    fid = g["frame_ids"]
+    assert [int(fid[s]), int(fid[e]) + 1] == g["post_sted"][0].tolist(), "start/end argmax frames"
+    # tube frame ids = the sampled frame ids inside [start, end) (evaluator.py:78-92 keeps one box per sampled frame)
+    tube = [int(f) for f in fid if int(fid[s]) <= f < int(fid[e]) + 1]
+    ref_tube = [int(f) for f in fid if g["post_sted"][0][0] <= f < g["post_sted"][0][1]]
+    assert tube == ref_tube
+    np.testing.assert_allclose(o["boxes_px"][0], g["post_boxes"], atol=TOL * 640)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_free_running_pass1_selection(name):
+    g, o = run_case(name, force=False)
     att = g["att_sequences"][0]
-    ref1 = np.zeros(T); ref1[g["choose_pass1"]] = 1
-    safe1 = np.abs(att - 0.45) > 1e-2
-    if (att > 0.45).any():   # otherwise the reference fell back to "every frame" (grounding_net.py:128)
-        assert (o["choose1"][0][safe1] == ref1[safe1]).all(), "pass-1 frame selection differs outside the margin"
-    act1 = g["actioness_pass1"]
-    ref2 = np.zeros(T); ref2[g["choose_pass2"]] = 1
-    if (o["choose1"][0] == ref1).all():
-        safe2 = np.abs(act1 - 0.5) > 1e-2
-        assert (o["choose2"][0][safe2] == ref2[safe2]).all(), "pass-2 frame selection differs outside the margin"
-        if (o["choose2"][0] == ref2).all():
-            assert float(np.abs(o["pred_boxes"][0] - g["pred_boxes"]).max()) <= TOL
-            assert float(np.abs(o["pred_sted"][0] - g["pred_sted"][0]).max()) <= TOL
+    if not (att > 0.45).any():
+        # the reference fell back to "every frame" (grounding_net.py:128): so must the library
+        assert (o["choose1"][0] == 1).all()
+        return
+    safe = np.abs(att - 0.45) > 1e-2
+    if not safe.any():
+        pytest.skip(f"every frame is within 1e-2 of theta (margin {float(g['margin_theta']):.4f})")
+    ref1 = _ref_sel(g, "choose_pass1")
+    assert (o["choose1"][0][safe] == ref1[safe]).all(), "pass-1 frame selection differs outside the margin"
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_free_running_pass2_selection_and_outputs(name):
+    g, o = run_case(name, force=False)
+    ref1, ref2 = _ref_sel(g, "choose_pass1"), _ref_sel(g, "choose_pass2")
+    if not (o["choose1"][0] == ref1).all():
+        pytest.skip(f"pass-1 selection differs inside the theta margin ({float(g['margin_theta']):.4f}): pass 2 is not comparable")
+    safe = np.abs(g["actioness_pass1"] - 0.5) > 1e-2
+    assert (o["choose2"][0][safe] == ref2[safe]).all(), "pass-2 frame selection differs outside the margin"
+    if not (o["choose2"][0] == ref2).all():
+        pytest.skip(f"pass-2 selection differs inside the 0.5 margin ({float(g['margin_act']):.4f})")
+    assert float(np.abs(o["pred_boxes"][0] - g["pred_boxes"]).max()) <= TOL
+    assert float(np.abs(o["pred_sted"][0] - g["pred_sted"][0]).max()) <= TOL
 
 
 def test_batch_of_clips_matches_single():
