@@ -38,7 +38,7 @@ typedef struct {
   int max_frames;    /* capacity: frames per clip (T), <= max_video_len + 1                */
   int max_hw;        /* capacity: feature-map tokens per frame (H*W)                       */
   int max_text;      /* capacity: text tokens (L)                                          */
-  int use_cuda_graph; /* 1: capture each (shape, pointer set) once and replay it           */
+  int use_cuda_graph; /* 1: capture each shape once and replay it (the caller's pointers may change) */
 } vgqa_config;
 
 /* Inputs of one forward call: `clips` independent clips (the reference is batch-1; a batch is N independent
@@ -47,7 +47,9 @@ typedef struct {
  *   vis, vid : [clips, T, 256, H, W]  = input_proj(ResNet101 feats), input_proj2(Video-Swin feats)
  *   text     : [clips, L, 256]        = text_encoder resizer output (reference shape (L,1,256) per clip)
  *   pos      : [pos_frames, 256, H, W] PositionEmbeddingSine; pos_frames = 1 (shared by every frame — the case
- *              of all-False masks) or clips*T (per frame)
+ *              of all-False masks) or clips*T (per frame).  NULL: the library generates it (PositionEmbeddingSine(128,
+ *              normalize=True), vgqa/core/vision/position_encoding.py:50-91, from vis_mask — one shared table when
+ *              vis_mask is NULL); pos_frames is then ignored
  *   vis_mask : [clips*T, H*W] uint8 (1 = padded) or NULL; text_mask: [clips, L] uint8 or NULL
  *   ori_sizes_hw : [clips, 2] fp32 (h, w) for PostProcess box scaling, or NULL (boxes_px is then not written)
  *   force_choose1/2 : optional [clips, T] fp32 0/1 masks overriding the pass-1 / pass-2 frame selection
@@ -185,6 +187,9 @@ int vgqa_text_tower_hidden(const vgqa_ctx* ctx);
 
 /* Counters: kernels launched by the last vgqa_forward call (graph replays count the captured launches). */
 int vgqa_last_launch_count(const vgqa_ctx* ctx);
+/* Number of CUDA graphs this context has captured so far.  Graphs are keyed on (phase, slot, shape, which optional inputs are
+ * present) — never on the caller's pointers: a serving loop that passes fresh tensors on every call captures once per shape. */
+int vgqa_graph_capture_count(const vgqa_ctx* ctx);
 /* Debug (VGQA_TIMELINE=1 in the environment at vgqa_create): device timestamps, in ms since the context's first call, of the
  * last forward issued on `slot`: [encoder phase start, end, decoder phase start, end]. */
 int vgqa_debug_phase_times(vgqa_ctx* ctx, int slot, float* ms4);

@@ -17,10 +17,30 @@ import sys
 import types
 from types import SimpleNamespace
 
-REF_ROOT = os.environ.get("VGQA_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_COMPILED = os.path.join(_REPO, "oracle", "_ref")     # tools/make_oracle_ref.py: the same modules byte-compiled (travels to the GPU box)
+
+
+def _pick_root() -> str:
+    env = os.environ.get("VGQA_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/vgqa/core/decoder"):
+        return "/root/reference"
+    return _COMPILED
+
+
+REF_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
+    """The reference SOURCE tree is mounted (build container): golden makers / live comparisons may run."""
+    return os.path.isdir(os.path.join(REF_ROOT, "vgqa", "core", "decoder")) and REF_ROOT != _COMPILED
+
+
+def reference_modules_available() -> bool:
+    """The reference's hot-path modules can be imported: from the source tree, or from `oracle/_ref` (byte-compiled by
+    tools/make_oracle_ref.py in the build container; that is what exists on the GPU box)."""
     return os.path.isdir(os.path.join(REF_ROOT, "vgqa", "core", "decoder"))
 
 
@@ -59,8 +79,8 @@ def _install_shims():
 
 def load_reference():
     """Returns a namespace with the reference classes/functions on the hot path."""
-    if not reference_available():
-        raise RuntimeError(f"reference not found at {REF_ROOT}")
+    if not reference_modules_available():
+        raise RuntimeError(f"reference modules not found at {REF_ROOT} (run tools/make_oracle_ref.py where /root/reference is mounted)")
     _install_shims()
     v = os.path.join(REF_ROOT, "vgqa")
     _namespace_pkg("vgqa", v)

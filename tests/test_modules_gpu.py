@@ -96,3 +96,33 @@ def test_postprocess_module_matches_golden():
     boxes, att, steds, _ = PP.PostProcess()(outputs, sizes, [g["frame_ids"].tolist()], [T])
     assert steds == g["post_sted"].tolist()
     np.testing.assert_allclose(boxes.cpu().numpy(), g["post_boxes"], atol=1e-3)
+
+
+@pytest.mark.parametrize("name", ["ev_cfg1_T32_7x7_L20_s0", "ev_masked_T32_7x7_L20_s20", "ev_ragged_T6_4x5_L7_masked_s0"])
+def test_position_embedding_generated_in_the_library(name):
+    """vgqa_inputs.pos == NULL: the library generates PositionEmbeddingSine(128, normalize=True) itself (vision/
+    position_encoding.py:50-91) — from the padding mask when there is one.  The forward must give what it gives with the
+    reference's own `pos` tensor (stored in the golden) passed in, and both must match the golden."""
+    import numpy as np
+    from conftest import golden_path
+    from vgqa_b200.engine import GroundingEngine
+    g = np.load(golden_path(name))
+    T, H, W, L, seed = (int(g[k]) for k in ("T", "H", "W", "L", "seed"))
+    masked = bool(g["masked"])
+    sd = O.apply_calibration(O.synth_state_dict(seed, max_video_len=int(g["max_video_len"])), g)
+    amp = float(g["event_amp"]) if "event_amp" in g.files else 0.0
+    vis, vid, _, text = O.synth_event_inputs(seed, T, H, W, L, amp=amp) if amp > 0 else O.synth_inputs(seed, T, H, W, L)
+    vm, tm = O.synth_masks(masked, T, H, W, L)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    kw = dict(vis_mask=t(vm.reshape(T, -1).astype(np.uint8)), text_mask=t(tm.astype(np.uint8))) if masked else {}
+    eng = GroundingEngine(sd, max_clips=1, max_frames=T, max_hw=H * W, max_text=L)
+    want = ["pred_boxes", "pred_sted", "logits_f_m", "frames_cls"]
+    given = eng.forward(t(vis[None]), t(vid[None]), t(text[None, :, 0]), t(g["pos"]), want=want, **kw)
+    given = {k: v.cpu().numpy() for k, v in given.items()}
+    own = eng.forward(t(vis[None]), t(vid[None]), t(text[None, :, 0]), None, want=want, **kw)
+    own = {k: v.cpu().numpy() for k, v in own.items()}
+    for k in want:
+        np.testing.assert_allclose(own[k], given[k], atol=8e-3, err_msg=k)   # pos differs by fp32 sin/cos rounding only (a few bf16 flips)
+    assert float(np.abs(own["pred_boxes"][0] - g["pred_boxes"]).max()) <= 2e-2
+    assert float(np.abs(own["frames_cls"] - g["frames_cls"]).max()) <= 2e-2
+    eng.close()

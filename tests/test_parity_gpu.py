@@ -26,6 +26,9 @@ from conftest import golden_path
 pytestmark = pytest.mark.gpu
 
 TOL = 2e-2
+# frames_cls is not an output of the reference forward but an internal activation of the encoder (token mean of LayerNorm rows, |x| up
+# to 4 — one bf16 ulp there is 1.6e-2); it is compared as a tripwire with a bound of its own
+TOL_INTERNAL = 3e-2
 CASES = ["tiny_T3_3x4_L3", "ragged_T6_4x5_L7_masked", "cfg1_T32_7x7_L20_s0", "cfg1_T32_7x7_L20_s1",
          "cfg2_T64_7x7_L20_s0", "cfg2_T64_7x7_L20_s2", "yaml_T16_14x14_L20_s0", "cfg4_T256_7x7_L20_s0",
          "cfg5_T128_12x12_L64_s0"]
@@ -103,6 +106,8 @@ def continuous_errors(g, o):
            "logits_r_m": g["logits_r_m"][0], "att_sequences": g["att_sequences"][0],
            "aux_boxes": g["aux_boxes"], "aux_sted": g["aux_sted"][:, 0], "aux_actioness": g["aux_actioness"][:, 0, :, 0],
            "frames_cls": g["frames_cls"], "actioness_pass1": g["actioness_pass1"]}
+    if "iteration_rate" in g.files and int(g["iteration_rate"]) >= 0:
+        cmp.pop("actioness_pass1")        # single-pass forward (grounding_net.py:143): the re-selection score is never computed
     worst = {}
     for k, ref in cmp.items():
         got = o[k][0] if k in ("pred_boxes", "pred_sted", "pred_actioness", "logits_f_m", "logits_f_a", "logits_r_a",
@@ -118,7 +123,7 @@ def test_continuous_outputs_with_reference_decisions(name):
     g, o = run_case(name, force=True)
     T = int(g["T"])
     worst = continuous_errors(g, o)
-    bad = {k: v for k, v in worst.items() if not v <= TOL}
+    bad = {k: v for k, v in worst.items() if not v <= (TOL_INTERNAL if k == "frames_cls" else TOL)}
     assert not bad, f"{name}: max-abs errors over {TOL}: {bad} (all: {worst})"
     # PostProcess (postprocessor.py:36-48): the (start,end) argmax must be the reference's whenever the reference's
     # top-2 gap is resolvable (> 4x the measured logit error of this run); it must always be near-optimal under the
@@ -168,7 +173,7 @@ def test_free_running_decisions_identical(name):
         assert float(g["margin_act"]) >= MIN_ACT and 0 < len(g["choose_pass2"]) < T
         np.testing.assert_array_equal(o["choose2"][0], _ref_sel(g, "choose_pass2"), "pass-2 frame selection")
     worst = continuous_errors(g, o)
-    bad = {k: v for k, v in worst.items() if not v <= TOL}
+    bad = {k: v for k, v in worst.items() if not v <= (TOL_INTERNAL if k == "frames_cls" else TOL)}
     assert not bad, f"{name} (free-running): max-abs errors over {TOL}: {bad} (all: {worst})"
     s, e = (int(x) for x in o["sted_idx"][0])
     fid = g["frame_ids"]

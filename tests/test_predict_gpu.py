@@ -87,3 +87,28 @@ def test_predictor_argument_checks():
     with pytest.raises(ValueError):
         pred.predict_many([{}] * 2)                                           # more queries than max_queries
     pred.close()
+
+
+def test_fresh_tensors_do_not_recapture_graphs():
+    """CUDA graphs are keyed on the shape of a call, never on the caller's pointers: ten predict() calls on freshly allocated
+    tensors capture each phase exactly once (two graphs), and `pos` may be left to the library."""
+    seed, T, H, W, L = 2, 16, 7, 7, 12
+    sd = O.synth_state_dict(seed)
+    pred = GroundingPredictor(sd, sample_num=T, max_hw=H * W, max_text=L, use_cuda_graph=True)
+    fids = list(range(0, 2 * T))
+    first = None
+    keep = []
+    for i in range(10):
+        vis, vid, pos, text = _inputs(seed, 2 * T, H, W, L)          # new device tensors on every call
+        keep.append((vis, vid, text))                                # keep them alive: the allocator cannot hand the addresses out again
+        got = pred.predict(vis, vid, text, None if i % 2 else pos, fids, (360, 640), 25.0)
+        if first is None:
+            first = got
+            captured = pred.engine.graph_capture_count
+            assert captured == 2, captured
+        else:
+            assert got["temporal"] == first["temporal"]
+            np.testing.assert_allclose(np.asarray([t["bbox"] for t in got["tube"]]), np.asarray([t["bbox"] for t in first["tube"]]),
+                                       atol=0.5)     # pixels; the library-generated pos differs from the given one by fp32 rounding
+    assert pred.engine.graph_capture_count == 2, "a new tensor address must not trigger a re-capture"
+    pred.close()

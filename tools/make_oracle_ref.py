@@ -1,0 +1,51 @@
+"""Build recipe of `oracle/_ref/`: the reference's own hot-path modules, byte-compiled FROM WHERE THEY LIE under /root/reference.
+
+    python tools/make_oracle_ref.py            # (build container only; __graft_entry__.build() runs it when the tree is mounted)
+
+The reference is Python source with no packaging, and `/root/reference` does not exist on the GPU box.  This recipe compiles the
+modules SURVEY.md §8(c) lists (`py_compile`, no source text is copied) into `oracle/_ref/vgqa/...*.pyc` — a build OUTPUT, git-
+ignored, which travels to the GPU box with the snapshot like the repo's own `.so`.  There `tests/golden/ref_loader.py` imports it
+sourcelessly, so that bench.py can time the REFERENCE'S OWN PyTorch modules (`cpu_baseline.kind = "reference"`, and the same
+modules in eager bf16 on the B200) instead of the numpy port.  Nothing under `vgqa_b200/` ever imports it.
+"""
+import os
+import py_compile
+import shutil
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("VGQA_REFERENCE_ROOT", "/root/reference")
+OUT = os.path.join(ROOT, "oracle", "_ref")
+
+# the hot path and what its modules import from the reference package
+FILES = [
+    "vgqa/core/decoder/__init__.py", "vgqa/core/decoder/modal_encoder.py", "vgqa/core/decoder/query_decoder.py",
+    "vgqa/core/decoder/attention.py", "vgqa/core/decoder/classifier.py", "vgqa/core/decoder/position_encoding.py",
+    "vgqa/core/language/bert_module.py", "vgqa/core/model_utils.py", "vgqa/core/vision/position_encoding.py",
+    "vgqa/core/postprocessor.py", "vgqa/training/evaluator.py", "vgqa/utils/training_utils.py", "vgqa/utils/box_ops.py",
+    "vgqa/utils/distributed.py",
+]
+
+
+def build(verbose: bool = True) -> bool:
+    if not os.path.isdir(os.path.join(REF, "vgqa", "core", "decoder")):
+        if verbose:
+            print(f"make_oracle_ref: {REF} is not mounted here — keeping whatever oracle/_ref already holds")
+        return False
+    if os.path.isdir(OUT):
+        shutil.rmtree(OUT)
+    for rel in FILES:
+        dst = os.path.join(OUT, rel[:-3] + ".pyc")
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        # unchecked hash-based pyc: valid without the source file next to it (sourceless import)
+        py_compile.compile(os.path.join(REF, rel), cfile=dst, dfile=rel, doraise=True,
+                           invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+    with open(os.path.join(OUT, "BUILD_INFO"), "w") as f:
+        f.write(f"byte-compiled from {REF} by tools/make_oracle_ref.py with python {sys.version.split()[0]}\n" + "\n".join(FILES) + "\n")
+    if verbose:
+        print(f"make_oracle_ref: {len(FILES)} modules compiled into {OUT}")
+    return True
+
+
+if __name__ == "__main__":
+    build()

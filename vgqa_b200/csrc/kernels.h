@@ -42,6 +42,8 @@ void text_attn(const bf16* QKV, const uint8_t* pad, bf16* ctx, int Q, int L, int
 // NCHW fp32 features → token-major bf16 rows: X[(f*S + tok0 + p), c] = in[f, c, p]   (in may be broadcast: fstride 0)
 void nchw_to_tokens(const float* in, long long in_fstride, bf16* X, float* X32, const float* pos, long long pos_fstride,
                     bf16* XP, int F, int S, int tok0, int P, cudaStream_t st);
+// PositionEmbeddingSine(128, normalize=True) of `frames` (H, W) masks (uint8, 1 = padded; nullptr = nothing padded) → [frames,256,H,W]
+void pos_sine(const uint8_t* mask, float* out, int frames, int H, int W, cudaStream_t st);
 // X[(f*S + tok0 + l), :] = text[(f / T), l, :]   (text == nullptr → zeros)
 void text_to_tokens(const float* text, bf16* X, float* X32, bf16* XP, int F, int T, int S, int tok0, int L,
                     cudaStream_t st);
@@ -88,7 +90,7 @@ void postprocess(const float* boxes, const float* sted, const float* sizes_hw, f
 void p2p_export(void*& state, int rank, int world, long long slot_bytes, unsigned char handle_out[64]);
 void p2p_import(void*& state, const unsigned char* handles);   // world x 64 bytes, rank-major
 bool p2p_ready(void* state);
-void p2p_exchange(void* state, int op, const void* send, void* recv, long long bytes, int channel, cudaStream_t st);   // op 0 gather, 1 fp32 sum; channel 0..2
+void p2p_exchange(void* state, int op, const void* send, void* recv, long long bytes, int channel, cudaStream_t st);   // op 0 gather, 1 fp32 sum; channel 0..3
 int p2p_error(void* state);
 void p2p_destroy(void*& state);
 

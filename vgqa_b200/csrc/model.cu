@@ -208,9 +208,16 @@ struct vgqa_ctx {
   void* p2p = nullptr;   // device-side exchange over peer memory (p2p_exchange.cu); replaces the callback when set up
   float *text_sums, *red[2];
   bf16 *t_qkv_all, *p_qkv_all;   // all-gathered in-projection rows of the temporal self-attention
-  // graph cache
+  // inputs read by the captured part of a forward are staged in context-owned buffers (per boundary slot), so that a CUDA
+  // graph depends on the SHAPE of a call only — never on the caller's pointers
+  struct InStage { float *sizes, *f1, *f2; } ins[2];   // read by the decoder phase: one set per boundary slot
+  float *text_in = nullptr, *pos_gen = nullptr;        // read by the encoder phase only (calls are serialised on its stream)
+  int* ids_in = nullptr;
+  uint8_t* tmask_in = nullptr;
+  // graph cache (key = phase, slot, shape and the presence flags of the optional inputs)
   struct GraphEntry { cudaGraphExec_t exec; int launches; };
   std::map<std::vector<uint64_t>, GraphEntry> graphs;
+  int graph_captures = 0;
   int last_launches = 0;
   int launches = 0;  // running count inside one forward
 };
@@ -597,6 +604,9 @@ static void carve_workspace(vgqa_ctx* c) {
     b.q0_32 = a.get<float>(F * 256);
     for (int k = 0; k < 2; ++k) { b.pool[k] = a.get<bf16>(F * 256); b.pool32[k] = a.get<float>(F * 256); }
   }
+  for (auto& i : c->ins) { i.sizes = a.get<float>(B * 2); i.f1 = a.get<float>(F); i.f2 = a.get<float>(F); }
+  c->text_in = a.get<float>(B * L * 256); c->ids_in = a.get<int>(B * L); c->tmask_in = a.get<uint8_t>(B * L);
+  c->pos_gen = a.get<float>(F * 256 * P);   // PositionEmbeddingSine generated in the library (vgqa_inputs.pos == NULL)
   for (auto& h : c->hs) {
     h.vis = a.get<float>(F * 256 * P); h.vid = a.get<float>(F * 256 * P); h.text = a.get<float>(B * L * 256);
     h.pos = a.get<float>(F * 256 * P); h.sizes = a.get<float>(B * 2); h.f1 = a.get<float>(F); h.f2 = a.get<float>(F);
@@ -657,6 +667,7 @@ struct Fwd {
   cudaStream_t main, aux;
   cudaStream_t aux2 = nullptr;   // side branch of the PosDecoder chain (query_scale MLP, absorbed-query GEMM)
   int ev_i = 0;
+  int phase = 1;
   int B, T, P, L, S, F, R;
   // independent sub-graphs (the two classifiers of a pair, TimeDecoder vs PosDecoder) run on two streams; under
   // stream capture this becomes two parallel branches of the CUDA graph.
@@ -706,7 +717,8 @@ struct Fwd {
   void count(int n = 1) { c->launches += n; }
   bool sharded() const { return c->sh_world > 1; }
   // exchange channel of the peer-memory exchange: one per graph branch, so that every channel sees one global order
-  int channel() const { return st == main ? 0 : (st == aux ? 1 : 2); }
+  // (the encoder phase of the NEXT call runs on another stream beside the decoder phase of this one: it owns channel 3)
+  int channel() const { return phase == 0 ? 3 : (st == main ? 0 : (st == aux ? 1 : 2)); }
   int T_global() const { return T * c->sh_world; }
   // in-place sum over ranks of `n` fp32 values (no-op for a single rank)
   void all_reduce_f32(float* buf, size_t n) {
@@ -750,17 +762,27 @@ static void run_text_tower(Fwd& f, const int* ids, const uint8_t* pad) {
   }
 }
 
-static void run_encoder(Fwd& f, const vgqa_inputs& in, bool have_mask, int pos_rows) {
+// How the text of a call reaches the encoder: 0 = projected tokens (text_in), 1 = hidden states (bf16 rows in traw, resizer in
+// the captured part), 2 = token ids (ids_in: text tower + resizer in the captured part)
+static int text_kind(const vgqa_inputs& in) { return in.text_ids ? 2 : (in.text_raw ? 1 : 0); }
+
+// Everything that READS THE CALLER'S POINTERS of the encoder phase: the positional table (given, or PositionEmbeddingSine
+// generated here — vision/position_encoding.py:50-91), the token-major re-layout of the visual maps (or input_proj /
+// input_proj2 on the raw extractor maps), the text staging and the key-padding mask.  Always launched eagerly; what follows
+// (run_encoder) only touches context-owned memory and is what a CUDA graph captures.
+static void ingest_encoder_inputs(Fwd& f, const vgqa_inputs& in, bool have_mask) {
   vgqa_ctx* c = f.c;
   cudaStream_t st = f.st;
-  const int S = f.S, P = f.P, L = f.L, R = f.R, F = f.F;
-  // tokens: [vis | text | vid] per frame (modal_encoder.py:64)
-  const long long pos_fs = in.pos_frames > 1 ? (long long)256 * P : 0;
-  // positional rows: [pos | 0 | pos] (modal_encoder.py:66)
+  const int S = f.S, P = f.P, L = f.L, F = f.F;
   const int pf = in.pos_frames;
-  nchw_to_tokens(in.pos, (long long)256 * P, c->pos_enc, nullptr, nullptr, 0, nullptr, pf, S, 0, P, st);
+  const float* pos = in.pos;
+  if (pos == nullptr) { pos_sine(in.vis_mask, c->pos_gen, pf, in.H, in.W, st); pos = c->pos_gen; f.count(); }
+  // tokens: [vis | text | vid] per frame (modal_encoder.py:64)
+  const long long pos_fs = pf > 1 ? (long long)256 * P : 0;
+  // positional rows: [pos | 0 | pos] (modal_encoder.py:66)
+  nchw_to_tokens(pos, (long long)256 * P, c->pos_enc, nullptr, nullptr, 0, nullptr, pf, S, 0, P, st);
   text_to_tokens(nullptr, c->pos_enc, nullptr, nullptr, pf, 1, S, P, L, st);
-  nchw_to_tokens(in.pos, (long long)256 * P, c->pos_enc, nullptr, nullptr, 0, nullptr, pf, S, P + L, P, st);
+  nchw_to_tokens(pos, (long long)256 * P, c->pos_enc, nullptr, nullptr, 0, nullptr, pf, S, P + L, P, st);
   f.count(3);
   // visual tokens: already-projected maps, or the raw extractor maps through input_proj / input_proj2 (input_proj.cu)
   if (in.vis_raw != nullptr && in.raw_layout == 1)
@@ -769,19 +791,37 @@ static void run_encoder(Fwd& f, const vgqa_inputs& in, bool have_mask, int pos_r
   else if (in.vis_raw != nullptr)
     input_proj(in.vis_raw, c->ip_vis.K, c->ip_vis.W, c->ip_vis.b, c->pos_enc, pf, c->X, c->X32, c->XP, F, S, 0, P, st);
   else
-    nchw_to_tokens(in.vis, (long long)256 * P, c->X, c->X32, in.pos, pos_fs, c->XP, F, S, 0, P, st);
+    nchw_to_tokens(in.vis, (long long)256 * P, c->X, c->X32, pos, pos_fs, c->XP, F, S, 0, P, st);
   if (in.vid_raw != nullptr && in.raw_layout == 1)
     input_proj_nhwc(reinterpret_cast<const bf16*>(in.vid_raw), c->ip_vid.K, c->ip_vid.W, c->ip_vid.b, c->pos_enc, pf, c->X, c->X32,
                     c->XP, F, S, P + L, P, st);
   else if (in.vid_raw != nullptr)
     input_proj(in.vid_raw, c->ip_vid.K, c->ip_vid.W, c->ip_vid.b, c->pos_enc, pf, c->X, c->X32, c->XP, F, S, P + L, P, st);
   else
-    nchw_to_tokens(in.vid, (long long)256 * P, c->X, c->X32, in.pos, pos_fs, c->XP, F, S, P + L, P, st);
+    nchw_to_tokens(in.vid, (long long)256 * P, c->X, c->X32, pos, pos_fs, c->XP, F, S, P + L, P, st);
   f.count(2);
-  const float* text = in.text;
-  if (in.text_ids != nullptr) run_text_tower(f, in.text_ids, in.text_mask);   // → c->traw (bf16 last_hidden_state rows)
-  if (in.text_raw != nullptr || in.text_ids != nullptr) {  // FeatureResizer: LayerNorm_1e-12(fc(hidden states)) (bert.py:90-96)
-    if (in.text_ids == nullptr) { f32_to_bf16(in.text_raw, c->traw, (size_t)f.B * L * c->ip_text.K, st); f.count(); }
+  const size_t BL = (size_t)f.B * L;
+  if (in.text_ids != nullptr) {
+    VG_CUDA(cudaMemcpyAsync(c->ids_in, in.text_ids, BL * 4, cudaMemcpyDeviceToDevice, st));
+    if (in.text_mask) VG_CUDA(cudaMemcpyAsync(c->tmask_in, in.text_mask, BL, cudaMemcpyDeviceToDevice, st));
+  } else if (in.text_raw != nullptr) {
+    f32_to_bf16(in.text_raw, c->traw, BL * c->ip_text.K, st);
+    f.count();
+  } else {
+    VG_CUDA(cudaMemcpyAsync(c->text_in, in.text, BL * 256 * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (have_mask) { build_encoded_mask(in.vis_mask, in.text_mask, c->encmask, F, f.T, P, L, st); f.count(); }
+}
+
+// The captured part of the encoder phase: text tower / resizer (when the call brought raw text), text tokens, the encoder layers,
+// the final norm and the pooled means.  Reads context-owned memory only (see ingest_encoder_inputs).
+static void run_encoder(Fwd& f, int tkind, bool text_pad, bool have_mask, int pos_rows) {
+  vgqa_ctx* c = f.c;
+  cudaStream_t st = f.st;
+  const int S = f.S, P = f.P, L = f.L, R = f.R, F = f.F;
+  const float* text = c->text_in;
+  if (tkind == 2) run_text_tower(f, c->ids_in, text_pad ? c->tmask_in : nullptr);   // → c->traw (bf16 last_hidden_state rows)
+  if (tkind >= 1) {  // FeatureResizer: LayerNorm_1e-12(fc(hidden states)) (bert.py:90-96)
     GemmEpi ep; ep.C = c->tproj; ep.ldc = 256; ep.bias = c->ip_text.b; ep.bias_ld = 256; ep.C32 = c->tproj32; ep.ldc32 = 256;
     ep.ln_w = c->ip_text_ln.w; ep.ln_b = c->ip_text_ln.b; ep.ln_eps = 1e-12f;
     f.gemm(c->traw, c->ip_text.K, c->ip_text, f.B * L, ep);
@@ -789,7 +829,6 @@ static void run_encoder(Fwd& f, const vgqa_inputs& in, bool have_mask, int pos_r
   }
   text_to_tokens(text, c->X, c->X32, c->XP, F, f.T, S, P, L, st);
   f.count();
-  if (have_mask) { build_encoded_mask(in.vis_mask, in.text_mask, c->encmask, F, f.T, P, L, st); f.count(); }
   const uint8_t* km = have_mask ? c->encmask : nullptr;
   for (size_t l = 0; l < c->enc.size(); ++l) {
     EncLayer& e = c->enc[l];
@@ -1033,8 +1072,8 @@ static void check_inputs(vgqa_ctx* c, const vgqa_inputs& in) {
            "shape exceeds the context capacity: " + shape_str(in));
   VG_CHECK(in.T <= c->cfg.max_video_len + 1,
            "T exceeds INPUT.MAX_VIDEO_LEN+1 rows of the time embedding (reference raises RuntimeError too)");
-  VG_CHECK((in.vis || in.vis_raw) && (in.vid || in.vid_raw) && (in.text || in.text_raw || in.text_ids) && in.pos,
-           "vis/vid/text (or their *_raw / text_ids forms) and pos must be non-null");
+  VG_CHECK((in.vis || in.vis_raw) && (in.vid || in.vid_raw) && (in.text || in.text_raw || in.text_ids),
+           "vis/vid/text (or their *_raw / text_ids forms) must be non-null");
   VG_CHECK(!in.text_ids || (!c->tt.empty() && c->ip_text.K > 0),
            "text_ids needs the 'text_encoder.body' (RoBERTa) and 'text_encoder.resizer' weights");
   VG_CHECK(!in.text_ids || in.L <= 64, "text_ids: a query has at most 64 tokens");
@@ -1045,7 +1084,7 @@ static void check_inputs(vgqa_ctx* c, const vgqa_inputs& in) {
            "vid_raw needs the 'input_proj2' weights and vid_raw_ch equal to their input channels");
   VG_CHECK(!in.text_raw || (c->ip_text.K > 0 && in.text_raw_ch == c->ip_text.K),
            "text_raw needs the 'text_encoder.resizer' weights and text_raw_ch equal to their input features");
-  VG_CHECK(in.pos_frames == 1 || in.pos_frames == in.clips * in.T, "pos_frames must be 1 or clips*T");
+  VG_CHECK(in.pos == nullptr || in.pos_frames == 1 || in.pos_frames == in.clips * in.T, "pos_frames must be 1 or clips*T");
   if (c->sh_world > 1) {
     VG_CHECK(in.clips == 1, "frame sharding handles one clip per call");
     VG_CHECK(in.T * c->sh_world <= c->cfg.max_video_len + 1, "sharded clip exceeds INPUT.MAX_VIDEO_LEN+1 frames");
@@ -1053,9 +1092,7 @@ static void check_inputs(vgqa_ctx* c, const vgqa_inputs& in) {
   }
 }
 
-// phase 0: CrossModalEncoder (+ final norm, pooled means); phase 1: everything after it.
-static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out, int phase, cudaStream_t st) {
-  Fwd f;
+static void init_fwd(Fwd& f, vgqa_ctx* c, const vgqa_inputs& in, int phase, cudaStream_t st) {
   if (!c->aux_stream) {
     int prio_lo = 0, prio_hi = 0;
     VG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -1065,24 +1102,28 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
   }
   f.c = c; f.st = st; f.main = st; const bool one_stream = c->sh_world > 1 && !p2p_ready(c->p2p);   // NCCL-callback sharding: collectives stay in program order
   f.aux = one_stream ? st : c->aux_stream; f.aux2 = one_stream ? st : c->aux2_stream; f.B = in.clips; f.T = in.T; f.P = in.H * in.W; f.L = in.L; f.S = 2 * f.P + f.L;
-  f.F = f.B * f.T; f.R = f.F * f.S;
+  f.F = f.B * f.T; f.R = f.F * f.S; f.phase = phase;
+}
+
+// The part of a phase that reads context-owned memory only (what a CUDA graph captures).  `in` carries the shape, the flags and —
+// for the decoder phase — the STAGED copies of ori_sizes_hw / force_choose1/2 (see forward_async).
+// phase 0: CrossModalEncoder (+ final norm, pooled means); phase 1: everything after it.
+static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, int phase, cudaStream_t st) {
+  Fwd f;
+  init_fwd(f, c, in, phase, st);
   const int F = f.F, D = (int)c->tl.size();
   const bool have_mask = in.vis_mask != nullptr || in.text_mask != nullptr;
   const int pos_rows = in.pos_frames * f.S;
-  c->launches = 0;
   if (phase == 0) {
     // Leave `dec_sms` SMs out of the encoder's persistent grids: the decoder phase of the previous batch (other stream,
     // higher priority) is a chain of small latency-bound launches that then runs beside the encoder instead of between
     // its kernels.
+    struct BudgetGuard { ~BudgetGuard() { set_sm_budget(0); } } guard;   // reset even when a launch throws
     set_sm_budget(c->enc_sm_budget);
-    run_encoder(f, in, have_mask, pos_rows);
-    set_sm_budget(0);
+    run_encoder(f, text_kind(in), in.text_mask != nullptr, have_mask, pos_rows);
     return;
   }
-  if (in.stop_after_encoder) {
-    if (out.frames_cls) VG_CUDA(cudaMemcpyAsync(out.frames_cls, c->frames_cls, (size_t)F * 256 * 4, cudaMemcpyDeviceToDevice, st));
-    return;
-  }
+  if (in.stop_after_encoder) return;
   run_temporal_sampling(f);
   select_pass1(c->logit_f[0], c->logit_f[1], 0.45f, in.force_choose1, c->att_seq, c->w1, c->K1, f.B, f.T, st);
   f.all_reduce_f32(c->K1, f.B);
@@ -1090,7 +1131,6 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
   f.count(2);
   run_spatial_seed(f, c->w1, c->K1, false);
   run_decoders(f, have_mask, in.pos_frames, false);
-  const float* wfinal = c->w1;
   if (in.iteration_rate < 0) {  // grounding_net.py:143-163
     f.linear(c->t_inter + (size_t)(D - 1) * F * 256, 256, c->action_embed.l0, F, c->t_hs, 256, ACT_RELU);
     rowvec_head(c->t_hs, 256, c->action_embed.w1, c->action_embed.b1, c->act1, 1, F, 1, 1, st);  // sigmoid
@@ -1100,7 +1140,6 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
     f.count(3);
     run_spatial_seed(f, c->w2, c->K2, true);
     run_decoders(f, have_mask, in.pos_frames, true);
-    wfinal = c->w2;
   }
   // heads over all decoder layers (grounding_net.py:177-181)
   f.linear(c->t_inter, 256, c->temp_embed.l0, D * F, c->t_hs, 256, ACT_RELU);
@@ -1114,7 +1153,18 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
     postprocess(last_boxes, last_sted, in.ori_sizes_hw, c->boxes_px, c->sted_idx, f.B, f.T, st);
     f.count();
   }
-  // ---- outputs
+}
+
+// Copies of the results into the caller's buffers — outside the captured part (they depend on the caller's pointers).
+static void emit_outputs(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out, cudaStream_t st) {
+  const int F = in.clips * in.T, D = (int)c->tl.size(), B = in.clips;
+  if (in.stop_after_encoder) {
+    if (out.frames_cls) VG_CUDA(cudaMemcpyAsync(out.frames_cls, c->frames_cls, (size_t)F * 256 * 4, cudaMemcpyDeviceToDevice, st));
+    return;
+  }
+  const float* wfinal = in.iteration_rate < 0 ? c->w2 : c->w1;
+  const float* last_boxes = c->anchors + (size_t)(D - 1) * F * 4;
+  const float* last_sted = c->sted_all + (size_t)(D - 1) * F * 2;
   auto cp = [&](void* dst, const void* src, size_t bytes) {
     if (dst != nullptr) VG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
   };
@@ -1132,12 +1182,12 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
   cp(out.actioness_pass1, c->act1, (size_t)F * 4);
   if (in.ori_sizes_hw != nullptr) {
     cp(out.boxes_px, c->boxes_px, (size_t)F * 4 * 4);
-    cp(out.sted_idx, c->sted_idx, (size_t)f.B * 2 * 4);
+    cp(out.sted_idx, c->sted_idx, (size_t)B * 2 * 4);
   }
   if (out.logits_r_m) VG_CUDA(cudaMemcpy2DAsync(out.logits_r_m, c->cfg.mot_num * 4, c->logits_r[0], c->cfg.mot_num * 4,
-                                                c->cfg.mot_num * 4, f.B, cudaMemcpyDeviceToDevice, st));
+                                                c->cfg.mot_num * 4, B, cudaMemcpyDeviceToDevice, st));
   if (out.logits_r_a) VG_CUDA(cudaMemcpy2DAsync(out.logits_r_a, c->cfg.app_num * 4, c->logits_r[1], c->cfg.app_num * 4,
-                                                c->cfg.app_num * 4, f.B, cudaMemcpyDeviceToDevice, st));
+                                                c->cfg.app_num * 4, B, cudaMemcpyDeviceToDevice, st));
   cp(out.frames_cls, c->frames_cls, (size_t)F * 256 * 4);
 }
 
@@ -1247,39 +1297,37 @@ static void ensure_streams(vgqa_ctx* c) {
   for (auto& h : c->hs) VG_CUDA(cudaEventCreateWithFlags(&h.done, cudaEventDisableTiming));
 }
 
-// Enqueue one phase on `ex`: eagerly, or as a cached CUDA graph (one graph per phase / slot / shape / pointer set).
-static int run_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out, int phase, int slot, cudaStream_t ex,
-                     bool eager) {
+// Enqueue the captured part of one phase on `ex`: eagerly, or as a cached CUDA graph.  The key holds the phase, the slot, the
+// shape and the presence flags of the optional inputs — no pointers: everything a graph reads or writes is context-owned
+// (ingest_encoder_inputs / the staging in forward_async / emit_outputs handle the caller's buffers outside of it).
+static int run_phase(vgqa_ctx* c, const vgqa_inputs& in, int phase, int slot, cudaStream_t ex, bool eager) {
+  c->launches = 0;
   if (eager) {
-    forward_phase(c, in, out, phase, ex);
+    forward_phase(c, in, phase, ex);
     return c->launches;
   }
-  std::vector<uint64_t> key = {(uint64_t)phase, (uint64_t)slot, (uint64_t)in.clips, (uint64_t)in.T, (uint64_t)in.H,
-                               (uint64_t)in.W, (uint64_t)in.L, (uint64_t)in.pos_frames, (uint64_t)(in.iteration_rate < 0),
-                               (uint64_t)in.raw_layout};
-  for (const void* q : {(const void*)in.vis, (const void*)in.vid, (const void*)in.text, (const void*)in.pos,
-                        (const void*)in.vis_mask, (const void*)in.text_mask, (const void*)in.ori_sizes_hw,
-                        (const void*)in.force_choose1, (const void*)in.force_choose2, (const void*)in.vis_raw,
-                        (const void*)in.vid_raw, (const void*)in.text_raw, (const void*)in.text_ids})
-    key.push_back((uint64_t)(uintptr_t)q);
-  if (phase == 1)
-    for (const void* q : {(const void*)out.pred_boxes, (const void*)out.pred_sted, (const void*)out.pred_actioness,
-                          (const void*)out.logits_f_m, (const void*)out.logits_f_a, (const void*)out.logits_r_a,
-                          (const void*)out.logits_r_m, (const void*)out.att_sequences, (const void*)out.aux_boxes,
-                          (const void*)out.aux_sted, (const void*)out.aux_actioness, (const void*)out.choose1,
-                          (const void*)out.choose2, (const void*)out.actioness_pass1, (const void*)out.boxes_px,
-                          (const void*)out.sted_idx, (const void*)out.frames_cls})
-      key.push_back((uint64_t)(uintptr_t)q);
+  const std::vector<uint64_t> key = {
+      (uint64_t)phase, (uint64_t)slot, (uint64_t)in.clips, (uint64_t)in.T, (uint64_t)in.H, (uint64_t)in.W, (uint64_t)in.L,
+      (uint64_t)in.pos_frames, (uint64_t)(in.iteration_rate < 0), (uint64_t)text_kind(in), (uint64_t)(in.vis_mask != nullptr),
+      (uint64_t)(in.text_mask != nullptr), (uint64_t)(in.ori_sizes_hw != nullptr), (uint64_t)(in.force_choose1 != nullptr),
+      (uint64_t)(in.force_choose2 != nullptr), (uint64_t)c->sh_world, (uint64_t)c->sh_rank};
   auto it = c->graphs.find(key);
   if (it == c->graphs.end()) {
-    forward_phase(c, in, out, phase, ex);  // eager warm-up (sets function attributes, validates, produces valid data)
+    // First call of this shape: run it eagerly — that IS this call's execution (it also sets the kernels' function attributes
+    // and validates the launches) — and then capture the same sequence for the calls to come.  The captured part is executed
+    // exactly once per call: the encoder layers update the ingested token rows in place, and a frame-sharded forward advances
+    // the device-side exchange sequence on every execution, so a second run would neither be idempotent nor stay in step
+    // with the other ranks.
+    forward_phase(c, in, phase, ex);
+    const int eager_launches = c->launches;
     VG_CUDA(cudaStreamSynchronize(ex));
     VG_CUDA(cudaStreamSynchronize(c->aux_stream));
     VG_CUDA(cudaStreamSynchronize(c->aux2_stream));
+    c->launches = 0;
     cudaGraph_t graph = nullptr;
     VG_CUDA(cudaStreamBeginCapture(ex, cudaStreamCaptureModeThreadLocal));
     try {
-      forward_phase(c, in, out, phase, ex);
+      forward_phase(c, in, phase, ex);
     } catch (...) {
       cudaStreamEndCapture(ex, &graph);
       if (graph) cudaGraphDestroy(graph);
@@ -1290,23 +1338,28 @@ static int run_phase(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out
     VG_CUDA(cudaGraphInstantiate(&ge.exec, graph, 0));
     cudaGraphDestroy(graph);
     ge.launches = c->launches;
-    if (c->graphs.size() >= 32) {
+    ++c->graph_captures;
+    if (c->graphs.size() >= 64) {   // shapes only: a serving process sees a handful; bound the cache anyway
       VG_CUDA(cudaDeviceSynchronize());
       for (auto& g : c->graphs) cudaGraphExecDestroy(g.second.exec);
       c->graphs.clear();
     }
-    it = c->graphs.emplace(key, ge).first;
+    c->graphs.emplace(key, ge);
+    return eager_launches;
   }
   VG_CUDA(cudaGraphLaunch(it->second.exec, ex));
   return it->second.launches;
 }
 
 // Both phases of one call, for boundary slot `slot`, ordered after everything enqueued on `st` so far.
-static void forward_async(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs& out, int slot, cudaStream_t st) {
-  check_inputs(c, in);
+static void forward_async(vgqa_ctx* c, const vgqa_inputs& user_in, const vgqa_outputs& out, int slot, cudaStream_t st) {
+  check_inputs(c, user_in);
   ensure_streams(c);
   select_slot(c, slot);
   vgqa_ctx::Boundary& b = c->bd[slot];
+  vgqa_inputs in = user_in;
+  // PositionEmbeddingSine generated in the library: one table for every frame unless a padding mask makes it per-frame
+  if (in.pos == nullptr) in.pos_frames = in.vis_mask != nullptr ? in.clips * in.T : 1;
   // a sharded forward that exchanges through the host callback (NCCL) cannot be captured; the peer-memory exchange can
   const bool eager = !c->cfg.use_cuda_graph || out.encoded_feature != nullptr || in.stop_after_encoder ||
                      (c->sh_world > 1 && !p2p_ready(c->p2p));
@@ -1314,12 +1367,33 @@ static void forward_async(vgqa_ctx* c, const vgqa_inputs& in, const vgqa_outputs
   VG_CUDA(cudaStreamWaitEvent(c->enc_stream, b.ev_in, 0));
   if (b.used) VG_CUDA(cudaStreamWaitEvent(c->enc_stream, b.dec_done, 0));  // phase 1 of the previous user of this slot
   if (c->timeline) VG_CUDA(cudaEventRecord(b.t_enc0, c->enc_stream));
-  int launches = run_phase(c, in, out, 0, slot, c->enc_stream, eager);
+  int launches = 0;
+  {  // ---- encoder phase: ingest the caller's tensors (eager), then the captured part
+    Fwd f;
+    init_fwd(f, c, in, 0, c->enc_stream);
+    c->launches = 0;
+    ingest_encoder_inputs(f, in, in.vis_mask != nullptr || in.text_mask != nullptr);
+    launches += c->launches;
+    launches += run_phase(c, in, 0, slot, c->enc_stream, eager);
+  }
   if (c->timeline) VG_CUDA(cudaEventRecord(b.t_enc1, c->enc_stream));
   VG_CUDA(cudaEventRecord(b.enc_done, c->enc_stream));
   VG_CUDA(cudaStreamWaitEvent(c->dec_stream, b.enc_done, 0));
   if (c->timeline) VG_CUDA(cudaEventRecord(b.t_dec0, c->dec_stream));
-  launches += run_phase(c, in, out, 1, slot, c->dec_stream, eager);
+  {  // ---- decoder phase: stage its (tiny) optional inputs, the captured part, then the copies into the caller's outputs
+    vgqa_ctx::InStage& is = c->ins[slot];
+    const size_t F = (size_t)in.clips * in.T;
+    auto stage = [&](const float*& ptr, float* dst, size_t n) {
+      if (ptr == nullptr) return;
+      VG_CUDA(cudaMemcpyAsync(dst, ptr, n * 4, cudaMemcpyDeviceToDevice, c->dec_stream));
+      ptr = dst;
+    };
+    stage(in.ori_sizes_hw, is.sizes, (size_t)in.clips * 2);
+    stage(in.force_choose1, is.f1, F);
+    stage(in.force_choose2, is.f2, F);
+    launches += run_phase(c, in, 1, slot, c->dec_stream, eager);
+    emit_outputs(c, in, out, c->dec_stream);
+  }
   if (c->timeline) VG_CUDA(cudaEventRecord(b.t_dec1, c->dec_stream));
   if (out.encoded_feature) {
     const size_t n = (size_t)in.clips * in.T * (2 * in.H * in.W + in.L) * 256;
@@ -1383,7 +1457,7 @@ int vgqa_forward_host_async(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outp
     if (hin->text_ids) { h2d(h.ids, hin->text_ids, B * L * 4); din.text_ids = h.ids; din.text = nullptr; din.text_raw = nullptr; }
     else if (hin->text_raw) { h2d(h.text_raw, hin->text_raw, B * L * c->ip_text.K * 4); din.text_raw = h.text_raw; din.text = nullptr; }
     else { h2d(h.text, hin->text, B * L * 256 * 4); din.text = h.text; }
-    h2d(h.pos, hin->pos, (size_t)hin->pos_frames * 256 * P * 4); din.pos = h.pos;
+    if (hin->pos) { h2d(h.pos, hin->pos, (size_t)hin->pos_frames * 256 * P * 4); din.pos = h.pos; }
     if (hin->vis_mask) { h2d(h.vmask, hin->vis_mask, F * P); din.vis_mask = h.vmask; }
     if (hin->text_mask) { h2d(h.tmask, hin->text_mask, B * L); din.text_mask = h.tmask; }
     // sizes / forced selections are read by phase 1: wait for the previous call's decoder phase (and result downloads)
@@ -1503,6 +1577,8 @@ int vgqa_text_tower(vgqa_ctx* c, const int32_t* ids, const uint8_t* text_mask, i
 }
 
 int vgqa_last_launch_count(const vgqa_ctx* c) { return c ? c->last_launches : 0; }
+
+int vgqa_graph_capture_count(const vgqa_ctx* c) { return c ? c->graph_captures : 0; }
 
 int vgqa_debug_phase_times(vgqa_ctx* c, int slot, float* ms4) {
   try {

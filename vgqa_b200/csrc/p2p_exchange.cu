@@ -33,7 +33,7 @@ struct P2pControl {            // at the start of every rank's exchange buffer
 };
 static_assert(sizeof(P2pControl) == 256, "control block");
 
-static constexpr int kP2pChannels = 3;
+static constexpr int kP2pChannels = 4;   // three graph branches of the decoder phase + the encoder phase (other stream)
 
 struct P2pParams {
   unsigned char* peer[16];     // peer[q] = base of rank q's exchange buffer as mapped in THIS process

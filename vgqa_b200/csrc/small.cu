@@ -43,6 +43,37 @@ void nchw_to_tokens(const float* in, long long in_fstride, bf16* X, float* X32, 
   VG_CUDA(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------- PositionEmbeddingSine(128, normalize=True)
+// vgqa/core/vision/position_encoding.py:50-91: cumsum of ~mask along y / x, normalised by the last row / column (+1e-6) and
+// scaled to 2*pi, divided by 10000^(2*floor(i/2)/128), sin on even / cos on odd feature indices, cat(pos_y, pos_x) → NCHW.
+// One CTA per frame (a frame has at most a few hundred positions); mask == nullptr → nothing is padded.
+__global__ void __launch_bounds__(256) pos_sine_kernel(const uint8_t* __restrict__ mask, float* __restrict__ out, int H, int W) {
+  extern __shared__ float emb[];   // [2][H*W]: y_embed, x_embed (normalised, scaled)
+  const int f = blockIdx.x, P = H * W;
+  const uint8_t* m = mask ? mask + (size_t)f * P : nullptr;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const int y = p / W, x = p % W;
+    float cy = 0.f, ty = 0.f, cx = 0.f, tx = 0.f;
+    for (int yy = 0; yy < H; ++yy) { const float v = (m && m[yy * W + x]) ? 0.f : 1.f; ty += v; if (yy <= y) cy += v; }
+    for (int xx = 0; xx < W; ++xx) { const float v = (m && m[y * W + xx]) ? 0.f : 1.f; tx += v; if (xx <= x) cx += v; }
+    const float scale = 6.283185307179586f;
+    emb[p] = cy / (ty + 1e-6f) * scale;
+    emb[P + p] = cx / (tx + 1e-6f) * scale;
+  }
+  __syncthreads();
+  float* o = out + (size_t)f * 256 * P;
+  for (int i = threadIdx.x; i < 256 * P; i += blockDim.x) {
+    const int c = i / P, p = i % P, k = c & 127;
+    const float dim_t = powf(10000.f, (float)(2 * (k >> 1)) / 128.f);
+    const float a = emb[(c >> 7) * P + p] / dim_t;
+    o[i] = (k & 1) ? cosf(a) : sinf(a);
+  }
+}
+void pos_sine(const uint8_t* mask, float* out, int frames, int H, int W, cudaStream_t st) {
+  pos_sine_kernel<<<frames, 256, (size_t)2 * H * W * sizeof(float), st>>>(mask, out, H, W);
+  VG_CUDA(cudaGetLastError());
+}
+
 __global__ void __launch_bounds__(256) text_to_tokens_kernel(const float* __restrict__ text, bf16* __restrict__ X,
                                                              float* __restrict__ X32, bf16* __restrict__ XP, int T, int S,
                                                              int tok0, int L) {

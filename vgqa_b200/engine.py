@@ -66,6 +66,8 @@ def _declare(L):
     L.vgqa_forward_host_wait.argtypes = [c_void_p, c_int]
     L.vgqa_last_launch_count.restype = c_int
     L.vgqa_last_launch_count.argtypes = [c_void_p]
+    L.vgqa_graph_capture_count.restype = c_int
+    L.vgqa_graph_capture_count.argtypes = [c_void_p]
     L.vgqa_postprocess.restype = c_int
     L.vgqa_postprocess.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
     L.vgqa_set_sharding.restype = c_int
@@ -218,12 +220,14 @@ class GroundingEngine:
             assert d == 256 and tuple(vid.shape) == tuple(vis.shape), "vis/vid must be [clips, T, 256, H, W]"
             assert tuple(text.shape) == (B, text.shape[1], 256), "text must be [clips, L, 256]"
         Lt = text.shape[1]
-        assert pos.shape[0] in (1, B * T) and tuple(pos.shape[1:]) == (256, H, W), "pos must be [1 or clips*T, 256, H, W]"
-        for t in (vis, vid, text, pos):
+        # pos = None: the library generates PositionEmbeddingSine itself (from vis_mask; one shared table without a mask)
+        assert pos is None or (pos.shape[0] in (1, B * T) and tuple(pos.shape[1:]) == (256, H, W)), \
+            "pos must be [1 or clips*T, 256, H, W] (or None)"
+        for t in (vis, vid, text) + (() if pos is None else (pos,)):
             assert (t.dtype == torch.float32 or (nhwc and (t is vis or t is vid))) and t.is_contiguous()
         n = None
         inp = VgqaInputs(B, T, H, W, Lt, n if raw else self._p(vis), n if raw else self._p(vid), n if raw else self._p(text),
-                         self._p(pos), pos.shape[0],
+                         self._p(pos), 0 if pos is None else pos.shape[0],
                          self._p(vis_mask), self._p(text_mask), self._p(ori_sizes_hw), self._p(force1), self._p(force2),
                          iteration_rate, stop_after_encoder,
                          self._p(vis) if raw else n, self._p(vid) if raw else n,
@@ -242,7 +246,7 @@ class GroundingEngine:
         _lib.check(self._L.vgqa_forward(self._ctx, ctypes.byref(inp), ctypes.byref(out), c_void_p(st)))
         return outs
 
-    def forward(self, vis, vid, text, pos, *, vis_mask=None, text_mask=None, ori_sizes_hw=None, force_choose1=None,
+    def forward(self, vis, vid, text, pos=None, *, vis_mask=None, text_mask=None, ori_sizes_hw=None, force_choose1=None,
                 force_choose2=None, iteration_rate=-1, outs=None, want=None, raw=False, text_ids=None):
         """Device-resident inputs (fp32 CUDA tensors, reference layouts); enqueues on the current stream."""
         B, T, H, W = self._dims(vis, raw)
@@ -313,3 +317,8 @@ class GroundingEngine:
     @property
     def last_launch_count(self) -> int:
         return int(self._L.vgqa_last_launch_count(self._ctx))
+
+    @property
+    def graph_capture_count(self) -> int:
+        """CUDA graphs captured so far: one per (phase, slot, shape) — fresh input / output tensors do not re-capture."""
+        return int(self._L.vgqa_graph_capture_count(self._ctx))

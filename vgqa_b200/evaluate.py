@@ -159,7 +159,7 @@ def precision_recall(predicted: Sequence[int], true: Sequence[int]) -> Tuple[flo
 @torch.no_grad()
 def do_eval(engine, items: Sequence[Mapping[str, Any]], evaluator: VidSTGEvaluator, *, clips_per_call: int = 1, rank: int = 0,
             world: int = 1, raw: bool = False):
-    """items[i]: {"item_id", "vis" [2T,C,H,W], "vid" [2T,C,H,W], "text" [L,C], "pos" [1,256,H,W], "frame_ids" (2T ascending ints),
+    """items[i]: {"item_id", "vis" [2T,C,H,W], "vid" [2T,C,H,W], "text" [L,C], optional "pos" [1,256,H,W] (generated in the library when absent), "frame_ids" (2T ascending ints),
     "ori_size" (h, w), "qtype" (default 'none', evaluator.py:107-109), "actioness" [2T] 0/1}.  All items share (T, H, W, L).
     Rank `rank` evaluates its contiguous share of the items (no data-path collective), `clips_per_call` items per engine call
     (2 * clips_per_call clips: even and odd passes); afterwards the dicts are merged on every rank and rank 0 summarizes."""
@@ -177,7 +177,7 @@ def do_eval(engine, items: Sequence[Mapping[str, Any]], evaluator: VidSTGEvaluat
                 sizes.append([float(it["ori_size"][0]), float(it["ori_size"][1])])
         T = vis[0].shape[0]
         o = engine.forward(torch.stack(vis).contiguous(), torch.stack(vid).contiguous(), torch.stack(text).contiguous(),
-                           f32(batch[0]["pos"])[:1].contiguous(), ori_sizes_hw=torch.tensor(sizes, device=dev),
+                           f32(batch[0]["pos"])[:1].contiguous() if batch[0].get("pos") is not None else None, ori_sizes_hw=torch.tensor(sizes, device=dev),
                            want=["att_sequences", "boxes_px", "sted_idx", "choose2"], raw=raw)
         boxes, att = o["boxes_px"].cpu().tolist(), o["att_sequences"].cpu().tolist()
         idx, chosen = o["sted_idx"].cpu().tolist(), (o["choose2"] > 0.5).cpu().numpy()

@@ -73,10 +73,12 @@ def nccl_exchange(group=None):
     return EXCHANGE_FN(cb), errors
 
 
-def forward_sharded_clip(engine, vis, vid, text, pos, *, ori_size_hw, group=None, iteration_rate=-1):
+def forward_sharded_clip(engine, vis, vid, text, pos, *, ori_size_hw, group=None, iteration_rate=-1, check_errors=True):
     """One long clip, frames sharded over the ranks of `group`.  vis/vid: THIS rank's frames [1, T_local, 256, H, W];
     text [1, L, 256] and pos [1, 256, H, W] replicated.  Returns the gathered outputs of the whole clip on every rank
-    (pred_boxes [T,4], pred_sted [T,2], pred_actioness [T], att_sequences [T], boxes_px [T,4], sted_idx [2])."""
+    (pred_boxes [T,4], pred_sted [T,2], pred_actioness [T], att_sequences [T], choose1/2 [T], boxes_px [T,4], sted_idx [2]).
+    `check_errors` reads the peer-memory exchange's error word after the call (one 4-byte D2H copy, a host sync): switch it
+    off inside a timed loop and call engine.p2p_error() once at the end."""
     import ctypes
     from . import _lib
     from .engine import _declare
@@ -85,13 +87,18 @@ def forward_sharded_clip(engine, vis, vid, text, pos, *, ori_size_hw, group=None
         cb, errors = nccl_exchange(group)
         engine.set_sharding(rank, world, cb)
         engine._shard_cfg, engine._shard_errors = (rank, world), errors
-    want = ["pred_boxes", "pred_sted", "pred_actioness", "att_sequences", "logits_r_a", "logits_r_m", "choose2"]
-    o = engine.forward(vis, vid, text, pos, iteration_rate=iteration_rate, want=want)
+    want = ["pred_boxes", "pred_sted", "pred_actioness", "att_sequences", "logits_r_a", "logits_r_m", "choose1", "choose2"]
+    T_loc, H, W = vis.shape[1], vis.shape[3], vis.shape[4]
+    key = (T_loc, H, W, text.shape[1])
+    if getattr(engine, "_shard_outs_key", None) != key:     # outputs are allocated once per shape and reused
+        engine._shard_outs, engine._shard_outs_key = engine.alloc_outputs(1, T_loc, H, W, text.shape[1], want), key
+    o = engine.forward(vis, vid, text, pos, iteration_rate=iteration_rate, outs=engine._shard_outs)
     if engine._shard_errors:
         raise engine._shard_errors.pop()
-    T_loc = vis.shape[1]
+    if check_errors and engine.p2p_error():                  # a peer never arrived within the kernel's ≈2 s bound
+        raise RuntimeError("frame-sharded forward: a peer-memory exchange timed out (ranks out of step or a peer died)")
     full = {}
-    for k in ("pred_boxes", "pred_sted", "pred_actioness", "att_sequences", "choose2"):
+    for k in ("pred_boxes", "pred_sted", "pred_actioness", "att_sequences", "choose1", "choose2"):
         loc = o[k][0].contiguous()
         buf = torch.empty((world,) + tuple(loc.shape), device=loc.device, dtype=loc.dtype)
         dist.all_gather_into_tensor(buf, loc, group=group)

@@ -35,8 +35,9 @@ class GroundingPredictor:
 
     @torch.no_grad()
     def predict_many(self, items: Sequence[Mapping[str, Any]]) -> List[Dict[str, Any]]:
-        """items[q]: {"vis": [2T,256,H,W], "vid": [2T,256,H,W], "text": [L,256], "pos": [1,256,H,W], "frame_ids": 2T ints
-        (ascending, as sampled by predict()), "ori_size": (h, w), "fps": float}.  All items share T, H, W, L.
+        """items[q]: {"vis": [2T,256,H,W], "vid": [2T,256,H,W], "text": [L,256], "frame_ids": 2T ints (ascending, as sampled
+        by predict()), "ori_size": (h, w), "fps": float}.  All items share T, H, W, L.  "pos" ([1,256,H,W]) is optional: the
+        library generates PositionEmbeddingSine itself (predict() resizes to a square, so nothing is padded, grounding.py:177).
         With raw_inputs=True the channel counts are those of the extractors (see __init__); an item may then carry
         "text_ids" ([L] RoBERTa token ids) instead of "text" — the text tower runs inside the library too (all items or none).
         Returns one {"temporal": {...}, "tube": [...]} dict per item (grounding.py:227-244)."""
@@ -62,7 +63,7 @@ class GroundingPredictor:
         T = vis[0].shape[0]
         assert all(x.shape[0] == T for x in vis), "all queries of a call must sample the same number of frames"
         vis, vid, text = torch.stack(vis).contiguous(), torch.stack(vid).contiguous(), torch.stack(text).contiguous()
-        pos = f32(items[0]["pos"])[:1].contiguous()
+        pos = f32(items[0]["pos"])[:1].contiguous() if items[0].get("pos") is not None else None
         o = self.engine.forward(vis, vid, None if use_ids else text, pos, ori_sizes_hw=torch.tensor(sizes, device=dev),
                                 want=["att_sequences", "boxes_px", "sted_idx"], raw=self.raw_inputs,
                                 text_ids=text if use_ids else None)
@@ -82,7 +83,7 @@ class GroundingPredictor:
             results.append(merge_predictions(passes[0], passes[1], float(it.get("fps", 25.0))))
         return results
 
-    def predict(self, vis, vid, text, pos, frame_ids, ori_size, fps=25.0, qtype="declar") -> Dict[str, Any]:
+    def predict(self, vis, vid, text, pos=None, frame_ids=None, ori_size=None, fps=25.0, qtype="declar") -> Dict[str, Any]:
         return self.predict_many([{"vis": vis, "vid": vid, "text": text, "pos": pos, "frame_ids": frame_ids,
                                    "ori_size": ori_size, "fps": fps, "qtype": qtype}])[0]
 
