@@ -11,9 +11,12 @@ random-init (seeded synthetic) weights.  Prints ONE JSON line (rank 0).
   e2e          clips/s through the C-ABI host path (`vgqa_forward_host_async/_wait`, two slots) with pinned HOST buffers:
                every step uploads its inputs, computes, downloads and reads its results inside the timed region
   roofline     the dominant kernel (fused FFN block, tcgen05 cta_group::2) timed alone with CUDA events: algorithmic FLOPs / duration
-  cpu_baseline the numpy oracle port timed on the host cores on a bounded sample (rank 0, N=1 only)
-  --impl reference : the reference arm = the oracle port on the host cores (the reference itself is PyTorch
-                     source under /root/reference which does not exist on the GPU box)
+  cpu_baseline the reference's OWN PyTorch modules (oracle/_ref, byte-compiled from /root/reference by tools/make_oracle_ref.py)
+               timed on the host cores on a bounded sample (rank 0, N=1 only); the numpy port only if oracle/_ref is absent
+  other_configs  cfg-5 (T=128, 12x12, L=64) at 1 / 8 / 64 clips per step and the real yaml shape (T=64, 14x14, L=20), timed in-run
+  sharded_cfg4   (WORLD_SIZE > 1) ONE 256-frame clip frame-sharded over all ranks, peer-memory exchange: ms per clip + error vs golden
+  eager_pytorch_b200  the reference modules in eager PyTorch bf16-autocast on the same B200 (the only existing implementation)
+  --impl reference : the reference arm = the reference's own modules on the host cores, all threads
 """
 import argparse
 import json
@@ -27,6 +30,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))    # ref_loader / make_golden: the reference-module harness (CPU arm only)
 
 T, H, W, L = 64, 7, 7, 20
 METRIC = "grounding clips/sec (64f@224, bf16)"   # BASELINE.json's metric; both arms print the same string
@@ -84,46 +88,101 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def oracle_clips_per_sec(n_clips, seed=0):
-    """The numpy oracle port on the host cores (all BLAS threads): seconds per clip of the same workload."""
-    from oracle import vgqa_oracle as O
-    sd = O.synth_state_dict(seed)
+def reference_arm_available():
+    try:
+        from ref_loader import reference_modules_available
+        return reference_modules_available()
+    except Exception:
+        return False
+
+
+class ReferenceHotPath:
+    """The reference's own PyTorch modules (imported from /root/reference here, from the byte-compiled oracle/_ref on the GPU
+    box), wired and driven exactly as VSTGNet.forward lines 114-181 drive them (tests/golden/make_golden.py: RefHotPath), on the
+    synthetic weights of `seed`.  fp32 on the host cores, or eager bf16-autocast on a CUDA device."""
+
+    def __init__(self, seed=0, device="cpu", shape=(T, H, W, L)):
+        import torch
+        from vgqa_b200 import synth
+        from make_golden import RefHotPath, load_synth, make_cfg
+        from ref_loader import load_reference
+        self.torch, self.device, self.shape = torch, device, shape
+        self.R = load_reference()
+        self.model = RefHotPath(self.R, make_cfg(max_video_len=max(200, shape[0]))).eval()
+        load_synth(self.model, synth.synth_state_dict(seed, max_video_len=max(200, shape[0])))
+        self.model.to(device)
+        self.synth = synth
+
+    def inputs(self, i):
+        torch = self.torch
+        Tn, Hn, Wn, Ln = self.shape
+        vis, vid, pos, text = self.synth.synth_inputs(i, Tn, Hn, Wn, Ln)
+        to = lambda a: torch.from_numpy(a).to(self.device)
+        return (to(vis), to(vid), to(pos), to(text), torch.zeros(Tn, Hn, Wn, dtype=torch.bool, device=self.device),
+                torch.zeros(1, Ln, dtype=torch.bool, device=self.device))
+
+    def run(self, inp, autocast=False):
+        torch = self.torch
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            out, _ = self.model(*inp)
+        return out
+
+
+def cpu_clips_per_sec(n_clips, warmup=1):
+    """Seconds per clip of the same workload on the host cores: the reference's own modules when they are importable (kind
+    "reference"), else the numpy oracle port (kind "port").  All host threads."""
+    cores = os.cpu_count()
     times = []
-    for i in range(n_clips):
-        vis, vid, pos, text = O.synth_inputs(i, T, H, W, L)
-        t0 = time.perf_counter()
-        O.hot_path_forward(sd, vis, vid, pos, text)
-        times.append(time.perf_counter() - t0)
-    return n_clips / sum(times), times
+    if reference_arm_available():
+        import torch
+        torch.set_num_threads(cores)     # torch.distributed.run exports OMP_NUM_THREADS=1: undo it for the CPU arm
+        ref = ReferenceHotPath(0, "cpu")
+        for i in range(warmup + n_clips):
+            inp = ref.inputs(i)
+            t0 = time.perf_counter()
+            ref.run(inp)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind = "reference"
+        from ref_loader import REF_ROOT
+        what = (f"the reference's own PyTorch modules (imported from {os.path.relpath(REF_ROOT, ROOT) if REF_ROOT.startswith(ROOT) else REF_ROOT}), "
+                f"fp32, torch {torch.__version__}, {torch.get_num_threads()} threads")
+    else:
+        from oracle import vgqa_oracle as O
+        from vgqa_b200 import synth
+        sd = synth.synth_state_dict(0)
+        for i in range(warmup + n_clips):
+            vis, vid, pos, text = synth.synth_inputs(i, T, H, W, L)
+            t0 = time.perf_counter()
+            O.hot_path_forward(sd, vis, vid, pos, text)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind, what = "port", "numpy oracle port of the reference modules (oracle/_ref absent), fp32, all BLAS threads"
+    return n_clips / sum(times), times, kind, what, cores
 
 
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    cores = os.cpu_count()
-    t_steps = []
-    from oracle import vgqa_oracle as O
-    sd = O.synth_state_dict(0)
-    for i in range(args.warmup + args.steps):
-        vis, vid, pos, text = O.synth_inputs(i, T, H, W, L)
-        t0 = time.perf_counter()
-        O.hot_path_forward(sd, vis, vid, pos, text)
-        if i >= args.warmup:
-            t_steps.append(time.perf_counter() - t0)
-    v = len(t_steps) / sum(t_steps)
+    v, t_steps, kind, what, cores = cpu_clips_per_sec(args.steps, warmup=max(1, args.warmup))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(t_steps) / len(t_steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clips_per_step": 1},
-            "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
-                             "sample": f"{len(t_steps)} clips of the same workload, one per step (numpy oracle port of the reference modules)"},
+            "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": kind,
+                             "sample": f"{len(t_steps)} clips of the same workload, one per step ({what})"},
             "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE ffn_fused_kernel launch at 64 clips (ncu, profiles/r01_ffn_fused_ncu.md):
-# 747.3 MB read + 941.3 MB written; the algorithmic bytes are 742 MB + 990 MB
-FFN_FUSED_DRAM_BYTES_AT_64_CLIPS = 747.30e6 + 941.25e6
+def static_metrics():
+    """ncu-derived figures that cannot be measured inside a timed run (DRAM bytes of one launch, tensor-pipe activity): read from
+    the tracked profiles/static_metrics.json, which names the commit and the ncu command they were taken with.  Absent → null."""
+    p = os.path.join(ROOT, "profiles", "static_metrics.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 def time_dominant_kernel(B, pk):
@@ -164,10 +223,11 @@ def time_dominant_kernel(B, pk):
     flops = 4.0 * M * F * 256
     alg_bytes = M * (512 + 1024 + 512 + 1024 + 512) + 2 * F * 256 * 2     # x, residual in; bf16, fp32, bf16(x+pos) out; weights once
     ach = flops / dt / 1e12
-    traffic = None if FFN_FUSED_DRAM_BYTES_AT_64_CLIPS is None else FFN_FUSED_DRAM_BYTES_AT_64_CLIPS * (B / 64.0)
+    sm = static_metrics().get("ffn_fused_dram_bytes", {})
+    traffic = sm["bytes_per_launch_at_64_clips"] * (B / 64.0) if "bytes_per_launch_at_64_clips" in sm else None
     return {"kernel": "ffn_fused_kernel (encoder FFN block linear1+ReLU+linear2+residual+LayerNorm, M=%d, 256->2048->256)" % M,
             "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
-            "traffic": traffic, "peak_source": pk["source"] + ", burst (kernel timed alone)",
+            "traffic": traffic, "traffic_source": sm.get("source") if traffic is not None else None, "peak_source": pk["source"] + ", burst (kernel timed alone)",
             "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dt * 1e3,
             "frac_of_sustained_peak": ach / pk["bf16_tflops_sustained"],
             "hbm_gbs_at_algorithmic_bytes": alg_bytes / dt / 1e9}
@@ -233,7 +293,8 @@ def main():
     ap.add_argument("--clips", type=int, default=64, help="clips per step per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--cpu-clips", type=int, default=10, help="clips of the bounded CPU-baseline sample (≈10-15 s of host work)")
+    ap.add_argument("--quick", action="store_true", help="headline + e2e + roofline only (skip the other configs / eager-PyTorch lines)")
+    ap.add_argument("--cpu-clips", type=int, default=60, help="clips of the bounded CPU-baseline sample (≈10-15 s of host work on 16 cores)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,7 +306,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from oracle import vgqa_oracle as O      # synthetic weights/inputs generator + cpu_baseline leg only
+    from vgqa_b200 import synth as O         # seeded synthetic weights / inputs (pure numpy; nothing from oracle/ on the GPU arm)
     from vgqa_b200.engine import GroundingEngine, reference_flops
 
     if not torch.cuda.is_available():
@@ -414,6 +475,131 @@ def main():
                           "of the same ≈455 launches, latency-bound; pipelined = two calls in flight, synchronous = host waits per clip"}
         return front_end, batch1
 
+    def other_configs():
+        """The other BASELINE.json shapes, timed in-run on their own engines (pipelined device path, CUDA graph, 5 steps):
+        cfg-5 (384 px → 12x12, T = 128, L = 64) at 1 / 8 / 64 clips per step and the real yaml resolution (14x14, T = 64, L = 20)."""
+        res = {}
+        sd = O.synth_state_dict(0)
+
+        def run(eng2, Bc, Tc, Hc, Wc, Lc, steps):
+            g = torch.Generator(device="cuda").manual_seed(77 + rank)
+            v = torch.randn(Bc, Tc, 256, Hc, Wc, device="cuda", generator=g)
+            w = torch.randn(Bc, Tc, 256, Hc, Wc, device="cuda", generator=g)
+            t = torch.randn(Bc, Lc, 256, device="cuda", generator=g)
+            sz = torch.tensor([[360.0, 640.0]] * Bc, device="cuda")
+            outs2 = [eng2.alloc_outputs(Bc, Tc, Hc, Wc, Lc, want) for _ in range(2)]
+            k = [0]
+
+            def step():
+                slot = k[0] & 1
+                eng2.forward_async(v, w, t, None, ori_sizes_hw=sz, outs=outs2[slot], slot=slot)   # pos generated in the library
+                k[0] += 1
+
+            sec2 = timed(step, steps, drain=lambda: (eng2.wait(0), eng2.wait(1)))
+            fl = reference_flops(Tc, Hc, Wc, Lc)
+            cps = Bc * steps / sec2
+            return {"value": cps * world, "unit": "clips/s", "clips_per_step_per_gpu": Bc, "ms_per_step": 1e3 * sec2 / steps,
+                    "algorithmic_gflop_per_clip": fl / 1e9, "algorithmic_tflops_per_gpu": cps * fl / 1e12,
+                    "frac_of_sustained_bf16_peak": cps * fl / 1e12 / pk["bf16_tflops_sustained"]}
+
+        e5 = GroundingEngine(sd, max_clips=64, max_frames=128, max_hw=144, max_text=64, use_cuda_graph=not args.no_graph)
+        for Bc in (1, 8, 64):
+            res[f"cfg5_T128_12x12_L64_B{Bc}"] = run(e5, Bc, 128, 12, 12, 64, 30 if Bc == 1 else 5)
+        e5.close()
+        torch.cuda.empty_cache()
+        ey = GroundingEngine(sd, max_clips=16, max_frames=64, max_hw=196, max_text=20, use_cuda_graph=not args.no_graph)
+        res["yaml_T64_14x14_L20_B16"] = run(ey, 16, 64, 14, 14, 20, 5)
+        ey.close()
+        torch.cuda.empty_cache()
+        return res
+
+    def sharded_cfg4():
+        """BASELINE configs[3]: ONE 256-frame clip, frames sharded over all ranks, exchanges on the device over
+        NVLink peer memory (csrc/p2p_exchange.cu) inside the CUDA graph.  Parity against the reference golden of the same clip
+        (tests/golden/ev_cfg4_*: 40 / 20 of 256 frames chosen in pass 1 / 2) is checked in the same run."""
+        from vgqa_b200.parallel import forward_sharded_clip, shard_frames
+        gp = os.path.join(ROOT, "tests", "golden", "ev_cfg4_T256_7x7_L20_s0.npz")
+        g = np.load(gp)
+        Tc, Hc, Wc, Lc, seed = (int(g[k]) for k in ("T", "H", "W", "L", "seed"))
+        if Tc % world != 0:
+            return {"skipped": f"T={Tc} is not divisible by {world} ranks"}
+        sd = O.apply_calibration(O.synth_state_dict(seed, max_video_len=int(g["max_video_len"])), g)
+        vis, vid, pos, text = O.synth_event_inputs(seed, Tc, Hc, Wc, Lc, amp=float(g["event_amp"]))
+        s0, e0 = shard_frames(Tc, world, rank)
+        es = GroundingEngine(sd, max_clips=1, max_frames=e0 - s0, max_hw=Hc * Wc, max_text=Lc, max_video_len=int(g["max_video_len"]),
+                             use_cuda_graph=True)
+        es.enable_p2p_sharding(rank, world)
+        tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        a4 = (tt(vis[None, s0:e0]), tt(vid[None, s0:e0]), tt(text[None, :, 0]), tt(pos[:1]))
+        out = forward_sharded_clip(es, *a4, ori_size_hw=(360, 640))
+        err = max(float(np.abs(out["pred_boxes"].cpu().numpy() - g["pred_boxes"]).max()),
+                  float(np.abs(out["pred_sted"].cpu().numpy() - g["pred_sted"][0]).max()),
+                  float(np.abs(out["pred_actioness"].cpu().numpy() - g["pred_actioness"][0, :, 0]).max()))
+        r1 = np.zeros(Tc); r1[g["choose_pass1"]] = 1
+        r2 = np.zeros(Tc); r2[g["choose_pass2"]] = 1
+        sel = bool((out["choose1"].cpu().numpy() == r1).all() and (out["choose2"].cpu().numpy() == r2).all())
+        si, ei = (int(x) for x in out["sted_idx"].cpu().numpy())
+        fid = g["frame_ids"]
+        sted_ok = [int(fid[si]), int(fid[ei]) + 1] == g["post_sted"][0].tolist()
+        n = 20
+        sec4 = timed(lambda: forward_sharded_clip(es, *a4, ori_size_hw=(360, 640), check_errors=False), n)
+        perr = es.p2p_error()
+        es.close()
+        return {"ms_per_clip": 1e3 * sec4 / n, "ranks": world, "frames_per_rank": e0 - s0, "exchange": "peer memory (NVLink), CUDA graph",
+                "max_abs_err_vs_golden": err, "selections_identical": sel, "sted_argmax_identical": sted_ok, "p2p_error": perr,
+                "what": "ONE 256-frame 7x7 clip (BASELINE configs[3]) frame-sharded over all ranks; includes the gather of the per-rank "
+                        "outputs and PostProcess; compare other_configs.cfg4_T256_7x7_L20_B1.ms_per_step of the 1-GPU run"}
+
+    def cfg4_single_gpu():
+        sd = O.synth_state_dict(0, max_video_len=256)
+        e4 = GroundingEngine(sd, max_clips=1, max_frames=256, max_hw=49, max_text=20, max_video_len=256, use_cuda_graph=not args.no_graph)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        v = torch.randn(1, 256, 256, 7, 7, device="cuda", generator=g)
+        w = torch.randn(1, 256, 256, 7, 7, device="cuda", generator=g)
+        t = torch.randn(1, 20, 256, device="cuda", generator=g)
+        sz = torch.tensor([[360.0, 640.0]], device="cuda")
+        o4 = e4.alloc_outputs(1, 256, 7, 7, 20, want)
+
+        def step():
+            e4.forward(v, w, t, None, ori_sizes_hw=sz, outs=o4)
+            torch.cuda.synchronize()
+
+        n = 20
+        sec4 = timed(step, n, device_events=False)
+        e4.close()
+        return {"ms_per_step": 1e3 * sec4 / n, "clips_per_step_per_gpu": 1, "what": "ONE 256-frame 7x7 clip on one GPU, synchronous "
+                "(the unsharded reference point of sharded_cfg4)"}
+
+    def eager_pytorch():
+        """The reference's own modules (oracle/_ref) in eager PyTorch under bf16 autocast on this B200, one clip per forward as the
+        reference runs them (grounding_net.py:108-110): the only pre-existing implementation on the same box."""
+        if not reference_arm_available():
+            return {"unavailable": "oracle/_ref (byte-compiled reference modules) is not present"}
+        ref = ReferenceHotPath(0, "cuda")
+        inp = ref.inputs(0)
+        res = {}
+        for name, ac in (("bf16_autocast", True), ("fp32", False)):
+            for _ in range(3):
+                ref.run(inp, autocast=ac)
+            torch.cuda.synchronize()
+            n, t0 = 10, time.perf_counter()
+            for _ in range(n):
+                ref.run(inp, autocast=ac)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n
+            res[name] = {"value": 1.0 / dt, "unit": "clips/s", "ms_per_clip": 1e3 * dt}
+        res["what"] = ("reference PyTorch modules (ground_encoder, *_clas, ground_decoder x2, heads), eager, cuBLAS/ATen kernels, one "
+                       f"clip per forward with its host syncs; torch {torch.__version__}")
+        del ref
+        torch.cuda.empty_cache()
+        return res
+
+    def guarded(fn):
+        try:
+            return fn()
+        except Exception as ex:   # noqa: BLE001 — reported in the line, must not lose the headline
+            return {"error": f"{type(ex).__name__}: {ex}"}
+
     try:
         front_end, batch1 = secondary()
     except Exception as ex:   # noqa: BLE001 — reported in the line
@@ -422,6 +608,13 @@ def main():
         with_bb = measure_with_backbone(eng, torch, d_pos, rank=rank) if rank == 0 else None
     except Exception as ex:   # noqa: BLE001
         with_bb = {"error": f"{type(ex).__name__}: {ex}"}
+    eng.close()
+    torch.cuda.empty_cache()
+    others = guarded(other_configs) if not args.quick else None
+    if world == 1 and not args.quick:
+        others = dict(others or {}, cfg4_T256_7x7_L20_B1=guarded(cfg4_single_gpu))
+    sharded = guarded(sharded_cfg4) if world > 1 else None
+    eager_ref = guarded(eager_pytorch) if (rank == 0 and world == 1 and not args.quick) else None
     value = total_clips / sec
     e2e = total_clips / sec_e2e
     h2d = int(h_vis.numel() * 4 * 2 + h_text.numel() * 4 + h_pos.numel() * 4 + h_sizes.numel() * 4)
@@ -442,21 +635,24 @@ def main():
             "front_end": front_end,
             "batch1": batch1,
             "with_backbone": with_bb,
+            "other_configs": others,
+            "sharded_cfg4": sharded,
+            "eager_pytorch_b200": eager_ref,
             "gpu_launches": int(launches) * args.steps,
             "gpu_launches_per_step": int(launches),
             "clocks": clocks,
             "roofline": roof,
-            # second half of BASELINE.json's metric: time-weighted sm__mem_tensor_cycles_active over the 412 decoder-phase launches
-            # of one step (ncu metric pass, profiles/r01_decoder_tensor_util.md); the decoder phase is latency-bound
-            "decoder_tensor_pipe_util_pct": {"value": 4.4, "gemm_launches_only": 6.7, "source": "ncu, profiles/r01_decoder_tensor_util.md"},
+            # second half of BASELINE.json's metric: an ncu figure (it cannot be measured inside a timed run): read from the tracked
+            # profiles/static_metrics.json, which names the commit / command it was taken with; null when absent
+            "decoder_tensor_pipe_util_pct": static_metrics().get("decoder_tensor_pipe_util_pct"),
             "algorithmic_gflop_per_clip": flops_clip / 1e9,
             "algorithmic_tflops_whole_path": value / world * flops_clip / 1e12,
             "frac_of_sustained_bf16_peak_whole_path": value / world * flops_clip / 1e12 / pk["bf16_tflops_sustained"],
         }
         if world == 1:
-            v, times = oracle_clips_per_sec(args.cpu_clips)
-            line["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"{args.cpu_clips} clips of the same workload (numpy oracle port, fp32, all BLAS threads), {sum(times):.1f} s"}
+            v, times, kind, what, cores = cpu_clips_per_sec(args.cpu_clips)
+            line["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": kind,
+                                    "sample": f"{args.cpu_clips} clips of the same workload, one per forward ({what}), {sum(times):.1f} s"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -41,7 +41,8 @@ def reference_available() -> bool:
 def reference_modules_available() -> bool:
     """The reference's hot-path modules can be imported: from the source tree, or from `oracle/_ref` (byte-compiled by
     tools/make_oracle_ref.py in the build container; that is what exists on the GPU box)."""
-    return os.path.isdir(os.path.join(REF_ROOT, "vgqa", "core", "decoder"))
+    return os.path.isdir(os.path.join(REF_ROOT, "vgqa", "core", "decoder")) and \
+        (REF_ROOT != _COMPILED or os.path.isfile(os.path.join(REF_ROOT, "vgqa", "core", "decoder", "__init__.bin")))
 
 
 def _namespace_pkg(name: str, path: str):
@@ -55,6 +56,40 @@ def _namespace_pkg(name: str, path: str):
     if parent:
         setattr(sys.modules[parent], child, mod)
     return mod
+
+
+class _CompiledFinder:
+    """Meta-path finder for `oracle/_ref`: `vgqa.a.b` → oracle/_ref/vgqa/a/b.bin (or .../b/__init__.bin), a marshalled code
+    object written by tools/make_oracle_ref.py with the same Python minor version."""
+
+    def __init__(self, root):
+        self.root = root
+        info = open(os.path.join(root, "BUILD_INFO")).readline().split()
+        want = f"{sys.version_info[0]}.{sys.version_info[1]}"
+        if len(info) < 2 or info[1] != want:
+            raise RuntimeError(f"oracle/_ref was compiled for python {info[1:2]} but this is python {want}: rebuild it")
+
+    def find_spec(self, name, path=None, target=None):
+        import importlib.util
+        if not name.startswith("vgqa."):
+            return None
+        base = os.path.join(self.root, *name.split("."))
+        for file, is_pkg in ((os.path.join(base, "__init__.bin"), True), (base + ".bin", False)):
+            if os.path.isfile(file):
+                spec = importlib.util.spec_from_loader(name, self, origin=file, is_package=is_pkg)
+                if is_pkg:
+                    spec.submodule_search_locations = [base]
+                return spec
+        return None
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        import marshal
+        with open(module.__spec__.origin, "rb") as f:
+            code = marshal.loads(f.read())
+        exec(code, module.__dict__)
 
 
 def _install_shims():
@@ -82,6 +117,8 @@ def load_reference():
     if not reference_modules_available():
         raise RuntimeError(f"reference modules not found at {REF_ROOT} (run tools/make_oracle_ref.py where /root/reference is mounted)")
     _install_shims()
+    if REF_ROOT == _COMPILED and not any(isinstance(f, _CompiledFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _CompiledFinder(REF_ROOT))
     v = os.path.join(REF_ROOT, "vgqa")
     _namespace_pkg("vgqa", v)
     _namespace_pkg("vgqa.core", os.path.join(v, "core"))

@@ -3,13 +3,14 @@
     python tools/make_oracle_ref.py            # (build container only; __graft_entry__.build() runs it when the tree is mounted)
 
 The reference is Python source with no packaging, and `/root/reference` does not exist on the GPU box.  This recipe compiles the
-modules SURVEY.md §8(c) lists (`py_compile`, no source text is copied) into `oracle/_ref/vgqa/...*.pyc` — a build OUTPUT, git-
-ignored, which travels to the GPU box with the snapshot like the repo's own `.so`.  There `tests/golden/ref_loader.py` imports it
-sourcelessly, so that bench.py can time the REFERENCE'S OWN PyTorch modules (`cpu_baseline.kind = "reference"`, and the same
+modules SURVEY.md §8(c) lists (`compile()` + `marshal`, no source text is copied) into `oracle/_ref/vgqa/...*.bin` — a build
+OUTPUT, git-ignored, which travels to the GPU box with the snapshot like the repo's own `.so` (`*.pyc` files do not travel, hence
+the suffix).  There `tests/golden/ref_loader.py` imports the code objects through a small meta-path finder, so that bench.py can
+time the REFERENCE'S OWN PyTorch modules (`cpu_baseline.kind = "reference"`, and the same
 modules in eager bf16 on the B200) instead of the numpy port.  Nothing under `vgqa_b200/` ever imports it.
 """
+import marshal
 import os
-import py_compile
 import shutil
 import sys
 
@@ -35,13 +36,14 @@ def build(verbose: bool = True) -> bool:
     if os.path.isdir(OUT):
         shutil.rmtree(OUT)
     for rel in FILES:
-        dst = os.path.join(OUT, rel[:-3] + ".pyc")
+        dst = os.path.join(OUT, rel[:-3] + ".bin")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
-        # unchecked hash-based pyc: valid without the source file next to it (sourceless import)
-        py_compile.compile(os.path.join(REF, rel), cfile=dst, dfile=rel, doraise=True,
-                           invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+        with open(os.path.join(REF, rel), "rb") as f:
+            code = compile(f.read(), rel, "exec", dont_inherit=True)
+        with open(dst, "wb") as f:
+            f.write(marshal.dumps(code))
     with open(os.path.join(OUT, "BUILD_INFO"), "w") as f:
-        f.write(f"byte-compiled from {REF} by tools/make_oracle_ref.py with python {sys.version.split()[0]}\n" + "\n".join(FILES) + "\n")
+        f.write(f"python {sys.version_info[0]}.{sys.version_info[1]}\nbyte-compiled from {REF} by tools/make_oracle_ref.py\n" + "\n".join(FILES) + "\n")
     if verbose:
         print(f"make_oracle_ref: {len(FILES)} modules compiled into {OUT}")
     return True
