@@ -347,6 +347,11 @@ def main():
 
     h_outs2 = [h_outs, eng.alloc_outputs(B, T, H, W, L, want, host=True)]
     host_i = [0]
+    # the host boundary's B200-native feature format (vgqa_inputs.feat_layout = 1): channels-last bf16 [clips, T, H, W, 256] —
+    # half the PCIe bytes of the reference's fp32 NCHW maps (the path rounds its GEMM operands to bf16 anyway)
+    h_vis_cl = h_vis.permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16).pin_memory()
+    h_vid_cl = h_vid.permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16).pin_memory()
+    host_fmt = [h_vis_cl, h_vid_cl]
 
     def step_host():
         # pipelined public API: the upload of this step overlaps the compute of the previous one; the results of step
@@ -354,7 +359,7 @@ def main():
         slot = host_i[0] & 1
         eng.wait_host(slot)
         _ = float(h_outs2[slot]["pred_boxes"][0, 0, 0])   # host read of the step's result
-        eng.forward_host_async(h_vis, h_vid, h_text, h_pos, ori_sizes_hw=h_sizes, outs=h_outs2[slot], slot=slot)
+        eng.forward_host_async(host_fmt[0], host_fmt[1], h_text, h_pos, ori_sizes_hw=h_sizes, outs=h_outs2[slot], slot=slot)
         host_i[0] += 1
 
     def drain_host():
@@ -399,6 +404,8 @@ def main():
     # e2e: pinned host buffers through the C-ABI (vgqa_forward_host_async/_wait, two slots); timed by wall clock
     # around enqueue + final drain (every step's H2D, compute and D2H are inside)
     sec_e2e = timed(step_host, args.steps, device_events=False, drain=drain_host)
+    host_fmt[0], host_fmt[1] = h_vis, h_vid          # the same through the reference's fp32 NCHW layout (twice the upload)
+    sec_e2e_f32 = timed(step_host, args.steps, device_events=False, drain=drain_host)
     total_clips = B * world * args.steps
 
     def secondary():
@@ -617,7 +624,8 @@ def main():
     eager_ref = guarded(eager_pytorch) if (rank == 0 and world == 1 and not args.quick) else None
     value = total_clips / sec
     e2e = total_clips / sec_e2e
-    h2d = int(h_vis.numel() * 4 * 2 + h_text.numel() * 4 + h_pos.numel() * 4 + h_sizes.numel() * 4)
+    h2d_f32 = int(h_vis.numel() * 4 * 2 + h_text.numel() * 4 + h_pos.numel() * 4 + h_sizes.numel() * 4)
+    h2d = int(h_vis_cl.numel() * 2 * 2 + h_text.numel() * 4 + h_pos.numel() * 4 + h_sizes.numel() * 4)
     d2h = int(sum(v.numel() * v.element_size() for v in h_outs.values()))
 
     if rank == 0:
@@ -628,10 +636,16 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clips_per_step_per_gpu": B, "T": T, "H": H, "W": W, "L": L,
-                       "l2_policy": f"inputs larger than L2: {h2d / 1e6:.0f} MB of fp32 features per step",
+                       "l2_policy": f"inputs larger than L2: {h2d_f32 / 1e6:.0f} MB of fp32 features per step",
                        "cuda_graph": not args.no_graph, "parallelism": f"clips partitioned over {world} GPU(s), no data-path collective"},
             "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * sec_e2e / args.steps},
+                    "ms_per_step": 1e3 * sec_e2e / args.steps,
+                    "input_format": "pinned host buffers; projected maps as channels-last bf16 [clips,T,H,W,256] (vgqa_inputs.feat_layout = 1), "
+                                    "text / pos / sizes fp32",
+                    "h2d_gbs_per_rank": h2d / (sec_e2e / args.steps) / 1e9,
+                    "fp32_nchw_inputs": {"value": total_clips / sec_e2e_f32, "unit": "clips/s", "h2d_bytes_per_step": h2d_f32,
+                                         "ms_per_step": 1e3 * sec_e2e_f32 / args.steps,
+                                         "what": "same call with the maps in the reference's fp32 NCHW layout (twice the upload)"}},
             "front_end": front_end,
             "batch1": batch1,
             "with_backbone": with_bb,

@@ -90,6 +90,11 @@ typedef struct {
    * ([clips, T, H, W, C] bf16 behind the same pointers — what a bf16 channels_last backbone emits on B200): the map is then the
    * K-major GEMM operand itself and is read by TMA at half the bytes, with no conversion pass. */
   int raw_layout;
+  /* Layout of the PROJECTED maps vis / vid: 0 = the reference's NCHW fp32 ([clips, T, 256, H, W]); 1 = channels-last bf16
+   * ([clips, T, H, W, 256] bf16 behind the same pointers): each (frame, position) is then already a token row of the encoder —
+   * half the bytes over PCIe for the host entry points and no transposition pass.  (The path rounds its GEMM operands to bf16
+   * anyway; only the fp32 residual stream starts from the rounded values.) */
+  int feat_layout;
 } vgqa_inputs;
 
 /* Outputs (fp32 unless noted); any pointer may be NULL to skip that output.

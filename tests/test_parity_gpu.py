@@ -214,6 +214,35 @@ def test_free_running_pass2_selection_and_outputs(name):
     assert float(np.abs(o["pred_sted"][0] - g["pred_sted"][0]).max()) <= TOL
 
 
+@pytest.mark.parametrize("name", ["ev_cfg1_T32_7x7_L20_s0", "ev_cfg2_T64_7x7_L20_a_s0"])
+def test_bf16_channels_last_features(name):
+    """vgqa_inputs.feat_layout = 1: the projected maps handed over as channels-last bf16 [clips, T, H, W, 256] (device and host
+    entry points) give the reference's decisions and outputs within the same 2e-2 bar."""
+    g = np.load(golden_path(name))
+    T, H, W, L = (int(g[k]) for k in ("T", "H", "W", "L"))
+    eng = engine_for(g, name, T, H * W, L)
+    vis, vid, _, text = case_inputs(g)
+    cl = lambda a: torch.from_numpy(np.ascontiguousarray(a.transpose(0, 2, 3, 1))[None]).to(torch.bfloat16)
+    sizes = torch.tensor([[float(g["ori_size"][0]), float(g["ori_size"][1])]])
+    ttext = torch.from_numpy(np.ascontiguousarray(text[None, :, 0, :]))
+    o = eng.forward(cl(vis).cuda(), cl(vid).cuda(), ttext.cuda(), None, ori_sizes_hw=sizes.cuda())
+    torch.cuda.synchronize()
+    o = {k: v.cpu().numpy() for k, v in o.items()}
+    oh = eng.forward_host(cl(vis).pin_memory(), cl(vid).pin_memory(), ttext.pin_memory(), None, ori_sizes_hw=sizes.pin_memory())
+    oh = {k: v.numpy() for k, v in oh.items()}
+    for out in (o, oh):
+        np.testing.assert_array_equal(out["choose1"][0], _ref_sel(g, "choose_pass1"))
+        np.testing.assert_array_equal(out["choose2"][0], _ref_sel(g, "choose_pass2"))
+        worst = continuous_errors(g, out)
+        bad = {k: v for k, v in worst.items() if not v <= (TOL_INTERNAL if k == "frames_cls" else TOL)}
+        assert not bad, f"{name} (bf16 channels-last features): {bad} (all: {worst})"
+        s_, e_ = (int(x) for x in out["sted_idx"][0])
+        fid = g["frame_ids"]
+        assert [int(fid[s_]), int(fid[e_]) + 1] == g["post_sted"][0].tolist()
+    for k in ("pred_boxes", "pred_sted", "logits_f_m"):
+        np.testing.assert_allclose(oh[k], o[k], atol=1e-6, err_msg=k)     # host and device entry points run the same kernels
+
+
 def test_batch_of_clips_matches_single():
     g, o1 = run_case("cfg1_T32_7x7_L20_s1", force=False, clips=1)
     _, o2 = run_case("cfg1_T32_7x7_L20_s1", force=False, clips=2)

@@ -42,6 +42,9 @@ void text_attn(const bf16* QKV, const uint8_t* pad, bf16* ctx, int Q, int L, int
 // NCHW fp32 features → token-major bf16 rows: X[(f*S + tok0 + p), c] = in[f, c, p]   (in may be broadcast: fstride 0)
 void nchw_to_tokens(const float* in, long long in_fstride, bf16* X, float* X32, const float* pos, long long pos_fstride,
                     bf16* XP, int F, int S, int tok0, int P, cudaStream_t st);
+// channels-last bf16 features [F, P, 256] → token rows: X[(f*S + tok0 + p), :] = in[f, p, :] (+ fp32 copy, + bf16(x + pos row))
+void rows_to_tokens(const bf16* in, const bf16* pos_tokens, int pos_frames, bf16* X, float* X32, bf16* XP, int F, int S, int tok0,
+                    int P, cudaStream_t st);
 // PositionEmbeddingSine(128, normalize=True) of `frames` (H, W) masks (uint8, 1 = padded; nullptr = nothing padded) → [frames,256,H,W]
 void pos_sine(const uint8_t* mask, float* out, int frames, int H, int W, cudaStream_t st);
 // X[(f*S + tok0 + l), :] = text[(f / T), l, :]   (text == nullptr → zeros)

@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "../../include/vgqa_b200.h"
+#include "chain.h"
 #include "kernels.h"
 
 namespace vg {
@@ -102,8 +103,9 @@ struct EncLayer { Lin qkv, out, ff1, ff2; LNp ln1, ln2; };
 struct TsLayer { Lin q, o, inter, outp; LNp ln_a, ln_o; int kv_off; };
 struct SaLayer { Lin qabs, vo, inter, outp; LNp ln_a, ln_o; };
 struct Head { Lin t; LNp ln; float* dw = nullptr; float* db = nullptr; int vocab = 0; };
-struct TimeLayer { Lin qkv, out, qabs, vo, ff1, ff2; LNp ln1, ln3, ln4; float* tab = nullptr; };
-struct PosLayer { Lin sa, sa_out, q, sine, qabs, vo, ff1, ff2; LNp ln1, ln3, ln4; float* tab_sa = nullptr; };
+// *_t: the same weights as 16 KB tiles of the UMMA operand layout, streamed by the fused chain kernels (chain.cu)
+struct TimeLayer { Lin qkv, out, qabs, vo, ff1, ff2; LNp ln1, ln3, ln4; float* tab = nullptr; bf16 *qkv_t = nullptr, *vo_t = nullptr, *ff1_t = nullptr, *ff2_t = nullptr; };
+struct PosLayer { Lin sa, sa_out, q, sine, qabs, vo, ff1, ff2; LNp ln1, ln3, ln4; float* tab_sa = nullptr; bf16 *vo_t = nullptr, *ff1_t = nullptr, *ff2_t = nullptr; };
 struct Mlp2 { Lin l0; float* w1 = nullptr; float* b1 = nullptr; int n1 = 0; };
 struct TextLayer { Lin qkv, out, ff1, ff2; LNp ln1, ln2; };   // one RobertaLayer (q;k;v packed into one [3*Hd, Hd] Linear)
 
@@ -136,7 +138,13 @@ struct vgqa_ctx {
   LNp time_norm;
   Lin kpos_all;  // [dec_layers*256, 256]
   Lin rph0, rph1, qs0, qs1, bb0, bb1;
+  bf16 *bb0_t = nullptr, *bb1_t = nullptr;
   float *bb2w = nullptr, *bb2b = nullptr;
+  // VGQA_CHAIN=1 runs the frame-local tail of every decoder layer as ONE fused row-tile GEMM chain (chain.cu) instead of one
+  // launch per Linear.  Measured (profiles/r02_chain.md): 455 → 301 launches per step, parity-identical, but a chain streams
+  // 3.4 MB of weights through ONE SM per 128-row tile (≈52 GB/s with 80 KB in flight) where the per-Linear launches spread the
+  // same weights over the whole GPU — 2.72 vs 1.92 ms per clip at batch 1, 13.96 vs 13.75 ms per 64-clip step.  Off by default.
+  bool use_chain = [] { const char* e = getenv("VGQA_CHAIN"); return e != nullptr && e[0] == '1'; }();
   Mlp2 temp_embed, action_embed;
   float *pfc_ln0w, *pfc_ln0b, *pfc_W, *pfc_b, *pfc_ln4w, *pfc_ln4b;
   // optional front end: input_proj / input_proj2 (1x1 convs) and the text resizer; K == 0 → not loaded
@@ -249,6 +257,15 @@ struct Packer {
     VG_CUDA(cudaMemcpy(d, h.data(), n * sizeof(bf16), cudaMemcpyHostToDevice));
     return d;
   }
+  // the matrix as [N/128][K/64] tiles of 128 x 64 bf16 in the swizzled K-major operand layout (chain.cu)
+  bf16* tiled(const float* W, int N, int K) {
+    std::vector<bf16> h;
+    chain_tile_weights(W, N, K, h);
+    bf16* d = c->warena.get<bf16>(h.size());
+    VG_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+    return d;
+  }
+  bf16* tiled(const std::string& p, int N, int K) { return tiled(get(p + ".weight", {N, K}).v.data(), N, K); }
   Lin lin(const float* W, const float* b, int N, int K) {
     Lin l; l.N = N; l.K = K; l.W = b16(W, (size_t)N * K); l.b = b ? f32(b, N) : nullptr; return l;
   }
@@ -307,7 +324,7 @@ static void pack_weights(vgqa_ctx* c) {
   size_t tower_bytes = 0;   // the optional text tower brings ≈330 MB of its own (fp32 embeddings + bf16 layers)
   for (const auto& kv : c->sd)
     if (kv.first.rfind("text_encoder.body.", 0) == 0) tower_bytes += (size_t)kv.second.numel() * 4 + 512;
-  c->warena.init(((size_t)320 << 20) + tower_bytes);
+  c->warena.init(((size_t)448 << 20) + tower_bytes);
   // ---------------- encoder (modal_encoder.py:143-178)
   c->enc.resize(cfg.enc_layers);
   for (int l = 0; l < cfg.enc_layers; ++l) {
@@ -393,6 +410,7 @@ static void pack_weights(vgqa_ctx* c) {
       const HostT& w = P.get(p + "self_attn.in_proj_weight", {768, 256});
       const HostT& b = P.get(p + "self_attn.in_proj_bias", {768});
       t.qkv = P.lin(w.v.data(), nullptr, 768, 256);
+      t.qkv_t = P.tiled(w.v.data(), 768, 256);
       // table[t] = [Wq;Wk] te_t + b  (v rows: bias only)   — folds `tgt + query_time` (:466)
       std::vector<float> tab((size_t)Tm * 768);
       parallel_for(Tm, [&](int ti) {
@@ -414,9 +432,12 @@ static void pack_weights(vgqa_ctx* c) {
                 P.get(p + "cross_attn_image.out_proj.bias", {256}).v.data(), cw.v.data() + (size_t)512 * 256,
                 cb.v.data() + 512, Wv, bv);
       t.vo = P.lin(Wv.data(), bv.data(), 256, 2048);
+      t.vo_t = P.tiled(Wv.data(), 256, 2048);
       t.ln3 = P.ln(p + "norm3");
       t.ff1 = P.lin(p + "linear1", F, 256);
       t.ff2 = P.lin(p + "linear2", 256, F);
+      t.ff1_t = P.tiled(p + "linear1", F, 256);
+      t.ff2_t = P.tiled(p + "linear2", 256, F);
       t.ln4 = P.ln(p + "norm4");
     }
     {  // ---- PosDecoderLayer (:208-375)
@@ -487,9 +508,12 @@ static void pack_weights(vgqa_ctx* c) {
       absorb_vo(P.get(p + "cross_attn.out_proj.weight", {256, 256}).v.data(),
                 P.get(p + "cross_attn.out_proj.bias", {256}).v.data(), W("ca_v_proj"), Bv("ca_v_proj"), Wv, bv);
       q.vo = P.lin(Wv.data(), bv.data(), 256, 2048);
+      q.vo_t = P.tiled(Wv.data(), 256, 2048);
       q.ln3 = P.ln(p + "norm3");
       q.ff1 = P.lin(p + "linear1", F, 256);
       q.ff2 = P.lin(p + "linear2", 256, F);
+      q.ff1_t = P.tiled(p + "linear1", F, 256);
+      q.ff2_t = P.tiled(p + "linear2", 256, F);
       q.ln4 = P.ln(p + "norm4");
       std::copy(W("ca_kpos_proj"), W("ca_kpos_proj") + 65536, kposW.begin() + (size_t)l * 65536);
       std::copy(Bv("ca_kpos_proj"), Bv("ca_kpos_proj") + 256, kposB.begin() + (size_t)l * 256);
@@ -503,6 +527,8 @@ static void pack_weights(vgqa_ctx* c) {
   c->qs1 = P.lin(g + "decoder.query_scale.layers.1", 256, 256);
   c->bb0 = P.lin("bbox_embed.layers.0", 256, 256);
   c->bb1 = P.lin("bbox_embed.layers.1", 256, 256);
+  c->bb0_t = P.tiled("bbox_embed.layers.0", 256, 256);
+  c->bb1_t = P.tiled("bbox_embed.layers.1", 256, 256);
   c->bb2w = P.f32(P.get("bbox_embed.layers.2.weight", {4, 256}).v);
   c->bb2b = P.f32(P.get("bbox_embed.layers.2.bias", {4}).v);
   c->temp_embed.l0 = P.lin("temp_embed.layers.0", 256, 256);
@@ -790,6 +816,8 @@ static void ingest_encoder_inputs(Fwd& f, const vgqa_inputs& in, bool have_mask)
                     c->XP, F, S, 0, P, st);
   else if (in.vis_raw != nullptr)
     input_proj(in.vis_raw, c->ip_vis.K, c->ip_vis.W, c->ip_vis.b, c->pos_enc, pf, c->X, c->X32, c->XP, F, S, 0, P, st);
+  else if (in.feat_layout == 1)
+    rows_to_tokens(reinterpret_cast<const bf16*>(in.vis), c->pos_enc, pf, c->X, c->X32, c->XP, F, S, 0, P, st);
   else
     nchw_to_tokens(in.vis, (long long)256 * P, c->X, c->X32, pos, pos_fs, c->XP, F, S, 0, P, st);
   if (in.vid_raw != nullptr && in.raw_layout == 1)
@@ -797,6 +825,8 @@ static void ingest_encoder_inputs(Fwd& f, const vgqa_inputs& in, bool have_mask)
                     c->XP, F, S, P + L, P, st);
   else if (in.vid_raw != nullptr)
     input_proj(in.vid_raw, c->ip_vid.K, c->ip_vid.W, c->ip_vid.b, c->pos_enc, pf, c->X, c->X32, c->XP, F, S, P + L, P, st);
+  else if (in.feat_layout == 1)
+    rows_to_tokens(reinterpret_cast<const bf16*>(in.vid), c->pos_enc, pf, c->X, c->X32, c->XP, F, S, P + L, P, st);
   else
     nchw_to_tokens(in.vid, (long long)256 * P, c->X, c->X32, pos, pos_fs, c->XP, F, S, P + L, P, st);
   f.count(2);
@@ -944,6 +974,9 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames, bool second_pas
   const int F = f.F, P = f.P, L = f.L, S = f.S, T = f.T, M = P + L;
   const int D = (int)c->tl.size();
   const long long pos_fs = pos_frames > 1 ? (long long)S * 256 : 0;
+  // fused row-tile GEMM chains (chain.cu) for the frame-local tails of the decoder layers; a frame-sharded clip keeps the
+  // one-launch-per-Linear form (its in-projection table is offset by the rank's first frame)
+  const bool chain = c->use_chain && !f.sharded();
   // anchors from frames_cls (query_decoder.py:92-94)
   if (!second_pass) {
     pos_fc_boxes(c->frames_cls, c->pfc_ln0w, c->pfc_ln0b, c->pfc_W, c->pfc_b, c->pfc_ln4w, c->pfc_ln4b, c->boxes0, F, st);
@@ -960,8 +993,10 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames, bool second_pas
   // ---------------- TimeDecoder (query_decoder.py:379-486), memory = [text | vid] tokens
   for (int l = 0; l < D; ++l) {
     TimeLayer& t = c->tl[l];
-    { GemmEpi ep; ep.C = c->t_qkv; ep.ldc = 768; ep.bias = t.tab + (size_t)c->sh_rank * T * 768; ep.bias_period = T; ep.bias_ld = 768;
-      f.gemm(c->t_tgt, 256, t.qkv, F, ep); }
+    if (!(chain && l > 0)) {   // (the fused tail of layer l-1 already produced this layer's in-projection)
+      GemmEpi ep; ep.C = c->t_qkv; ep.ldc = 768; ep.bias = t.tab + (size_t)c->sh_rank * T * 768; ep.bias_period = T; ep.bias_ld = 768;
+      f.gemm(c->t_tgt, 256, t.qkv, F, ep);
+    }
     {  // temporal self-attention across ALL frames of the clip: a sharded clip all-gathers the K|V rows (§8e)
       const bf16* kv = c->t_qkv;
       if (f.sharded()) { f.all_gather_bf16(c->t_qkv, c->t_qkv_all, (size_t)T * 768); kv = c->t_qkv_all; }
@@ -980,11 +1015,35 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames, bool second_pas
       xattn1(c->t_qabs, c->Xf + (size_t)P * 256, S, F, M, c->pos_enc + (size_t)P * 256, pos_fs, nullptr, nullptr, 0, 0,
              have_mask ? c->encmask : nullptr, S, 0.17677669529663687f, c->t_ctx8, nullptr, st);
     }
-    f.linear_res_ln(c->t_ctx8, 2048, t.vo, F, c->t_x32, t.ln3, 1e-5f, c->t_x2, 256, c->t_x2_32);
-    f.linear(c->t_x2, 256, t.ff1, F, c->t_hid, t.ff1.N, ACT_RELU);
-    f.linear_res_ln(c->t_hid, t.ff2.K, t.ff2, F, c->t_x2_32, t.ln4, 1e-5f, c->t_tgt, 256, c->t_tgt32);
-    ln_rows(c->t_tgt32, 256, c->time_norm.w, c->time_norm.b, 1e-5f, c->t_inter + (size_t)l * F * 256, 256, F, st);  // :412
-    f.count(3);
+    if (chain) {
+      // ONE launch (chain.cu): [vo + LN3] → [linear1 + ReLU → linear2 + LN4] → time_decoder.norm → next layer's in-projection
+      ChainParams cp;
+      cp.M = F; cp.T = T;
+      chain_set_tmap(cp, 0, c->t_ctx8, F, 2048, 2048);
+      ChOp& o0 = cp.ops[0];
+      o0.a_kind = CH_A_STREAM; o0.a_tm = 0; o0.w = t.vo_t; o0.nkb = 32; o0.nblk = 2; o0.cn = 2; o0.acc0 = 0; o0.bias = t.vo.b;
+      o0.res32 = c->t_x32; o0.ln_w = t.ln3.w; o0.ln_b = t.ln3.b; o0.out32 = c->t_x2_32; o0.out_act = 0;
+      ChOp& o1 = cp.ops[1];
+      o1.kind = CH_FFN; o1.a_blk = 0; o1.a_wait = CH_WAIT_EPI; o1.w = t.ff1_t; o1.bias = t.ff1.b; o1.w2 = t.ff2_t; o1.bias2 = t.ff2.b;
+      o1.ff_chunks = t.ff1.N / 128; o1.res32 = c->t_x2_32; o1.ln_w = t.ln4.w; o1.ln_b = t.ln4.b; o1.out32 = c->t_tgt32; o1.out_act = 0;
+      o1.ln2_w = c->time_norm.w; o1.ln2_b = c->time_norm.b; o1.out2 = c->t_inter + (size_t)l * F * 256; o1.ld_out2 = 256;   // :412
+      cp.n_ops = 2;
+      if (l + 1 < D) {
+        TimeLayer& tn = c->tl[l + 1];
+        ChOp& o2 = cp.ops[2];
+        o2.a_blk = 0; o2.a_wait = CH_WAIT_EPI; o2.w = tn.qkv_t; o2.nkb = 4; o2.nblk = 6; o2.cn = 2; o2.acc0 = 1;
+        o2.table = tn.tab; o2.table_ld = 768; o2.out_bf16 = c->t_qkv; o2.ld_out = 768;
+        cp.n_ops = 3;
+      }
+      chain_launch(cp, st);
+      f.count();
+    } else {
+      f.linear_res_ln(c->t_ctx8, 2048, t.vo, F, c->t_x32, t.ln3, 1e-5f, c->t_x2, 256, c->t_x2_32);
+      f.linear(c->t_x2, 256, t.ff1, F, c->t_hid, t.ff1.N, ACT_RELU);
+      f.linear_res_ln(c->t_hid, t.ff2.K, t.ff2, F, c->t_x2_32, t.ln4, 1e-5f, c->t_tgt, 256, c->t_tgt32);
+      ln_rows(c->t_tgt32, 256, c->time_norm.w, c->time_norm.b, 1e-5f, c->t_inter + (size_t)l * F * 256, 256, F, st);  // :412
+      f.count(3);
+    }
   }
   // ---------------- PosDecoder (query_decoder.py:129-375), memory = [vis | text] tokens — second branch
   f.st = f.aux;
@@ -1046,15 +1105,38 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames, bool second_pas
              nullptr, 0, 0.125f, c->p_ctx8, nullptr, st);
     }
     f.count();
-    f.linear_res_ln(c->p_ctx8, 2048, q.vo, F, c->p_x32, q.ln3, 1e-5f, c->p_x2, 256, c->p_x2_32);
-    f.linear(c->p_x2, 256, q.ff1, F, c->p_hid, q.ff1.N, ACT_RELU);
-    f.linear_res_ln(c->p_hid, q.ff2.K, q.ff2, F, c->p_x2_32, q.ln4, 1e-5f, c->p_cat, 768, c->p_tgt32);
-    f.linear(c->p_cat, 768, c->bb0, F, c->p_b1, 256, ACT_RELU);                 // bbox_embed (:188-192)
-    f.linear(c->p_b1, 256, c->bb1, F, c->p_b2, 256, ACT_RELU);
     float* anc = c->anchors + (size_t)l * F * 4;
-    rowvec_head(c->p_b2, 256, c->bb2w, c->bb2b, anc, 4, F, 4, 1, st);
+    if (chain) {
+      // ONE launch (chain.cu): [vo + LN3] → [linear1 + ReLU → linear2 + LN4] → bbox_embed (256 → 256 → 256 → 4) → sigmoid
+      ChainParams cp;
+      cp.M = F; cp.T = T;
+      chain_set_tmap(cp, 0, c->p_ctx8, F, 2048, 2048);
+      ChOp& o0 = cp.ops[0];
+      o0.a_kind = CH_A_STREAM; o0.a_tm = 0; o0.w = q.vo_t; o0.nkb = 32; o0.nblk = 2; o0.cn = 2; o0.acc0 = 0; o0.bias = q.vo.b;
+      o0.res32 = c->p_x32; o0.ln_w = q.ln3.w; o0.ln_b = q.ln3.b; o0.out32 = c->p_x2_32; o0.out_act = 0;
+      ChOp& o1 = cp.ops[1];
+      o1.kind = CH_FFN; o1.a_blk = 0; o1.a_wait = CH_WAIT_EPI; o1.w = q.ff1_t; o1.bias = q.ff1.b; o1.w2 = q.ff2_t; o1.bias2 = q.ff2.b;
+      o1.ff_chunks = q.ff1.N / 128; o1.res32 = c->p_x2_32; o1.ln_w = q.ln4.w; o1.ln_b = q.ln4.b; o1.out32 = c->p_tgt32; o1.out_act = 0;
+      o1.out_bf16 = c->p_cat; o1.ld_out = 768;
+      ChOp& o2 = cp.ops[2];                                                     // bbox_embed (:188-192)
+      o2.a_blk = 0; o2.a_wait = CH_WAIT_EPI; o2.w = c->bb0_t; o2.nkb = 4; o2.nblk = 2; o2.cn = 2; o2.acc0 = 1; o2.bias = c->bb0.b;
+      o2.act = ACT_RELU; o2.out_act = 4;
+      ChOp& o3 = cp.ops[3];
+      o3.a_blk = 4; o3.a_wait = CH_WAIT_EPI; o3.w = c->bb1_t; o3.nkb = 4; o3.nblk = 2; o3.cn = 2; o3.acc0 = 0; o3.bias = c->bb1.b;
+      o3.act = ACT_RELU; o3.head_w = c->bb2w; o3.head_b = c->bb2b; o3.head_n = 4; o3.head_act = 1; o3.head_out = anc;
+      cp.n_ops = 4;
+      chain_launch(cp, st);
+      f.count();
+    } else {
+      f.linear_res_ln(c->p_ctx8, 2048, q.vo, F, c->p_x32, q.ln3, 1e-5f, c->p_x2, 256, c->p_x2_32);
+      f.linear(c->p_x2, 256, q.ff1, F, c->p_hid, q.ff1.N, ACT_RELU);
+      f.linear_res_ln(c->p_hid, q.ff2.K, q.ff2, F, c->p_x2_32, q.ln4, 1e-5f, c->p_cat, 768, c->p_tgt32);
+      f.linear(c->p_cat, 768, c->bb0, F, c->p_b1, 256, ACT_RELU);                 // bbox_embed (:188-192)
+      f.linear(c->p_b1, 256, c->bb1, F, c->p_b2, 256, ACT_RELU);
+      rowvec_head(c->p_b2, 256, c->bb2w, c->bb2b, anc, 4, F, 4, 1, st);
+      f.count(3);
+    }
     boxes = anc;
-    f.count(3);
   }
   f.join();
 }
@@ -1078,6 +1160,7 @@ static void check_inputs(vgqa_ctx* c, const vgqa_inputs& in) {
            "text_ids needs the 'text_encoder.body' (RoBERTa) and 'text_encoder.resizer' weights");
   VG_CHECK(!in.text_ids || in.L <= 64, "text_ids: a query has at most 64 tokens");
   VG_CHECK(in.raw_layout == 0 || in.raw_layout == 1, "raw_layout must be 0 (NCHW fp32) or 1 (channels-last bf16)");
+  VG_CHECK(in.feat_layout == 0 || in.feat_layout == 1, "feat_layout must be 0 (NCHW fp32) or 1 (channels-last bf16)");
   VG_CHECK(!in.vis_raw || (c->ip_vis.K > 0 && in.vis_raw_ch == c->ip_vis.K),
            "vis_raw needs the 'input_proj' weights and vis_raw_ch equal to their input channels");
   VG_CHECK(!in.vid_raw || (c->ip_vid.K > 0 && in.vid_raw_ch == c->ip_vid.K),
@@ -1451,9 +1534,9 @@ int vgqa_forward_host_async(vgqa_ctx* c, const vgqa_inputs* hin, const vgqa_outp
     vgqa_inputs din = *hin;
     const size_t raw_es = hin->raw_layout == 1 ? 2 : 4;   // channels-last bf16 or NCHW fp32 maps
     if (hin->vis_raw) { h2d(h.vis_raw, hin->vis_raw, F * c->ip_vis.K * P * raw_es); din.vis_raw = h.vis_raw; din.vis = nullptr; }
-    else { h2d(h.vis, hin->vis, F * 256 * P * 4); din.vis = h.vis; }
+    else { h2d(h.vis, hin->vis, F * 256 * P * (hin->feat_layout == 1 ? 2 : 4)); din.vis = h.vis; }
     if (hin->vid_raw) { h2d(h.vid_raw, hin->vid_raw, F * c->ip_vid.K * P * raw_es); din.vid_raw = h.vid_raw; din.vid = nullptr; }
-    else { h2d(h.vid, hin->vid, F * 256 * P * 4); din.vid = h.vid; }
+    else { h2d(h.vid, hin->vid, F * 256 * P * (hin->feat_layout == 1 ? 2 : 4)); din.vid = h.vid; }
     if (hin->text_ids) { h2d(h.ids, hin->text_ids, B * L * 4); din.text_ids = h.ids; din.text = nullptr; din.text_raw = nullptr; }
     else if (hin->text_raw) { h2d(h.text_raw, hin->text_raw, B * L * c->ip_text.K * 4); din.text_raw = h.text_raw; din.text = nullptr; }
     else { h2d(h.text, hin->text, B * L * 256 * 4); din.text = h.text; }

@@ -1,6 +1,8 @@
 // Bandwidth-bound kernels of the grounding hot path: layout conversion, LayerNorm + pooled means, tiny heads,
 // on-device frame selection (no host sync), query seeding, box sine embedding and PostProcess.
 // Coalesced 16-byte accesses, warp-shuffle reductions, fp32 statistics.
+#include <algorithm>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -71,6 +73,41 @@ __global__ void __launch_bounds__(256) pos_sine_kernel(const uint8_t* __restrict
 }
 void pos_sine(const uint8_t* mask, float* out, int frames, int H, int W, cudaStream_t st) {
   pos_sine_kernel<<<frames, 256, (size_t)2 * H * W * sizeof(float), st>>>(mask, out, H, W);
+  VG_CUDA(cudaGetLastError());
+}
+
+// channels-last bf16 features (vgqa_inputs.feat_layout = 1): a (frame, position) IS a token row — copy, widen and add pos
+__global__ void __launch_bounds__(256) rows_to_tokens_kernel(const bf16* __restrict__ in, const bf16* __restrict__ pos_tokens,
+                                                             int pos_frames, bf16* __restrict__ X, float* __restrict__ X32,
+                                                             bf16* __restrict__ XP, int S, int tok0, int P, long long n_chunks) {
+  // one thread per 8 channels (16 bytes in, 16 + 32 + 16 bytes out)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i >> 5;            // f * P + p
+    const int c = (int)(i & 31) * 8;
+    const long long f = row / P;
+    const int p = (int)(row - f * P);
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + row * 256 + c));
+    const size_t o = ((size_t)f * S + tok0 + p) * 256 + c;
+    *reinterpret_cast<uint4*>(X + o) = q;
+    const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), cc = unpack_bf16(q.z), d = unpack_bf16(q.w);
+    if (X32 != nullptr) {
+      *reinterpret_cast<float4*>(X32 + o) = make_float4(a.x, a.y, b.x, b.y);
+      *reinterpret_cast<float4*>(X32 + o + 4) = make_float4(cc.x, cc.y, d.x, d.y);
+    }
+    if (XP != nullptr) {
+      const size_t po = ((size_t)(pos_frames > 1 ? f : 0) * S + tok0 + p) * 256 + c;
+      const uint4 pq = __ldg(reinterpret_cast<const uint4*>(pos_tokens + po));
+      const float2 pa = unpack_bf16(pq.x), pb = unpack_bf16(pq.y), pc = unpack_bf16(pq.z), pd = unpack_bf16(pq.w);
+      *reinterpret_cast<uint4*>(XP + o) = make_uint4(pack_bf16(a.x + pa.x, a.y + pa.y), pack_bf16(b.x + pb.x, b.y + pb.y),
+                                                     pack_bf16(cc.x + pc.x, cc.y + pc.y), pack_bf16(d.x + pd.x, d.y + pd.y));
+    }
+  }
+}
+void rows_to_tokens(const bf16* in, const bf16* pos_tokens, int pos_frames, bf16* X, float* X32, bf16* XP, int F, int S, int tok0,
+                    int P, cudaStream_t st) {
+  const long long n = (long long)F * P * 32;
+  const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+  rows_to_tokens_kernel<<<grid, 256, 0, st>>>(in, pos_tokens, pos_frames, X, X32, XP, S, tok0, P, n);
   VG_CUDA(cudaGetLastError());
 }
 

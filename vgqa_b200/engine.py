@@ -29,7 +29,7 @@ class VgqaInputs(ctypes.Structure):
                 ("stop_after_encoder", c_int),
                 ("vis_raw", c_void_p), ("vid_raw", c_void_p), ("text_raw", c_void_p),
                 ("vis_raw_ch", c_int), ("vid_raw_ch", c_int), ("text_raw_ch", c_int), ("text_ids", c_void_p),
-                ("raw_layout", c_int)]
+                ("raw_layout", c_int), ("feat_layout", c_int)]
 
 
 OUTPUT_FIELDS = ("pred_boxes", "pred_sted", "pred_actioness", "logits_f_m", "logits_f_a", "logits_r_a", "logits_r_m",
@@ -191,7 +191,7 @@ class GroundingEngine:
     @staticmethod
     def _dims(vis, raw):
         """(clips, T, H, W) of a feature tensor: [clips,T,C,H,W] fp32, or channels-last bf16 [clips,T,H,W,C] (raw only)."""
-        if raw and vis.dtype == torch.bfloat16:
+        if vis.dtype == torch.bfloat16:
             return vis.shape[0], vis.shape[1], vis.shape[2], vis.shape[3]
         return vis.shape[0], vis.shape[1], vis.shape[3], vis.shape[4]
 
@@ -204,14 +204,18 @@ class GroundingEngine:
         """raw=True: vis / vid / text are the extractor outputs ([clips,T,Cv,H,W], [clips,T,Cd,H,W], [clips,L,Ct]) and the
         library applies input_proj / input_proj2 / text_encoder.resizer itself (their weights must be in the state_dict)."""
         nhwc = bool(raw and vis.dtype == torch.bfloat16)   # channels-last bf16 maps [clips, T, H, W, C] (raw_layout = 1)
-        if nhwc:
+        rows = bool(not raw and vis.dtype == torch.bfloat16)   # projected maps as channels-last bf16 [clips, T, H, W, 256] (feat_layout = 1)
+        if nhwc or rows:
             B, T, H, W, d = vis.shape
         else:
             B, T, d, H, W = vis.shape
         if text_ids is not None:   # RoBERTa token ids [clips, L] int32: the library runs the text tower + resizer (raw=True only)
             assert raw and text_ids.dtype == torch.int32 and text_ids.dim() == 2 and text_ids.shape[0] == B and text_ids.is_contiguous()
             text = torch.empty(B, text_ids.shape[1], 0, dtype=torch.float32, device=text_ids.device)   # placeholder (shape only)
-        if nhwc:
+        if rows:
+            assert d == 256 and vid.dtype == torch.bfloat16 and tuple(vid.shape) == (B, T, H, W, 256), "vis / vid must both be bf16 [clips, T, H, W, 256]"
+            assert tuple(text.shape) == (B, text.shape[1], 256), "text must be [clips, L, 256]"
+        elif nhwc:
             assert vid.dtype == torch.bfloat16 and tuple(vid.shape[:4]) == (B, T, H, W), "vid_raw must be bf16 [clips, T, H, W, C] too"
         elif raw:
             assert tuple(vid.shape[:2]) == (B, T) and tuple(vid.shape[3:]) == (H, W), "vid_raw must be [clips, T, C, H, W]"
@@ -224,7 +228,7 @@ class GroundingEngine:
         assert pos is None or (pos.shape[0] in (1, B * T) and tuple(pos.shape[1:]) == (256, H, W)), \
             "pos must be [1 or clips*T, 256, H, W] (or None)"
         for t in (vis, vid, text) + (() if pos is None else (pos,)):
-            assert (t.dtype == torch.float32 or (nhwc and (t is vis or t is vid))) and t.is_contiguous()
+            assert (t.dtype == torch.float32 or ((nhwc or rows) and (t is vis or t is vid))) and t.is_contiguous()
         n = None
         inp = VgqaInputs(B, T, H, W, Lt, n if raw else self._p(vis), n if raw else self._p(vid), n if raw else self._p(text),
                          self._p(pos), 0 if pos is None else pos.shape[0],
@@ -233,7 +237,7 @@ class GroundingEngine:
                          self._p(vis) if raw else n, self._p(vid) if raw else n,
                          self._p(text) if (raw and text_ids is None) else n,
                          (vis.shape[4] if nhwc else vis.shape[2]) if raw else 0, (vid.shape[4] if nhwc else vid.shape[2]) if raw else 0,
-                         text.shape[2] if raw else 0, self._p(text_ids), 1 if nhwc else 0)
+                         text.shape[2] if raw else 0, self._p(text_ids), 1 if nhwc else 0, 1 if rows else 0)
         out = VgqaOutputs(**{k: self._p(outs.get(k)) for k in OUTPUT_FIELDS})
         return inp, out
 
