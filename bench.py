@@ -520,12 +520,12 @@ def main():
         torch.cuda.empty_cache()
         return res
 
-    def sharded_cfg4():
+    def sharded_clip(gname):
         """BASELINE configs[3]: ONE 256-frame clip, frames sharded over all ranks, exchanges on the device over
         NVLink peer memory (csrc/p2p_exchange.cu) inside the CUDA graph.  Parity against the reference golden of the same clip
-        (tests/golden/ev_cfg4_*: 40 / 20 of 256 frames chosen in pass 1 / 2) is checked in the same run."""
+        (tests/golden/ev_cfg4_* at 7x7, ev_long_* at 12x12: partial frame selections in both passes) is checked in the same run."""
         from vgqa_b200.parallel import forward_sharded_clip, shard_frames
-        gp = os.path.join(ROOT, "tests", "golden", "ev_cfg4_T256_7x7_L20_s0.npz")
+        gp = os.path.join(ROOT, "tests", "golden", gname + ".npz")
         g = np.load(gp)
         Tc, Hc, Wc, Lc, seed = (int(g[k]) for k in ("T", "H", "W", "L", "seed"))
         if Tc % world != 0:
@@ -554,18 +554,20 @@ def main():
         es.close()
         return {"ms_per_clip": 1e3 * sec4 / n, "ranks": world, "frames_per_rank": e0 - s0, "exchange": "peer memory (NVLink), CUDA graph",
                 "max_abs_err_vs_golden": err, "selections_identical": sel, "sted_argmax_identical": sted_ok, "p2p_error": perr,
-                "what": "ONE 256-frame 7x7 clip (BASELINE configs[3]) frame-sharded over all ranks; includes the gather of the per-rank "
-                        "outputs and PostProcess; compare other_configs.cfg4_T256_7x7_L20_B1.ms_per_step of the 1-GPU run"}
+                "fixture": gname,
+                "what": f"ONE {Tc}-frame {Hc}x{Wc} clip (BASELINE configs[3]) frame-sharded over all ranks; includes the gather of the "
+                        f"per-rank outputs and PostProcess; the unsharded reference point is other_configs.long_T{Tc}_{Hc}x{Wc}_L{Lc}_B1 "
+                        "of the 1-GPU run"}
 
-    def cfg4_single_gpu():
+    def long_clip_single_gpu(Hc):
         sd = O.synth_state_dict(0, max_video_len=256)
-        e4 = GroundingEngine(sd, max_clips=1, max_frames=256, max_hw=49, max_text=20, max_video_len=256, use_cuda_graph=not args.no_graph)
+        e4 = GroundingEngine(sd, max_clips=1, max_frames=256, max_hw=Hc * Hc, max_text=20, max_video_len=256, use_cuda_graph=not args.no_graph)
         g = torch.Generator(device="cuda").manual_seed(5)
-        v = torch.randn(1, 256, 256, 7, 7, device="cuda", generator=g)
-        w = torch.randn(1, 256, 256, 7, 7, device="cuda", generator=g)
+        v = torch.randn(1, 256, 256, Hc, Hc, device="cuda", generator=g)
+        w = torch.randn(1, 256, 256, Hc, Hc, device="cuda", generator=g)
         t = torch.randn(1, 20, 256, device="cuda", generator=g)
         sz = torch.tensor([[360.0, 640.0]], device="cuda")
-        o4 = e4.alloc_outputs(1, 256, 7, 7, 20, want)
+        o4 = e4.alloc_outputs(1, 256, Hc, Hc, 20, want)
 
         def step():
             e4.forward(v, w, t, None, ori_sizes_hw=sz, outs=o4)
@@ -574,8 +576,8 @@ def main():
         n = 20
         sec4 = timed(step, n, device_events=False)
         e4.close()
-        return {"ms_per_step": 1e3 * sec4 / n, "clips_per_step_per_gpu": 1, "what": "ONE 256-frame 7x7 clip on one GPU, synchronous "
-                "(the unsharded reference point of sharded_cfg4)"}
+        return {"ms_per_step": 1e3 * sec4 / n, "clips_per_step_per_gpu": 1, "what": f"ONE 256-frame {Hc}x{Hc} clip on one GPU, synchronous "
+                "(the unsharded reference point of the sharded_* lines of the N > 1 runs)"}
 
     def eager_pytorch():
         """The reference's own modules (oracle/_ref) in eager PyTorch under bf16 autocast on this B200, one clip per forward as the
@@ -619,8 +621,10 @@ def main():
     torch.cuda.empty_cache()
     others = guarded(other_configs) if not args.quick else None
     if world == 1 and not args.quick:
-        others = dict(others or {}, cfg4_T256_7x7_L20_B1=guarded(cfg4_single_gpu))
-    sharded = guarded(sharded_cfg4) if world > 1 else None
+        others = dict(others or {}, long_T256_7x7_L20_B1=guarded(lambda: long_clip_single_gpu(7)),
+                      long_T256_12x12_L20_B1=guarded(lambda: long_clip_single_gpu(12)))
+    sharded = guarded(lambda: sharded_clip("ev_cfg4_T256_7x7_L20_s0")) if world > 1 else None
+    sharded_long = guarded(lambda: sharded_clip("ev_long_T256_12x12_L20_s0")) if world > 1 else None
     eager_ref = guarded(eager_pytorch) if (rank == 0 and world == 1 and not args.quick) else None
     value = total_clips / sec
     e2e = total_clips / sec_e2e
@@ -651,6 +655,7 @@ def main():
             "with_backbone": with_bb,
             "other_configs": others,
             "sharded_cfg4": sharded,
+            "sharded_long": sharded_long,
             "eager_pytorch_b200": eager_ref,
             "gpu_launches": int(launches) * args.steps,
             "gpu_launches_per_step": int(launches),

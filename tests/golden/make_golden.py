@@ -322,6 +322,8 @@ EV_CASES = [
     ("ev_yaml_T16_14x14_L20", 16, 14, 14, 20, 0, 200, False, -1),
     ("ev_cfg4_T256_7x7_L20", 256, 7, 7, 20, 0, 256, False, -1),
     ("ev_cfg5_T128_12x12_L64", 128, 12, 12, 64, 0, 200, False, -1),
+    # a long clip at 384 px (12x12): the shape where frame sharding pays (the encoder dominates) — bench `sharded_long`
+    ("ev_long_T256_12x12_L20", 256, 12, 12, 20, 0, 256, False, -1),
 ]
 EVENT_AMP = 2.0
 

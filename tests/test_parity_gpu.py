@@ -243,6 +243,39 @@ def test_bf16_channels_last_features(name):
         np.testing.assert_allclose(oh[k], o[k], atol=1e-6, err_msg=k)     # host and device entry points run the same kernels
 
 
+def test_fused_decoder_tail_chain(monkeypatch):
+    """VGQA_CHAIN=1: the frame-local tail of every decoder layer ([vo + LN3] → FFN + LN4 → norm / next in-projection / bbox_embed)
+    runs as ONE fused row-tile GEMM chain (csrc/chain.cu).  Same decisions and outputs as the reference, and fewer launches."""
+    from vgqa_b200.engine import GroundingEngine
+    name = "ev_cfg2_T64_7x7_L20_a_s0"
+    g = np.load(golden_path(name))
+    T, H, W, L, seed = (int(g[k]) for k in ("T", "H", "W", "L", "seed"))
+    sd = O.apply_calibration(O.synth_state_dict(seed, max_video_len=int(g["max_video_len"])), g)
+    vis, vid, _, text = case_inputs(g)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    sizes = torch.tensor([[float(g["ori_size"][0]), float(g["ori_size"][1])]] * 3, device="cuda")
+    launches = {}
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VGQA_CHAIN", flag)          # read when the context is created
+        eng = GroundingEngine(sd, max_clips=3, max_frames=T, max_hw=H * W, max_text=L)
+        o = eng.forward(t(np.stack([vis] * 3)), t(np.stack([vid] * 3)), t(np.stack([text[:, 0]] * 3)), None, ori_sizes_hw=sizes)
+        torch.cuda.synchronize()
+        outs[flag] = {k: v.cpu().numpy() for k, v in o.items()}
+        launches[flag] = eng.last_launch_count
+        eng.close()
+    assert launches["1"] < launches["0"] - 100, launches      # 192 rows = two row tiles (one ragged)
+    o = outs["1"]
+    for b in range(3):
+        np.testing.assert_array_equal(o["choose1"][b], _ref_sel(g, "choose_pass1"))
+        np.testing.assert_array_equal(o["choose2"][b], _ref_sel(g, "choose_pass2"))
+    worst = continuous_errors(g, o)
+    bad = {k: v for k, v in worst.items() if not v <= (TOL_INTERNAL if k == "frames_cls" else TOL)}
+    assert not bad, f"chain: {bad} (all: {worst})"
+    for k in ("pred_boxes", "pred_sted", "pred_actioness", "aux_boxes"):
+        np.testing.assert_allclose(outs["1"][k], outs["0"][k], atol=5e-3, err_msg=k)   # same math, different summation order
+
+
 def test_batch_of_clips_matches_single():
     g, o1 = run_case("cfg1_T32_7x7_L20_s1", force=False, clips=1)
     _, o2 = run_case("cfg1_T32_7x7_L20_s1", force=False, clips=2)
