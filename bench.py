@@ -603,6 +603,47 @@ def main():
         torch.cuda.empty_cache()
         return res
 
+    def swin_stage_line():
+        """SURVEY §8f rank 3, first piece: the LAST stage of the Video-Swin-T extractor (`vid.layers[3]`: 2 SwinTransformerBlock3D,
+        dim 768, 24 heads, window (8,7,7)) on this library's kernels (csrc/swin.cu), 8 clips x 64 frames at 7x7, next to the
+        reference's own `BasicLayer` in eager PyTorch bf16-autocast on the same B200 (oracle/_ref)."""
+        clips = 8
+        sd = O.synth_state_dict(0)
+        sd.update(O.synth_swin_stage(0))
+        es = GroundingEngine(sd, max_clips=1, max_frames=8, max_hw=49, max_text=8)
+        g = torch.Generator(device="cuda").manual_seed(21)
+        x = torch.randn(clips, T, 7, 7, 768, device="cuda", generator=g)
+        n = 10
+        sec_s = timed(lambda: es.swin_stage(x), n)
+        launches_s = es.last_launch_count
+        tokens = clips * T * 49
+        flops = 2 * tokens * (2.0 * 768 * 2304 + 2.0 * 768 * 768 + 4.0 * 768 * 3072 + 4.0 * 392 * 768)
+        res = {"ms_per_step": 1e3 * sec_s / n, "clips_per_step": clips, "value": clips * n / sec_s, "unit": "clips/s",
+               "tflops": flops / (sec_s / n) / 1e12, "launches": launches_s,
+               "what": "vid.layers[3] (2 Swin blocks: LN, qkv, 392-token window attention with relative position bias / shift mask on "
+                       "tcgen05, proj, LN, fc1 + GELU, fc2) on 8 x 64 frames of 7x7x768; output = the channels-last bf16 vid_raw map"}
+        es.close()
+        try:
+            if reference_arm_available():
+                from make_golden_swin import load_swin_module
+                M = load_swin_module()
+                layer = M.BasicLayer(dim=768, depth=2, num_heads=24, window_size=(8, 7, 7), mlp_ratio=4.0, qkv_bias=True).eval()
+                layer.load_state_dict({k: torch.from_numpy(v) for k, v in O.synth_swin_stage(0, prefix="").items()}, strict=False)
+                layer.cuda()
+                xt = x.permute(0, 4, 1, 2, 3).contiguous()
+
+                def ref_step():
+                    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                        layer(xt)
+
+                sec_r = timed(ref_step, n)
+                res["eager_pytorch_b200_ms_per_step"] = 1e3 * sec_r / n
+                del layer
+        except Exception as ex:   # noqa: BLE001
+            res["eager_pytorch_b200_ms_per_step"] = f"unavailable: {type(ex).__name__}: {ex}"
+        torch.cuda.empty_cache()
+        return res
+
     def guarded(fn):
         try:
             return fn()
@@ -626,6 +667,7 @@ def main():
     sharded = guarded(lambda: sharded_clip("ev_cfg4_T256_7x7_L20_s0")) if world > 1 else None
     sharded_long = guarded(lambda: sharded_clip("ev_long_T256_12x12_L20_s0")) if world > 1 else None
     eager_ref = guarded(eager_pytorch) if (rank == 0 and world == 1 and not args.quick) else None
+    swin_line = guarded(swin_stage_line) if (world == 1 and not args.quick) else None
     value = total_clips / sec
     e2e = total_clips / sec_e2e
     h2d_f32 = int(h_vis.numel() * 4 * 2 + h_text.numel() * 4 + h_pos.numel() * 4 + h_sizes.numel() * 4)
@@ -657,6 +699,7 @@ def main():
             "sharded_cfg4": sharded,
             "sharded_long": sharded_long,
             "eager_pytorch_b200": eager_ref,
+            "swin_stage4": swin_line,
             "gpu_launches": int(launches) * args.steps,
             "gpu_launches_per_step": int(launches),
             "clocks": clocks,

@@ -190,6 +190,14 @@ int vgqa_text_tower(vgqa_ctx* ctx, const int32_t* ids, const uint8_t* text_mask,
                     void* stream);
 int vgqa_text_tower_hidden(const vgqa_ctx* ctx);
 
+/* The LAST STAGE of the Video-Swin-T extractor (first piece): `vid.layers[3]` of VSTGNet = BasicLayer of two
+ * SwinTransformerBlock3D (dim 768, 24 heads, window (8,7,7), mlp ratio 4; vgqa/core/vision/video_swin_transformer.py:176-275,337-398;
+ * grounding_net.py:67-71,104-105), weights "vid.layers.3.blocks.{0,1}.*" under the reference's names (optional at
+ * vgqa_finalize_weights).  x: channels-last fp32 [clips, T, H, W, 768] (what the stage-3 PatchMerging leaves, `b t h w c`),
+ * H = W = 7 (224 px clips), T a multiple of 8.  out_bf16: channels-last bf16 [clips, T, H, W, 768] — exactly the vid_raw /
+ * raw_layout = 1 input of vgqa_forward; out_f32: the same in fp32; either may be NULL.  Device pointers. */
+int vgqa_swin_stage(vgqa_ctx* ctx, const float* x, int clips, int T, int H, int W, void* out_bf16, float* out_f32, void* stream);
+
 /* Counters: kernels launched by the last vgqa_forward call (graph replays count the captured launches). */
 int vgqa_last_launch_count(const vgqa_ctx* ctx);
 /* Number of CUDA graphs this context has captured so far.  Graphs are keyed on (phase, slot, shape, which optional inputs are

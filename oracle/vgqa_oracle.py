@@ -618,8 +618,70 @@ def front_end(sd, vis_raw: np.ndarray, vid_raw: np.ndarray, text_raw: np.ndarray
 
 
 # ----------------------------------------------------------------------------------------------
+# widened row: the last stage of the Video-Swin-T extractor
+# ----------------------------------------------------------------------------------------------
+def swin_relative_position_index(window: Tuple[int, int, int]) -> np.ndarray:
+    """WindowAttention3D.__init__ — vgqa/core/vision/video_swin_transformer.py:97-112: (N, N) indices into the bias table."""
+    wd, wh, ww = window
+    coords = np.stack(np.meshgrid(np.arange(wd), np.arange(wh), np.arange(ww), indexing="ij")).reshape(3, -1)
+    rel = (coords[:, :, None] - coords[:, None, :]).transpose(1, 2, 0).copy()
+    rel[:, :, 0] += wd - 1
+    rel[:, :, 1] += wh - 1
+    rel[:, :, 2] += ww - 1
+    rel[:, :, 0] *= (2 * wh - 1) * (2 * ww - 1)
+    rel[:, :, 1] *= (2 * ww - 1)
+    return rel.sum(-1)
+
+
+def swin_stage(sd, x: np.ndarray, prefix: str = "vid.layers.3.", heads: int = 24, window=(8, 7, 7), depth: int = 2) -> np.ndarray:
+    """BasicLayer.forward of the LAST Video-Swin stage (no downsample) — video_swin_transformer.py:377-398 — on a channels-last
+    map x (B, D, H, W, C) whose H, W do not exceed the window (224 px clips: 7x7), D a multiple of the temporal window:
+    per block (:210-275)  x += proj(W-MSA(LN1(x)));  x += fc2(gelu(fc1(LN2(x)))), window attention with the relative position bias
+    (:143-165), odd blocks on the temporally rolled map with the -100 mask of compute_mask (:311-325)."""
+    B, D, H, W, C = x.shape
+    wd = min(window[0], D)
+    assert H <= window[1] and W <= window[2] and D % wd == 0, "oracle: one spatial window per frame, D % window == 0"
+    shift = window[0] // 2 if D > window[0] else 0                    # get_window_size (:53-66): no shift along a clamped axis
+    N = wd * H * W
+    dh = C // heads
+    idx = swin_relative_position_index(window)[:N, :N] if (H, W) == (window[1], window[2]) else None
+    assert idx is not None, "oracle: the map must fill the window in H and W"
+    x = x.astype(F32)
+    for i in range(depth):
+        p = f"{prefix}blocks.{i}."
+        sh = shift if i % 2 == 1 else 0
+        h = layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+        if sh:
+            h = np.roll(h, -sh, axis=1)
+        win = h.reshape(B * (D // wd), N, C)
+        qkv = linear(win, sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"]).reshape(-1, N, 3, heads, dh).transpose(2, 0, 3, 1, 4)
+        q, k, v = qkv[0] * F32(dh ** -0.5), qkv[1], qkv[2]
+        attn = q @ k.transpose(0, 1, 3, 2)
+        bias = sd[p + "attn.relative_position_bias_table"][idx.reshape(-1)].reshape(N, N, heads).transpose(2, 0, 1)
+        attn = attn + bias[None]
+        if sh:                                                        # compute_mask: groups along the rolled time axis
+            g = np.zeros(D, np.int64)
+            g[D - wd:D - sh] = 1
+            g[D - sh:] = 2
+            gw = np.repeat(g.reshape(D // wd, wd), H * W, axis=1)                 # (nW, N)
+            mask = np.where(gw[:, :, None] != gw[:, None, :], F32(-100.0), F32(0.0))
+            attn = attn.reshape(B, D // wd, heads, N, N) + mask[None, :, None]
+            attn = attn.reshape(-1, heads, N, N)
+        attn = softmax(attn, -1)
+        o = (attn @ v).transpose(0, 2, 1, 3).reshape(-1, N, C)
+        o = linear(o, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"]).reshape(B, D, H, W, C)
+        if sh:
+            o = np.roll(o, sh, axis=1)
+        x = x + o
+        h = layer_norm(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+        h = gelu_erf(linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]))
+        x = x + linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+    return x.astype(F32)
+
+
+# ----------------------------------------------------------------------------------------------
 # deterministic synthetic weights / inputs: they live in the product package (pure numpy, vgqa_b200/synth.py) so that the
 # GPU arm of bench.py imports nothing from oracle/; re-exported here for the tests and fixture makers
 # ----------------------------------------------------------------------------------------------
 from vgqa_b200.synth import (CALIB_PREFIX, apply_calibration, hot_path_param_shapes, synth_event_inputs, synth_inputs,  # noqa: E402,F401
-                             synth_masks, synth_raw_inputs, synth_state_dict, synth_text_ids)
+                             synth_masks, synth_raw_inputs, synth_state_dict, synth_swin_stage, synth_text_ids)

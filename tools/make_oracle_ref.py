@@ -25,6 +25,9 @@ FILES = [
     "vgqa/core/language/bert_module.py", "vgqa/core/model_utils.py", "vgqa/core/vision/position_encoding.py",
     "vgqa/core/postprocessor.py", "vgqa/training/evaluator.py", "vgqa/utils/training_utils.py", "vgqa/utils/box_ops.py",
     "vgqa/utils/distributed.py",
+    # widened row (§8f rank 3): the Video-Swin extractor whose last stage csrc/swin.cu restates (needs timm's DropPath /
+    # trunc_normal_: stubbed by tests/golden/make_golden_swin.py)
+    "vgqa/core/vision/video_swin_transformer.py",
 ]
 
 

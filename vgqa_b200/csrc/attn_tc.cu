@@ -275,7 +275,8 @@ void enc_attn_tc(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* kmask, 
   }
   CUtensorMap tq = make_tmap_frames(QKV, F, S, 768, 768);
   CUtensorMap to = make_tmap_frames(AO, F, S, 256, 256);
-  AttnTcParams p{kmask, S, F, scale * 1.4426950408889634f};
+  AttnTcParams p;
+  p.kmask = kmask; p.S = S; p.F = F; p.scale_log2e = scale * 1.4426950408889634f;
   const int grid = F < device_sm_count() ? F : device_sm_count();
   enc_attn_tc_kernel<<<grid, kAtThreads, kAtSmem, stream>>>(tq, to, p);
   VG_CUDA(cudaGetLastError());

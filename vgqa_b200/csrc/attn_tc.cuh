@@ -22,6 +22,13 @@ struct AttnTcParams {
   const uint8_t* kmask;  // [F, S] or nullptr
   int S, F;
   float scale_log2e;
+  // attn_tc_long.cu only — window attention of the Video-Swin stage (swin.cu): `heads` heads of 32 in a packed [q | k | v] row of
+  // 3 * 32 * heads columns, and an additive score term sbias[set][head][q][k] (fp32, ALREADY divided by the softmax scale, so
+  // that scale * (q·k + sbias) = scale * q·k + bias): the relative position bias, plus the -100 shift mask in set 1, which the
+  // last of every `wpc` consecutive groups (the wrapped window of a clip) uses when bias_sets == 2.
+  int heads = 8;
+  const float* sbias = nullptr;
+  int bias_sets = 1, wpc = 1;
 };
 
 // K-major operand, rows of 64 B (32 bf16), 64B swizzle: 8-row groups 512 B apart.

@@ -49,7 +49,9 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   const int nt = (S + 127) >> 7;   // 128-token tiles per frame (queries and keys)
   int my_frames = 0;
   for (int f = blockIdx.x; f < p.F; f += gridDim.x) ++my_frames;
-  const int items = my_frames * 8 * nt;                  // (frame, head, query tile)
+  const int NH = p.heads;                                 // heads per frame (8 in the encoder, 24 in the Video-Swin stage)
+  const int koff = NH * 32, voff = NH * 64;               // column of the K / V slices in the packed [q | k | v] row
+  const int items = my_frames * NH * nt;                  // (frame, head, query tile)
   const int slots = ((items + kAtWgs - 1) / kAtWgs) * kAtWgs * nt;   // sub-unit slots, stream-interleaved: slot u → stream u % 4
   // slot u → sub-unit (u / 4) of stream (u % 4): item = stream + 4 * (sub / nt), key tile = sub % nt
   auto decode = [&](int u) {
@@ -58,7 +60,7 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const int it = wg + kAtWgs * (sub / nt);
     x.j = sub % nt;
     x.valid = it < items;
-    const int fi = it / (8 * nt), rem = it - fi * 8 * nt;
+    const int fi = it / (NH * nt), rem = it - fi * NH * nt;
     x.f = (int)blockIdx.x + fi * (int)gridDim.x;
     x.h = rem / nt;
     x.qt = rem - x.h * nt;
@@ -102,10 +104,10 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         mbar_expect_tx(&qk_full[sq], kAtQkBytes);
         uint8_t* dst = s_qk + sq * kAtQkBytes;
         tma_load_3d(dst, &tm_qkv, &qk_full[sq], x.h * 32, x.qt * 128, x.f);
-        tma_load_3d(dst + 8192, &tm_qkv, &qk_full[sq], 256 + x.h * 32, x.j * 128, x.f);
+        tma_load_3d(dst + 8192, &tm_qkv, &qk_full[sq], koff + x.h * 32, x.j * 128, x.f);
         mbar_wait(&v_empty[sv], ((n / kAtVStages) & 1) ^ 1);
         mbar_expect_tx(&v_full[sv], kAtVBytes);
-        tma_load_3d(s_v + sv * kAtVBytes, &tm_qkv, &v_full[sv], 512 + x.h * 32, x.j * 128, x.f);
+        tma_load_3d(s_v + sv * kAtVBytes, &tm_qkv, &v_full[sv], voff + x.h * 32, x.j * 128, x.f);
         ++n;
       }
     }
@@ -167,9 +169,16 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const uint32_t sw = static_cast<uint32_t>(row & 7) << 4;
     int sub = 0;                             // sub-units this stream has processed (barrier phases)
     for (int it = wg; it < items; it += kAtWgs) {
-      const int fi = it / (8 * nt), rem = it - fi * 8 * nt;
+      const int fi = it / (NH * nt), rem = it - fi * NH * nt;
       const int f = (int)blockIdx.x + fi * (int)gridDim.x, h = rem / nt, qt = rem - h * nt;
       const uint8_t* km = p.kmask ? p.kmask + (size_t)f * S : nullptr;
+      // additive score row of this query (relative position bias [+ shift mask]); rows beyond S are clipped on store
+      const float* brow = nullptr;
+      if (p.sbias != nullptr) {
+        const int set = (p.bias_sets == 2 && (f % p.wpc) == p.wpc - 1) ? 1 : 0;
+        const int qrow = min(qt * 128 + row, S - 1);
+        brow = p.sbias + (((size_t)set * NH + h) * S + qrow) * S;
+      }
       float m_run = -INFINITY, l_run = 0.f;
       float o_run[32];
 #pragma unroll
@@ -197,6 +206,20 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(raw[i]);
+          }
+          if (brow != nullptr) {   // rows of S fp32 with S % 4 == 0: 16-byte loads on full chunks, guarded scalars on the tail chunk
+            const float* b = brow + kbase + c * 32;
+            if (c * 32 + 32 <= nkeys) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(b) + i);
+                x[4 * i] += q.x; x[4 * i + 1] += q.y; x[4 * i + 2] += q.z; x[4 * i + 3] += q.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i < nkeys) x[i] += __ldg(b + i);
+            }
           }
         };
         float x[32];
@@ -278,19 +301,37 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 CUtensorMap make_tmap_frames(const bf16* ptr, int F, int S, int cols, int ld);   // attn_tc.cu
 int device_sm_count();
 
-void enc_attn_tc_long(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* kmask, float scale, cudaStream_t stream) {
-  VG_CHECK(S > 128 && F > 0, "enc_attn_tc_long: S must exceed 128 (attn_tc.cu handles the single-tile case)");
+static void launch_long(const bf16* QKV, bf16* AO, const AttnTcParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     VG_CUDA(cudaFuncSetAttribute(enc_attn_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
     attr_set = true;
   }
-  CUtensorMap tq = make_tmap_frames(QKV, F, S, 768, 768);
-  CUtensorMap to = make_tmap_frames(AO, F, S, 256, 256);
-  AttnTcParams p{kmask, S, F, scale * 1.4426950408889634f};
-  const int grid = F < device_sm_count() ? F : device_sm_count();
+  CUtensorMap tq = make_tmap_frames(QKV, p.F, p.S, 96 * p.heads, 96 * p.heads);
+  CUtensorMap to = make_tmap_frames(AO, p.F, p.S, 32 * p.heads, 32 * p.heads);
+  const int grid = p.F < device_sm_count() ? p.F : device_sm_count();
   enc_attn_tc_long_kernel<<<grid, kAtLongThreads, kAtSmem, stream>>>(tq, to, p);
   VG_CUDA(cudaGetLastError());
+}
+
+void enc_attn_tc_long(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* kmask, float scale, cudaStream_t stream) {
+  VG_CHECK(S > 128 && F > 0, "enc_attn_tc_long: S must exceed 128 (attn_tc.cu handles the single-tile case)");
+  AttnTcParams p;
+  p.kmask = kmask; p.S = S; p.F = F; p.scale_log2e = scale * 1.4426950408889634f;
+  launch_long(QKV, AO, p, stream);
+}
+
+// Window attention with an additive score term (Video-Swin W-MSA / SW-MSA, video_swin_transformer.py:143-165): `groups` windows of
+// S tokens, `heads` heads of 32; QKV [groups * S, 96 * heads] (q | k | v), AO [groups * S, 32 * heads];
+// sbias [bias_sets][heads][S][S] fp32 = (relative position bias [+ shift mask]) / scale — see AttnTcParams.
+void window_attn_tc(const bf16* QKV, bf16* AO, int groups, int S, int heads, const float* sbias, int bias_sets, int wpc, float scale,
+                    cudaStream_t stream) {
+  VG_CHECK(S > 128 && groups > 0 && heads >= 1 && sbias != nullptr && (bias_sets == 1 || bias_sets == 2) && wpc >= 1,
+           "window_attn_tc: bad arguments (windows of more than 128 tokens)");
+  AttnTcParams p;
+  p.kmask = nullptr; p.S = S; p.F = groups; p.scale_log2e = scale * 1.4426950408889634f;
+  p.heads = heads; p.sbias = sbias; p.bias_sets = bias_sets; p.wpc = wpc;
+  launch_long(QKV, AO, p, stream);
 }
 
 }  // namespace vg

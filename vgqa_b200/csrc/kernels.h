@@ -24,6 +24,10 @@ void pad_rows_bf16(const bf16* src, bf16* dst, int rows, int rows_pad, cudaStrea
 bool enc_attn_tc_supported(int S);
 void enc_attn_tc(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* kmask, float scale, cudaStream_t stream);
 
+// ---- attn_tc_long.cu: window attention with an additive score term (Video-Swin stage, swin.cu)
+void window_attn_tc(const bf16* QKV, bf16* AO, int groups, int S, int heads, const float* sbias, int bias_sets, int wpc, float scale,
+                    cudaStream_t stream);
+
 // ---- input_proj.cu: 1x1-conv projection of the extractor feature maps straight into the encoder's token rows
 bool input_proj_supported(int C);
 void input_proj(const float* in, int C, const bf16* W, const float* bias, const bf16* pos, int pos_frames, bf16* X, float* X32,

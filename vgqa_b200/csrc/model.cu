@@ -28,6 +28,7 @@
 #include "../../include/vgqa_b200.h"
 #include "chain.h"
 #include "kernels.h"
+#include "swin.h"
 
 namespace vg {
 
@@ -222,6 +223,8 @@ struct vgqa_ctx {
   float *text_in = nullptr, *pos_gen = nullptr;        // read by the encoder phase only (calls are serialised on its stream)
   int* ids_in = nullptr;
   uint8_t* tmask_in = nullptr;
+  // optional last stage of the Video-Swin-T extractor (vid.layers.3.*, swin.cu)
+  SwinStage swin;
   // graph cache (key = phase, slot, shape and the presence flags of the optional inputs)
   struct GraphEntry { cudaGraphExec_t exec; int launches; };
   std::map<std::vector<uint64_t>, GraphEntry> graphs;
@@ -324,7 +327,8 @@ static void pack_weights(vgqa_ctx* c) {
   size_t tower_bytes = 0;   // the optional text tower brings ≈330 MB of its own (fp32 embeddings + bf16 layers)
   for (const auto& kv : c->sd)
     if (kv.first.rfind("text_encoder.body.", 0) == 0) tower_bytes += (size_t)kv.second.numel() * 4 + 512;
-  c->warena.init(((size_t)448 << 20) + tower_bytes);
+  const bool have_swin = c->sd.count("vid.layers.3.blocks.0.attn.qkv.weight") != 0;
+  c->warena.init(((size_t)448 << 20) + tower_bytes + (have_swin ? ((size_t)128 << 20) : 0));
   // ---------------- encoder (modal_encoder.py:143-178)
   c->enc.resize(cfg.enc_layers);
   for (int l = 0; l < cfg.enc_layers; ++l) {
@@ -599,6 +603,15 @@ static void pack_weights(vgqa_ctx* c) {
     }
     VG_CHECK(!c->tt.empty(), "text tower: no encoder layers found under text_encoder.body.encoder.layer.*");
   }
+  // ---------------- optional last Video-Swin stage (vid.layers.3.blocks.*, video_swin_transformer.py:176-275)
+  if (have_swin)
+    c->swin.pack([&](const std::string& n, std::vector<int64_t> shp) -> const float* {
+                   auto it = c->sd.find(n);
+                   VG_CHECK(it != c->sd.end(), "missing weight '" + n + "'");
+                   VG_CHECK(it->second.shape == shp, "weight '" + n + "' has an unexpected shape");
+                   return it->second.v.data();
+                 },
+                 [&](const float* v, size_t n) { return P.b16(v, n); }, [&](const float* v, size_t n) { return P.f32(v, n); });
 }
 
 // ------------------------------------------------------------------------------------------------ workspace
@@ -1325,6 +1338,7 @@ void vgqa_destroy(vgqa_ctx* c) {
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   if (c->aux2_stream) cudaStreamDestroy(c->aux2_stream);
   vg::p2p_destroy(c->p2p);
+  c->swin.release();
   for (auto& e : c->fj) if (e) cudaEventDestroy(e);
   c->warena.release();
   c->ws.release();
@@ -1655,6 +1669,14 @@ int vgqa_text_tower(vgqa_ctx* c, const int32_t* ids, const uint8_t* text_mask, i
     const size_t n = (size_t)clips * L * c->tt_hd;
     if (hidden) bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->traw, hidden, n);
     if (text) VG_CUDA(cudaMemcpyAsync(text, c->tproj32, (size_t)clips * L * 256 * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_swin_stage(vgqa_ctx* c, const float* x, int clips, int T, int H, int W, void* out_bf16, float* out_f32, void* stream) {
+  try {
+    VG_CHECK(c && c->finalized && x && (out_bf16 || out_f32), "vgqa_swin_stage: bad argument");
+    c->last_launches = c->swin.forward(x, clips, T, H, W, static_cast<vg::bf16*>(out_bf16), out_f32, static_cast<cudaStream_t>(stream));
     return 0;
   } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
 }

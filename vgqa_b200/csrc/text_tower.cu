@@ -46,7 +46,7 @@ void roberta_embed_ln(const int* ids, const float* word, const float* pos, const
 }
 
 // y = LN(x) * w + b over rows of Hd <= 1024 fp32 values (one warp per row, the row held in registers: one global read);
-// writes fp32 (may alias x) and bf16
+// writes fp32 (optional; may alias x) and bf16
 __global__ void __launch_bounds__(256) ln_rows_wide_kernel(const float* x, const float* __restrict__ w, const float* __restrict__ b,
                                                            float eps, float* y32, bf16* __restrict__ y, int rows, int Hd) {
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) ln_rows_wide_kernel(const float* x, const
     const int c = lane + 32 * i;
     if (c < Hd) {
       const float o = (v[i] - mean) * rstd * w[c] + b[c];
-      y32[(size_t)r * Hd + c] = o;
+      if (y32 != nullptr) y32[(size_t)r * Hd + c] = o;
       y[(size_t)r * Hd + c] = __float2bfloat16(o);
     }
   }

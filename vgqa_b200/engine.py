@@ -318,6 +318,19 @@ class GroundingEngine:
                                            c_void_p(st)))
         return hidden, text
 
+    def swin_stage(self, x, want_f32=False):
+        """Last Video-Swin-T stage (`vid.layers[3]`, csrc/swin.cu): x fp32 channels-last [clips, T, H, W, 768] (device) →
+        channels-last bf16 map of the same shape (the `vid` raw input of forward(raw=True)), and the fp32 map when asked."""
+        assert x.dtype == torch.float32 and x.dim() == 5 and x.is_contiguous()
+        B, T, H, W, C = x.shape
+        self._L.vgqa_swin_stage.restype = c_int
+        self._L.vgqa_swin_stage.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+        out = torch.empty(B, T, H, W, C, dtype=torch.bfloat16, device=self.device)
+        out32 = torch.empty(B, T, H, W, C, dtype=torch.float32, device=self.device) if want_f32 else None
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self._L.vgqa_swin_stage(self._ctx, self._p(x), B, T, H, W, self._p(out), self._p(out32), c_void_p(st)))
+        return (out, out32) if want_f32 else out
+
     @property
     def last_launch_count(self) -> int:
         return int(self._L.vgqa_last_launch_count(self._ctx))

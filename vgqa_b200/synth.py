@@ -209,6 +209,26 @@ def synth_raw_inputs(seed: int, T: int, H: int, W: int, L: int, ch: Tuple[int, i
     return vis_raw, vid_raw, text_raw
 
 
+def synth_swin_stage(seed: int, dim: int = 768, heads: int = 24, window=(8, 7, 7), depth: int = 2, prefix: str = "vid.layers.3."):
+    """Synthetic weights of the last Video-Swin stage (`BasicLayer`: `depth` SwinTransformerBlock3D, video_swin_transformer.py:
+    176-275) under the reference's key names, at the scale of its init (trunc_normal 0.02 for Linear weights and the bias table —
+    widened so that attention and bias matter against the random-init LayerNorm regime), non-zero biases, LayerNorm gains 1 ± 0.1."""
+    rng = np.random.Generator(np.random.PCG64(11000 + seed))
+    sd: Dict[str, np.ndarray] = {}
+    u = lambda b, shp: rng.uniform(-b, b, size=shp).astype(F32)
+    nb = (2 * window[0] - 1) * (2 * window[1] - 1) * (2 * window[2] - 1)
+    for i in range(depth):
+        p = f"{prefix}blocks.{i}."
+        for n in ("norm1", "norm2"):
+            sd[p + n + ".weight"] = (1.0 + u(0.1, (dim,))).astype(F32)
+            sd[p + n + ".bias"] = u(0.05, (dim,))
+        sd[p + "attn.relative_position_bias_table"] = u(1.0, (nb, heads))
+        for n, (o, k) in (("attn.qkv", (3 * dim, dim)), ("attn.proj", (dim, dim)), ("mlp.fc1", (4 * dim, dim)), ("mlp.fc2", (dim, 4 * dim))):
+            sd[p + n + ".weight"] = u(2.5 / math.sqrt(k), (o, k))
+            sd[p + n + ".bias"] = u(0.05, (o,))
+    return sd
+
+
 def synth_text_ids(seed: int, B: int, L: int, vocab: int, pad_tail: int = 0) -> Tuple[np.ndarray, np.ndarray]:
     """Token ids as RobertaTokenizer emits them: <s>=0 ... </s>=2, pad=1 on the last `pad_tail` positions of the odd rows.
     Returns (ids (B, L) int32, pad mask (B, L) bool, True = padded)."""
