@@ -180,8 +180,8 @@ struct vgqa_ctx {
   cudaStream_t h2d_stream = nullptr;
   float* frames_cls;
   bf16 *pool[2], *ftext, *q0, *kv_ts;
-  float *pool32[2], *q0_32, *c_h32[2], *c_a32[2];
-  bf16 *c_h[2], *c_q[2], *c_ctx[2], *c_a[2], *c_i[2], *c_qabs[2], *c_ctx8[2];  // per-classifier scratch
+  float *pool32[2], *q0_32, *c_h32[4], *c_a32[4];
+  bf16 *c_h[4], *c_q[2], *c_ctx[2], *c_a[4], *c_i[4], *c_qabs[2], *c_ctx8[2];  // per-classifier scratch (sets 0,1: TemporalSampling; 2,3: SpatialActivation)
   float *logit_f[2], *att_seq, *w1, *w2, *K1, *K2, *attmap[2], *logit_rows[2], *logits_r[2], *part[2], *seedq[2];
   float *t_tgt32, *t_x32, *t_x2_32, *p_tgt32, *p_x32, *p_x2_32;
   bf16 *t_tgt, *t_qkv, *t_ao, *t_x, *t_qabs, *t_ctx8, *t_x2, *t_hid, *t_inter, *t_hs;
@@ -209,6 +209,7 @@ struct vgqa_ctx {
   cudaStream_t enc_stream = nullptr, dec_stream = nullptr;
   cudaStream_t aux_stream = nullptr;   // second branch of the fork/join sections (classifier pairs, the two decoders)
   cudaStream_t aux2_stream = nullptr;  // side branch inside the PosDecoder chain
+  cudaStream_t aux3_stream = nullptr;  // fourth branch of the classifier section (TemporalSampling x2 ‖ SpatialActivation x2)
   cudaEvent_t fj[32] = {};
   // frame sharding of one long clip over `sh_world` ranks (vgqa_set_sharding); exchanges go through the callback
   int sh_rank = 0, sh_world = 1;
@@ -667,10 +668,12 @@ static void carve_workspace(vgqa_ctx* c) {
   c->text_sums = a.get<float>(B * L * 256);
   c->red[0] = a.get<float>(B * 320); c->red[1] = a.get<float>(B * 320);
   c->t_qkv_all = a.get<bf16>((size_t)(g.max_video_len + 1) * 768); c->p_qkv_all = a.get<bf16>((size_t)(g.max_video_len + 1) * 768);
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 4; ++k) {
     c->c_h32[k] = a.get<float>(F * 256); c->c_a32[k] = a.get<float>(F * 256);
-    c->c_h[k] = a.get<bf16>(F * 256); c->c_q[k] = a.get<bf16>(F * 256); c->c_ctx[k] = a.get<bf16>(F * 256);
-    c->c_a[k] = a.get<bf16>(F * 256); c->c_i[k] = a.get<bf16>(F * 256);
+    c->c_h[k] = a.get<bf16>(F * 256); c->c_a[k] = a.get<bf16>(F * 256); c->c_i[k] = a.get<bf16>(F * 256);
+  }
+  for (int k = 0; k < 2; ++k) {
+    c->c_q[k] = a.get<bf16>(F * 256); c->c_ctx[k] = a.get<bf16>(F * 256);
     c->c_qabs[k] = a.get<bf16>(F * 2048); c->c_ctx8[k] = a.get<bf16>(F * 2048);
     c->logit_f[k] = a.get<float>(F); c->attmap[k] = a.get<float>(F * P); c->logit_rows[k] = a.get<float>(F * 64);
     c->logits_r[k] = a.get<float>(B * 64); c->part[k] = a.get<float>(F * 256); c->seedq[k] = a.get<float>(B * 256);
@@ -705,6 +708,7 @@ struct Fwd {
   cudaStream_t st;          // stream the helpers below launch on (main or aux)
   cudaStream_t main, aux;
   cudaStream_t aux2 = nullptr;   // side branch of the PosDecoder chain (query_scale MLP, absorbed-query GEMM)
+  cudaStream_t aux3 = nullptr;   // with aux2: third / fourth branch of the classifier section
   int ev_i = 0;
   int phase = 1;
   int B, T, P, L, S, F, R;
@@ -734,6 +738,19 @@ struct Fwd {
   void side_join(cudaStream_t into) {
     if (aux2 == into) return;
     VG_CUDA(cudaEventRecord(c->fj[ev_i], aux2));
+    VG_CUDA(cudaStreamWaitEvent(into, c->fj[ev_i], 0));
+    ev_i = (ev_i + 1) & 31;
+  }
+  // generic branch: `br` starts after everything enqueued on `from` so far / `into` continues after everything on `br`
+  void branch_fork(cudaStream_t from, cudaStream_t br) {
+    if (br == from) return;
+    VG_CUDA(cudaEventRecord(c->fj[ev_i], from));
+    VG_CUDA(cudaStreamWaitEvent(br, c->fj[ev_i], 0));
+    ev_i = (ev_i + 1) & 31;
+  }
+  void branch_join(cudaStream_t br, cudaStream_t into) {
+    if (br == into) return;
+    VG_CUDA(cudaEventRecord(c->fj[ev_i], br));
     VG_CUDA(cudaStreamWaitEvent(into, c->fj[ev_i], 0));
     ev_i = (ev_i + 1) & 31;
   }
@@ -909,65 +926,80 @@ static void run_encoder(Fwd& f, int tkind, bool text_pad, bool have_mask, int po
   f.count(3);
 }
 
-// TemporalSampling (classifier.py:32-37): k = 0 → t_temporal_clas on vid tokens, 1 → s_temporal_clas on vis tokens
-static void run_temporal_sampling(Fwd& f) {
+// TemporalSampling (classifier.py:32-37) of classifier k (0 → t_temporal_clas on vid tokens, 1 → s_temporal_clas on vis tokens),
+// enqueued on f.st
+static void temporal_chain(Fwd& f, int k) {
   vgqa_ctx* c = f.c;
   const int F = f.F;
-  f.linear(c->ftext, 256, c->ts_kv, f.B * f.L, c->kv_ts, 2048);
-  f.fork();
-  for (int k = 0; k < 2; ++k) {
-    f.st = k == 0 ? f.main : f.aux;
-    const bf16* h = c->pool[k];
-    const float* h32 = c->pool32[k];
-    for (int i = 0; i < 2; ++i) {
-      TsLayer& t = c->ts[k][i];
-      f.linear(h, 256, t.q, F, c->c_q[k], 256);
-      mha32(c->c_q[k], 256, c->kv_ts + t.kv_off, 2048, c->kv_ts + t.kv_off + 256, 2048, c->c_ctx[k], 256, f.B, f.T, f.L,
-            nullptr, 0.17677669529663687f, f.st);
-      f.count();
-      f.linear_res_ln(c->c_ctx[k], 256, t.o, F, h32, t.ln_a, 1e-12f, c->c_a[k], 256, c->c_a32[k]);
-      f.linear(c->c_a[k], 256, t.inter, F, c->c_i[k], 256, ACT_GELU);
-      f.linear_res_ln(c->c_i[k], 256, t.outp, F, c->c_a32[k], t.ln_o, 1e-12f, c->c_h[k], 256, c->c_h32[k]);
-      h = c->c_h[k]; h32 = c->c_h32[k];
-    }
-    Head& hd = c->ts_head[k];
-    f.linear_res_ln(h, 256, hd.t, F, nullptr, hd.ln, 1e-12f, c->c_a[k], 256, nullptr, ACT_GELU);
-    rowvec_head(c->c_a[k], 256, hd.dw, hd.db, c->logit_f[k], 1, F, 1, 0, f.st);
+  const bf16* h = c->pool[k];
+  const float* h32 = c->pool32[k];
+  for (int i = 0; i < 2; ++i) {
+    TsLayer& t = c->ts[k][i];
+    f.linear(h, 256, t.q, F, c->c_q[k], 256);
+    mha32(c->c_q[k], 256, c->kv_ts + t.kv_off, 2048, c->kv_ts + t.kv_off + 256, 2048, c->c_ctx[k], 256, f.B, f.T, f.L,
+          nullptr, 0.17677669529663687f, f.st);
     f.count();
+    f.linear_res_ln(c->c_ctx[k], 256, t.o, F, h32, t.ln_a, 1e-12f, c->c_a[k], 256, c->c_a32[k]);
+    f.linear(c->c_a[k], 256, t.inter, F, c->c_i[k], 256, ACT_GELU);
+    f.linear_res_ln(c->c_i[k], 256, t.outp, F, c->c_a32[k], t.ln_o, 1e-12f, c->c_h[k], 256, c->c_h32[k]);
+    h = c->c_h[k]; h32 = c->c_h32[k];
   }
-  f.join();
+  Head& hd = c->ts_head[k];
+  f.linear_res_ln(h, 256, hd.t, F, nullptr, hd.ln, 1e-12f, c->c_a[k], 256, nullptr, ACT_GELU);
+  rowvec_head(c->c_a[k], 256, hd.dw, hd.db, c->logit_f[k], 1, F, 1, 0, f.st);
+  f.count();
 }
 
-// SpatialActivation + query seeding (classifier.py:64-81; grounding_net.py:131-136)
-// The per-frame part (two BertLayer_Cross blocks + head, attention map) does not depend on which frames were chosen —
-// every frame attends only to its own tokens — so the second pass reuses logit_rows / attmap of the first and only redoes the
-// masked means over the newly chosen frames.
-static void run_spatial_seed(Fwd& f, const float* w, const float* K, bool second_pass) {
+// The per-frame part of SpatialActivation k (classifier.py:64-81: two BertLayer_Cross blocks, head, attention map) on ALL frames,
+// enqueued on f.st (scratch set k + 2).  It does not depend on which frames get chosen — every frame attends only to its own
+// tokens — so it runs BESIDE TemporalSampling, and the second decoder pass reuses its logit rows / attention maps.
+static void spatial_frames(Fwd& f, int k) {
+  vgqa_ctx* c = f.c;
+  const int F = f.F, P = f.P, S = f.S, z = k + 2;
+  const int tok0 = k == 0 ? P + f.L : 0;  // t_* reads vid tokens, s_* reads vis tokens
+  const bf16* q = c->q0;
+  const float* q32 = c->q0_32;
+  for (int i = 0; i < 2; ++i) {
+    SaLayer& s = c->sa[k][i];
+    f.linear(q, 256, s.qabs, F, c->c_qabs[k], 2048);
+    xattn1(c->c_qabs[k], c->Xf + (size_t)tok0 * 256, S, F, P, nullptr, 0, nullptr, nullptr, 0, 0, nullptr, 0,
+           0.17677669529663687f, c->c_ctx8[k], i == 1 ? c->attmap[k] : nullptr, f.st);
+    f.count();
+    f.linear_res_ln(c->c_ctx8[k], 2048, s.vo, F, q32, s.ln_a, 1e-12f, c->c_a[z], 256, c->c_a32[z]);
+    f.linear(c->c_a[z], 256, s.inter, F, c->c_i[z], 256, ACT_GELU);
+    f.linear_res_ln(c->c_i[z], 256, s.outp, F, c->c_a32[z], s.ln_o, 1e-12f, c->c_h[z], 256, c->c_h32[z]);
+    q = c->c_h[z]; q32 = c->c_h32[z];
+  }
+  Head& hd = c->sa_head[k];
+  f.linear_res_ln(q, 256, hd.t, F, nullptr, hd.ln, 1e-12f, c->c_a[z], 256, nullptr, ACT_GELU);
+  rowvec_head(c->c_a[z], 256, hd.dw, hd.db, c->logit_rows[k], 64, F, hd.vocab, 0, f.st);
+  f.count();
+}
+
+// The four classifier chains as four concurrent branches (graph branches under capture): TemporalSampling x2 ‖ SpatialActivation x2
+static void run_classifiers(Fwd& f) {
+  vgqa_ctx* c = f.c;
+  f.linear(c->ftext, 256, c->ts_kv, f.B * f.L, c->kv_ts, 2048);
+  cudaStream_t br[4] = {f.main, f.aux, f.aux2, f.aux3};
+  for (int i = 1; i < 4; ++i) f.branch_fork(f.main, br[i]);
+  for (int i = 0; i < 4; ++i) {
+    f.st = br[i];
+    if (i < 2) temporal_chain(f, i); else spatial_frames(f, i - 2);
+  }
+  for (int i = 1; i < 4; ++i) f.branch_join(br[i], f.main);
+  f.st = f.main;
+}
+
+// Query seeding (grounding_net.py:131-136,155-160): masked means over the chosen frames of the per-frame classifier logits and of
+// the attention-weighted tokens; both decoder passes.
+static void run_spatial_seed(Fwd& f, const float* w, const float* K) {
   vgqa_ctx* c = f.c;
   const int F = f.F, P = f.P, S = f.S;
   f.fork();
   for (int k = 0; k < 2; ++k) {
     f.st = k == 0 ? f.main : f.aux;
-    const int tok0 = k == 0 ? P + f.L : 0;  // t_* reads vid tokens, s_* reads vis tokens
-    const bf16* q = c->q0;
-    const float* q32 = c->q0_32;
-    for (int i = 0; i < 2 && !second_pass; ++i) {
-      SaLayer& s = c->sa[k][i];
-      f.linear(q, 256, s.qabs, F, c->c_qabs[k], 2048);
-      xattn1(c->c_qabs[k], c->Xf + (size_t)tok0 * 256, S, F, P, nullptr, 0, nullptr, nullptr, 0, 0, nullptr, 0,
-             0.17677669529663687f, c->c_ctx8[k], i == 1 ? c->attmap[k] : nullptr, f.st);
-      f.count();
-      f.linear_res_ln(c->c_ctx8[k], 2048, s.vo, F, q32, s.ln_a, 1e-12f, c->c_a[k], 256, c->c_a32[k]);
-      f.linear(c->c_a[k], 256, s.inter, F, c->c_i[k], 256, ACT_GELU);
-      f.linear_res_ln(c->c_i[k], 256, s.outp, F, c->c_a32[k], s.ln_o, 1e-12f, c->c_h[k], 256, c->c_h32[k]);
-      q = c->c_h[k]; q32 = c->c_h32[k];
-    }
+    const int tok0 = k == 0 ? P + f.L : 0;
     Head& hd = c->sa_head[k];
-    if (!second_pass) {
-      f.linear_res_ln(q, 256, hd.t, F, nullptr, hd.ln, 1e-12f, c->c_a[k], 256, nullptr, ACT_GELU);
-      rowvec_head(c->c_a[k], 256, hd.dw, hd.db, c->logit_rows[k], 64, F, hd.vocab, 0, f.st);
-      f.count();
-    }
     seed_partial(c->Xf, c->attmap[k], w, c->part[k], F, S, tok0, P, f.st);
     masked_sums(c->logit_rows[k], 64, hd.vocab, c->part[k], w, c->red[k], f.B, f.T, f.st);
     f.all_reduce_f32(c->red[k], (size_t)f.B * 320);
@@ -1194,10 +1226,11 @@ static void init_fwd(Fwd& f, vgqa_ctx* c, const vgqa_inputs& in, int phase, cuda
     VG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     VG_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_hi));
     VG_CUDA(cudaStreamCreateWithPriority(&c->aux2_stream, cudaStreamNonBlocking, prio_hi));
+    VG_CUDA(cudaStreamCreateWithPriority(&c->aux3_stream, cudaStreamNonBlocking, prio_hi));
     for (auto& e : c->fj) VG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   f.c = c; f.st = st; f.main = st; const bool one_stream = c->sh_world > 1 && !p2p_ready(c->p2p);   // NCCL-callback sharding: collectives stay in program order
-  f.aux = one_stream ? st : c->aux_stream; f.aux2 = one_stream ? st : c->aux2_stream; f.B = in.clips; f.T = in.T; f.P = in.H * in.W; f.L = in.L; f.S = 2 * f.P + f.L;
+  f.aux = one_stream ? st : c->aux_stream; f.aux2 = one_stream ? st : c->aux2_stream; f.aux3 = one_stream ? st : c->aux3_stream; f.B = in.clips; f.T = in.T; f.P = in.H * in.W; f.L = in.L; f.S = 2 * f.P + f.L;
   f.F = f.B * f.T; f.R = f.F * f.S; f.phase = phase;
 }
 
@@ -1220,12 +1253,12 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, int phase, cudaStr
     return;
   }
   if (in.stop_after_encoder) return;
-  run_temporal_sampling(f);
+  run_classifiers(f);
   select_pass1(c->logit_f[0], c->logit_f[1], 0.45f, in.force_choose1, c->att_seq, c->w1, c->K1, f.B, f.T, st);
   f.all_reduce_f32(c->K1, f.B);
   select_finish(c->w1, c->K1, f.B, f.T, f.T_global(), st);
   f.count(2);
-  run_spatial_seed(f, c->w1, c->K1, false);
+  run_spatial_seed(f, c->w1, c->K1);
   run_decoders(f, have_mask, in.pos_frames, false);
   if (in.iteration_rate < 0) {  // grounding_net.py:143-163
     f.linear(c->t_inter + (size_t)(D - 1) * F * 256, 256, c->action_embed.l0, F, c->t_hs, 256, ACT_RELU);
@@ -1234,7 +1267,7 @@ static void forward_phase(vgqa_ctx* c, const vgqa_inputs& in, int phase, cudaStr
     f.all_reduce_f32(c->K2, f.B);
     select_finish(c->w2, c->K2, f.B, f.T, f.T_global(), st);
     f.count(3);
-    run_spatial_seed(f, c->w2, c->K2, true);
+    run_spatial_seed(f, c->w2, c->K2);
     run_decoders(f, have_mask, in.pos_frames, true);
   }
   // heads over all decoder layers (grounding_net.py:177-181)
@@ -1337,6 +1370,7 @@ void vgqa_destroy(vgqa_ctx* c) {
   }
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   if (c->aux2_stream) cudaStreamDestroy(c->aux2_stream);
+  if (c->aux3_stream) cudaStreamDestroy(c->aux3_stream);
   vg::p2p_destroy(c->p2p);
   c->swin.release();
   for (auto& e : c->fj) if (e) cudaEventDestroy(e);
@@ -1420,6 +1454,7 @@ static int run_phase(vgqa_ctx* c, const vgqa_inputs& in, int phase, int slot, cu
     VG_CUDA(cudaStreamSynchronize(ex));
     VG_CUDA(cudaStreamSynchronize(c->aux_stream));
     VG_CUDA(cudaStreamSynchronize(c->aux2_stream));
+    VG_CUDA(cudaStreamSynchronize(c->aux3_stream));
     c->launches = 0;
     cudaGraph_t graph = nullptr;
     VG_CUDA(cudaStreamBeginCapture(ex, cudaStreamCaptureModeThreadLocal));
@@ -1661,7 +1696,7 @@ int vgqa_text_tower(vgqa_ctx* c, const int32_t* ids, const uint8_t* text_mask, i
     VG_CHECK(clips <= c->cfg.max_clips && L <= c->cfg.max_text && L <= 64, "vgqa_text_tower: shape exceeds the context capacity");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     vg::Fwd f;
-    f.c = c; f.st = st; f.main = st; f.aux = st; f.aux2 = st; f.B = clips; f.L = L;
+    f.c = c; f.st = st; f.main = st; f.aux = st; f.aux2 = st; f.aux3 = st; f.B = clips; f.L = L;
     vg::run_text_tower(f, ids, text_mask);
     vg::GemmEpi ep; ep.C = c->tproj; ep.ldc = 256; ep.bias = c->ip_text.b; ep.bias_ld = 256; ep.C32 = c->tproj32; ep.ldc32 = 256;
     ep.ln_w = c->ip_text_ln.w; ep.ln_b = c->ip_text_ln.b; ep.ln_eps = 1e-12f;
