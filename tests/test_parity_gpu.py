@@ -256,24 +256,27 @@ def test_fused_decoder_tail_chain(monkeypatch):
     sizes = torch.tensor([[float(g["ori_size"][0]), float(g["ori_size"][1])]] * 3, device="cuda")
     launches = {}
     outs = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("VGQA_CHAIN", flag)          # read when the context is created
+    monkeypatch.setenv("VGQA_CHAIN_HEAD", "0")
+    for flag in ("0", "1", "head"):
+        monkeypatch.setenv("VGQA_CHAIN", "1" if flag == "1" else "0")          # read when the context is created
+        monkeypatch.setenv("VGQA_CHAIN_HEAD", "1" if flag == "head" else "0")  # the light chain only: bbox_embed → sine → ref_point_head
         eng = GroundingEngine(sd, max_clips=3, max_frames=T, max_hw=H * W, max_text=L)
         o = eng.forward(t(np.stack([vis] * 3)), t(np.stack([vid] * 3)), t(np.stack([text[:, 0]] * 3)), None, ori_sizes_hw=sizes)
         torch.cuda.synchronize()
         outs[flag] = {k: v.cpu().numpy() for k, v in o.items()}
         launches[flag] = eng.last_launch_count
         eng.close()
-    assert launches["1"] < launches["0"] - 100, launches      # 192 rows = two row tiles (one ragged)
-    o = dict(outs["1"], frames_cls=outs["1"]["frames_cls"][:T])     # continuous_errors looks at clip 0
-    for b in range(3):
-        np.testing.assert_array_equal(o["choose1"][b], _ref_sel(g, "choose_pass1"))
-        np.testing.assert_array_equal(o["choose2"][b], _ref_sel(g, "choose_pass2"))
-    worst = continuous_errors(g, o)
-    bad = {k: v for k, v in worst.items() if not v <= (TOL_INTERNAL if k == "frames_cls" else TOL)}
-    assert not bad, f"chain: {bad} (all: {worst})"
-    for k in ("pred_boxes", "pred_sted", "pred_actioness", "aux_boxes"):
-        np.testing.assert_allclose(outs["1"][k], outs["0"][k], atol=5e-3, err_msg=k)   # same math, different summation order
+    assert launches["1"] < launches["0"] - 100 and launches["head"] < launches["0"] - 50, launches   # 192 rows = two row tiles (one ragged)
+    for flag in ("1", "head"):
+        o = dict(outs[flag], frames_cls=outs[flag]["frames_cls"][:T])     # continuous_errors looks at clip 0
+        for b in range(3):
+            np.testing.assert_array_equal(o["choose1"][b], _ref_sel(g, "choose_pass1"))
+            np.testing.assert_array_equal(o["choose2"][b], _ref_sel(g, "choose_pass2"))
+        worst = continuous_errors(g, o)
+        bad = {k: v for k, v in worst.items() if not v <= (TOL_INTERNAL if k == "frames_cls" else TOL)}
+        assert not bad, f"chain {flag}: {bad} (all: {worst})"
+        for k in ("pred_boxes", "pred_sted", "pred_actioness", "aux_boxes"):
+            np.testing.assert_allclose(outs[flag][k], outs["0"][k], atol=5e-3, err_msg=k)   # same math, different summation order
 
 
 def test_batch_of_clips_matches_single():

@@ -22,6 +22,7 @@
 // The FFN pair follows ffn_fused.cu's scheme on one CTA: the hidden activation is walked in 128-wide chunks, H_c = relu(x W1_c^T)
 // accumulates in one half of the second accumulator, is converted to bf16 into one half of ACT1 and immediately consumed as the
 // K-slice of Out += H_c · W2_c^T; the first GEMM runs two chunks ahead of the second.
+#include <math.h>
 #include <stdlib.h>
 
 #include <string>
@@ -47,6 +48,7 @@ __device__ __forceinline__ float ch_gelu(float x) { return 0.5f * x * (1.0f + er
 
 // ------------------------------------------------------------------------------------------------ epilogue helpers
 struct EpiCtx {
+  const float* sine_inv;   // 64 frequencies of the box sine embedding (kernel parameter space)
   uint32_t tmem_row;   // TMEM address of this thread's lane, column 0
   uint8_t* act;        // ACT tiles (8 x 16 KB)
   const float* headw;  // staged head weights [head_n][256]
@@ -128,13 +130,31 @@ __device__ void epi_plain(const ChOp& op, const EpiCtx& e, uint32_t tacc, int nc
       }
     }
   }
-  if (op.head_n > 0 && e.valid) {
+  if (op.head_n > 0) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (j < op.head_n) {
         float y = hacc[j] + __ldg(op.head_b + j);
         if (op.head_act == 1) y = 1.f / (1.f + expf(-y));
-        op.head_out[(size_t)e.grow * op.head_n + j] = y;
+        hacc[j] = y;
+        if (e.valid) op.head_out[(size_t)e.grow * op.head_n + j] = y;
+      }
+    }
+    if (op.gen_sine) {   // boxes (cx, cy, w, h) → 4 x 128 sine features in the order (y, x, w, h): sin on even, cos on odd indices
+#pragma unroll 1
+      for (int grp = 0; grp < 4; ++grp) {
+        const float x = grp == 0 ? hacc[1] : (grp == 1 ? hacc[0] : (grp == 2 ? hacc[2] : hacc[3]));
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float sv, cv;
+            __sincosf(x * e.sine_inv[c * 16 + i], &sv, &cv);
+            v[2 * i] = sv; v[2 * i + 1] = cv;
+          }
+          store_act32(e, 0, grp * 128 + c * 32, v);
+          if (e.valid && op.sine_out != nullptr) store_bf16_32(op.sine_out + (size_t)e.grow * 512 + grp * 128 + c * 32, v);
+        }
       }
     }
   }
@@ -439,6 +459,7 @@ __global__ void __launch_bounds__(192, 1) chain_kernel(const __grid_constant__ C
     e.t = (e.valid ? e.grow : 0) % P.T;
     e.act = act;
     e.headw = headw;
+    e.sine_inv = P.sine_inv;
     e.tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     uint32_t acc_use[2] = {0, 0};
     uint32_t hbase = 0;
@@ -468,6 +489,7 @@ __global__ void __launch_bounds__(192, 1) chain_kernel(const __grid_constant__ C
           release_acc(acc);
         }
         if (op.out_act >= 0) act_written(op.out_act);
+        else if (op.gen_sine) act_written(0);
       } else {   // CH_FFN
         const int nc = op.ff_chunks;
         uint32_t raw[32];
@@ -521,8 +543,9 @@ void chain_set_tmap(ChainParams& p, int i, const bf16* ptr, int rows, int cols, 
   if (p.n_tm < i + 1) p.n_tm = i + 1;
 }
 
-void chain_launch(const ChainParams& p, cudaStream_t stream) {
+void chain_launch(ChainParams& p, cudaStream_t stream) {
   VG_CHECK(p.n_ops >= 1 && p.n_ops <= CH_MAX_OPS && p.M >= 1 && p.T >= 1, "chain: bad program");
+  for (int k = 0; k < 64; ++k) p.sine_inv[k] = 6.283185307179586f / powf(10000.f, (float)(2 * k) / 128.f);
   static bool attr_set = false;
   if (!attr_set) {
     VG_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));

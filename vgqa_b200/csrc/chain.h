@@ -49,6 +49,10 @@ struct ChOp {
   const float* head_b = nullptr;
   int head_n = 0, head_act = 0;   // head_act 1 = sigmoid
   float* head_out = nullptr;      // [M, head_n] fp32
+  // with head_n == 4 (boxes cx, cy, w, h): gen_sineembed_for_position of the head's output (model_utils.py:15-40; order y, x, w, h,
+  // 128 features each) written as the 512-wide bf16 A operand of the next GEMM into ACT blocks 0..7 (and to sine_out [M, 512])
+  int gen_sine = 0;
+  bf16* sine_out = nullptr;
   // ---- CH_FFN:  y = LN(res32 + W2 relu(W1 x + bias) + bias2), x = ACT0; w = W1 tiles [ff_chunks][4], w2 = W2 tiles [2][2 ff_chunks]
   const bf16* w2 = nullptr;
   const float* bias2 = nullptr;
@@ -61,11 +65,12 @@ struct ChainParams {
   int n_ops = 0;
   int M = 0;    // rows (clips x frames)
   int T = 1;    // frames per clip: table row of a query row = row % T
+  float sine_inv[64];   // 2*pi / 10000^(2k/128): filled by chain_launch
   ChOp ops[CH_MAX_OPS];
 };
 
 void chain_set_tmap(ChainParams& p, int i, const bf16* ptr, int rows, int cols, int ld);
-void chain_launch(const ChainParams& p, cudaStream_t stream);
+void chain_launch(ChainParams& p, cudaStream_t stream);
 size_t chain_tile_weights(const float* W, int N, int K, std::vector<bf16>& out);
 
 }  // namespace vg

@@ -139,13 +139,19 @@ struct vgqa_ctx {
   LNp time_norm;
   Lin kpos_all;  // [dec_layers*256, 256]
   Lin rph0, rph1, qs0, qs1, bb0, bb1;
-  bf16 *bb0_t = nullptr, *bb1_t = nullptr;
+  bf16 *bb0_t = nullptr, *bb1_t = nullptr, *rph0_t = nullptr, *rph1_t = nullptr;
   float *bb2w = nullptr, *bb2b = nullptr;
   // VGQA_CHAIN=1 runs the frame-local tail of every decoder layer as ONE fused row-tile GEMM chain (chain.cu) instead of one
   // launch per Linear.  Measured (profiles/r02_chain.md): 455 → 301 launches per step, parity-identical, but a chain streams
   // 3.4 MB of weights through ONE SM per 128-row tile (≈52 GB/s with 80 KB in flight) where the per-Linear launches spread the
   // same weights over the whole GPU — 2.72 vs 1.92 ms per clip at batch 1, 13.96 vs 13.75 ms per 64-clip step.  Off by default.
   bool use_chain = [] { const char* e = getenv("VGQA_CHAIN"); return e != nullptr && e[0] == '1'; }();
+  // VGQA_CHAIN_HEAD=1: only the light end of the PosDecoder tail as a chain — bbox_embed (3 Linear) → sigmoid → box sine embedding
+  // → ref_point_head (2 Linear) of the NEXT layer, one launch instead of seven, 640 KB of weights per row tile.  Measured: 455 → 377
+  // launches, parity-identical, still slower (13.89 vs 13.61 ms per 64-clip step, 2.09 vs 1.83 ms per clip at batch 1): inside one
+  // CTA every Linear of the dependent chain costs ≈10 us (row-per-thread epilogue over 256 columns + weight latency), a graph
+  // node with PDL ≈5.5 us.  Off by default.
+  bool use_chain_head = [] { const char* e = getenv("VGQA_CHAIN_HEAD"); return e != nullptr && e[0] == '1'; }();
   Mlp2 temp_embed, action_embed;
   float *pfc_ln0w, *pfc_ln0b, *pfc_W, *pfc_b, *pfc_ln4w, *pfc_ln4b;
   // optional front end: input_proj / input_proj2 (1x1 convs) and the text resizer; K == 0 → not loaded
@@ -532,6 +538,8 @@ static void pack_weights(vgqa_ctx* c) {
   c->qs1 = P.lin(g + "decoder.query_scale.layers.1", 256, 256);
   c->bb0 = P.lin("bbox_embed.layers.0", 256, 256);
   c->bb1 = P.lin("bbox_embed.layers.1", 256, 256);
+  c->rph0_t = P.tiled(g + "decoder.ref_point_head.layers.0", 256, 512);
+  c->rph1_t = P.tiled(g + "decoder.ref_point_head.layers.1", 256, 256);
   c->bb0_t = P.tiled("bbox_embed.layers.0", 256, 256);
   c->bb1_t = P.tiled("bbox_embed.layers.1", 256, 256);
   c->bb2w = P.f32(P.get("bbox_embed.layers.2.weight", {4, 256}).v);
@@ -1022,6 +1030,7 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames, bool second_pas
   // fused row-tile GEMM chains (chain.cu) for the frame-local tails of the decoder layers; a frame-sharded clip keeps the
   // one-launch-per-Linear form (its in-projection table is offset by the rank's first frame)
   const bool chain = c->use_chain && !f.sharded();
+  const bool chain_head = c->use_chain_head && !chain;
   // anchors from frames_cls (query_decoder.py:92-94)
   if (!second_pass) {
     pos_fc_boxes(c->frames_cls, c->pfc_ln0w, c->pfc_ln0b, c->pfc_W, c->pfc_b, c->pfc_ln4w, c->pfc_ln4b, c->boxes0, F, st);
@@ -1105,8 +1114,8 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames, bool second_pas
     // self-attention chain and is joined where its product (the scaled sine embedding) is first used.
     const bf16* s256 = c->p_sine;
     int lds = 512;
-    sine_embed(boxes, c->p_sine, F, st);                                        // :169
-    f.count();
+    const bool have_qpos = chain_head && l > 0;   // the head chain of layer l-1 produced p_sine and query_pos already
+    if (!have_qpos) { sine_embed(boxes, c->p_sine, F, st); f.count(); }         // :169
     if (l > 0) {
       f.side_fork(st);
       f.st = f.aux2;
@@ -1116,8 +1125,10 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames, bool second_pas
       f.st = st;
       s256 = c->p_s256; lds = 256;
     }
-    f.linear(c->p_sine, 512, c->rph0, F, c->p_h, 256, ACT_RELU);                // ref_point_head (:170)
-    f.linear(c->p_h, 256, c->rph1, F, c->p_cat + 256, 768);
+    if (!have_qpos) {
+      f.linear(c->p_sine, 512, c->rph0, F, c->p_h, 256, ACT_RELU);              // ref_point_head (:170)
+      f.linear(c->p_h, 256, c->rph1, F, c->p_cat + 256, 768);
+    }
     { GemmEpi ep; ep.C = c->p_qkv; ep.ldc = 768; ep.bias = q.tab_sa + (size_t)c->sh_rank * T * 768; ep.bias_period = T; ep.bias_ld = 768;
       f.gemm(c->p_cat, 768, q.sa, F, ep); }                                     // 7 sa_* projs ∘ in_proj (:282-294)
     {
@@ -1176,10 +1187,39 @@ static void run_decoders(Fwd& f, bool have_mask, int pos_frames, bool second_pas
       f.linear_res_ln(c->p_ctx8, 2048, q.vo, F, c->p_x32, q.ln3, 1e-5f, c->p_x2, 256, c->p_x2_32);
       f.linear(c->p_x2, 256, q.ff1, F, c->p_hid, q.ff1.N, ACT_RELU);
       f.linear_res_ln(c->p_hid, q.ff2.K, q.ff2, F, c->p_x2_32, q.ln4, 1e-5f, c->p_cat, 768, c->p_tgt32);
-      f.linear(c->p_cat, 768, c->bb0, F, c->p_b1, 256, ACT_RELU);                 // bbox_embed (:188-192)
-      f.linear(c->p_b1, 256, c->bb1, F, c->p_b2, 256, ACT_RELU);
-      rowvec_head(c->p_b2, 256, c->bb2w, c->bb2b, anc, 4, F, 4, 1, st);
-      f.count(3);
+      if (chain_head) {
+        // ONE launch (chain.cu): bbox_embed 256 → 256 → 256 → 4, sigmoid (:188-192), and — for the next layer — the box sine
+        // embedding (:169) and ref_point_head 512 → 256 → 256 (:170): seven launches of the per-Linear form
+        ChainParams cp;
+        cp.M = F; cp.T = T;
+        chain_set_tmap(cp, 0, c->p_cat, F, 256, 768);
+        ChOp& o0 = cp.ops[0];
+        o0.kind = CH_LOAD; o0.a_tm = 0; o0.a_col0 = 0; o0.a_blk = 0; o0.nkb = 4;
+        ChOp& o1 = cp.ops[1];
+        o1.a_blk = 0; o1.a_wait = CH_WAIT_TMA; o1.w = c->bb0_t; o1.nkb = 4; o1.nblk = 2; o1.cn = 2; o1.acc0 = 0; o1.bias = c->bb0.b;
+        o1.act = ACT_RELU; o1.out_act = 4;
+        ChOp& o2 = cp.ops[2];
+        o2.a_blk = 4; o2.a_wait = CH_WAIT_EPI; o2.w = c->bb1_t; o2.nkb = 4; o2.nblk = 2; o2.cn = 2; o2.acc0 = 1; o2.bias = c->bb1.b;
+        o2.act = ACT_RELU; o2.head_w = c->bb2w; o2.head_b = c->bb2b; o2.head_n = 4; o2.head_act = 1; o2.head_out = anc;
+        cp.n_ops = 3;
+        if (l + 1 < D) {
+          o2.gen_sine = 1; o2.sine_out = c->p_sine;
+          ChOp& o3 = cp.ops[3];
+          o3.a_blk = 0; o3.a_wait = CH_WAIT_EPI; o3.w = c->rph0_t; o3.nkb = 8; o3.nblk = 2; o3.cn = 2; o3.acc0 = 0; o3.bias = c->rph0.b;
+          o3.act = ACT_RELU; o3.out_act = 0;
+          ChOp& o4 = cp.ops[4];
+          o4.a_blk = 0; o4.a_wait = CH_WAIT_EPI; o4.w = c->rph1_t; o4.nkb = 4; o4.nblk = 2; o4.cn = 2; o4.acc0 = 1; o4.bias = c->rph1.b;
+          o4.out_bf16 = c->p_cat + 256; o4.ld_out = 768;
+          cp.n_ops = 5;
+        }
+        chain_launch(cp, st);
+        f.count();
+      } else {
+        f.linear(c->p_cat, 768, c->bb0, F, c->p_b1, 256, ACT_RELU);               // bbox_embed (:188-192)
+        f.linear(c->p_b1, 256, c->bb1, F, c->p_b2, 256, ACT_RELU);
+        rowvec_head(c->p_b2, 256, c->bb2w, c->bb2b, anc, 4, F, 4, 1, st);
+        f.count(3);
+      }
     }
     boxes = anc;
   }
