@@ -29,6 +29,9 @@ struct AttnTcParams {
   int heads = 8;
   const float* sbias = nullptr;
   int bias_sets = 1, wpc = 1;
+  // work distribution: a CTA walks "pseudo-frames" = (frame, block of heads / hsplit heads).  hsplit = 1: a frame and its heads stay on
+  // one CTA (many frames); hsplit = heads: every (frame, head) is a unit of its own, so that a few large windows still fill the GPU
+  int hsplit = 1;
 };
 
 // K-major operand, rows of 64 B (32 bf16), 64B swizzle: 8-row groups 512 B apart.

@@ -48,10 +48,11 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   const int S = p.S;
   const int nt = (S + 127) >> 7;   // 128-token tiles per frame (queries and keys)
   int my_frames = 0;
-  for (int f = blockIdx.x; f < p.F; f += gridDim.x) ++my_frames;
-  const int NH = p.heads;                                 // heads per frame (8 in the encoder, 24 in the Video-Swin stage)
-  const int koff = NH * 32, voff = NH * 64;               // column of the K / V slices in the packed [q | k | v] row
-  const int items = my_frames * NH * nt;                  // (frame, head, query tile)
+  for (int f = blockIdx.x; f < p.F * p.hsplit; f += gridDim.x) ++my_frames;
+  const int NH = p.heads / p.hsplit;                      // heads per pseudo-frame (8 in the encoder; 1 in the Video-Swin stage)
+  const int HS = p.hsplit;                                // pseudo-frames per frame
+  const int koff = p.heads * 32, voff = p.heads * 64;     // column of the K / V slices in the packed [q | k | v] row
+  const int items = my_frames * NH * nt;                  // (pseudo-frame, head, query tile)
   const int slots = ((items + kAtWgs - 1) / kAtWgs) * kAtWgs * nt;   // sub-unit slots, stream-interleaved: slot u → stream u % 4
   // slot u → sub-unit (u / 4) of stream (u % 4): item = stream + 4 * (sub / nt), key tile = sub % nt
   auto decode = [&](int u) {
@@ -61,9 +62,11 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     x.j = sub % nt;
     x.valid = it < items;
     const int fi = it / (NH * nt), rem = it - fi * NH * nt;
-    x.f = (int)blockIdx.x + fi * (int)gridDim.x;
-    x.h = rem / nt;
-    x.qt = rem - x.h * nt;
+    const int pf = (int)blockIdx.x + fi * (int)gridDim.x;   // pseudo-frame → (frame, first head of its block)
+    const int hl = rem / nt;
+    x.f = pf / HS;
+    x.h = (pf - x.f * HS) * NH + hl;
+    x.qt = rem - hl * nt;
     return x;
   };
 
@@ -170,14 +173,15 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     int sub = 0;                             // sub-units this stream has processed (barrier phases)
     for (int it = wg; it < items; it += kAtWgs) {
       const int fi = it / (NH * nt), rem = it - fi * NH * nt;
-      const int f = (int)blockIdx.x + fi * (int)gridDim.x, h = rem / nt, qt = rem - h * nt;
+      const int pf = (int)blockIdx.x + fi * (int)gridDim.x, hl = rem / nt, qt = rem - hl * nt;
+      const int f = pf / HS, h = (pf - f * HS) * NH + hl;
       const uint8_t* km = p.kmask ? p.kmask + (size_t)f * S : nullptr;
       // additive score row of this query (relative position bias [+ shift mask]); rows beyond S are clipped on store
       const float* brow = nullptr;
       if (p.sbias != nullptr) {
         const int set = (p.bias_sets == 2 && (f % p.wpc) == p.wpc - 1) ? 1 : 0;
         const int qrow = min(qt * 128 + row, S - 1);
-        brow = p.sbias + (((size_t)set * NH + h) * S + qrow) * S;
+        brow = p.sbias + (((size_t)set * p.heads + h) * S + qrow) * S;
       }
       float m_run = -INFINITY, l_run = 0.f;
       float o_run[32];
@@ -190,7 +194,7 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         mbar_wait(&s_full[wg], ph);
         tc_fence_after();
         uint32_t raw[32];
-        auto load_chunk = [&](int c, float (&x)[32]) {
+        auto load_chunk = [&](int c, float (&x)[32], bool add_bias) {
           tmem_ld32(t_s + c * 32, raw);
           tmem_ld_wait();
           if (km != nullptr) {
@@ -207,7 +211,7 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(raw[i]);
           }
-          if (brow != nullptr) {   // rows of S fp32 with S % 4 == 0: 16-byte loads on full chunks, guarded scalars on the tail chunk
+          if (brow != nullptr && add_bias) {   // rows of S fp32 with S % 4 == 0: 16-byte loads on full chunks, guarded scalars on the tail chunk
             const float* b = brow + kbase + c * 32;
             if (c * 32 + 32 <= nkeys) {
 #pragma unroll
@@ -220,16 +224,21 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
               for (int i = 0; i < 32; ++i)
                 if (c * 32 + i < nkeys) x[i] += __ldg(b + i);
             }
+            // park the biased scores in TMEM: the exponential pass reads them back instead of fetching the bias row again
+#pragma unroll
+            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(x[i]);
+            tmem_st32(t_s + c * 32, raw);
           }
         };
         float x[32];
         float m_new = m_run;
 #pragma unroll 1
         for (int c = 0; c * 32 < nkeys; ++c) {
-          load_chunk(c, x);
+          load_chunk(c, x, true);
 #pragma unroll
           for (int i = 0; i < 32; ++i) m_new = fmaxf(m_new, x[i]);
         }
+        if (brow != nullptr) tmem_st_wait();
         const float base = m_new == -INFINITY ? 0.f : m_new;
         const float nbase = -base * p.scale_log2e;
         if (wg_tid == 0) tma_store_wait_read<0>();  // the previous item's output store has drained the head of p_buf
@@ -238,7 +247,7 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
           if (c * 32 < nkeys) {
-            load_chunk(c, x);
+            load_chunk(c, x, false);
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               pk[i] = ex2_bf16x2(pack_bf16(fmaf(x[2 * i], p.scale_log2e, nbase), fmaf(x[2 * i + 1], p.scale_log2e, nbase)));
@@ -301,7 +310,9 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 CUtensorMap make_tmap_frames(const bf16* ptr, int F, int S, int cols, int ld);   // attn_tc.cu
 int device_sm_count();
 
-static void launch_long(const bf16* QKV, bf16* AO, const AttnTcParams& p, cudaStream_t stream) {
+static void launch_long(const bf16* QKV, bf16* AO, AttnTcParams& p, cudaStream_t stream) {
+  // few frames (one long clip, a handful of Swin windows): spread the heads of a frame over CTAs as well
+  p.hsplit = p.F < 2 * device_sm_count() ? p.heads : 1;
   static bool attr_set = false;
   if (!attr_set) {
     VG_CUDA(cudaFuncSetAttribute(enc_attn_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
@@ -309,7 +320,8 @@ static void launch_long(const bf16* QKV, bf16* AO, const AttnTcParams& p, cudaSt
   }
   CUtensorMap tq = make_tmap_frames(QKV, p.F, p.S, 96 * p.heads, 96 * p.heads);
   CUtensorMap to = make_tmap_frames(AO, p.F, p.S, 32 * p.heads, 32 * p.heads);
-  const int grid = p.F < device_sm_count() ? p.F : device_sm_count();
+  const int units = p.F * p.hsplit;
+  const int grid = units < device_sm_count() ? units : device_sm_count();
   enc_attn_tc_long_kernel<<<grid, kAtLongThreads, kAtSmem, stream>>>(tq, to, p);
   VG_CUDA(cudaGetLastError());
 }
