@@ -165,13 +165,24 @@ def run_reference_arm(args, rank):
     if rank != 0:
         return
     v, t_steps, kind, what, cores = cpu_clips_per_sec(args.steps, warmup=max(1, args.warmup))
+    # BASELINE.json configs[0]: the reference's FULL VSTGNet.forward (backbones + RoBERTa + hot path) on the host cores, mini yaml
+    # (224 px, 32 frames), synthetic clip, random-init weights — one warm-up + one timed call (≈15 s on 16 cores)
+    full = None
+    if kind == "reference" and not args.no_full_forward:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from full_forward_cpu import full_forward_seconds
+            full = full_forward_seconds()
+        except Exception as ex:   # noqa: BLE001 — reported in the line
+            full = {"error": f"{type(ex).__name__}: {ex}"}
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(t_steps) / len(t_steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clips_per_step": 1},
             "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": kind,
                              "sample": f"{len(t_steps)} clips of the same workload, one per step ({what})"},
-            "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "full_forward_cfg1": full}
     print(json.dumps(line), flush=True)
 
 
@@ -293,6 +304,7 @@ def main():
     ap.add_argument("--clips", type=int, default=64, help="clips per step per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-full-forward", action="store_true", help="reference arm: skip the full VSTGNet.forward (cfg-1) measurement")
     ap.add_argument("--quick", action="store_true", help="headline + e2e + roofline only (skip the other configs / eager-PyTorch lines)")
     ap.add_argument("--cpu-clips", type=int, default=60, help="clips of the bounded CPU-baseline sample (≈10-15 s of host work on 16 cores)")
     args = ap.parse_args()

@@ -18,17 +18,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("VGQA_REFERENCE_ROOT", "/root/reference")
 OUT = os.path.join(ROOT, "oracle", "_ref")
 
-# the hot path and what its modules import from the reference package
-FILES = [
-    "vgqa/core/decoder/__init__.py", "vgqa/core/decoder/modal_encoder.py", "vgqa/core/decoder/query_decoder.py",
-    "vgqa/core/decoder/attention.py", "vgqa/core/decoder/classifier.py", "vgqa/core/decoder/position_encoding.py",
-    "vgqa/core/language/bert_module.py", "vgqa/core/model_utils.py", "vgqa/core/vision/position_encoding.py",
-    "vgqa/core/postprocessor.py", "vgqa/training/evaluator.py", "vgqa/utils/training_utils.py", "vgqa/utils/box_ops.py",
-    "vgqa/utils/distributed.py",
-    # widened row (§8f rank 3): the Video-Swin extractor whose last stage csrc/swin.cu restates (needs timm's DropPath /
-    # trunc_normal_: stubbed by tests/golden/make_golden_swin.py)
-    "vgqa/core/vision/video_swin_transformer.py",
-]
+# The hot path and what its modules import from the reference package, the Video-Swin extractor whose last stage
+# csrc/swin.cu restates, and — for BASELINE configs[0], the FULL VSTGNet.forward on the host cores (tools/full_forward_cpu.py) — the
+# rest of vgqa/core, vgqa/utils and vgqa/config.  (vgqa/data, vgqa/inference, tools/, app/ are not needed and not compiled.)
+def _files():
+    out = []
+    for sub in ("core", "utils", "config"):
+        for dirpath, _, names in os.walk(os.path.join(REF, "vgqa", sub)):
+            for n in sorted(names):
+                if n.endswith(".py"):
+                    out.append(os.path.relpath(os.path.join(dirpath, n), REF))
+    out.append("vgqa/training/evaluator.py")
+    return sorted(out)
 
 
 def build(verbose: bool = True) -> bool:
@@ -38,6 +39,7 @@ def build(verbose: bool = True) -> bool:
         return False
     if os.path.isdir(OUT):
         shutil.rmtree(OUT)
+    FILES = _files()
     for rel in FILES:
         dst = os.path.join(OUT, rel[:-3] + ".bin")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
