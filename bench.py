@@ -169,10 +169,12 @@ def run_reference_arm(args, rank):
     # (224 px, 32 frames), synthetic clip, random-init weights — one warm-up + one timed call (≈15 s on 16 cores)
     full = None
     if kind == "reference" and not args.no_full_forward:
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            from full_forward_cpu import full_forward_seconds
-            full = full_forward_seconds()
+        try:   # own process: the hot-path harness above imported the reference packages with their __init__ files bypassed
+            env = dict(os.environ)
+            env.pop("OMP_NUM_THREADS", None)          # torch.distributed.run exports OMP_NUM_THREADS=1
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "full_forward_cpu.py")], capture_output=True, text=True,
+                               timeout=900, cwd=ROOT, env=env)
+            full = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-500:]}
         except Exception as ex:   # noqa: BLE001 — reported in the line
             full = {"error": f"{type(ex).__name__}: {ex}"}
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus,
