@@ -246,35 +246,72 @@ def time_dominant_kernel(B, pk):
             "hbm_gbs_at_algorithmic_bytes": alg_bytes / dt / 1e9}
 
 
-def measure_with_backbone(eng, torch, d_pos, rank=0, clips=8, steps=5):
-    """SURVEY §8d secondary number: clips/s with a PyTorch bf16 backbone in front of the library — torchvision ResNet101 (random
-    init, eval, bf16, channels_last: cuDNN/cuBLAS LIBRARY code, not part of this repo's kernels) on `clips` x 64 frames of 3x224x224,
-    its layer-4 map fed to the raw-input forward.  The Video-Swin map and the RoBERTa states stay synthetic (the reference's
-    Video-Swin implementation lives in /root/reference, which does not exist on the GPU box).  Returns None if torchvision is absent."""
+def measure_with_backbone(torch, rank=0, clips=8, steps=5):
+    """SURVEY §8d secondary number: clips/s with the extractors in front of the library, 8 clips x 64 frames of 3x224x224 per step.
+      * ResNet101: torchvision (random init, eval, bf16, channels_last — cuDNN / cuBLAS LIBRARY code, not this repo's kernels) → layer-4
+        map, handed over zero-copy (channels-last bf16 = raw_layout 1);
+      * Video-Swin-T: the reference's own module (oracle/_ref, random init, eager PyTorch bf16) for patch embedding, stages 1-3 and the
+        PatchMerging layers; the LAST stage (`vid.layers[3]`) runs on this library's kernels (csrc/swin.cu) with that module's weights,
+        and its channels-last bf16 output goes straight into the forward.  Without oracle/_ref the Video-Swin map is synthetic;
+      * RoBERTa states synthetic (the text tower has its own `front_end.from_token_ids` line).
+    The repo's stage 4 is cross-checked against the PyTorch module's stage 4 on the same activations in the same run."""
     try:
         import torchvision
     except Exception:
         return None
+    from vgqa_b200 import synth
+    from vgqa_b200.engine import GroundingEngine
     net = torchvision.models.resnet101(weights=None)
     body = torch.nn.Sequential(net.conv1, net.bn1, net.relu, net.maxpool, net.layer1, net.layer2, net.layer3, net.layer4)
     body = body.eval().cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
     g = torch.Generator(device="cuda").manual_seed(99 + rank)
     frames = torch.randn(clips * T, 3, 224, 224, device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    vid = torch.randn(clips, T, H, W, FRONT_END_CH[1], device="cuda", generator=g).to(torch.bfloat16)   # channels-last bf16
     text = torch.randn(clips, L, FRONT_END_CH[2], device="cuda", generator=g)
     sizes = torch.tensor([[360.0, 640.0]] * clips, device="cuda")
+    sd = synth.synth_state_dict(0, front_end_ch=FRONT_END_CH)
+    swin = None
+    swin_note = "Video-Swin map synthetic (oracle/_ref absent)"
+    if reference_arm_available():
+        try:
+            from make_golden_swin import load_swin_module
+            M = load_swin_module()
+            torch.manual_seed(5)
+            swin = M.vidswin_model("video_swin_t_p4w7", None).eval().cuda()
+            for k, v in swin.state_dict().items():
+                if k.startswith("layers.3.blocks.") and "relative_position_index" not in k:
+                    sd["vid." + k] = v.detach().float().cpu().numpy()
+            swin_note = ("Video-Swin-T: the reference module (eager PyTorch bf16) for stages 1-3, its LAST stage on this library's kernels "
+                         "(csrc/swin.cu)")
+        except Exception as ex:   # noqa: BLE001
+            swin, swin_note = None, f"Video-Swin map synthetic ({type(ex).__name__}: {ex})"
+    eng = GroundingEngine(sd, max_clips=clips, max_frames=T, max_hw=H * W, max_text=L, use_cuda_graph=True)
+    vid_syn = torch.randn(clips, T, H, W, FRONT_END_CH[1], device="cuda", generator=g).to(torch.bfloat16)
     want = ["pred_boxes", "pred_sted", "boxes_px", "sted_idx"]
     outs = eng.alloc_outputs(clips, T, H, W, L, want)
+    from einops import rearrange
 
-    def step(backbone_only=False):
+    def swin_front():
+        """patch embedding + stages 1-3 + PatchMerging of the reference module → the channels-last input of the last stage"""
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            x = rearrange(frames, "(b t) c h w -> b c t h w", b=clips, t=T)
+            x = swin.pos_drop(swin.patch_embed(x))
+            for idx in range(3):
+                x = swin.layers[idx](x.contiguous())
+                x = rearrange(swin.downsamples[idx](rearrange(x, "b c t h w -> b t h w c")), "b t h w c -> b c t h w")
+        return rearrange(x, "b c t h w -> b t h w c").float().contiguous()          # [clips, T, 7, 7, 768]
+
+    def step(mode="all"):
         with torch.no_grad():
             fmap = body(frames)                                            # [clips*T, 2048, 7, 7] bf16
-        if backbone_only:
+        if mode == "resnet":
+            return
+        vid = eng.swin_stage(swin_front()) if swin is not None else vid_syn
+        if mode == "extractors":
             return
         # a channels_last bf16 tensor IS [N, H, W, C] in memory: handed over zero-copy (raw_layout = 1)
         vis = fmap.permute(0, 2, 3, 1).view(clips, T, H, W, FRONT_END_CH[0])
         assert vis.is_contiguous()
-        eng.forward(vis, vid, text, d_pos, ori_sizes_hw=sizes, outs=outs, raw=True)
+        eng.forward(vis, vid, text, None, ori_sizes_hw=sizes, outs=outs, raw=True)
 
     def timed(fn):
         for _ in range(3):
@@ -288,14 +325,30 @@ def measure_with_backbone(eng, torch, d_pos, rank=0, clips=8, steps=5):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) * 1e-3 / steps
 
-    sec, sec_bb = timed(step), timed(lambda: step(True))
-    del body, frames
+    res = {}
+    if swin is not None:   # the repo's last stage against the PyTorch module's on the same activations
+        x4 = swin_front()
+        mine = eng.swin_stage(x4, want_f32=True)[1]
+        with torch.no_grad():
+            ref4 = swin.layers[3](rearrange(x4, "b t h w c -> b c t h w").contiguous())
+        ref4 = rearrange(ref4, "b c t h w -> b t h w c")
+        res["swin_stage4_max_abs_err_vs_pytorch_fp32"] = float((mine - ref4).abs().max())
+        res["swin_stage4_mean_abs"] = float(ref4.abs().mean())
+        sec_sw_front = timed(lambda: swin_front())
+        sec_sw4 = timed(lambda: eng.swin_stage(x4))
+        res["swin_stages123_pytorch_ms_per_step"] = 1e3 * sec_sw_front
+        res["swin_stage4_repo_ms_per_step"] = 1e3 * sec_sw4
+    sec, sec_bb = timed(step), timed(lambda: step("resnet"))
+    sec_ex = timed(lambda: step("extractors"))
+    eng.close()
+    del body, frames, swin
     torch.cuda.empty_cache()
-    return {"value": clips / sec, "unit": "clips/s", "ms_per_step": 1e3 * sec, "clips_per_step": clips,
-            "backbone_only_ms_per_step": 1e3 * sec_bb,
-            "what": "torchvision ResNet101 (random init, bf16, channels_last; PyTorch/cuDNN library code) on 64 x 3x224x224 frames per clip "
-                    "→ layer-4 map handed over zero-copy (channels-last bf16, raw_layout = 1) → this library's raw-input forward; "
-                    "Video-Swin map and RoBERTa states synthetic"}
+    res.update({"value": clips / sec, "unit": "clips/s", "ms_per_step": 1e3 * sec, "clips_per_step": clips,
+                "backbone_only_ms_per_step": 1e3 * sec_bb, "extractors_ms_per_step": 1e3 * sec_ex,
+                "what": "torchvision ResNet101 (random init, bf16, channels_last; PyTorch/cuDNN library code) on 64 x 3x224x224 frames per clip "
+                        "→ layer-4 map handed over zero-copy (channels-last bf16, raw_layout = 1); " + swin_note +
+                        " → this library's raw-input forward; RoBERTa states synthetic"})
+    return res
 
 
 def main():
@@ -668,12 +721,10 @@ def main():
         front_end, batch1 = secondary()
     except Exception as ex:   # noqa: BLE001 — reported in the line
         front_end = batch1 = {"error": f"{type(ex).__name__}: {ex}"}
-    try:
-        with_bb = measure_with_backbone(eng, torch, d_pos, rank=rank) if rank == 0 else None
-    except Exception as ex:   # noqa: BLE001
-        with_bb = {"error": f"{type(ex).__name__}: {ex}"}
     eng.close()
     torch.cuda.empty_cache()
+    # (own engine: it carries the weights of the Video-Swin module's last stage)
+    with_bb = guarded(lambda: measure_with_backbone(torch, rank=rank)) if (rank == 0 and not args.quick) else None
     others = guarded(other_configs) if not args.quick else None
     if world == 1 and not args.quick:
         others = dict(others or {}, long_T256_7x7_L20_B1=guarded(lambda: long_clip_single_gpu(7)),
