@@ -633,45 +633,73 @@ def swin_relative_position_index(window: Tuple[int, int, int]) -> np.ndarray:
     return rel.sum(-1)
 
 
-def swin_stage(sd, x: np.ndarray, prefix: str = "vid.layers.3.", heads: int = 24, window=(8, 7, 7), depth: int = 2) -> np.ndarray:
-    """BasicLayer.forward of the LAST Video-Swin stage (no downsample) — video_swin_transformer.py:377-398 — on a channels-last
-    map x (B, D, H, W, C) whose H, W do not exceed the window (224 px clips: 7x7), D a multiple of the temporal window:
-    per block (:210-275)  x += proj(W-MSA(LN1(x)));  x += fc2(gelu(fc1(LN2(x)))), window attention with the relative position bias
-    (:143-165), odd blocks on the temporally rolled map with the -100 mask of compute_mask (:311-325)."""
+def _swin_windows(x: np.ndarray, win) -> np.ndarray:
+    """window_partition (video_swin_transformer.py:36-42): (B, D, H, W, C) → (B*nW, wd*wh*ww, C)."""
     B, D, H, W, C = x.shape
-    wd = min(window[0], D)
-    assert H <= window[1] and W <= window[2] and D % wd == 0, "oracle: one spatial window per frame, D % window == 0"
-    shift = window[0] // 2 if D > window[0] else 0                    # get_window_size (:53-66): no shift along a clamped axis
-    N = wd * H * W
+    wd, wh, ww = win
+    x = x.reshape(B, D // wd, wd, H // wh, wh, W // ww, ww, C).transpose(0, 1, 3, 5, 2, 4, 6, 7)
+    return x.reshape(-1, wd * wh * ww, C)
+
+
+def _swin_unwindows(w: np.ndarray, win, B, D, H, W) -> np.ndarray:
+    """window_reverse (:45-50)."""
+    wd, wh, ww = win
+    x = w.reshape(B, D // wd, H // wh, W // ww, wd, wh, ww, -1).transpose(0, 1, 4, 2, 5, 3, 6, 7)
+    return x.reshape(B, D, H, W, -1)
+
+
+def swin_shift_mask(D, H, W, win, shift) -> np.ndarray:
+    """compute_mask (:311-325): (nW, N, N) of 0 / -100 for the rolled map."""
+    img = np.zeros((D, H, W), np.int64)
+    cnt = 0
+    for d in (slice(-win[0]), slice(-win[0], -shift[0]), slice(-shift[0], None)):
+        for h in (slice(-win[1]), slice(-win[1], -shift[1]), slice(-shift[1], None)):
+            for w in (slice(-win[2]), slice(-win[2], -shift[2]), slice(-shift[2], None)):
+                img[d, h, w] = cnt
+                cnt += 1
+    mw = _swin_windows(img[None, ..., None].astype(F32), win)[..., 0]
+    return np.where(mw[:, None, :] != mw[:, :, None], F32(-100.0), F32(0.0))
+
+
+def swin_stage(sd, x: np.ndarray, prefix: str = "vid.layers.3.", heads: int = 24, window=(8, 7, 7), depth: int = 2) -> np.ndarray:
+    """BasicLayer.forward of one Video-Swin stage (no downsample) — video_swin_transformer.py:377-398 — on a channels-last map
+    x (B, D, H, W, C) whose sides are multiples of the (clamped) window:
+    per block (:210-275)  x += proj(W-MSA(LN1(x)));  x += fc2(gelu(fc1(LN2(x)))), window attention with the relative position bias
+    (:143-165), odd blocks on the cyclically rolled map with the -100 mask of compute_mask (:311-325)."""
+    B, D, H, W, C = x.shape
+    size = (D, H, W)
+    win = tuple(min(window[i], size[i]) for i in range(3))           # get_window_size (:53-66)
+    shift = tuple(0 if size[i] <= window[i] else window[i] // 2 for i in range(3))
+    assert all(size[i] % win[i] == 0 for i in range(3)), "oracle: sides must be multiples of the window (no padding path)"
+    N = win[0] * win[1] * win[2]
     dh = C // heads
-    idx = swin_relative_position_index(window)[:N, :N] if (H, W) == (window[1], window[2]) else None
-    assert idx is not None, "oracle: the map must fill the window in H and W"
+    idx = swin_relative_position_index(window)
+    # tokens of a clamped window: the first win[i] coordinates of every axis of the configured window (index[:N, :N] in the
+    # reference is only the same thing when the window is not clamped in H or W)
+    assert win[1:] == tuple(window[1:]) or win == tuple(window), "oracle: spatially clamped windows are not restated"
+    idx = idx[:N, :N]
+    mask = swin_shift_mask(D, H, W, win, shift) if any(shift) else None
     x = x.astype(F32)
     for i in range(depth):
         p = f"{prefix}blocks.{i}."
-        sh = shift if i % 2 == 1 else 0
+        sh = shift if (i % 2 == 1 and any(shift)) else None
         h = layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
         if sh:
-            h = np.roll(h, -sh, axis=1)
-        win = h.reshape(B * (D // wd), N, C)
-        qkv = linear(win, sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"]).reshape(-1, N, 3, heads, dh).transpose(2, 0, 3, 1, 4)
+            h = np.roll(h, (-sh[0], -sh[1], -sh[2]), axis=(1, 2, 3))
+        winx = _swin_windows(h, win)
+        qkv = linear(winx, sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"]).reshape(-1, N, 3, heads, dh).transpose(2, 0, 3, 1, 4)
         q, k, v = qkv[0] * F32(dh ** -0.5), qkv[1], qkv[2]
         attn = q @ k.transpose(0, 1, 3, 2)
         bias = sd[p + "attn.relative_position_bias_table"][idx.reshape(-1)].reshape(N, N, heads).transpose(2, 0, 1)
         attn = attn + bias[None]
-        if sh:                                                        # compute_mask: groups along the rolled time axis
-            g = np.zeros(D, np.int64)
-            g[D - wd:D - sh] = 1
-            g[D - sh:] = 2
-            gw = np.repeat(g.reshape(D // wd, wd), H * W, axis=1)                 # (nW, N)
-            mask = np.where(gw[:, :, None] != gw[:, None, :], F32(-100.0), F32(0.0))
-            attn = attn.reshape(B, D // wd, heads, N, N) + mask[None, :, None]
-            attn = attn.reshape(-1, heads, N, N)
+        if sh:
+            nW = mask.shape[0]
+            attn = (attn.reshape(B, nW, heads, N, N) + mask[None, :, None]).reshape(-1, heads, N, N)
         attn = softmax(attn, -1)
         o = (attn @ v).transpose(0, 2, 1, 3).reshape(-1, N, C)
-        o = linear(o, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"]).reshape(B, D, H, W, C)
+        o = _swin_unwindows(linear(o, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"]), win, B, D, H, W)
         if sh:
-            o = np.roll(o, sh, axis=1)
+            o = np.roll(o, sh, axis=(1, 2, 3))
         x = x + o
         h = layer_norm(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
         h = gelu_erf(linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]))
@@ -679,9 +707,38 @@ def swin_stage(sd, x: np.ndarray, prefix: str = "vid.layers.3.", heads: int = 24
     return x.astype(F32)
 
 
+def swin_patch_merging(sd, x: np.ndarray, prefix: str) -> np.ndarray:
+    """PatchMerging.forward (:291-308) for even H, W: 2x2 neighbours concatenated (x0, x1, x2, x3 order), LayerNorm(4C), Linear(4C → 2C)."""
+    x0, x1, x2, x3 = x[:, :, 0::2, 0::2], x[:, :, 1::2, 0::2], x[:, :, 0::2, 1::2], x[:, :, 1::2, 1::2]
+    h = np.concatenate([x0, x1, x2, x3], -1)
+    h = layer_norm(h, sd[prefix + "norm.weight"], sd[prefix + "norm.bias"])
+    return linear(h, sd[prefix + "reduction.weight"])
+
+
+def video_swin_backbone(sd, frames: np.ndarray, clips: int, prefix: str = "vid.", depths=(2, 2, 6, 2), heads=(3, 6, 12, 24),
+                        window=(8, 7, 7)):
+    """VideoSwinTransformerBackbone.forward (:666-685) on frames (clips*T, 3, R, R), R a multiple of 4: PatchEmbed3D with patch
+    (1,4,4) + LayerNorm (:426-443), four stages with PatchMerging between them.  Returns the four stage outputs as channels-last
+    maps [(clips, T, H_s, W_s, C_s)] ('0'..'3' of the reference, which are (clips*T, C, H, W))."""
+    n, c, R, _ = frames.shape
+    T = n // clips
+    w = sd[prefix + "patch_embed.proj.weight"]                      # (96, 3, 1, 4, 4)
+    E = w.shape[0]
+    x = frames.reshape(clips, T, c, R // 4, 4, R // 4, 4).transpose(0, 1, 3, 5, 2, 4, 6).reshape(clips, T, R // 4, R // 4, c * 16)
+    x = linear(x.astype(F32), w.reshape(E, -1), sd[prefix + "patch_embed.proj.bias"])
+    x = layer_norm(x, sd[prefix + "patch_embed.norm.weight"], sd[prefix + "patch_embed.norm.bias"])
+    outs = []
+    for s in range(len(depths)):
+        x = swin_stage(sd, x, f"{prefix}layers.{s}.", heads[s], window, depths[s])
+        outs.append(x)
+        if s + 1 < len(depths):
+            x = swin_patch_merging(sd, x, f"{prefix}downsamples.{s}.")
+    return outs
+
+
 # ----------------------------------------------------------------------------------------------
 # deterministic synthetic weights / inputs: they live in the product package (pure numpy, vgqa_b200/synth.py) so that the
 # GPU arm of bench.py imports nothing from oracle/; re-exported here for the tests and fixture makers
 # ----------------------------------------------------------------------------------------------
 from vgqa_b200.synth import (CALIB_PREFIX, apply_calibration, hot_path_param_shapes, synth_event_inputs, synth_inputs,  # noqa: E402,F401
-                             synth_masks, synth_raw_inputs, synth_state_dict, synth_swin_stage, synth_text_ids)
+                             synth_masks, synth_raw_inputs, synth_state_dict, synth_swin_backbone, synth_swin_stage, synth_text_ids)

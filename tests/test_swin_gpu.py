@@ -56,3 +56,30 @@ def test_swin_stage_feeds_the_raw_forward():
     torch.cuda.synchronize()
     assert torch.isfinite(o["pred_boxes"]).all() and torch.isfinite(o["pred_sted"]).all()
     eng.close()
+
+
+def test_video_swin_backbone_matches_reference_golden():
+    """The WHOLE Video-Swin-T extractor (patch embedding, four stages with shifted 3-D windows and their masks, PatchMerging) on the
+    library's kernels against the golden of the reference's own `VideoSwinTransformerBackbone` (tests/golden/make_golden_swin_full.py):
+    every 97th token row of all four stage outputs, and the last stage's map in full.  Yardstick per stage: the deviation of torch's
+    own bf16-autocast run of the reference module from its fp32 run (stored in the fixture)."""
+    from make_golden_swin_full import swin_frames
+    from vgqa_b200.engine import GroundingEngine
+    g = np.load(golden_path("swin_full_T16_224_s0"))
+    clips, T, R, seed = (int(g[k]) for k in ("clips", "T", "R", "seed"))
+    sd = O.synth_state_dict(0)
+    sd.update(O.synth_swin_backbone(seed))
+    eng = GroundingEngine(sd, max_clips=clips, max_frames=T, max_hw=49, max_text=8)
+    frames = torch.from_numpy(swin_frames(seed, clips, T, R)).cuda()
+    out, stages = eng.swin_backbone(frames, clips, want_stages=True)
+    torch.cuda.synchronize()
+    for s in range(4):
+        got = stages[s].cpu().numpy().reshape(-1, 96 << s)[::97]
+        err = np.abs(got - g[f"rows{s}"])
+        assert float(err.mean()) <= 1.25 * float(g[f"autocast_err_mean{s}"]), (s, float(err.mean()), float(g[f"autocast_err_mean{s}"]))
+        assert float(err.max()) <= 1.25 * float(g[f"autocast_err_max{s}"]), (s, float(err.max()), float(g[f"autocast_err_max{s}"]))
+    y3 = g["y3"].astype(np.float32)
+    e3 = np.abs(stages[3].cpu().numpy() - y3)
+    assert float(e3.max()) <= 1.25 * float(g["autocast_err_max3"]) + 8e-3
+    np.testing.assert_allclose(out.float().cpu().numpy(), stages[3].cpu().numpy(), atol=6e-2)      # the bf16 map handed to input_proj2
+    eng.close()

@@ -21,3 +21,14 @@ def test_relative_position_index_shape_and_range():
     idx = O.swin_relative_position_index((8, 7, 7))
     assert idx.shape == (392, 392) and idx.min() == 0 and idx.max() == 15 * 13 * 13 - 1
     assert (np.diag(idx) == idx[0, 0]).all()
+
+
+def test_video_swin_backbone_oracle_matches_reference_golden():
+    """The whole extractor (patch embedding, 4 stages with shifted 3-D windows + masks, PatchMerging) against the golden of the
+    reference's own VideoSwinTransformerBackbone (every 97th token row of all four stage outputs)."""
+    from make_golden_swin_full import swin_frames
+    g = np.load(golden_path("swin_full_T16_224_s0"))
+    clips, T, R, seed = (int(g[k]) for k in ("clips", "T", "R", "seed"))
+    outs = O.video_swin_backbone(O.synth_swin_backbone(seed), swin_frames(seed, clips, T, R), clips)
+    for s in range(4):
+        np.testing.assert_allclose(outs[s].reshape(-1, 96 << s)[::97], g[f"rows{s}"], atol=3e-4, err_msg=f"stage {s}")

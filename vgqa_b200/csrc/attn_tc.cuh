@@ -22,13 +22,17 @@ struct AttnTcParams {
   const uint8_t* kmask;  // [F, S] or nullptr
   int S, F;
   float scale_log2e;
-  // attn_tc_long.cu only — window attention of the Video-Swin stage (swin.cu): `heads` heads of 32 in a packed [q | k | v] row of
-  // 3 * 32 * heads columns, and an additive score term sbias[set][head][q][k] (fp32, ALREADY divided by the softmax scale, so
-  // that scale * (q·k + sbias) = scale * q·k + bias): the relative position bias, plus the -100 shift mask in set 1, which the
-  // last of every `wpc` consecutive groups (the wrapped window of a clip) uses when bias_sets == 2.
+  // attn_tc_long.cu only — window attention of the Video-Swin stages (swin.cu): `heads` heads of 32 in a packed [q | k | v] row
+  // (row strides ldq / ldo elements), an additive score term sbias[head][q][k] (fp32, ALREADY divided by the softmax scale, so
+  // that scale * (q·k + sbias) = scale * q·k + bias: the relative position bias) and the shift mask of SW-MSA: rid[set][token] =
+  // region id of a window token (compute_mask), gset[group] = the set a window uses (0 = unmasked); a key whose region differs from
+  // the query's gets mask_add (= -100 / scale).
   int heads = 8;
+  int ldq = 768, ldo = 256;
   const float* sbias = nullptr;
-  int bias_sets = 1, wpc = 1;
+  const uint8_t* rid = nullptr;
+  const uint8_t* gset = nullptr;
+  float mask_add = 0.f;
   // work distribution: a CTA walks "pseudo-frames" = (frame, block of heads / hsplit heads).  hsplit = 1: a frame and its heads stay on
   // one CTA (many frames); hsplit = heads: every (frame, head) is a unit of its own, so that a few large windows still fill the GPU
   int hsplit = 1;

@@ -178,10 +178,13 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       const uint8_t* km = p.kmask ? p.kmask + (size_t)f * S : nullptr;
       // additive score row of this query (relative position bias [+ shift mask]); rows beyond S are clipped on store
       const float* brow = nullptr;
+      const uint8_t* ridk = nullptr;   // region ids of this window's tokens (shifted windows only)
+      uint8_t ridq = 0;
       if (p.sbias != nullptr) {
-        const int set = (p.bias_sets == 2 && (f % p.wpc) == p.wpc - 1) ? 1 : 0;
         const int qrow = min(qt * 128 + row, S - 1);
-        brow = p.sbias + (((size_t)set * p.heads + h) * S + qrow) * S;
+        brow = p.sbias + ((size_t)h * S + qrow) * S;
+        const int set = p.gset != nullptr ? (int)p.gset[f] : 0;
+        if (set != 0) { ridk = p.rid + (size_t)set * S; ridq = ridk[qrow]; }
       }
       float m_run = -INFINITY, l_run = 0.f;
       float o_run[32];
@@ -223,6 +226,11 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 #pragma unroll
               for (int i = 0; i < 32; ++i)
                 if (c * 32 + i < nkeys) x[i] += __ldg(b + i);
+            }
+            if (ridk != nullptr) {   // SW-MSA: keys of another region of the rolled map are masked (-100 in the reference)
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i < nkeys && ridk[kbase + c * 32 + i] != ridq) x[i] += p.mask_add;
             }
             // park the biased scores in TMEM: the exponential pass reads them back instead of fetching the bias row again
 #pragma unroll
@@ -318,8 +326,8 @@ static void launch_long(const bf16* QKV, bf16* AO, AttnTcParams& p, cudaStream_t
     VG_CUDA(cudaFuncSetAttribute(enc_attn_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
     attr_set = true;
   }
-  CUtensorMap tq = make_tmap_frames(QKV, p.F, p.S, 96 * p.heads, 96 * p.heads);
-  CUtensorMap to = make_tmap_frames(AO, p.F, p.S, 32 * p.heads, 32 * p.heads);
+  CUtensorMap tq = make_tmap_frames(QKV, p.F, p.S, 96 * p.heads, p.ldq);
+  CUtensorMap to = make_tmap_frames(AO, p.F, p.S, 32 * p.heads, p.ldo);
   const int units = p.F * p.hsplit;
   const int grid = units < device_sm_count() ? units : device_sm_count();
   enc_attn_tc_long_kernel<<<grid, kAtLongThreads, kAtSmem, stream>>>(tq, to, p);
@@ -334,15 +342,14 @@ void enc_attn_tc_long(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* km
 }
 
 // Window attention with an additive score term (Video-Swin W-MSA / SW-MSA, video_swin_transformer.py:143-165): `groups` windows of
-// S tokens, `heads` heads of 32; QKV [groups * S, 96 * heads] (q | k | v), AO [groups * S, 32 * heads];
-// sbias [bias_sets][heads][S][S] fp32 = (relative position bias [+ shift mask]) / scale — see AttnTcParams.
-void window_attn_tc(const bf16* QKV, bf16* AO, int groups, int S, int heads, const float* sbias, int bias_sets, int wpc, float scale,
-                    cudaStream_t stream) {
-  VG_CHECK(S > 128 && groups > 0 && heads >= 1 && sbias != nullptr && (bias_sets == 1 || bias_sets == 2) && wpc >= 1,
-           "window_attn_tc: bad arguments (windows of more than 128 tokens)");
+// S tokens, `heads` heads of 32; QKV [groups * S, ldq] (q | k | v in the first 96 * heads columns), AO [groups * S, ldo];
+// sbias [heads][S][S] fp32 = relative position bias / scale; rid / gset / mask_add: the shift mask — see AttnTcParams.
+void window_attn_tc(const bf16* QKV, int ldq, bf16* AO, int ldo, int groups, int S, int heads, const float* sbias, const uint8_t* rid,
+                    const uint8_t* gset, float scale, cudaStream_t stream) {
+  VG_CHECK(S > 128 && groups > 0 && heads >= 1 && sbias != nullptr && S % 4 == 0, "window_attn_tc: bad arguments (windows of more than 128 tokens)");
   AttnTcParams p;
   p.kmask = nullptr; p.S = S; p.F = groups; p.scale_log2e = scale * 1.4426950408889634f;
-  p.heads = heads; p.sbias = sbias; p.bias_sets = bias_sets; p.wpc = wpc;
+  p.heads = heads; p.ldq = ldq; p.ldo = ldo; p.sbias = sbias; p.rid = rid; p.gset = rid != nullptr ? gset : nullptr; p.mask_add = -100.0f / scale;
   launch_long(QKV, AO, p, stream);
 }
 

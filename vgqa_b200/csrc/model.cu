@@ -230,8 +230,8 @@ struct vgqa_ctx {
   float *text_in = nullptr, *pos_gen = nullptr;        // read by the encoder phase only (calls are serialised on its stream)
   int* ids_in = nullptr;
   uint8_t* tmask_in = nullptr;
-  // optional last stage of the Video-Swin-T extractor (vid.layers.3.*, swin.cu)
-  SwinStage swin;
+  // optional Video-Swin-T extractor: the whole `vid.*` module or its last stage alone (vid.layers.3.*) — swin.cu
+  SwinNet swin;
   // graph cache (key = phase, slot, shape and the presence flags of the optional inputs)
   struct GraphEntry { cudaGraphExec_t exec; int launches; };
   std::map<std::vector<uint64_t>, GraphEntry> graphs;
@@ -335,7 +335,8 @@ static void pack_weights(vgqa_ctx* c) {
   for (const auto& kv : c->sd)
     if (kv.first.rfind("text_encoder.body.", 0) == 0) tower_bytes += (size_t)kv.second.numel() * 4 + 512;
   const bool have_swin = c->sd.count("vid.layers.3.blocks.0.attn.qkv.weight") != 0;
-  c->warena.init(((size_t)448 << 20) + tower_bytes + (have_swin ? ((size_t)128 << 20) : 0));
+  const bool have_swin_full = c->sd.count("vid.patch_embed.proj.weight") != 0;
+  c->warena.init(((size_t)448 << 20) + tower_bytes + (have_swin ? ((size_t)128 << 20) : 0) + (have_swin_full ? ((size_t)192 << 20) : 0));
   // ---------------- encoder (modal_encoder.py:143-178)
   c->enc.resize(cfg.enc_layers);
   for (int l = 0; l < cfg.enc_layers; ++l) {
@@ -612,9 +613,10 @@ static void pack_weights(vgqa_ctx* c) {
     }
     VG_CHECK(!c->tt.empty(), "text tower: no encoder layers found under text_encoder.body.encoder.layer.*");
   }
-  // ---------------- optional last Video-Swin stage (vid.layers.3.blocks.*, video_swin_transformer.py:176-275)
+  // ---------------- optional Video-Swin-T extractor (vid.patch_embed / layers / downsamples; video_swin_transformer.py:626-664)
   if (have_swin)
-    c->swin.pack([&](const std::string& n, std::vector<int64_t> shp) -> const float* {
+    c->swin.pack([&](const std::string& n) { return c->sd.count(n) != 0; },
+                 [&](const std::string& n, std::vector<int64_t> shp) -> const float* {
                    auto it = c->sd.find(n);
                    VG_CHECK(it != c->sd.end(), "missing weight '" + n + "'");
                    VG_CHECK(it->second.shape == shp, "weight '" + n + "' has an unexpected shape");
@@ -1751,7 +1753,17 @@ int vgqa_text_tower(vgqa_ctx* c, const int32_t* ids, const uint8_t* text_mask, i
 int vgqa_swin_stage(vgqa_ctx* c, const float* x, int clips, int T, int H, int W, void* out_bf16, float* out_f32, void* stream) {
   try {
     VG_CHECK(c && c->finalized && x && (out_bf16 || out_f32), "vgqa_swin_stage: bad argument");
-    c->last_launches = c->swin.forward(x, clips, T, H, W, static_cast<vg::bf16*>(out_bf16), out_f32, static_cast<cudaStream_t>(stream));
+    c->last_launches = c->swin.forward_stage4(x, clips, T, H, W, static_cast<vg::bf16*>(out_bf16), out_f32, static_cast<cudaStream_t>(stream));
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_swin_backbone(vgqa_ctx* c, const float* frames, int clips, int T, int R, void* out_bf16, float* out_f32, float* const* stage_out,
+                       void* stream) {
+  try {
+    VG_CHECK(c && c->finalized && frames && (out_bf16 || out_f32), "vgqa_swin_backbone: bad argument");
+    c->last_launches = c->swin.forward_full(frames, clips, T, R, static_cast<vg::bf16*>(out_bf16), out_f32, stage_out,
+                                            static_cast<cudaStream_t>(stream));
     return 0;
   } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
 }

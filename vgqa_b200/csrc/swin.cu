@@ -1,18 +1,24 @@
-// The last stage of the Video-Swin-T extractor on this library's kernels (first piece):
-// `BasicLayer` = 2 x SwinTransformerBlock3D, dim 768, 24 heads of 32, window (8,7,7), mlp ratio 4 — the module behind
-// `vid.layers[3]` of VSTGNet (vgqa/core/vision/video_swin_transformer.py:176-275,337-398; grounding_net.py:67-71,104-105).
+// The Video-Swin-T extractor on this library's kernels: `self.vid` of VSTGNet = VideoSwinTransformerBackbone
+// (vgqa/core/vision/video_swin_transformer.py:626-685; grounding_net.py:67-71,104-105) — PatchEmbed3D with patch (1,4,4) +
+// LayerNorm (:403-443), four stages of SwinTransformerBlock3D (depths 2/2/6/2, dims 96/192/384/768, heads 3/6/12/24 of 32, window
+// (8,7,7), mlp ratio 4; :176-275,337-398) with PatchMerging between them (:278-308).  Either the whole extractor (frames in, the
+// last stage's map out) or the last stage alone (`vid.layers[3]`), depending on which weights were given.
 //
-//   per block:   x += proj( W-MSA( LN1(x) ) )          window attention with the relative position bias (:143-165); odd blocks
-//                                                      on the map rolled by 4 frames, with the -100 mask between the two
-//                                                      halves of the wrapped window (compute_mask, :311-325)
+//   per block:   x += proj( W-MSA( LN1(x) ) )          window attention with the relative position bias (:143-165); odd blocks on
+//                                                      the cyclically rolled map with the -100 mask of compute_mask (:311-325)
 //                x += fc2( gelu( fc1( LN2(x) ) ) )     erf GELU
 //
-// A 224 px clip leaves a 7x7 map at this stage, so a window is 8 consecutive frames x all 49 positions = 392 CONTIGUOUS token
-// rows of the channels-last map: the window partition is free, the temporal roll is a row gather.  Kernels: LayerNorm rows
-// (text_tower.cu), the tcgen05 GEMMs (qkv 768 → 2304, proj + fp32 residual, fc1 + GELU, fc2 + fp32 residual) and the multi-tile
-// tcgen05 attention of attn_tc_long.cu generalised to 24 heads and an additive score term (bias / scale, fp32, L2-resident).
-// The fp32 residual stream stays fp32 as in the encoder.  Output: channels-last bf16 = exactly the `vid_raw` / raw_layout = 1
-// input of vgqa_forward (input_proj2 reads it as its GEMM operand), and optionally fp32.
+// Layout: channels-last fp32 residual stream x32 [clips, D, H, W, Cp] (Cp = channels padded to a multiple of 64: 96 → 128 in the
+// first stage, zero in the pad columns), exactly as in the encoder.  Kernels:
+//   * LayerNorm rows (one warp per token) → bf16 GEMM operand;
+//   * window partition + cyclic roll = ONE row gather (window_gather), window reverse + un-roll + residual add = ONE scatter-add;
+//     where a window is a run of whole frames and nothing is rolled (last stage at 7x7, even blocks) the partition is free;
+//   * the tcgen05 GEMMs of the encoder (qkv, proj → fp32, fc1 + GELU, fc2 + fp32 residual, patch embedding, PatchMerging reduction);
+//   * the multi-tile tcgen05 attention of attn_tc_long.cu with `heads` heads, the bias table [heads][392][392] (divided by the
+//     scale, L2-resident) and the shift mask from per-token region ids (a few hundred bytes per distinct window kind);
+//   * PatchMerging: 2x2 gather + LayerNorm(4C) in one kernel, then the reduction GEMM.
+// Supported maps: sides that are multiples of the window after every stage (224 / 448 px clips, T a multiple of 8).
+#include <algorithm>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -23,152 +29,383 @@
 
 namespace vg {
 
-// dst[(b, d, :)] = src[(b, (d + shift) mod D, :)]  — torch.roll(x, -shift, dims=1) on frames of `frame_elems` bf16 (16-byte chunks)
-__global__ void __launch_bounds__(256) roll_frames_bf16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int D,
-                                                               long long chunks_per_frame, int shift, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long fr = i / chunks_per_frame, off = i - fr * chunks_per_frame;
-    const long long b = fr / D;
-    const int d = (int)(fr - b * D);
-    dst[i] = __ldg(src + (b * D + (d + shift) % D) * chunks_per_frame + off);
+// ------------------------------------------------------------------------------------------------ kernels
+// LayerNorm over the C real columns of rows with stride ld (one warp per row): y16 (bf16, stride ldy, pad columns zeroed) and / or
+// y32 (fp32, stride ld, may alias x, pad columns zeroed)
+__global__ void __launch_bounds__(256) ln_rows_ld_kernel(const float* x, int ld, int C, const float* __restrict__ w,
+                                                         const float* __restrict__ b, float eps, float* y32, bf16* __restrict__ y16,
+                                                         int ldy, long long rows) {
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + r * ld);
+  const int n4 = C >> 2;
+  float s = 0.f;
+  for (int i = lane; i < n4; i += 32) { const float4 v = xr[i]; s += v.x + v.y + v.z + v.w; }
+  const float mean = warp_sum(s) / (float)C;
+  float m2 = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xr[i];
+    const float a = v.x - mean, bb = v.y - mean, c = v.z - mean, d = v.w - mean;
+    m2 += a * a + bb * bb + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(m2) / (float)C + eps);
+  const int np4 = (y16 != nullptr ? ldy : ld) >> 2;
+  for (int i = lane; i < np4; i += 32) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) {
+      const float4 v = xr[i];
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + i), bv = __ldg(reinterpret_cast<const float4*>(b) + i);
+      o = make_float4((v.x - mean) * rstd * ww.x + bv.x, (v.y - mean) * rstd * ww.y + bv.y, (v.z - mean) * rstd * ww.z + bv.z,
+                      (v.w - mean) * rstd * ww.w + bv.w);
+    }
+    if (y32 != nullptr && i < (ld >> 2)) reinterpret_cast<float4*>(y32 + r * ld)[i] = o;
+    if (y16 != nullptr) reinterpret_cast<uint2*>(y16 + r * ldy)[i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
   }
 }
-// x[(b, d, :)] += y[(b, (d - shift) mod D, :)]  — the reverse roll fused with the residual add (fp32, 16-byte chunks)
-__global__ void __launch_bounds__(256) add_rolled_f32_kernel(float4* __restrict__ x, const float4* __restrict__ y, int D,
-                                                             long long chunks_per_frame, int shift, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long fr = i / chunks_per_frame, off = i - fr * chunks_per_frame;
-    const long long b = fr / D;
-    const int d = (int)(fr - b * D);
-    const float4 a = x[i], q = __ldg(y + (b * D + (d - shift + D) % D) * chunks_per_frame + off);
-    x[i] = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
-  }
+static void ln_rows_ld(const float* x, int ld, int C, const float* w, const float* b, float eps, float* y32, bf16* y16, int ldy,
+                       long long rows, cudaStream_t st) {
+  ln_rows_ld_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, ld, C, w, b, eps, y32, y16, ldy, rows);
+  VG_CUDA(cudaGetLastError());
 }
-__global__ void __launch_bounds__(256) f32_to_bf16_rows_kernel(const float4* __restrict__ x, uint2* __restrict__ y, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float4 a = __ldg(x + i);
-    y[i] = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+
+// PatchEmbed3D operand (patch (1,4,4)): frames NCHW fp32 [n, 3, R, R] → A [n * (R/4)^2, 64] bf16, column c*16 + dy*4 + dx (the
+// order of proj.weight.reshape(96, 48)), columns 48..63 zero
+__global__ void __launch_bounds__(256) patch_im2col_kernel(const float* __restrict__ fr, bf16* __restrict__ A, int R, long long n16) {
+  const int G = R >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+    const long long tok = i >> 4;
+    const int j = (int)(i & 15);
+    uint2 o = make_uint2(0u, 0u);
+    if (j < 12) {
+      const int c = j >> 2, dy = j & 3;
+      const long long n = tok / (G * G);
+      const int rem = (int)(tok - n * G * G), py = rem / G, px = rem - py * G;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(fr + ((n * 3 + c) * R + py * 4 + dy) * (long long)R + px * 4));
+      o = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+    reinterpret_cast<uint2*>(A)[i] = o;
   }
 }
 
-static int grid_for(long long n) { return (int)std::min<long long>((n + 255) / 256, 148 * 16); }
+struct WinGeom { int B, D, H, W, wd, wh, ww, sd, sh, sw; };
+__device__ __forceinline__ long long win_src_row(const WinGeom& g, long long r) {   // window-order row → row of the (unrolled) map
+  const int N = g.wd * g.wh * g.ww;
+  const long long grp = r / N;
+  const int n = (int)(r - grp * N);
+  const int nWh = g.H / g.wh, nWw = g.W / g.ww, nWd = g.D / g.wd;
+  const int wwi = (int)(grp % nWw), hwi = (int)((grp / nWw) % nWh), dwi = (int)((grp / (nWw * nWh)) % nWd);
+  const long long b = grp / ((long long)nWw * nWh * nWd);
+  const int dd = n / (g.wh * g.ww), hh = (n / g.ww) % g.wh, wl = n % g.ww;
+  const int d = (dwi * g.wd + dd + g.sd) % g.D, h = (hwi * g.wh + hh + g.sh) % g.H, w = (wwi * g.ww + wl + g.sw) % g.W;
+  return ((b * g.D + d) * g.H + h) * g.W + w;
+}
+// window_partition(roll(x, -shift)) as one gather of bf16 rows (16-byte chunks)
+__global__ void __launch_bounds__(256) window_gather_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, WinGeom g, int cpr,
+                                                            long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cpr;
+    const int off = (int)(i - r * cpr);
+    dst[i] = __ldg(src + win_src_row(g, r) * cpr + off);
+  }
+}
+// x += roll(window_reverse(y), +shift): every map row receives exactly one window row (fp32, 16-byte chunks)
+__global__ void __launch_bounds__(256) window_scatter_add_kernel(float4* __restrict__ x, const float4* __restrict__ y, WinGeom g, int cpr,
+                                                                 long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cpr;
+    const int off = (int)(i - r * cpr);
+    float4* p = x + win_src_row(g, r) * cpr + off;
+    const float4 a = *p, q = __ldg(y + i);
+    *p = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+  }
+}
+// PatchMerging (:291-308), even H and W: out[(b, d, h2, w2), k*C + c] = LayerNorm_4C(cat(x[2h2, 2w2], x[2h2+1, 2w2], x[2h2, 2w2+1],
+// x[2h2+1, 2w2+1])) as bf16; one warp per output token
+__global__ void __launch_bounds__(256) merge_ln_kernel(const float* __restrict__ x, int ld, int C, int H, int W, const float* __restrict__ w,
+                                                       const float* __restrict__ b, float eps, bf16* __restrict__ out, long long tokens) {
+  const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= tokens) return;
+  const int H2 = H >> 1, W2 = W >> 1;
+  const long long bd = t / (H2 * W2);
+  const int rem = (int)(t - bd * H2 * W2), h2 = rem / W2, w2 = rem - h2 * W2;
+  const float* src[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) src[k] = x + ((bd * H + 2 * h2 + (k & 1)) * W + 2 * w2 + (k >> 1)) * (long long)ld;
+  const int n4 = C >> 2;
+  float s = 0.f;
+  for (int k = 0; k < 4; ++k)
+    for (int i = lane; i < n4; i += 32) { const float4 v = reinterpret_cast<const float4*>(src[k])[i]; s += v.x + v.y + v.z + v.w; }
+  const float mean = warp_sum(s) / (float)(4 * C);
+  float m2 = 0.f;
+  for (int k = 0; k < 4; ++k)
+    for (int i = lane; i < n4; i += 32) {
+      const float4 v = reinterpret_cast<const float4*>(src[k])[i];
+      const float a = v.x - mean, bb = v.y - mean, c = v.z - mean, d = v.w - mean;
+      m2 += a * a + bb * bb + c * c + d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(m2) / (float)(4 * C) + eps);
+  for (int k = 0; k < 4; ++k)
+    for (int i = lane; i < n4; i += 32) {
+      const float4 v = reinterpret_cast<const float4*>(src[k])[i];
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w + k * C) + i), bv = __ldg(reinterpret_cast<const float4*>(b + k * C) + i);
+      reinterpret_cast<uint2*>(out + t * 4 * C + k * C)[i] =
+          make_uint2(pack_bf16((v.x - mean) * rstd * ww.x + bv.x, (v.y - mean) * rstd * ww.y + bv.y),
+                     pack_bf16((v.z - mean) * rstd * ww.z + bv.z, (v.w - mean) * rstd * ww.w + bv.w));
+    }
+}
+// strided rows fp32 [rows, ld] → compact bf16 / fp32 [rows, C]
+__global__ void __launch_bounds__(256) rows_out_kernel(const float* __restrict__ x, int ld, int C, bf16* __restrict__ o16, float* __restrict__ o32,
+                                                       long long n4) {
+  const int c4 = C >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c4;
+    const int j = (int)(i - r * c4);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ld) + j);
+    if (o16 != nullptr) reinterpret_cast<uint2*>(o16)[i] = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+    if (o32 != nullptr) reinterpret_cast<float4*>(o32)[i] = a;
+  }
+}
 
-void SwinStage::pack(const std::function<const float*(const std::string&, std::vector<int64_t>)>& get,
-                     const std::function<bf16*(const float*, size_t)>& to_bf16, const std::function<float*(const float*, size_t)>& to_f32) {
+static int grid_for(long long n) { return (int)std::min<long long>((n + 255) / 256, 148 * 32); }
+static int pad64(int c) { return (c + 63) / 64 * 64; }
+
+// ------------------------------------------------------------------------------------------------ weights
+void SwinNet::pack(const HasFn& has, const GetFn& get, const std::function<bf16*(const float*, size_t)>& to_bf16,
+                   const std::function<float*(const float*, size_t)>& to_f32) {
   const int nb = (2 * wd - 1) * (2 * wh - 1) * (2 * ww - 1), N = wd * wh * ww;
-  const float inv_scale = std::sqrt((float)(dim / heads));
-  // relative position index (video_swin_transformer.py:97-112) and the shift-mask groups of the wrapped window (:311-325)
+  // relative position index (video_swin_transformer.py:97-112)
   std::vector<int> idx((size_t)N * N);
   for (int a = 0; a < N; ++a)
     for (int b = 0; b < N; ++b) {
       const int da = a / (wh * ww), ha = (a / ww) % wh, wa = a % ww, db = b / (wh * ww), hb = (b / ww) % wh, wb = b % ww;
       idx[(size_t)a * N + b] = (da - db + wd - 1) * (2 * wh - 1) * (2 * ww - 1) + (ha - hb + wh - 1) * (2 * ww - 1) + (wa - wb + ww - 1);
     }
-  blocks.resize(depth);
-  for (int i = 0; i < depth; ++i) {
-    const std::string p = "vid.layers.3.blocks." + std::to_string(i) + ".";
-    Block& k = blocks[i];
-    auto lin = [&](const std::string& n, int o, int in, bf16*& W, float*& b) {
-      W = to_bf16(get(p + n + ".weight", {o, in}), (size_t)o * in);
-      b = to_f32(get(p + n + ".bias", {o}), o);
-    };
-    k.n1w = to_f32(get(p + "norm1.weight", {dim}), dim); k.n1b = to_f32(get(p + "norm1.bias", {dim}), dim);
-    k.n2w = to_f32(get(p + "norm2.weight", {dim}), dim); k.n2b = to_f32(get(p + "norm2.bias", {dim}), dim);
-    lin("attn.qkv", 3 * dim, dim, k.Wqkv, k.bqkv);
-    lin("attn.proj", dim, dim, k.Wproj, k.bproj);
-    lin("mlp.fc1", 4 * dim, dim, k.Wfc1, k.bfc1);
-    lin("mlp.fc2", dim, 4 * dim, k.Wfc2, k.bfc2);
-    const float* tab = get(p + "attn.relative_position_bias_table", {nb, heads});
-    const int sets = (i % 2 == 1) ? 2 : 1;
-    std::vector<float> sb((size_t)sets * heads * N * N);
-    for (int s = 0; s < sets; ++s)
-      for (int h = 0; h < heads; ++h)
-        for (int a = 0; a < N; ++a)
-          for (int b = 0; b < N; ++b) {
-            float v = tab[(size_t)idx[(size_t)a * N + b] * heads + h];
-            if (s == 1) {   // wrapped window of the rolled map: frames [0, wd - shift) and [wd - shift, wd) belong to different groups
-              const int ga = (a / (wh * ww)) < wd - wd / 2, gb = (b / (wh * ww)) < wd - wd / 2;
-              if (ga != gb) v += -100.0f;
-            }
-            sb[(((size_t)s * heads + h) * N + a) * N + b] = v * inv_scale;
-          }
-    k.sbias = to_f32(sb.data(), sb.size());
-    k.bias_sets = sets;
-  }
-  loaded = true;
-}
-
-void SwinStage::ensure_workspace(size_t rows) {
-  if (rows <= cap_rows) return;
-  for (void* q : {(void*)x32, (void*)y32, (void*)xn, (void*)xs, (void*)qkv, (void*)ao, (void*)hid})
-    if (q) cudaFree(q);
-  const size_t C = dim;
-  VG_CUDA(cudaMalloc(&x32, rows * C * 4)); VG_CUDA(cudaMalloc(&y32, rows * C * 4));
-  VG_CUDA(cudaMalloc(&xn, rows * C * 2)); VG_CUDA(cudaMalloc(&xs, rows * C * 2));
-  VG_CUDA(cudaMalloc(&qkv, rows * 3 * C * 2)); VG_CUDA(cudaMalloc(&ao, rows * C * 2)); VG_CUDA(cudaMalloc(&hid, rows * 4 * C * 2));
-  cap_rows = rows;
-}
-
-void SwinStage::release() {
-  for (void* q : {(void*)x32, (void*)y32, (void*)xn, (void*)xs, (void*)qkv, (void*)ao, (void*)hid})
-    if (q) cudaFree(q);
-  x32 = y32 = nullptr; xn = xs = qkv = ao = hid = nullptr; cap_rows = 0;
-}
-
-// x: channels-last fp32 [clips, D, H, W, dim]; out_bf16 (channels-last bf16) and / or out_f32 receive the stage output
-int SwinStage::forward(const float* x, int clips, int D, int H, int W, bf16* out_bf16, float* out_f32, cudaStream_t st) {
-  VG_CHECK(loaded, "vgqa_swin_stage needs the 'vid.layers.3.blocks.*' weights");
-  VG_CHECK(clips >= 1 && H == wh && W == ww, "vgqa_swin_stage: the map must fill the window in H and W (7x7: 224 px clips)");
-  const int w_d = D < wd ? D : wd;
-  VG_CHECK(D >= 1 && D % w_d == 0, "vgqa_swin_stage: the number of frames must be a multiple of the temporal window (8)");
-  VG_CHECK(w_d * H * W > 128, "vgqa_swin_stage: windows of at most 128 tokens are not supported (needs at least 3 frames)");
-  VG_CHECK(w_d == wd, "vgqa_swin_stage: clips shorter than the temporal window (8 frames) are not supported");
-  const int shift = D > wd ? wd / 2 : 0;                    // get_window_size: no shift along a clamped axis (:53-66)
-  const size_t P = (size_t)H * W, rows = (size_t)clips * D * P, C = dim;
-  const int N = w_d * H * W, groups = clips * (D / w_d), wpc = D / w_d;
-  const int launches0 = launches;
-  ensure_workspace(rows);
-  VG_CUDA(cudaMemcpyAsync(x32, x, rows * C * 4, cudaMemcpyDeviceToDevice, st));
-  const long long cpf_bf16 = (long long)P * C / 8, cpf_f32 = (long long)P * C / 4;
-  for (int i = 0; i < depth; ++i) {
-    Block& k = blocks[i];
-    const int sh = (i % 2 == 1) ? shift : 0;
-    ln_rows_wide(x32, k.n1w, k.n1b, 1e-5f, nullptr, xn, (int)rows, (int)C, st);
-    const bf16* a = xn;
-    if (sh) {
-      const long long n = (long long)rows * C / 8;
-      roll_frames_bf16_kernel<<<grid_for(n), 256, 0, st>>>(reinterpret_cast<const uint4*>(xn), reinterpret_cast<uint4*>(xs), D, cpf_bf16, sh, n);
-      a = xs; ++launches;
+  // W [o, in] → channel-padded [op, inp] bf16 (zeros in the pad rows / columns); bias [o] → [op]
+  auto lin_pad = [&](const std::string& name, int o, int in, int op, int inp, bf16*& W, float** bias) {
+    const float* w = get(name + ".weight", {o, in});
+    std::vector<float> wp((size_t)op * inp, 0.f);
+    for (int r = 0; r < o; ++r) std::copy(w + (size_t)r * in, w + (size_t)(r + 1) * in, wp.begin() + (size_t)r * inp);
+    W = to_bf16(wp.data(), wp.size());
+    if (bias != nullptr) {
+      const float* bb = get(name + ".bias", {o});
+      std::vector<float> bp(op, 0.f);
+      std::copy(bb, bb + o, bp.begin());
+      *bias = to_f32(bp.data(), bp.size());
     }
-    { GemmEpi ep; ep.C = qkv; ep.ldc = 3 * (int)C; ep.bias = k.bqkv; ep.bias_ld = 3 * (int)C;
-      gemm_bf16_tn(a, (int)C, k.Wqkv, (int)C, (int)rows, 3 * (int)C, (int)C, ep, st); }
-    window_attn_tc(qkv, ao, groups, N, heads, k.sbias, sh ? k.bias_sets : 1, wpc, 1.0f / std::sqrt((float)(C / heads)), st);
-    if (sh) {   // proj → fp32, then the reverse roll fused with the residual add
-      GemmEpi ep; ep.C = y32; ep.ldc = (int)C; ep.c_f32 = 1; ep.bias = k.bproj; ep.bias_ld = (int)C;
-      gemm_bf16_tn(ao, (int)C, k.Wproj, (int)C, (int)rows, (int)C, (int)C, ep, st);
-      const long long n = (long long)rows * C / 4;
-      add_rolled_f32_kernel<<<grid_for(n), 256, 0, st>>>(reinterpret_cast<float4*>(x32), reinterpret_cast<const float4*>(y32), D, cpf_f32, sh, n);
+  };
+  for (int s = 0; s < kStages; ++s) {
+    Stage& S = st[s];
+    S.C = embed << s; S.Cp = pad64(S.C); S.Nqkv = pad64(3 * S.C); S.heads = heads[s];
+    const std::string lp = "vid.layers." + std::to_string(s) + ".";
+    if (!has(lp + "blocks.0.attn.qkv.weight")) continue;
+    const int C = S.C, Cp = S.Cp;
+    const float inv_scale = std::sqrt((float)(C / S.heads));
+    S.blocks.resize(depths[s]);
+    for (int i = 0; i < depths[s]; ++i) {
+      const std::string p = lp + "blocks." + std::to_string(i) + ".";
+      Block& k = S.blocks[i];
+      k.n1w = to_f32(get(p + "norm1.weight", {C}), C); k.n1b = to_f32(get(p + "norm1.bias", {C}), C);
+      k.n2w = to_f32(get(p + "norm2.weight", {C}), C); k.n2b = to_f32(get(p + "norm2.bias", {C}), C);
+      lin_pad(p + "attn.qkv", 3 * C, C, S.Nqkv, Cp, k.Wqkv, &k.bqkv);
+      lin_pad(p + "attn.proj", C, C, Cp, Cp, k.Wproj, &k.bproj);
+      lin_pad(p + "mlp.fc1", 4 * C, C, 4 * C, Cp, k.Wfc1, &k.bfc1);
+      lin_pad(p + "mlp.fc2", C, 4 * C, Cp, 4 * C, k.Wfc2, &k.bfc2);
+      const float* tab = get(p + "attn.relative_position_bias_table", {nb, S.heads});
+      std::vector<float> sb((size_t)S.heads * N * N);
+      for (int h = 0; h < S.heads; ++h)
+        for (size_t ab = 0; ab < (size_t)N * N; ++ab) sb[(size_t)h * N * N + ab] = tab[(size_t)idx[ab] * S.heads + h] * inv_scale;
+      k.sbias = to_f32(sb.data(), sb.size());
+    }
+    S.loaded = true;
+    const std::string dp = "vid.downsamples." + std::to_string(s) + ".";
+    if (s + 1 < kStages && has(dp + "reduction.weight")) {
+      S.mnw = to_f32(get(dp + "norm.weight", {4 * C}), 4 * C); S.mnb = to_f32(get(dp + "norm.bias", {4 * C}), 4 * C);
+      lin_pad(dp + "reduction", 2 * C, 4 * C, pad64(2 * C), 4 * C, S.Wred, nullptr);
+    }
+  }
+  if (has("vid.patch_embed.proj.weight")) {
+    const float* w = get("vid.patch_embed.proj.weight", {embed, 3, 1, 4, 4});
+    std::vector<float> wp((size_t)pad64(embed) * 64, 0.f);
+    for (int r = 0; r < embed; ++r) std::copy(w + (size_t)r * 48, w + (size_t)(r + 1) * 48, wp.begin() + (size_t)r * 64);
+    Wpe = to_bf16(wp.data(), wp.size());
+    std::vector<float> bp(pad64(embed), 0.f);
+    const float* bb = get("vid.patch_embed.proj.bias", {embed});
+    std::copy(bb, bb + embed, bp.begin());
+    bpe = to_f32(bp.data(), bp.size());
+    pnw = to_f32(get("vid.patch_embed.norm.weight", {embed}), embed); pnb = to_f32(get("vid.patch_embed.norm.bias", {embed}), embed);
+    full = st[0].loaded && st[1].loaded && st[2].loaded && st[3].loaded && st[0].Wred && st[1].Wred && st[2].Wred;
+    VG_CHECK(full, "Video-Swin: 'vid.patch_embed' is given but a stage or a downsample layer is missing");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+void SwinNet::ensure_workspace(size_t rows, int Cp, int Nqkv, bool with_frames) {
+  const size_t units = rows * (size_t)Cp;
+  const size_t need = std::max(units, rows * (size_t)Nqkv / 3 + 1);
+  if (need <= cap_units && (!with_frames || a0 != nullptr)) return;
+  release();
+  const size_t u = need;
+  VG_CUDA(cudaMalloc(&x32, u * 4)); VG_CUDA(cudaMalloc(&y32, u * 4));
+  VG_CUDA(cudaMalloc(&xn, u * 2)); VG_CUDA(cudaMalloc(&xw, u * 2)); VG_CUDA(cudaMalloc(&ao, u * 2)); VG_CUDA(cudaMalloc(&xm, u * 2));
+  VG_CUDA(cudaMalloc(&qkv, u * 3 * 2 + 4096)); VG_CUDA(cudaMalloc(&hid, u * 4 * 2));
+  if (with_frames) VG_CUDA(cudaMalloc(&a0, rows * 64 * 2));
+  cap_units = u;
+}
+
+void SwinNet::release() {
+  for (void* q : {(void*)x32, (void*)y32, (void*)xn, (void*)xw, (void*)qkv, (void*)ao, (void*)hid, (void*)xm, (void*)a0})
+    if (q) cudaFree(q);
+  x32 = y32 = nullptr; xn = xw = qkv = ao = hid = xm = a0 = nullptr; cap_units = 0;
+  for (auto& m : masks) { if (m.second.rid) cudaFree(m.second.rid); if (m.second.gset) cudaFree(m.second.gset); }
+  masks.clear();
+}
+
+// ------------------------------------------------------------------------------------------------ one stage
+void SwinNet::run_stage(int s, int clips, int D, int H, int W, cudaStream_t st_) {
+  Stage& S = st[s];
+  VG_CHECK(S.loaded, "Video-Swin: the weights of stage " + std::to_string(s) + " ('vid.layers." + std::to_string(s) + ".*') were not given");
+  const int C = S.C, Cp = S.Cp;
+  const int w_d = std::min(wd, D), w_h = std::min(wh, H), w_w = std::min(ww, W);     // get_window_size (:53-66)
+  VG_CHECK(w_d == wd && w_h == wh && w_w == ww, "Video-Swin: maps smaller than the window (8,7,7) are not supported");
+  VG_CHECK(D % wd == 0 && H % wh == 0 && W % ww == 0, "Video-Swin: map sides must be multiples of the window (8 frames, 7x7 positions)");
+  const int shd = D > wd ? wd / 2 : 0, shh = H > wh ? wh / 2 : 0, shw = W > ww ? ww / 2 : 0;
+  const int N = wd * wh * ww, nW = (D / wd) * (H / wh) * (W / ww), groups = clips * nW;
+  const long long rows = (long long)clips * D * H * W;
+  const bool contiguous = H == wh && W == ww;          // a window = a run of whole frames: the partition is the identity
+  const float scale = 1.0f / std::sqrt((float)(C / S.heads));
+  // region ids of the shifted windows (compute_mask, :311-325), built once per map shape
+  MaskTab* mt = nullptr;
+  if (shd || shh || shw) {
+    auto key = std::make_tuple(D, H, W, clips);
+    MaskTab& m = masks[key];
+    if (m.rid == nullptr) {
+      auto region = [](int x, int X, int w, int sft) { return sft == 0 ? 0 : (x < X - w ? 0 : (x < X - sft ? 1 : 2)); };
+      std::vector<std::vector<uint8_t>> sets(1, std::vector<uint8_t>(N, 0));
+      std::vector<uint8_t> gs(nW);
+      for (int g = 0; g < nW; ++g) {
+        const int wwi = g % (W / ww), hwi = (g / (W / ww)) % (H / wh), dwi = g / ((W / ww) * (H / wh));
+        std::vector<uint8_t> v(N);
+        for (int n = 0; n < N; ++n) {
+          const int dd = n / (wh * ww), hh = (n / ww) % wh, wl = n % ww;
+          v[n] = (uint8_t)(region(dwi * wd + dd, D, wd, shd) * 9 + region(hwi * wh + hh, H, wh, shh) * 3 + region(wwi * ww + wl, W, ww, shw));
+        }
+        const bool constant = std::all_of(v.begin(), v.end(), [&](uint8_t q) { return q == v[0]; });
+        int id = 0;
+        if (!constant) {
+          auto it = std::find(sets.begin() + 1, sets.end(), v);
+          id = (int)(it - sets.begin());
+          if (it == sets.end()) sets.push_back(v);
+        }
+        gs[g] = (uint8_t)id;
+      }
+      m.h_rid.clear();
+      for (auto& v : sets) m.h_rid.insert(m.h_rid.end(), v.begin(), v.end());
+      m.h_gset.resize((size_t)groups);
+      for (int c = 0; c < clips; ++c) std::copy(gs.begin(), gs.end(), m.h_gset.begin() + (size_t)c * nW);
+      VG_CUDA(cudaMalloc(&m.rid, m.h_rid.size()));
+      VG_CUDA(cudaMalloc(&m.gset, m.h_gset.size()));
+      VG_CUDA(cudaMemcpyAsync(m.rid, m.h_rid.data(), m.h_rid.size(), cudaMemcpyHostToDevice, st_));
+      VG_CUDA(cudaMemcpyAsync(m.gset, m.h_gset.data(), m.h_gset.size(), cudaMemcpyHostToDevice, st_));
+      m.nW = nW;
+    }
+    mt = &m;
+  }
+  if (Cp != C) VG_CUDA(cudaMemsetAsync(ao, 0, (size_t)rows * Cp * 2, st_));   // pad columns of the attention output stay zero
+  for (size_t i = 0; i < S.blocks.size(); ++i) {
+    Block& k = S.blocks[i];
+    const bool shifted = (i % 2 == 1) && (shd || shh || shw);
+    const WinGeom g{clips, D, H, W, wd, wh, ww, shifted ? shd : 0, shifted ? shh : 0, shifted ? shw : 0};
+    const bool gather = shifted || !contiguous;
+    ln_rows_ld(x32, Cp, C, k.n1w, k.n1b, 1e-5f, nullptr, xn, Cp, rows, st_);
+    const bf16* a = xn;
+    if (gather) {
+      const long long n = rows * (Cp / 8);
+      window_gather_kernel<<<grid_for(n), 256, 0, st_>>>(reinterpret_cast<const uint4*>(xn), reinterpret_cast<uint4*>(xw), g, Cp / 8, n);
+      a = xw; ++launches;
+    }
+    { GemmEpi ep; ep.C = qkv; ep.ldc = S.Nqkv; ep.bias = k.bqkv; ep.bias_ld = S.Nqkv;
+      gemm_bf16_tn(a, Cp, k.Wqkv, Cp, (int)rows, S.Nqkv, Cp, ep, st_); }
+    window_attn_tc(qkv, S.Nqkv, ao, Cp, groups, N, S.heads, k.sbias, shifted ? mt->rid : nullptr, shifted ? mt->gset : nullptr, scale, st_);
+    if (gather) {   // proj → fp32 in window order, then window reverse + un-roll fused with the residual add
+      GemmEpi ep; ep.C = y32; ep.ldc = Cp; ep.c_f32 = 1; ep.bias = k.bproj; ep.bias_ld = Cp;
+      gemm_bf16_tn(ao, Cp, k.Wproj, Cp, (int)rows, Cp, Cp, ep, st_);
+      const long long n = rows * (Cp / 4);
+      window_scatter_add_kernel<<<grid_for(n), 256, 0, st_>>>(reinterpret_cast<float4*>(x32), reinterpret_cast<const float4*>(y32), g, Cp / 4, n);
       ++launches;
     } else {
-      GemmEpi ep; ep.C = y32; ep.ldc = (int)C; ep.c_f32 = 1; ep.bias = k.bproj; ep.bias_ld = (int)C; ep.res32 = x32; ep.ldres32 = (int)C;
-      gemm_bf16_tn(ao, (int)C, k.Wproj, (int)C, (int)rows, (int)C, (int)C, ep, st);
+      GemmEpi ep; ep.C = y32; ep.ldc = Cp; ep.c_f32 = 1; ep.bias = k.bproj; ep.bias_ld = Cp; ep.res32 = x32; ep.ldres32 = Cp;
+      gemm_bf16_tn(ao, Cp, k.Wproj, Cp, (int)rows, Cp, Cp, ep, st_);
       std::swap(x32, y32);
     }
-    ln_rows_wide(x32, k.n2w, k.n2b, 1e-5f, nullptr, xn, (int)rows, (int)C, st);
-    { GemmEpi ep; ep.C = hid; ep.ldc = 4 * (int)C; ep.bias = k.bfc1; ep.bias_ld = 4 * (int)C; ep.act = ACT_GELU;
-      gemm_bf16_tn(xn, (int)C, k.Wfc1, (int)C, (int)rows, 4 * (int)C, (int)C, ep, st); }
-    { GemmEpi ep; ep.C = y32; ep.ldc = (int)C; ep.c_f32 = 1; ep.bias = k.bfc2; ep.bias_ld = (int)C; ep.res32 = x32; ep.ldres32 = (int)C;
-      gemm_bf16_tn(hid, 4 * (int)C, k.Wfc2, 4 * (int)C, (int)rows, (int)C, 4 * (int)C, ep, st); }
+    ln_rows_ld(x32, Cp, C, k.n2w, k.n2b, 1e-5f, nullptr, xn, Cp, rows, st_);
+    { GemmEpi ep; ep.C = hid; ep.ldc = 4 * C; ep.bias = k.bfc1; ep.bias_ld = 4 * C; ep.act = ACT_GELU;
+      gemm_bf16_tn(xn, Cp, k.Wfc1, Cp, (int)rows, 4 * C, Cp, ep, st_); }
+    { GemmEpi ep; ep.C = y32; ep.ldc = Cp; ep.c_f32 = 1; ep.bias = k.bfc2; ep.bias_ld = Cp; ep.res32 = x32; ep.ldres32 = Cp;
+      gemm_bf16_tn(hid, 4 * C, k.Wfc2, 4 * C, (int)rows, Cp, 4 * C, ep, st_); }
     std::swap(x32, y32);
     launches += 7;
   }
   VG_CUDA(cudaGetLastError());
-  if (out_f32) VG_CUDA(cudaMemcpyAsync(out_f32, x32, rows * C * 4, cudaMemcpyDeviceToDevice, st));
-  if (out_bf16) {
-    const long long n = (long long)rows * C / 4;
-    f32_to_bf16_rows_kernel<<<grid_for(n), 256, 0, st>>>(reinterpret_cast<const float4*>(x32), reinterpret_cast<uint2*>(out_bf16), n);
-    ++launches;
+}
+
+// ------------------------------------------------------------------------------------------------ entry points
+int SwinNet::forward_stage4(const float* x, int clips, int D, int H, int W, bf16* out_bf16, float* out_f32, cudaStream_t st_) {
+  Stage& S = st[3];
+  VG_CHECK(S.loaded, "vgqa_swin_stage needs the 'vid.layers.3.blocks.*' weights");
+  VG_CHECK(clips >= 1 && D >= 1, "vgqa_swin_stage: bad shape");
+  const int launches0 = launches;
+  const long long rows = (long long)clips * D * H * W;
+  ensure_workspace((size_t)rows, S.Cp, S.Nqkv, false);
+  VG_CUDA(cudaMemcpyAsync(x32, x, (size_t)rows * S.C * 4, cudaMemcpyDeviceToDevice, st_));
+  run_stage(3, clips, D, H, W, st_);
+  const long long n4 = rows * (S.C / 4);
+  rows_out_kernel<<<grid_for(n4), 256, 0, st_>>>(x32, S.Cp, S.C, out_bf16, out_f32, n4);
+  ++launches;
+  VG_CUDA(cudaGetLastError());
+  return launches - launches0;
+}
+
+int SwinNet::forward_full(const float* frames, int clips, int T, int R, bf16* out_bf16, float* out_f32, float* const* stage_out,
+                          cudaStream_t st_) {
+  VG_CHECK(full, "vgqa_swin_backbone needs the whole 'vid.*' state dict (patch_embed, layers.0-3, downsamples.0-2)");
+  VG_CHECK(clips >= 1 && T >= 1 && R >= 32 && R % 32 == 0, "vgqa_swin_backbone: the frame side must be a multiple of 32");
+  const int launches0 = launches;
+  int H = R / 4;
+  long long rows = (long long)clips * T * H * H;
+  ensure_workspace((size_t)rows, st[0].Cp, st[0].Nqkv, true);
+  {  // PatchEmbed3D (:426-443): 4x4 patches → GEMM [rows, 64] x [128, 64]^T + bias → LayerNorm(96), in place
+    const long long n16 = rows * 16;
+    patch_im2col_kernel<<<grid_for(n16), 256, 0, st_>>>(frames, a0, R, n16);
+    GemmEpi ep; ep.C = x32; ep.ldc = st[0].Cp; ep.c_f32 = 1; ep.bias = bpe; ep.bias_ld = st[0].Cp;
+    gemm_bf16_tn(a0, 64, Wpe, 64, (int)rows, st[0].Cp, 64, ep, st_);
+    ln_rows_ld(x32, st[0].Cp, st[0].C, pnw, pnb, 1e-5f, x32, nullptr, 0, rows, st_);
+    launches += 3;
   }
+  for (int s = 0; s < kStages; ++s) {
+    Stage& S = st[s];
+    run_stage(s, clips, T, H, H, st_);
+    if (stage_out != nullptr && stage_out[s] != nullptr) {
+      const long long n4 = rows * (S.C / 4);
+      rows_out_kernel<<<grid_for(n4), 256, 0, st_>>>(x32, S.Cp, S.C, nullptr, stage_out[s], n4);
+      ++launches;
+    }
+    if (s + 1 < kStages) {   // PatchMerging (:291-308): 2x2 gather + LayerNorm(4C) → reduction GEMM → the next stage's stream
+      VG_CHECK(H % 2 == 0, "Video-Swin: odd map side before PatchMerging");
+      const long long tokens = rows / 4;
+      merge_ln_kernel<<<(unsigned)((tokens + 7) / 8), 256, 0, st_>>>(x32, S.Cp, S.C, H, H, S.mnw, S.mnb, 1e-5f, xm, tokens);
+      GemmEpi ep; ep.C = y32; ep.ldc = st[s + 1].Cp; ep.c_f32 = 1;
+      gemm_bf16_tn(xm, 4 * S.C, S.Wred, 4 * S.C, (int)tokens, st[s + 1].Cp, 4 * S.C, ep, st_);
+      std::swap(x32, y32);
+      launches += 2;
+      H /= 2;
+      rows = tokens;
+    }
+  }
+  const long long n4 = rows * (st[3].C / 4);
+  rows_out_kernel<<<grid_for(n4), 256, 0, st_>>>(x32, st[3].Cp, st[3].C, out_bf16, out_f32, n4);
+  ++launches;
   VG_CUDA(cudaGetLastError());
   return launches - launches0;
 }

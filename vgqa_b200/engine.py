@@ -331,6 +331,23 @@ class GroundingEngine:
         _lib.check(self._L.vgqa_swin_stage(self._ctx, self._p(x), B, T, H, W, self._p(out), self._p(out32), c_void_p(st)))
         return (out, out32) if want_f32 else out
 
+    def swin_backbone(self, frames, clips, want_stages=False):
+        """Whole Video-Swin-T extractor (csrc/swin.cu): frames fp32 NCHW [clips*T, 3, R, R] (device) → the last stage's map as
+        channels-last bf16 [clips, T, R/32, R/32, 768]; with want_stages also the four stage outputs (channels-last fp32)."""
+        assert frames.dtype == torch.float32 and frames.dim() == 4 and frames.shape[1] == 3 and frames.is_contiguous()
+        n, _, R, _ = frames.shape
+        T = n // clips
+        self._L.vgqa_swin_backbone.restype = c_int
+        self._L.vgqa_swin_backbone.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+        out = torch.empty(clips, T, R // 32, R // 32, 768, dtype=torch.bfloat16, device=self.device)
+        stages, ptrs = None, None
+        if want_stages:
+            stages = [torch.empty(clips, T, (R // 4) >> s, (R // 4) >> s, 96 << s, device=self.device) for s in range(4)]
+            ptrs = (c_void_p * 4)(*[c_void_p(t.data_ptr()) for t in stages])
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self._L.vgqa_swin_backbone(self._ctx, self._p(frames), clips, T, R, self._p(out), None, ptrs, c_void_p(st)))
+        return (out, stages) if want_stages else out
+
     @property
     def last_launch_count(self) -> int:
         return int(self._L.vgqa_last_launch_count(self._ctx))

@@ -229,6 +229,27 @@ def synth_swin_stage(seed: int, dim: int = 768, heads: int = 24, window=(8, 7, 7
     return sd
 
 
+def synth_swin_backbone(seed: int, embed: int = 96, depths=(2, 2, 6, 2), heads=(3, 6, 12, 24), window=(8, 7, 7), prefix: str = "vid."):
+    """Synthetic weights of the whole Video-Swin-T extractor as VSTGNet holds it (`self.vid`, VideoSwinTransformerBackbone:
+    patch_embed.{proj,norm}, layers.{s}.blocks.{i}.*, downsamples.{s}.{norm,reduction}) — video_swin_transformer.py:626-664."""
+    rng = np.random.Generator(np.random.PCG64(13000 + seed))
+    u = lambda b, shp: rng.uniform(-b, b, size=shp).astype(F32)
+    sd: Dict[str, np.ndarray] = {}
+    sd[prefix + "patch_embed.proj.weight"] = u(1.0 / math.sqrt(48), (embed, 3, 1, 4, 4))
+    sd[prefix + "patch_embed.proj.bias"] = u(0.05, (embed,))
+    sd[prefix + "patch_embed.norm.weight"] = (1.0 + u(0.1, (embed,))).astype(F32)
+    sd[prefix + "patch_embed.norm.bias"] = u(0.05, (embed,))
+    for s, (dep, nh) in enumerate(zip(depths, heads)):
+        dim = embed * 2 ** s
+        stage = synth_swin_stage(seed * 10 + s, dim=dim, heads=nh, window=window, depth=dep, prefix=f"{prefix}layers.{s}.")
+        sd.update(stage)
+        if s + 1 < len(depths):
+            sd[f"{prefix}downsamples.{s}.norm.weight"] = (1.0 + u(0.1, (4 * dim,))).astype(F32)
+            sd[f"{prefix}downsamples.{s}.norm.bias"] = u(0.05, (4 * dim,))
+            sd[f"{prefix}downsamples.{s}.reduction.weight"] = u(1.5 / math.sqrt(4 * dim), (2 * dim, 4 * dim))
+    return sd
+
+
 def synth_text_ids(seed: int, B: int, L: int, vocab: int, pad_tail: int = 0) -> Tuple[np.ndarray, np.ndarray]:
     """Token ids as RobertaTokenizer emits them: <s>=0 ... </s>=2, pad=1 on the last `pad_tail` positions of the odd rows.
     Returns (ids (B, L) int32, pad mask (B, L) bool, True = padded)."""
