@@ -23,13 +23,13 @@ struct AttnTcParams {
   int S, F;
   float scale_log2e;
   // attn_tc_long.cu only — window attention of the Video-Swin stages (swin.cu): `heads` heads of 32 in a packed [q | k | v] row
-  // (row strides ldq / ldo elements), an additive score term sbias[head][q][k] (fp32, ALREADY divided by the softmax scale, so
-  // that scale * (q·k + sbias) = scale * q·k + bias: the relative position bias) and the shift mask of SW-MSA: rid[set][token] =
+  // (row strides ldq / ldo elements), an additive score term sbias[head][q][k] (bf16, ALREADY divided by the softmax scale, so
+  // that scale * (q·k + sbias) = scale * q·k + bias: the relative position bias) and the shift mask of SW-MSA: rid[set][token] (rows of 512 bytes) =
   // region id of a window token (compute_mask), gset[group] = the set a window uses (0 = unmasked); a key whose region differs from
   // the query's gets mask_add (= -100 / scale).
   int heads = 8;
   int ldq = 768, ldo = 256;
-  const float* sbias = nullptr;
+  const bf16* sbias = nullptr;   // bf16: the table is read once per key tile by every query row — half the L2 → SM bytes of fp32
   const uint8_t* rid = nullptr;
   const uint8_t* gset = nullptr;
   float mask_add = 0.f;

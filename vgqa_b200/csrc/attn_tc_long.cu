@@ -177,14 +177,14 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       const int f = pf / HS, h = (pf - f * HS) * NH + hl;
       const uint8_t* km = p.kmask ? p.kmask + (size_t)f * S : nullptr;
       // additive score row of this query (relative position bias [+ shift mask]); rows beyond S are clipped on store
-      const float* brow = nullptr;
+      const bf16* brow = nullptr;
       const uint8_t* ridk = nullptr;   // region ids of this window's tokens (shifted windows only)
       uint8_t ridq = 0;
       if (p.sbias != nullptr) {
         const int qrow = min(qt * 128 + row, S - 1);
         brow = p.sbias + ((size_t)h * S + qrow) * S;
         const int set = p.gset != nullptr ? (int)p.gset[f] : 0;
-        if (set != 0) { ridk = p.rid + (size_t)set * S; ridq = ridk[qrow]; }
+        if (set != 0) { ridk = p.rid + (size_t)set * 512; ridq = ridk[qrow]; }   // region-id rows are padded to 512 bytes
       }
       float m_run = -INFINITY, l_run = 0.f;
       float o_run[32];
@@ -214,23 +214,35 @@ enc_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(raw[i]);
           }
-          if (brow != nullptr && add_bias) {   // rows of S fp32 with S % 4 == 0: 16-byte loads on full chunks, guarded scalars on the tail chunk
-            const float* b = brow + kbase + c * 32;
+          if (brow != nullptr && add_bias) {   // rows of S bf16 with S % 8 == 0: 16-byte loads on full chunks, guarded scalars on the tail chunk
+            const bf16* b = brow + kbase + c * 32;
             if (c * 32 + 32 <= nkeys) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(b) + i);
-                x[4 * i] += q.x; x[4 * i + 1] += q.y; x[4 * i + 2] += q.z; x[4 * i + 3] += q.w;
+              for (int i = 0; i < 4; ++i) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(b) + i);
+                const float2 a0 = unpack_bf16(q.x), a1 = unpack_bf16(q.y), a2 = unpack_bf16(q.z), a3 = unpack_bf16(q.w);
+                x[8 * i] += a0.x; x[8 * i + 1] += a0.y; x[8 * i + 2] += a1.x; x[8 * i + 3] += a1.y;
+                x[8 * i + 4] += a2.x; x[8 * i + 5] += a2.y; x[8 * i + 6] += a3.x; x[8 * i + 7] += a3.y;
               }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (c * 32 + i < nkeys) x[i] += __ldg(b + i);
+                if (c * 32 + i < nkeys) x[i] += __bfloat162float(b[i]);
             }
             if (ridk != nullptr) {   // SW-MSA: keys of another region of the rolled map are masked (-100 in the reference)
+              // 32 region ids of this chunk as eight words (rows of 512 bytes: aligned), compared four at a time; most chunks differ nowhere
+              const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(ridk + kbase + c * 32));
+              const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(ridk + kbase + c * 32) + 1);
+              const uint32_t q4 = (uint32_t)ridq * 0x01010101u;
+              const uint32_t wds[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+              uint32_t any = 0;
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c * 32 + i < nkeys && ridk[kbase + c * 32 + i] != ridq) x[i] += p.mask_add;
+              for (int wi = 0; wi < 8; ++wi) any |= __vcmpne4(wds[wi], q4);
+              if (any != 0) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (c * 32 + i < nkeys && ((__vcmpne4(wds[i >> 2], q4) >> ((i & 3) * 8)) & 1u)) x[i] += p.mask_add;
+              }
             }
             // park the biased scores in TMEM: the exponential pass reads them back instead of fetching the bias row again
 #pragma unroll
@@ -343,10 +355,11 @@ void enc_attn_tc_long(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* km
 
 // Window attention with an additive score term (Video-Swin W-MSA / SW-MSA, video_swin_transformer.py:143-165): `groups` windows of
 // S tokens, `heads` heads of 32; QKV [groups * S, ldq] (q | k | v in the first 96 * heads columns), AO [groups * S, ldo];
-// sbias [heads][S][S] fp32 = relative position bias / scale; rid / gset / mask_add: the shift mask — see AttnTcParams.
-void window_attn_tc(const bf16* QKV, int ldq, bf16* AO, int ldo, int groups, int S, int heads, const float* sbias, const uint8_t* rid,
+// sbias [heads][S][S] bf16 = relative position bias / scale; rid / gset / mask_add: the shift mask — see AttnTcParams.
+void window_attn_tc(const bf16* QKV, int ldq, bf16* AO, int ldo, int groups, int S, int heads, const bf16* sbias, const uint8_t* rid,
                     const uint8_t* gset, float scale, cudaStream_t stream) {
-  VG_CHECK(S > 128 && groups > 0 && heads >= 1 && sbias != nullptr && S % 4 == 0, "window_attn_tc: bad arguments (windows of more than 128 tokens)");
+  VG_CHECK(S > 128 && S <= 512 && groups > 0 && heads >= 1 && sbias != nullptr && S % 8 == 0,
+           "window_attn_tc: bad arguments (windows of 129..512 tokens)");
   AttnTcParams p;
   p.kmask = nullptr; p.S = S; p.F = groups; p.scale_log2e = scale * 1.4426950408889634f;
   p.heads = heads; p.ldq = ldq; p.ldo = ldo; p.sbias = sbias; p.rid = rid; p.gset = rid != nullptr ? gset : nullptr; p.mask_add = -100.0f / scale;

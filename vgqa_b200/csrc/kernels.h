@@ -25,7 +25,7 @@ bool enc_attn_tc_supported(int S);
 void enc_attn_tc(const bf16* QKV, bf16* AO, int F, int S, const uint8_t* kmask, float scale, cudaStream_t stream);
 
 // ---- attn_tc_long.cu: window attention with an additive score term (Video-Swin stage, swin.cu)
-void window_attn_tc(const bf16* QKV, int ldq, bf16* AO, int ldo, int groups, int S, int heads, const float* sbias, const uint8_t* rid,
+void window_attn_tc(const bf16* QKV, int ldq, bf16* AO, int ldo, int groups, int S, int heads, const bf16* sbias, const uint8_t* rid,
                     const uint8_t* gset, float scale, cudaStream_t stream);
 
 // ---- input_proj.cu: 1x1-conv projection of the extractor feature maps straight into the encoder's token rows

@@ -40,24 +40,34 @@ __global__ void __launch_bounds__(256) ln_rows_ld_kernel(const float* x, int ld,
   if (r >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + r * ld);
   const int n4 = C >> 2;
+  float4 v[8];                      // the row in registers (C <= 1024): one global read
   float s = 0.f;
-  for (int i = lane; i < n4; i += 32) { const float4 v = xr[i]; s += v.x + v.y + v.z + v.w; }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = lane + 32 * j;
+    v[j] = i < n4 ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += v[j].x + v[j].y + v[j].z + v[j].w;
+  }
   const float mean = warp_sum(s) / (float)C;
   float m2 = 0.f;
-  for (int i = lane; i < n4; i += 32) {
-    const float4 v = xr[i];
-    const float a = v.x - mean, bb = v.y - mean, c = v.z - mean, d = v.w - mean;
-    m2 += a * a + bb * bb + c * c + d * d;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (lane + 32 * j < n4) {
+      const float a = v[j].x - mean, bb = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      m2 += a * a + bb * bb + c * c + d * d;
+    }
   }
   const float rstd = rsqrtf(warp_sum(m2) / (float)C + eps);
   const int np4 = (y16 != nullptr ? ldy : ld) >> 2;
-  for (int i = lane; i < np4; i += 32) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = lane + 32 * j;
+    if (i >= np4) break;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < n4) {
-      const float4 v = xr[i];
       const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + i), bv = __ldg(reinterpret_cast<const float4*>(b) + i);
-      o = make_float4((v.x - mean) * rstd * ww.x + bv.x, (v.y - mean) * rstd * ww.y + bv.y, (v.z - mean) * rstd * ww.z + bv.z,
-                      (v.w - mean) * rstd * ww.w + bv.w);
+      o = make_float4((v[j].x - mean) * rstd * ww.x + bv.x, (v[j].y - mean) * rstd * ww.y + bv.y, (v[j].z - mean) * rstd * ww.z + bv.z,
+                      (v[j].w - mean) * rstd * ww.w + bv.w);
     }
     if (y32 != nullptr && i < (ld >> 2)) reinterpret_cast<float4*>(y32 + r * ld)[i] = o;
     if (y16 != nullptr) reinterpret_cast<uint2*>(y16 + r * ldy)[i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
@@ -65,6 +75,7 @@ __global__ void __launch_bounds__(256) ln_rows_ld_kernel(const float* x, int ld,
 }
 static void ln_rows_ld(const float* x, int ld, int C, const float* w, const float* b, float eps, float* y32, bf16* y16, int ldy,
                        long long rows, cudaStream_t st) {
+  VG_CHECK(C % 4 == 0 && C <= 1024 && ld <= 1024, "ln_rows_ld: rows of at most 1024 channels");
   ln_rows_ld_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, ld, C, w, b, eps, y32, y16, ldy, rows);
   VG_CUDA(cudaGetLastError());
 }
@@ -216,7 +227,7 @@ void SwinNet::pack(const HasFn& has, const GetFn& get, const std::function<bf16*
       std::vector<float> sb((size_t)S.heads * N * N);
       for (int h = 0; h < S.heads; ++h)
         for (size_t ab = 0; ab < (size_t)N * N; ++ab) sb[(size_t)h * N * N + ab] = tab[(size_t)idx[ab] * S.heads + h] * inv_scale;
-      k.sbias = to_f32(sb.data(), sb.size());
+      k.sbias = to_bf16(sb.data(), sb.size());
     }
     S.loaded = true;
     const std::string dp = "vid.downsamples." + std::to_string(s) + ".";
@@ -301,7 +312,7 @@ void SwinNet::run_stage(int s, int clips, int D, int H, int W, cudaStream_t st_)
         gs[g] = (uint8_t)id;
       }
       m.h_rid.clear();
-      for (auto& v : sets) m.h_rid.insert(m.h_rid.end(), v.begin(), v.end());
+      for (auto& v : sets) { v.resize(512, 0); m.h_rid.insert(m.h_rid.end(), v.begin(), v.end()); }   // rows of 512 bytes
       m.h_gset.resize((size_t)groups);
       for (int c = 0; c < clips; ++c) std::copy(gs.begin(), gs.end(), m.h_gset.begin() + (size_t)c * nW);
       VG_CUDA(cudaMalloc(&m.rid, m.h_rid.size()));

@@ -18,8 +18,9 @@ struct SwinNet {
   int depths[kStages] = {2, 2, 6, 2};
   int heads[kStages] = {3, 6, 12, 24};
   struct Block {
-    float *n1w, *n1b, *n2w, *n2b, *bqkv, *bproj, *bfc1, *bfc2, *sbias;   // sbias [heads][N][N] = relative position bias / scale
+    float *n1w, *n1b, *n2w, *n2b, *bqkv, *bproj, *bfc1, *bfc2;
     bf16 *Wqkv, *Wproj, *Wfc1, *Wfc2;                                    // channel-padded to multiples of 64
+    bf16* sbias;                                                         // [heads][N][N] = relative position bias / scale
   };
   struct Stage {
     int C = 0, Cp = 0, Nqkv = 0, heads = 0;   // channels, padded channel stride, padded packed q|k|v width
