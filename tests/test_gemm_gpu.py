@@ -60,6 +60,28 @@ def test_gemm_plain(M, N, K):
     _close(C, _ref(A, W, b))
 
 
+def test_gemm_narrow_tiles_many_per_cta_on_fresh_memory():
+    """N = 320 → 64-column tiles with ONE bf16 store unit per tile and 13 tiles per CTA: the epilogue's two staging slabs must
+    alternate per store, not per unit index (a slab was once rewritten while its previous TMA store was still reading it; the
+    race showed only on slow first-touch stores — hence the freshly allocated outputs).  Shape of the first Video-Swin stage."""
+    M, N, K = 50176, 320, 128
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    ref = _ref(A, W, b)
+    first = None
+    for _ in range(6):
+        torch.cuda.empty_cache()                     # the next output comes from a new cudaMalloc
+        C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        _gemm(A, W, C, bias=b)
+        _close(C, ref)
+        if first is None:
+            first = C.clone()
+        assert torch.equal(C, first), "the GEMM must be bit-reproducible"
+        del C
+
+
 def test_gemm_fp32_out_table_relu():
     g = torch.Generator(device="cuda").manual_seed(3)
     M, N, K, period = 1180, 768, 256, 118

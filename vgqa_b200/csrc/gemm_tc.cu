@@ -234,6 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool do_ln = ep.ln_w != nullptr;
+    uint32_t nstore = 0;   // TMA stores this warp has issued: the slab alternates per STORE (a tile may have an odd number of units)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * BM;
       const int n0 = (tile % num_n) * BN;
@@ -251,7 +252,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int units = BN / cols_per_unit;
 #pragma unroll 1
         for (int u = 0; u < units; ++u) {
-          uint8_t* buf = my_stage + (u & 1) * 4096;
+          uint8_t* buf = my_stage + (nstore & 1) * 4096;
+          ++nstore;
           if (lane == 0) tma_store_wait_read<1>();      // the store issued two units ago has drained this buffer
           __syncwarp();
           const int halves = ep.c_f32 ? 1 : 2;
