@@ -206,6 +206,15 @@ int vgqa_swin_stage(vgqa_ctx* ctx, const float* x, int clips, int T, int H, int 
  * receive the four stage outputs channels-last fp32 [clips, T, R/4/2^s, R/4/2^s, 96 * 2^s].  Device pointers. */
 int vgqa_swin_backbone(vgqa_ctx* ctx, const float* frames, int clips, int T, int R, void* out_bf16, float* out_f32,
                        float* const* stage_out, void* stream);
+/* The ResNet101 extractor (`self.vis_encoder[0].body` of VSTGNet: torchvision resnet101 with FrozenBatchNorm2d, layer4 output —
+ * vgqa/core/vision/backbone.py:13-57,104-113; grounding_net.py:49,99); weights "vis_encoder.0.body.{conv1,bn1,layer1-4.*}" under the
+ * reference's names (optional at vgqa_finalize_weights; the BN buffers weight / bias / running_mean / running_var are folded into
+ * the convolutions).  frames: NCHW fp32 [n_frames, 3, R, R] (`videos.tensors`), R a multiple of 32 (at most 512).  out_bf16 / out_f32:
+ * the layer4 map channels-last [n_frames, R/32, R/32, 2048] (out_bf16 = the vis_raw / raw_layout = 1 input of vgqa_forward);
+ * layer_out: NULL or 4 device pointers (each may be NULL) that receive the outputs of layer1..4 channels-last fp32
+ * [n_frames, R/4/2^l, R/4/2^l, 256 * 2^l].  Device pointers. */
+int vgqa_resnet_backbone(vgqa_ctx* ctx, const float* frames, int n_frames, int R, void* out_bf16, float* out_f32,
+                         float* const* layer_out, void* stream);
 
 /* Counters: kernels launched by the last vgqa_forward call (graph replays count the captured launches). */
 int vgqa_last_launch_count(const vgqa_ctx* ctx);

@@ -737,8 +737,61 @@ def video_swin_backbone(sd, frames: np.ndarray, clips: int, prefix: str = "vid."
 
 
 # ----------------------------------------------------------------------------------------------
+# ResNet101 extractor.  The network itself is torchvision's (third-party, not vendored in the reference: torchvision 0.26.0 in
+# this image; `torchvision.models.resnet.ResNet._forward_impl` / `Bottleneck.forward`, v1.5 = the stride sits on the 3x3
+# convolution); the reference's part is the construction (backbone.py:104-113: resnet101, norm_layer=FrozenBatchNorm2d, no
+# dilation, IntermediateLayerGetter → layer4) and FrozenBatchNorm2d (:13-57).  Pinned by tests/golden/resnet101_*.npz
+# (generated from exactly that construction by tests/golden/make_golden_resnet.py).
+# ----------------------------------------------------------------------------------------------
+def conv2d(x: np.ndarray, w: np.ndarray, stride: int = 1, pad: int = 0) -> np.ndarray:
+    """F.conv2d without bias: x (n, C, H, W), w (O, C, k, k)."""
+    k = w.shape[2]
+    if pad:
+        x = np.pad(x, ((0, 0), (0, 0), (pad, pad), (pad, pad)))
+    win = np.lib.stride_tricks.sliding_window_view(x, (k, k), axis=(2, 3))[:, :, ::stride, ::stride]   # (n, C, Ho, Wo, k, k)
+    return np.einsum("nchwyx,ocyx->nohw", win, w, optimize=True).astype(F32)
+
+
+def frozen_bn(x: np.ndarray, sd, p: str) -> np.ndarray:
+    """FrozenBatchNorm2d.forward (backbone.py:47-57): eps = 1e-5, scale = weight * rsqrt(var + eps), bias = bias - mean * scale."""
+    scale = sd[p + ".weight"] / np.sqrt(sd[p + ".running_var"] + 1e-5)
+    bias = sd[p + ".bias"] - sd[p + ".running_mean"] * scale
+    return (x * scale[None, :, None, None] + bias[None, :, None, None]).astype(F32)
+
+
+def max_pool_3x3_s2(x: np.ndarray) -> np.ndarray:
+    """nn.MaxPool2d(kernel_size=3, stride=2, padding=1)."""
+    xp = np.pad(x, ((0, 0), (0, 0), (1, 1), (1, 1)), constant_values=-np.inf)
+    win = np.lib.stride_tricks.sliding_window_view(xp, (3, 3), axis=(2, 3))[:, :, ::2, ::2]
+    return win.max(axis=(-1, -2)).astype(F32)
+
+
+def resnet101_backbone(sd, frames: np.ndarray, prefix: str = "vis_encoder.0.body.", blocks=(3, 4, 23, 3)):
+    """`Backbone.body` (backbone.py:80-84,104-113) on frames (n, 3, R, R): stem (7x7 / 2 conv, FrozenBN, ReLU, 3x3 / 2 max-pool),
+    then the Bottleneck layers.  Returns the outputs of layer1..4 as channels-last maps [(n, H_l, W_l, C_l)]; the reference keeps
+    layer4 (n, 2048, R/32, R/32)."""
+    relu = lambda v: np.maximum(v, 0.0)
+    x = relu(frozen_bn(conv2d(frames.astype(F32), sd[prefix + "conv1.weight"], 2, 3), sd, prefix + "bn1"))
+    x = max_pool_3x3_s2(x)
+    outs = []
+    for l, nb in enumerate(blocks):
+        for b in range(nb):
+            q = f"{prefix}layer{l + 1}.{b}."
+            stride = 2 if (b == 0 and l > 0) else 1
+            o = relu(frozen_bn(conv2d(x, sd[q + "conv1.weight"]), sd, q + "bn1"))
+            o = relu(frozen_bn(conv2d(o, sd[q + "conv2.weight"], stride, 1), sd, q + "bn2"))
+            o = frozen_bn(conv2d(o, sd[q + "conv3.weight"]), sd, q + "bn3")
+            idn = x
+            if b == 0:
+                idn = frozen_bn(conv2d(x, sd[q + "downsample.0.weight"], stride, 0), sd, q + "downsample.1")
+            x = relu(o + idn)
+        outs.append(np.ascontiguousarray(x.transpose(0, 2, 3, 1)))
+    return outs
+
+
+# ----------------------------------------------------------------------------------------------
 # deterministic synthetic weights / inputs: they live in the product package (pure numpy, vgqa_b200/synth.py) so that the
 # GPU arm of bench.py imports nothing from oracle/; re-exported here for the tests and fixture makers
 # ----------------------------------------------------------------------------------------------
 from vgqa_b200.synth import (CALIB_PREFIX, apply_calibration, hot_path_param_shapes, synth_event_inputs, synth_inputs,  # noqa: E402,F401
-                             synth_masks, synth_raw_inputs, synth_state_dict, synth_swin_backbone, synth_swin_stage, synth_text_ids)
+                             synth_masks, synth_raw_inputs, synth_resnet101, synth_state_dict, synth_swin_backbone, synth_swin_stage, synth_text_ids)

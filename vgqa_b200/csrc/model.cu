@@ -28,6 +28,7 @@
 #include "../../include/vgqa_b200.h"
 #include "chain.h"
 #include "kernels.h"
+#include "resnet.h"
 #include "swin.h"
 
 namespace vg {
@@ -232,6 +233,8 @@ struct vgqa_ctx {
   uint8_t* tmask_in = nullptr;
   // optional Video-Swin-T extractor: the whole `vid.*` module or its last stage alone (vid.layers.3.*) — swin.cu
   SwinNet swin;
+  // optional ResNet101 extractor (`vis_encoder.0.body.*`) — resnet.cu
+  ResNet resnet;
   // graph cache (key = phase, slot, shape and the presence flags of the optional inputs)
   struct GraphEntry { cudaGraphExec_t exec; int launches; };
   std::map<std::vector<uint64_t>, GraphEntry> graphs;
@@ -336,7 +339,9 @@ static void pack_weights(vgqa_ctx* c) {
     if (kv.first.rfind("text_encoder.body.", 0) == 0) tower_bytes += (size_t)kv.second.numel() * 4 + 512;
   const bool have_swin = c->sd.count("vid.layers.3.blocks.0.attn.qkv.weight") != 0;
   const bool have_swin_full = c->sd.count("vid.patch_embed.proj.weight") != 0;
-  c->warena.init(((size_t)448 << 20) + tower_bytes + (have_swin ? ((size_t)128 << 20) : 0) + (have_swin_full ? ((size_t)192 << 20) : 0));
+  const bool have_resnet = c->sd.count("vis_encoder.0.body.conv1.weight") != 0;
+  c->warena.init(((size_t)448 << 20) + tower_bytes + (have_swin ? ((size_t)128 << 20) : 0) + (have_swin_full ? ((size_t)192 << 20) : 0) +
+                 (have_resnet ? ((size_t)160 << 20) : 0));
   // ---------------- encoder (modal_encoder.py:143-178)
   c->enc.resize(cfg.enc_layers);
   for (int l = 0; l < cfg.enc_layers; ++l) {
@@ -623,6 +628,16 @@ static void pack_weights(vgqa_ctx* c) {
                    return it->second.v.data();
                  },
                  [&](const float* v, size_t n) { return P.b16(v, n); }, [&](const float* v, size_t n) { return P.f32(v, n); });
+  // ---------------- optional ResNet101 extractor (vis_encoder.0.body.*; backbone.py:104-113)
+  if (have_resnet)
+    c->resnet.pack([&](const std::string& n) { return c->sd.count(n) != 0; },
+                   [&](const std::string& n, std::vector<int64_t> shp) -> const float* {
+                     auto it = c->sd.find(n);
+                     VG_CHECK(it != c->sd.end(), "missing weight '" + n + "'");
+                     VG_CHECK(it->second.shape == shp, "weight '" + n + "' has an unexpected shape");
+                     return it->second.v.data();
+                   },
+                   [&](const float* v, size_t n) { return P.b16(v, n); }, [&](const float* v, size_t n) { return P.f32(v, n); });
 }
 
 // ------------------------------------------------------------------------------------------------ workspace
@@ -1415,6 +1430,7 @@ void vgqa_destroy(vgqa_ctx* c) {
   if (c->aux3_stream) cudaStreamDestroy(c->aux3_stream);
   vg::p2p_destroy(c->p2p);
   c->swin.release();
+  c->resnet.release();
   for (auto& e : c->fj) if (e) cudaEventDestroy(e);
   c->warena.release();
   c->ws.release();
@@ -1764,6 +1780,16 @@ int vgqa_swin_backbone(vgqa_ctx* c, const float* frames, int clips, int T, int R
     VG_CHECK(c && c->finalized && frames && (out_bf16 || out_f32), "vgqa_swin_backbone: bad argument");
     c->last_launches = c->swin.forward_full(frames, clips, T, R, static_cast<vg::bf16*>(out_bf16), out_f32, stage_out,
                                             static_cast<cudaStream_t>(stream));
+    return 0;
+  } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
+}
+
+int vgqa_resnet_backbone(vgqa_ctx* c, const float* frames, int n_frames, int R, void* out_bf16, float* out_f32, float* const* layer_out,
+                         void* stream) {
+  try {
+    VG_CHECK(c && c->finalized && frames && (out_bf16 || out_f32), "vgqa_resnet_backbone: bad argument");
+    c->last_launches = c->resnet.forward(frames, n_frames, R, static_cast<vg::bf16*>(out_bf16), out_f32, layer_out,
+                                         static_cast<cudaStream_t>(stream));
     return 0;
   } catch (const std::exception& e) { vg::set_last_error(e.what()); return 1; }
 }

@@ -348,6 +348,22 @@ class GroundingEngine:
         _lib.check(self._L.vgqa_swin_backbone(self._ctx, self._p(frames), clips, T, R, self._p(out), None, ptrs, c_void_p(st)))
         return (out, stages) if want_stages else out
 
+    def resnet_backbone(self, frames, want_layers=False):
+        """ResNet101 extractor (csrc/resnet.cu): frames fp32 NCHW [n, 3, R, R] (device) → the layer4 map as channels-last bf16
+        [n, R/32, R/32, 2048]; with want_layers also the outputs of layer1..4 (channels-last fp32)."""
+        assert frames.dtype == torch.float32 and frames.dim() == 4 and frames.shape[1] == 3 and frames.is_contiguous()
+        n, _, R, _ = frames.shape
+        self._L.vgqa_resnet_backbone.restype = c_int
+        self._L.vgqa_resnet_backbone.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+        out = torch.empty(n, R // 32, R // 32, 2048, dtype=torch.bfloat16, device=self.device)
+        layers, ptrs = None, None
+        if want_layers:
+            layers = [torch.empty(n, (R // 4) >> l, (R // 4) >> l, 256 << l, device=self.device) for l in range(4)]
+            ptrs = (c_void_p * 4)(*[c_void_p(t.data_ptr()) for t in layers])
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self._L.vgqa_resnet_backbone(self._ctx, self._p(frames), n, R, self._p(out), None, ptrs, c_void_p(st)))
+        return (out, layers) if want_layers else out
+
     @property
     def last_launch_count(self) -> int:
         return int(self._L.vgqa_last_launch_count(self._ctx))

@@ -250,6 +250,37 @@ def synth_swin_backbone(seed: int, embed: int = 96, depths=(2, 2, 6, 2), heads=(
     return sd
 
 
+def synth_resnet101(seed: int, blocks=(3, 4, 23, 3), prefix: str = "vis_encoder.0.body."):
+    """Synthetic weights of the ResNet101 extractor as VSTGNet holds it (`self.vis_encoder[0].body`: torchvision resnet101 with
+    FrozenBatchNorm2d buffers, backbone.py:13-57,104-113): conv1 / bn1, layer{1-4}.{b}.conv{1,2,3} / bn{1,2,3} / downsample.{0,1}.
+    He-scaled convolutions; the third BN of a block has a small gain so that 33 residual additions stay O(1)."""
+    rng = np.random.Generator(np.random.PCG64(15000 + seed))
+    sd: Dict[str, np.ndarray] = {}
+
+    def conv(name, o, c, k):
+        sd[prefix + name + ".weight"] = (rng.standard_normal((o, c, k, k)) * math.sqrt(2.0 / (c * k * k))).astype(F32)
+
+    def bn(name, o, gain=1.0):
+        sd[prefix + name + ".weight"] = (gain * rng.uniform(0.8, 1.2, size=(o,))).astype(F32)
+        sd[prefix + name + ".bias"] = (0.05 * rng.standard_normal((o,))).astype(F32)
+        sd[prefix + name + ".running_mean"] = (0.05 * rng.standard_normal((o,))).astype(F32)
+        sd[prefix + name + ".running_var"] = rng.uniform(0.8, 1.2, size=(o,)).astype(F32)
+
+    conv("conv1", 64, 3, 7); bn("bn1", 64)
+    cin = 64
+    for l, nb in enumerate(blocks):
+        width = 64 << l
+        for b in range(nb):
+            q = f"layer{l + 1}.{b}."
+            conv(q + "conv1", width, cin, 1); bn(q + "bn1", width)
+            conv(q + "conv2", width, width, 3); bn(q + "bn2", width)
+            conv(q + "conv3", 4 * width, width, 1); bn(q + "bn3", 4 * width, gain=0.3)
+            if b == 0:
+                conv(q + "downsample.0", 4 * width, cin, 1); bn(q + "downsample.1", 4 * width)
+            cin = 4 * width
+    return sd
+
+
 def synth_text_ids(seed: int, B: int, L: int, vocab: int, pad_tail: int = 0) -> Tuple[np.ndarray, np.ndarray]:
     """Token ids as RobertaTokenizer emits them: <s>=0 ... </s>=2, pad=1 on the last `pad_tail` positions of the odd rows.
     Returns (ids (B, L) int32, pad mask (B, L) bool, True = padded)."""
