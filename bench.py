@@ -248,27 +248,30 @@ def time_dominant_kernel(B, pk):
 
 def measure_with_backbone(torch, rank=0, clips=8, steps=5):
     """SURVEY §8d secondary number: clips/s with the extractors in front of the library, 8 clips x 64 frames of 3x224x224 per step.
-      * ResNet101: torchvision (random init, eval, bf16, channels_last — cuDNN / cuBLAS LIBRARY code, not this repo's kernels) → layer-4
-        map, handed over zero-copy (channels-last bf16 = raw_layout 1);
-      * Video-Swin-T: the reference's own module (oracle/_ref, random init, eager PyTorch bf16) for patch embedding, stages 1-3 and the
-        PatchMerging layers; the LAST stage (`vid.layers[3]`) runs on this library's kernels (csrc/swin.cu) with that module's weights,
-        and its channels-last bf16 output goes straight into the forward.  Without oracle/_ref the Video-Swin map is synthetic;
-      * RoBERTa states synthetic (the text tower has its own `front_end.from_token_ids` line).
-    The repo's stage 4 is cross-checked against the PyTorch module's stage 4 on the same activations in the same run."""
+      * ResNet101: this library's kernels (csrc/resnet.cu) with seeded weights; the same network in torchvision (FrozenBatchNorm2d,
+        bf16 autocast, channels_last — cuDNN) is timed beside it and cross-checked against it; the layer-4 map goes into the forward
+        zero-copy (channels-last bf16 = raw_layout 1);
+      * Video-Swin-T: the whole extractor on this library's kernels (csrc/swin.cu) with the weights of the reference's own module
+        (oracle/_ref, random init), which is timed beside it in eager PyTorch bf16.  Without oracle/_ref the Video-Swin map is synthetic;
+      * RoBERTa states synthetic (the text tower has its own `front_end.from_token_ids` line)."""
     try:
         import torchvision
     except Exception:
         return None
     from vgqa_b200 import synth
     from vgqa_b200.engine import GroundingEngine
-    net = torchvision.models.resnet101(weights=None)
+    from torchvision.ops.misc import FrozenBatchNorm2d            # the arithmetic of the reference's class (backbone.py:47-57, eps 1e-5)
+    rsd = synth.synth_resnet101(0)
+    net = torchvision.models.resnet101(weights=None, norm_layer=FrozenBatchNorm2d)
+    net.load_state_dict({k[len("vis_encoder.0.body."):]: torch.from_numpy(v) for k, v in rsd.items()}, strict=False)
     body = torch.nn.Sequential(net.conv1, net.bn1, net.relu, net.maxpool, net.layer1, net.layer2, net.layer3, net.layer4)
-    body = body.eval().cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+    body = body.eval().cuda().to(memory_format=torch.channels_last)
     g = torch.Generator(device="cuda").manual_seed(99 + rank)
     frames = torch.randn(clips * T, 3, 224, 224, device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     text = torch.randn(clips, L, FRONT_END_CH[2], device="cuda", generator=g)
     sizes = torch.tensor([[360.0, 640.0]] * clips, device="cuda")
     sd = synth.synth_state_dict(0, front_end_ch=FRONT_END_CH)
+    sd.update(rsd)
     swin = None
     swin_note = "Video-Swin map synthetic (oracle/_ref absent)"
     if reference_arm_available():
@@ -300,23 +303,24 @@ def measure_with_backbone(torch, rank=0, clips=8, steps=5):
                 x = rearrange(swin.downsamples[idx](rearrange(x, "b c t h w -> b t h w c")), "b t h w c -> b c t h w")
         return rearrange(x, "b c t h w -> b t h w c").float().contiguous()          # [clips, T, 7, 7, 768]
 
-    frames32 = frames.float().contiguous() if swin is not None else None       # `videos.tensors` as the reference feeds them (NCHW fp32)
+    frames32 = frames.float().contiguous()       # `videos.tensors` as the reference feeds them (NCHW fp32)
+
+    def resnet_pytorch():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return body(frames)
 
     def swin_pytorch():
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
             return swin(frames, T)["3"]
 
     def step(mode="all"):
-        with torch.no_grad():
-            fmap = body(frames)                                            # [clips*T, 2048, 7, 7] bf16
+        fmap = eng.resnet_backbone(frames32)                               # [clips*T, 7, 7, 2048] bf16, channels-last
         if mode == "resnet":
             return
         vid = eng.swin_backbone(frames32, clips) if swin is not None else vid_syn
         if mode == "extractors":
             return
-        # a channels_last bf16 tensor IS [N, H, W, C] in memory: handed over zero-copy (raw_layout = 1)
-        vis = fmap.permute(0, 2, 3, 1).view(clips, T, H, W, FRONT_END_CH[0])
-        assert vis.is_contiguous()
+        vis = fmap.view(clips, T, H, W, FRONT_END_CH[0])                   # handed over zero-copy (raw_layout = 1)
         eng.forward(vis, vid, text, None, ori_sizes_hw=sizes, outs=outs, raw=True)
 
     def timed(fn):
@@ -352,6 +356,16 @@ def measure_with_backbone(torch, rank=0, clips=8, steps=5):
         res["swin_backbone_repo_ms_per_step"] = 1e3 * timed(lambda: eng.swin_backbone(frames32, clips))
         res["swin_backbone_launches"] = eng.last_launch_count
         res["swin_backbone_pytorch_bf16_ms_per_step"] = 1e3 * timed(swin_pytorch)
+    # the library's ResNet101 against the same network in PyTorch (fp32) on the same frames / weights
+    with torch.no_grad():
+        ref_r = body(frames32.contiguous(memory_format=torch.channels_last)).permute(0, 2, 3, 1)
+    mine_r = eng.resnet_backbone(frames32).float()
+    res["resnet_mean_abs_err_vs_pytorch_fp32"] = float((mine_r - ref_r).abs().mean())
+    res["resnet_mean_abs"] = float(ref_r.abs().mean())
+    res["resnet_pytorch_autocast_mean_abs_err"] = float((resnet_pytorch().permute(0, 2, 3, 1).float() - ref_r).abs().mean())
+    res["resnet_launches"] = eng.last_launch_count
+    res["resnet_pytorch_bf16_ms_per_step"] = 1e3 * timed(resnet_pytorch)
+    del ref_r, mine_r
     sec, sec_bb = timed(step), timed(lambda: step("resnet"))
     sec_ex = timed(lambda: step("extractors"))
     eng.close()
@@ -359,8 +373,9 @@ def measure_with_backbone(torch, rank=0, clips=8, steps=5):
     torch.cuda.empty_cache()
     res.update({"value": clips / sec, "unit": "clips/s", "ms_per_step": 1e3 * sec, "clips_per_step": clips,
                 "backbone_only_ms_per_step": 1e3 * sec_bb, "extractors_ms_per_step": 1e3 * sec_ex,
-                "what": "torchvision ResNet101 (random init, bf16, channels_last; PyTorch/cuDNN library code) on 64 x 3x224x224 frames per clip "
-                        "→ layer-4 map handed over zero-copy (channels-last bf16, raw_layout = 1); " + swin_note +
+                "what": "ResNet101 on this library's kernels (csrc/resnet.cu; `backbone_only_ms_per_step`; the same network in torchvision / cuDNN "
+                        "bf16 channels_last = `resnet_pytorch_bf16_ms_per_step`) on 64 x 3x224x224 frames per clip → layer-4 map handed over "
+                        "zero-copy (channels-last bf16, raw_layout = 1); " + swin_note +
                         " → this library's raw-input forward; RoBERTa states synthetic"})
     return res
 

@@ -40,16 +40,19 @@ struct ConvParams {
 
 template <int BN>
 struct ConvCfg {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = BN == 256 ? 3 : (BN == 128 ? 5 : 8);
   static constexpr int kABytes = 128 * 64 * 2;
   static constexpr int kBBytes = BN * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStaging = 4 * 2 * 4096;   // 4 epilogue warps x 2 slabs of 32 rows x 128 B
+  static constexpr int kEpiWarps = BN >= 128 ? 8 : 4;   // two warps per TMEM lane quadrant (half of the tile's columns each) from 128 columns on
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kStaging = kEpiWarps * 2 * 4096;   // 2 slabs of 32 rows x 128 B per epilogue warp
   static constexpr int kSmem = kStages * kStageBytes + kStaging + 1024 + 256;
+  static_assert(kSmem <= 232448, "conv_gemm smem");
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(ConvCfg<BN>::kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_c, const ConvParams p) {
   using Cfg = ConvCfg<BN>;
@@ -71,7 +74,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_b); tma_prefetch_desc(&tma_c);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], Cfg::kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
@@ -127,26 +130,44 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5): bias, residual, ReLU, border mask → bf16 slab → TMA store =====================
+    // ===================== epilogue: bias, residual, ReLU, border mask → bf16 slab → TMA store =====================
+    // warps 2..5 (and 6..9 from 128 columns on): a warp owns the TMEM lane quadrant warp % 4 and one half of the tile's columns
     pdl_wait();
     const int quad = warp & 3;
+    const int part = (warp - 2) >> 2;                          // which half of the columns (always 0 with four warps)
+    constexpr int kUnits = BN / 64 / (Cfg::kEpiWarps / 4);     // 64-column store units per warp and tile
     uint8_t* my_stage = smem_out + (warp - 2) * 8192;
     int acc = 0;
     uint32_t acc_phase = 0, nstore = 0;
     const int fr = p.Hp * p.Wp;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * 128, n0 = (tile % num_n) * BN;
+      const int m0 = (tile / num_n) * 128, n0 = (tile % num_n) * BN + part * kUnits * 64;
       const int row = m0 + quad * 32 + lane;
       bool live = row < p.M;
       if (fr > 0 && live) {
         const int rr = row % fr, hp = rr / p.Wp, wp = rr - hp * p.Wp;
         live = hp != 0 && hp != p.Hp - 1 && wp != 0 && wp != p.Wp - 1;
       }
+      // the residual row segment of a unit (128 bytes) is fetched one unit ahead: the loads of the first one are in flight while
+      // the accumulator is still being computed
+      const bool has_res = p.res != nullptr && live;
+      uint4 rq[8];
+      if (has_res) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(p.res + (size_t)row * p.ldres + n0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rq[i] = __ldg(r4 + i);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int u = 0; u < BN / 64; ++u) {
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + part * kUnits * 64;
+#pragma unroll
+      for (int u = 0; u < kUnits; ++u) {
+        uint4 rn[8];
+        if (u + 1 < kUnits && has_res) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(p.res + (size_t)row * p.ldres + n0 + (u + 1) * 64);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rn[i] = __ldg(r4 + i);
+        }
         uint8_t* buf = my_stage + (nstore & 1) * 4096;
         ++nstore;
         if (lane == 0) tma_store_wait_read<1>();   // the store issued two units ago has drained this slab
@@ -166,11 +187,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               v[4 * i] = __uint_as_float(raw[4 * i]) + b.x; v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + b.y;
               v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + b.z; v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + b.w;
             }
-            if (p.res != nullptr) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(p.res + (size_t)row * p.ldres + col);
+            if (has_res) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const uint4 q = __ldg(r4 + i);
+                const uint4 q = rq[hf * 4 + i];
                 const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
                 v[8 * i] += a.x; v[8 * i + 1] += a.y; v[8 * i + 2] += b.x; v[8 * i + 3] += b.y;
                 v[8 * i + 4] += c.x; v[8 * i + 5] += c.y; v[8 * i + 6] += d.x; v[8 * i + 7] += d.y;
@@ -196,6 +216,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (lane == 0) {
           tma_store_2d(&tma_c, buf, n0 + u * 64, m0 + quad * 32);
           tma_store_commit();
+        }
+        if (u + 1 < kUnits) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rq[i] = rn[i];
         }
       }
       tc_fence_before();
@@ -227,7 +251,7 @@ static void launch_conv(const bf16* A, int C, const bf16* W, const ConvParams& p
   CUtensorMap tc = make_tmap_2d(out, p.M, p.N, p.N, 32, false);
   const int tiles = ((p.M + 127) / 128) * (p.N / BN);
   const int grid = std::min(tiles, device_sm_count());
-  launch_pdl(conv_gemm_kernel<BN>, dim3(grid), dim3(192), Cfg::kSmem, st, ta, tb, tc, p);
+  launch_pdl(conv_gemm_kernel<BN>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, st, ta, tb, tc, p);
   VG_CUDA(cudaGetLastError());
 }
 
@@ -250,12 +274,21 @@ static void conv_gemm(const bf16* A, const ResNet::Conv& cv, int taps, int M, in
 // needs are staged (zero-padded by 3 on both sides) in shared memory.
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ fr, bf16* __restrict__ A, int R) {
   extern __shared__ float srow[];   // [3][7][R + 6]
+  __shared__ int koff[192];         // operand column → offset of its tap in srow (relative to 2 ox), -1 = padding column
   const int Ho = R >> 1, Rp = R + 6;
   const int n = blockIdx.x / Ho, oy = blockIdx.x - n * Ho;
-  for (int i = threadIdx.x; i < 21 * Rp; i += blockDim.x) {
-    const int cr = i / Rp, xx = i - cr * Rp, c = cr / 7, ky = cr - c * 7;
-    const int iy = 2 * oy - 3 + ky, ix = xx - 3;
-    srow[i] = (iy >= 0 && iy < R && ix >= 0 && ix < R) ? __ldg(fr + (((size_t)n * 3 + c) * R + iy) * R + ix) : 0.f;
+  if (threadIdx.x < 192) {
+    const int k = threadIdx.x, c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
+    koff[k] = k < 147 ? (c * 7 + ky) * Rp + kx : -1;
+  }
+  for (int cr = threadIdx.x >> 5; cr < 21; cr += 8) {   // one warp per (channel, ky) row: coalesced reads
+    const int c = cr / 7, ky = cr - c * 7, iy = 2 * oy - 3 + ky;
+    const float* src = fr + (((size_t)n * 3 + c) * R + iy) * R;
+    const bool in = iy >= 0 && iy < R;
+    for (int xx = threadIdx.x & 31; xx < Rp; xx += 32) {
+      const int ix = xx - 3;
+      srow[cr * Rp + xx] = (in && ix >= 0 && ix < R) ? __ldg(src + ix) : 0.f;
+    }
   }
   __syncthreads();
   uint4* dst = reinterpret_cast<uint4*>(A + ((size_t)n * Ho + oy) * Ho * 192);
@@ -264,13 +297,8 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int k = j * 8 + e;
-      float a = 0.f;
-      if (k < 147) {
-        const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
-        a = srow[(c * 7 + ky) * Rp + 2 * ox + kx];
-      }
-      v[e] = a;
+      const int o = koff[j * 8 + e];
+      v[e] = o >= 0 ? srow[o + 2 * ox] : 0.f;
     }
     dst[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
   }
