@@ -1,0 +1,59 @@
+"""GPU: the reference's WHOLE `VSTGNet.forward` (vgqa/core/grounding_net.py:88-203) reproduced from pixels and token ids by this
+library alone — ResNet101 (csrc/resnet.cu), Video-Swin-T (csrc/swin.cu), the RoBERTa tower + resizer, input_proj / input_proj2,
+PositionEmbeddingSine, the encoder, the classifiers, both decoder passes and the heads — against the golden of the unmodified
+reference model run in fp32 on the same seeded frames, token ids and weights (tests/golden/make_golden_full.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_path
+from make_golden_full import FRONT_END_CH, full_frames, full_state_dict  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+# Tolerances (max-abs, outputs are O(1) logits / sigmoids): the hot path alone holds 2e-2 on exact inputs (test_parity_gpu.py); here
+# its inputs come from 101 + 24 + 12 layers of bf16 extractors (ResNet map: mean deviation 0.8 % of mean |y|).  Measured on a B200:
+# pred_boxes 4e-4, pred_sted 5.5e-3, pred_actioness 3.2e-3, logits_f_m 8.2e-3, logits_f_a 2.2e-2, logits_r_a / r_m 1.4e-2,
+# att_sequences 3.2e-3, actioness_pass1 7e-4.
+TOL = {"pred_boxes": 5e-3, "pred_sted": 4e-2, "pred_actioness": 4e-2, "logits_f_m": 4e-2, "logits_f_a": 4e-2, "logits_r_a": 4e-2,
+       "logits_r_m": 4e-2, "att_sequences": 1e-2, "actioness_pass1": 1e-2}
+
+def test_whole_forward_from_pixels_matches_the_reference_model():
+    from vgqa_b200.engine import GroundingEngine
+    g = np.load(golden_path("full_vstgnet_T16_224_s0"))
+    T, R, seed = (int(g[k]) for k in ("T", "R", "seed"))
+    ids = torch.from_numpy(g["text_ids"]).cuda()
+    L = ids.shape[1]
+    eng = GroundingEngine(full_state_dict(seed), max_clips=1, max_frames=T, max_hw=49, max_text=L)
+    frames = torch.from_numpy(full_frames(seed, T, R)).cuda()
+    vis_map = eng.resnet_backbone(frames).view(1, T, 7, 7, 2048)        # `vis_res_features` (channels-last bf16)
+    vid_map = eng.swin_backbone(frames, 1)                               # `vid_features_all['3']`
+    want = ["pred_boxes", "pred_sted", "pred_actioness", "logits_f_m", "logits_f_a", "logits_r_a", "logits_r_m", "att_sequences",
+            "choose1", "choose2", "actioness_pass1", "aux_boxes", "aux_sted"]
+    o = eng.forward(vis_map, vid_map, None, None, raw=True, text_ids=ids, want=want)      # free-running: no decision is forced
+    torch.cuda.synchronize()
+    o = {k: v.float().cpu().numpy() for k, v in o.items()}
+    ref = {"pred_boxes": g["pred_boxes"], "pred_sted": g["pred_sted"][0], "pred_actioness": g["pred_actioness"][0, :, 0],
+           "logits_f_m": g["logits_f_m"], "logits_f_a": g["logits_f_a"], "logits_r_a": g["logits_r_a"][0], "logits_r_m": g["logits_r_m"][0],
+           "att_sequences": g["att_sequences"][0], "actioness_pass1": g["actioness_pass1"]}
+    # the two frame selections are the reference's (its margins: |att - theta| >= 0.036, |actioness - 0.5| >= 0.14)
+    sel = lambda w: np.flatnonzero(w.reshape(-1)[:T] > 0.5).tolist()
+    assert sel(o["choose1"]) == g["choose1"].tolist() and sel(o["choose2"]) == g["choose2"].tolist()
+    worst = {k: float(np.abs(o[k][0].reshape(r.shape) - r).max()) for k, r in ref.items()}
+    print("whole-model max-abs errors:", {k: round(v, 4) for k, v in worst.items()})
+    bad = {k: v for k, v in worst.items() if not v <= TOL[k]}
+    assert not bad, f"max-abs errors over tolerance: {bad} (all: {worst})"
+    # the decoded answer: same (start, end) frames as the reference's scores give, boxes within 2 % of the frame
+    sted = g["pred_sted"][0]
+    s_ref, e_ref = int(sted[:, 0].argmax()), int(sted[:, 1].argmax())
+    s, e = int(o["pred_sted"][0][:, 0].argmax()), int(o["pred_sted"][0][:, 1].argmax())
+    gap = lambda v: float(np.sort(v)[-1] - np.sort(v)[-2])
+    if gap(sted[:, 0]) > 4 * worst["pred_sted"]:
+        assert s == s_ref
+    if gap(sted[:, 1]) > 4 * worst["pred_sted"]:
+        assert e == e_ref
+    # the auxiliary outputs (decoder layers 1..5 of 6; aux_boxes / aux_sted hold all six layers)
+    for i in range(5):
+        np.testing.assert_allclose(o["aux_boxes"][i][0].reshape(T, 4), g[f"aux{i}_pred_boxes"].reshape(T, 4), atol=5e-3, err_msg=f"aux {i}")
+        np.testing.assert_allclose(o["aux_sted"][i][0].reshape(T, 2), g[f"aux{i}_pred_sted"].reshape(T, 2), atol=4e-2, err_msg=f"aux {i}")
+    eng.close()
