@@ -57,3 +57,35 @@ def test_whole_forward_from_pixels_matches_the_reference_model():
         np.testing.assert_allclose(o["aux_boxes"][i][0].reshape(T, 4), g[f"aux{i}_pred_boxes"].reshape(T, 4), atol=5e-3, err_msg=f"aux {i}")
         np.testing.assert_allclose(o["aux_sted"][i][0].reshape(T, 2), g[f"aux{i}_pred_sted"].reshape(T, 2), atol=4e-2, err_msg=f"aux {i}")
     eng.close()
+
+
+def test_vstgnet_dropin_with_every_extractor_in_the_library():
+    """`B200VSTGNet` given the whole state_dict: no PyTorch module of the model is called (the extractor modules passed in raise) —
+    `videos.tensors` and the tokenizer's ids go into the library; output dict as grounding_net.py:164-203."""
+    from make_golden import make_cfg
+    from vgqa_b200 import modules as M
+    g = np.load(golden_path("full_vstgnet_T16_224_s0"))
+    T, R, seed = (int(g[k]) for k in ("T", "R", "seed"))
+    ids = torch.from_numpy(g["text_ids"]).long()
+
+    class TextEncoder:            # what the drop-in calls of the reference's RoBERTa wrapper: the tokenizer (bert.py:50,65)
+        @staticmethod
+        def tokenizer(texts, padding, return_tensors):
+            assert texts == [" a person jumping over the fence"]       # grounding_net.py:110: subject + " " + sentence
+            return {"input_ids": ids, "attention_mask": torch.ones_like(ids)}
+
+    def boom(*a, **k):
+        raise AssertionError("a PyTorch extractor module was called")
+
+    model = M.B200VSTGNet(make_cfg(), boom, boom, TextEncoder(), boom, boom, full_state_dict(seed), verb_label2={"0": {"sub": ""}},
+                          max_frames=T, max_hw=49, max_text=ids.shape[1]).eval()
+    assert model.fused_backbones and model.fused_front_end and model.fused_text_tower
+    videos = M.NestedTensor(torch.from_numpy(full_frames(seed, T, R)).cuda(), torch.zeros(T, R, R, dtype=torch.bool, device="cuda"), [T])
+    out = model(videos, ["a person jumping over the fence"], [{"item_id": 0, "actioness": torch.ones(T, device="cuda")}])
+    for k in ("pred_boxes", "pred_sted", "pred_actioness", "logits_f_m", "logits_f_a", "logits_r_a", "logits_r_m", "att_sequences"):
+        got = out[k].float().cpu().numpy()
+        assert got.shape == g[k].shape, (k, got.shape, g[k].shape)
+        assert float(np.abs(got - g[k]).max()) <= TOL[k], (k, float(np.abs(got - g[k]).max()))
+    assert len(out["aux_outputs"]) == 5 and out["pr"] == (1.0, 1.0)
+    for i, a in enumerate(out["aux_outputs"]):
+        assert float(np.abs(a["pred_boxes"].cpu().numpy() - g[f"aux{i}_pred_boxes"]).max()) <= TOL["pred_boxes"], i

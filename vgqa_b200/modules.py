@@ -3,7 +3,8 @@
     build_hot_path(cfg, state_dict)        fused replacement of ground_encoder + *_clas + ground_decoder + MLP heads
     build_encoder(cfg, state_dict)         CrossModalEncoder drop-in: (videos, vis_pos, texts, vid) -> dict   (modal_encoder.py:41-85)
     B200VSTGNet                            VSTGNet drop-in: forward(videos, texts, targets, iteration_rate=-1) -> dict
-                                           (grounding_net.py:88-204); backbones / text tower stay the caller's PyTorch modules
+                                           (grounding_net.py:88-204); the extractors are the caller's PyTorch modules — or, when
+                                           their weights are in the state_dict, the library's own (ResNet101, Video-Swin-T, RoBERTa)
     NestedTensor                           (tensors, mask, durations) container (utils/training_utils.py:44-72)
 
 All math of the path runs in libvgqa_b200.so (vgqa_b200/engine.py); there is no PyTorch fallback.
@@ -72,24 +73,29 @@ class HotPath(torch.nn.Module):
 
     @torch.no_grad()
     def forward(self, vis_features, vis_mask, vis_pos, text_mask, text_features, vid_features, iteration_rate=-1, raw=False,
-                text_ids=None):
+                text_ids=None, nhwc=False):
         """vis/vid_features [T,256,H,W], vis_mask [T,H,W] bool, vis_pos [T,256,H,W], text_features [L,1,256],
         text_mask [1,L] bool → the reference's output dict entries that depend on the hot path.
         raw=True: the features are the extractor outputs (ResNet map [T,Cv,H,W], Video-Swin map [T,Cd,H,W], RoBERTa states
         [L,1,Ct]) and input_proj / input_proj2 / text_encoder.resizer run fused inside the library (grounding_net.py:101,105;
         bert.py:73) — their weights must be in the state_dict.  text_ids [1, L] int32 (raw=True): RoBERTa token ids instead of
-        text_features; the text tower (`text_encoder.body.*`) then runs inside the library too."""
-        T, d, H, W = vis_features.shape
-        assert vis_pos.shape[0] == T, "{} != {}".format(vis_pos.shape[0], T)          # modal_encoder.py:44
+        text_features; the text tower (`text_encoder.body.*`) then runs inside the library too.  nhwc=True (raw only): the maps are
+        already channels-last bf16 [T,H,W,C] (the library's own extractors).  vis_pos=None: PositionEmbeddingSine is generated in the
+        library from vis_mask (position_encoding.py:50-91)."""
+        if nhwc:
+            T, H, W, d = vis_features.shape
+        else:
+            T, d, H, W = vis_features.shape
+        assert vis_pos is None or vis_pos.shape[0] == T, "{} != {}".format(vis_pos.shape[0], T)          # modal_encoder.py:44
         f32 = lambda t: t.detach().to(torch.float32).contiguous()
         masked = bool(vis_mask is not None and vis_mask.any()) or bool(text_mask is not None and text_mask.any())
         kw = {}
         if masked:
             kw["vis_mask"] = vis_mask.reshape(T, H * W).to(torch.uint8).contiguous()
             kw["text_mask"] = text_mask.reshape(1, -1).to(torch.uint8).contiguous()
-            pos = f32(vis_pos)
+            pos = None if vis_pos is None else f32(vis_pos)
         else:
-            pos = f32(vis_pos[:1])   # PositionEmbeddingSine of an all-False mask is identical on every frame
+            pos = None if vis_pos is None else f32(vis_pos[:1])   # PositionEmbeddingSine of an all-False mask is identical on every frame
         if text_ids is not None:
             kw["text_ids"] = text_ids.reshape(1, -1).to(torch.int32).contiguous()
         fmap = f32
@@ -97,6 +103,9 @@ class HotPath(torch.nn.Module):
             # bf16 backbones: hand the maps over as channels-last bf16 (raw_layout = 1).  A channels_last tensor already IS
             # [T, H, W, C] in memory, so this is a zero-copy view; a plain NCHW bf16 tensor is permuted once.
             fmap = lambda t: t.detach().permute(0, 2, 3, 1).contiguous()
+        if nhwc:
+            assert raw and vis_features.dtype == torch.bfloat16 and vid_features.dtype == torch.bfloat16
+            fmap = lambda t: t.detach().contiguous()
         o = self.engine.forward(fmap(vis_features)[None], fmap(vid_features)[None],
                                 None if text_ids is not None else f32(text_features[:, 0])[None], pos,
                                 iteration_rate=iteration_rate, raw=raw, **kw)
@@ -169,6 +178,10 @@ class B200VSTGNet(torch.nn.Module):
         # fused text tower: only the TOKENIZER of the text encoder is called (bert.py:65), RoBERTa itself runs inside the library
         self.fused_text_tower = self.fused_front_end and hasattr(text_encoder, "tokenizer") and \
             "text_encoder.body.embeddings.word_embeddings.weight" in state_dict
+        # fused extractors (csrc/resnet.cu, csrc/swin.cu): with the `vis_encoder.0.body.*` and `vid.*` weights in the state_dict the
+        # ResNet101 / Video-Swin-T modules are not called either — `videos.tensors` go straight into the library
+        self.fused_backbones = self.fused_front_end and "vis_encoder.0.body.conv1.weight" in state_dict and \
+            "vid.patch_embed.proj.weight" in state_dict
         self.hot = HotPath(cfg, state_dict, **cap)
         self.verb_label = verb_label or {}
         self.verb_label2 = verb_label2 or {}
@@ -181,12 +194,25 @@ class B200VSTGNet(torch.nn.Module):
 
     @torch.no_grad()
     def forward(self, videos, texts, targets, iteration_rate: int = -1):
-        vis_outputs, vis_pos = self.vis_encoder(videos)
-        vis_res, vis_mask, vis_durations = vis_outputs.decompose()
-        vid_res = self.vid(videos.tensors, len(videos.tensors))["3"]
+        frames = videos.tensors
+        nhwc = self.fused_backbones and frames.shape[0] % 8 == 0 and frames.shape[-1] == frames.shape[-2] and frames.shape[-1] in (224, 448)
+        if nhwc:
+            # the library's extractors: layer4 map of ResNet101 and the last Video-Swin-T stage, both channels-last bf16; the mask is
+            # interpolated as BackboneBase.forward does (backbone.py:92-96) and the positional encoding is generated from it
+            eng = self.hot.engine
+            frames = frames.detach().to(torch.float32).contiguous()
+            vis_features = eng.resnet_backbone(frames)
+            vid_features = eng.swin_backbone(frames, 1)[0]
+            vis_mask = torch.nn.functional.interpolate(videos.mask[None].float(), size=vis_features.shape[1:3]).to(torch.bool)[0]
+            vis_pos = None
+        else:
+            vis_outputs, vis_pos = self.vis_encoder(videos)
+            vis_res, vis_mask, vis_durations = vis_outputs.decompose()
+            vid_res = self.vid(videos.tensors, len(videos.tensors))["3"]
+            fused = self.fused_front_end
+            vis_features = vis_res if fused else self.input_proj(vis_res)
+            vid_features = vid_res if fused else self.input_proj2(vid_res)
         fused = self.fused_front_end
-        vis_features = vis_res if fused else self.input_proj(vis_res)
-        vid_features = vid_res if fused else self.input_proj2(vid_res)
         info_key = str(targets[0]["item_id"])
         labels = self.verb_label if self.training else self.verb_label2
         texts = [labels[info_key]["sub"] + " " + texts[0]]
@@ -196,11 +222,11 @@ class B200VSTGNet(torch.nn.Module):
             tok = self.text_encoder.tokenizer(texts, padding="longest", return_tensors="pt")      # bert.py:65
             ids = tok["input_ids"].to(vis_features.device)
             text_mask = tok["attention_mask"].to(vis_features.device).ne(1)                       # bert.py:70
-            out = self.hot(vis_features, vm, vis_pos, text_mask, None, vid_features, iteration_rate, raw=True, text_ids=ids)
+            out = self.hot(vis_features, vm, vis_pos, text_mask, None, vid_features, iteration_rate, raw=True, text_ids=ids, nhwc=nhwc)
         else:
             (text_mask, text_features, text_memory), _ = self.text_encoder(texts, vis_features.device)
             out = self.hot(vis_features, vm, vis_pos, text_mask, text_memory if fused else text_features, vid_features,
-                           iteration_rate, raw=fused)
+                           iteration_rate, raw=fused, nhwc=nhwc)
         choose_index = out.pop("_choose_index").tolist()
         out["verb_labels"] = labels.get(info_key, {}).get("verb_index_list", [])
         out["attr_labels"] = labels.get(info_key, {}).get("adj_index_list", [])
