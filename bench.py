@@ -380,6 +380,47 @@ def measure_with_backbone(torch, rank=0, clips=8, steps=5):
     return res
 
 
+def measure_full_forward(torch, frames=32, reps=10):
+    """BASELINE.json configs[0] (the reference's CPU-runnable case: ONE full `VSTGNet.forward`, 32 frames @224, batch 1) on the
+    library alone: ResNet101 + Video-Swin-T + RoBERTa-base tower + front end + hot path from NCHW fp32 pixels and token ids.  Its
+    CPU counterpart is `full_forward_cfg1` of `--impl reference` (the unmodified reference model on the host cores)."""
+    from vgqa_b200 import synth
+    from vgqa_b200.engine import GroundingEngine
+    sd = synth.synth_state_dict(0, front_end_ch=FRONT_END_CH, text_tower=(12, 50265))
+    sd.update(synth.synth_resnet101(0))
+    sd.update(synth.synth_swin_backbone(0))
+    ids = torch.tensor([[0, 5910, 36777, 43933, 5772, 33081, 34763, 2]], dtype=torch.int32, device="cuda")   # "a person jumping over the fence"
+    eng = GroundingEngine(sd, max_clips=1, max_frames=frames, max_hw=H * W, max_text=ids.shape[1], use_cuda_graph=True)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(frames, 3, 224, 224, device="cuda", generator=g)
+    sizes = torch.tensor([[360.0, 640.0]], device="cuda")
+    outs = eng.alloc_outputs(1, frames, H, W, ids.shape[1], ["pred_boxes", "pred_sted", "boxes_px", "sted_idx"])
+    host = torch.empty(frames, 4).pin_memory()
+
+    def step():
+        vis = eng.resnet_backbone(x).view(1, frames, H, W, FRONT_END_CH[0])
+        vid = eng.swin_backbone(x, 1)
+        eng.forward(vis, vid, None, None, ori_sizes_hw=sizes, outs=outs, raw=True, text_ids=ids)
+        host.copy_(outs["boxes_px"][0], non_blocking=True)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    eng.close()
+    torch.cuda.empty_cache()
+    return {"ms_per_forward": ms, "forwards_per_s": 1e3 / ms, "frames": frames, "resolution": 224,
+            "what": "one full forward of the model from pixels (NCHW fp32, device) + token ids to PostProcess boxes read back to the host, "
+                    "every layer on this library's kernels (ResNet101, Video-Swin-T, RoBERTa-base, input_proj*, encoder, decoders, heads); "
+                    "seeded random weights; the reference's own number is `full_forward_cfg1.seconds_per_forward` of `--impl reference`"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -762,6 +803,7 @@ def main():
     sharded_long = guarded(lambda: sharded_clip("ev_long_T256_12x12_L20_s0")) if world > 1 else None
     eager_ref = guarded(eager_pytorch) if (rank == 0 and world == 1 and not args.quick) else None
     swin_line = guarded(swin_stage_line) if (world == 1 and not args.quick) else None
+    full_fwd = guarded(lambda: measure_full_forward(torch)) if (rank == 0 and world == 1 and not args.quick) else None
     value = total_clips / sec
     e2e = total_clips / sec_e2e
     h2d_f32 = int(h_vis.numel() * 4 * 2 + h_text.numel() * 4 + h_pos.numel() * 4 + h_sizes.numel() * 4)
@@ -789,6 +831,7 @@ def main():
             "front_end": front_end,
             "batch1": batch1,
             "with_backbone": with_bb,
+            "full_forward_cfg1": full_fwd,
             "other_configs": others,
             "sharded_cfg4": sharded,
             "sharded_long": sharded_long,
