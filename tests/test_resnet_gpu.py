@@ -77,3 +77,21 @@ def test_resnet101_feeds_the_raw_forward():
     torch.cuda.synchronize()
     assert torch.isfinite(o["pred_boxes"]).all() and torch.isfinite(o["pred_sted"]).all()
     eng.close()
+
+
+@pytest.mark.parametrize("n,R", [(2, 32), (1, 96), (1, 160)])
+def test_resnet101_other_resolutions_match_the_oracle(n, R):
+    """Frame sides that are not 224 (odd map sides after the strides: 96 → 24 / 12 / 6 / 3, 160 → 40 / 20 / 10 / 5; 32 → a 1x1 layer4
+    map) against the numpy oracle on the same seeded frames: relative deviation of every layer output of the order of bf16 (1 %)."""
+    seed = 5
+    x = resnet_frames(seed, n, R)
+    ref = O.resnet101_backbone(O.synth_resnet101(seed), x)
+    eng = _engine(seed, None)
+    out, layers = eng.resnet_backbone(torch.from_numpy(x).cuda(), want_layers=True)
+    torch.cuda.synchronize()
+    for l in range(4):
+        got = layers[l].cpu().numpy()
+        assert got.shape == ref[l].shape
+        rel = float(np.abs(got - ref[l]).mean() / np.abs(ref[l]).mean())
+        assert rel <= 1.5e-2, (l, rel)
+    eng.close()
