@@ -398,8 +398,7 @@ def measure_full_forward(torch, frames=32, reps=10):
     host = torch.empty(frames, 4).pin_memory()
 
     def step():
-        vis = eng.resnet_backbone(x).view(1, frames, H, W, FRONT_END_CH[0])
-        vid = eng.swin_backbone(x, 1)
+        vis, vid = eng.extract_features(x, 1)
         eng.forward(vis, vid, None, None, ori_sizes_hw=sizes, outs=outs, raw=True, text_ids=ids)
         host.copy_(outs["boxes_px"][0], non_blocking=True)
 

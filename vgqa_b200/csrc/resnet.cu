@@ -482,7 +482,11 @@ int ResNet::forward(const float* frames, int n, int R, bf16* out_bf16, float* ou
   VG_CHECK(loaded, "vgqa_resnet_backbone needs the 'vis_encoder.0.body.*' weights (conv1, bn1, layer1-4)");
   VG_CHECK(n >= 1 && R >= 32 && R % 32 == 0 && R <= 512, "vgqa_resnet_backbone: the frame side must be a multiple of 32 (at most 512)");
   const int launches0 = launches;
-  const int chunk = std::min(n, 128);   // frames per pass: bounds the workspace (2.3 GB at 224 px)
+  // frames per pass (bounds the workspace: 2.7 GB at 224 px).  One frame is two 128-row tiles of the 14x14 (+ border) maps of
+  // layer3, where most of the time goes: a pass of as many frames as there are SMs fills whole waves of its 256-column GEMMs
+  int sms = 148;
+  { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int chunk = std::min(n, std::max(sms, 32));
   ensure_workspace(chunk, R);
   const int Ho = R / 2;
   for (int f0 = 0; f0 < n; f0 += chunk) {

@@ -364,6 +364,27 @@ class GroundingEngine:
         _lib.check(self._L.vgqa_resnet_backbone(self._ctx, self._p(frames), n, R, self._p(out), None, ptrs, c_void_p(st)))
         return (out, layers) if want_layers else out
 
+    def extract_features(self, frames, clips):
+        """Both extractors on `frames` fp32 NCHW [clips*T, 3, R, R] → (ResNet101 layer4 map [clips, T, R/32, R/32, 2048],
+        Video-Swin-T map [clips, T, R/32, R/32, 768]), channels-last bf16 = the raw_layout 1 inputs of forward().  Short clips do
+        not fill the GPU with either network (layer3 of 32 frames is 64 tiles for 148 SMs), so up to 64 frames the two run
+        concurrently on two streams."""
+        n = frames.shape[0]
+        if n > 64:
+            vis = self.resnet_backbone(frames)
+            vid = self.swin_backbone(frames, clips)
+        else:
+            cur = torch.cuda.current_stream()
+            if getattr(self, "_aux_stream", None) is None:
+                self._aux_stream = torch.cuda.Stream()
+            self._aux_stream.wait_stream(cur)
+            with torch.cuda.stream(self._aux_stream):
+                vis = self.resnet_backbone(frames)
+            vid = self.swin_backbone(frames, clips)
+            cur.wait_stream(self._aux_stream)
+            vis.record_stream(cur)
+        return vis.view(clips, n // clips, vis.shape[1], vis.shape[2], 2048), vid
+
     @property
     def last_launch_count(self) -> int:
         return int(self._L.vgqa_last_launch_count(self._ctx))

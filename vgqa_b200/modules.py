@@ -201,8 +201,7 @@ class B200VSTGNet(torch.nn.Module):
             # interpolated as BackboneBase.forward does (backbone.py:92-96) and the positional encoding is generated from it
             eng = self.hot.engine
             frames = frames.detach().to(torch.float32).contiguous()
-            vis_features = eng.resnet_backbone(frames)
-            vid_features = eng.swin_backbone(frames, 1)[0]
+            vis_features, vid_features = (m[0] for m in eng.extract_features(frames, 1))
             vis_mask = torch.nn.functional.interpolate(videos.mask[None].float(), size=vis_features.shape[1:3]).to(torch.bool)[0]
             vis_pos = None
         else:
