@@ -38,24 +38,28 @@ struct ConvParams {
   int Hp;              // rows per frame = Hp * Wp, border rows are written as zeros; 0 = plain row-major output
 };
 
-template <int BN>
+// DEEP: one more pipeline stage instead of the second staging slab per epilogue warp — for long-K GEMMs without a residual (the 3x3
+// convolutions, the 1x1 reductions of layer3 / layer4), whose time is the main loop: three 48 KB stages hold 0.8 us of MMA work, less
+// than the latency of a TMA load
+template <int BN, bool DEEP>
 struct ConvCfg {
-  static constexpr int kStages = BN == 256 ? 3 : (BN == 128 ? 5 : 8);
+  static constexpr int kStages = BN == 256 ? (DEEP ? 4 : 3) : (BN == 128 ? (DEEP ? 6 : 5) : 8);
   static constexpr int kABytes = 128 * 64 * 2;
   static constexpr int kBBytes = BN * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiWarps = BN >= 128 ? 8 : 4;   // two warps per TMEM lane quadrant (half of the tile's columns each) from 128 columns on
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
-  static constexpr int kStaging = kEpiWarps * 2 * 4096;   // 2 slabs of 32 rows x 128 B per epilogue warp
-  static constexpr int kSmem = kStages * kStageBytes + kStaging + 1024 + 256;
+  static constexpr int kSlabs = DEEP ? 1 : 2;             // staging slabs of 32 rows x 128 B per epilogue warp
+  static constexpr int kStaging = kEpiWarps * kSlabs * 4096;
+  static constexpr int kSmem = kStages * kStageBytes + kStaging + 1024 + 512;   // + alignment slack + barriers
   static_assert(kSmem <= 232448, "conv_gemm smem");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(ConvCfg<BN>::kThreads, 1)
+template <int BN, bool DEEP>
+__global__ void __launch_bounds__(ConvCfg<BN, DEEP>::kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const __grid_constant__ CUtensorMap tma_c, const ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+                 const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r, const ConvParams p) {
+  using Cfg = ConvCfg<BN, DEEP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -66,14 +70,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;              // [epilogue warps][2]: the residual segment of a store unit has landed in the slab
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * Cfg::kEpiWarps);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (p.M + 127) / 128, num_n = p.N / BN, num_tiles = num_m * num_n, num_k = p.K / 64;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_b); tma_prefetch_desc(&tma_c);
+    tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_b); tma_prefetch_desc(&tma_c); tma_prefetch_desc(&tma_r);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2 * Cfg::kEpiWarps; ++s) mbar_init(&res_bar[s], 1);
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], Cfg::kEpiWarps); }
     fence_mbar_init();
   }
@@ -136,10 +142,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int quad = warp & 3;
     const int part = (warp - 2) >> 2;                          // which half of the columns (always 0 with four warps)
     constexpr int kUnits = BN / 64 / (Cfg::kEpiWarps / 4);     // 64-column store units per warp and tile
-    uint8_t* my_stage = smem_out + (warp - 2) * 8192;
+    uint8_t* my_stage = smem_out + (warp - 2) * (Cfg::kSlabs * 4096);
+    uint64_t* my_rbar = res_bar + 2 * (warp - 2);
     int acc = 0;
-    uint32_t acc_phase = 0, nstore = 0;
+    uint32_t acc_phase = 0, q = 0;   // q: store units this warp has processed (slab = q & 1)
     const int fr = p.Hp * p.Wp;
+    const bool has_res = p.res != nullptr;
+    // The residual segment of a unit (32 rows x 128 bytes, the same box as the store) is brought INTO the unit's slab by TMA, one unit
+    // ahead; the threads add their row in place and the slab goes out again.  unit q of this warp = (tile q / kUnits, unit q % kUnits)
+    auto unit_coords = [&](uint32_t qq, int& col0, int& row0) -> bool {
+      const int tile = (int)blockIdx.x + (int)(qq / kUnits) * (int)gridDim.x;
+      if (tile >= num_tiles) return false;
+      col0 = (tile % num_n) * BN + part * kUnits * 64 + (int)(qq % kUnits) * 64;
+      row0 = (tile / num_n) * 128 + quad * 32;
+      return true;
+    };
+    auto prefetch_res = [&](uint32_t qq) {   // lane 0
+      int col0, row0;
+      if (!unit_coords(qq, col0, row0)) return;
+      mbar_expect_tx(&my_rbar[qq & 1], 4096);
+      tma_load_2d(my_stage + (qq & 1) * 4096, &tma_r, &my_rbar[qq & 1], col0, row0);
+    };
+    if (has_res && lane == 0) prefetch_res(0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * 128, n0 = (tile % num_n) * BN + part * kUnits * 64;
       const int row = m0 + quad * 32 + lane;
@@ -148,30 +172,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int rr = row % fr, hp = rr / p.Wp, wp = rr - hp * p.Wp;
         live = hp != 0 && hp != p.Hp - 1 && wp != 0 && wp != p.Wp - 1;
       }
-      // the residual row segment of a unit (128 bytes) is fetched one unit ahead: the loads of the first one are in flight while
-      // the accumulator is still being computed
-      const bool has_res = p.res != nullptr && live;
-      uint4 rq[8];
-      if (has_res) {
-        const uint4* r4 = reinterpret_cast<const uint4*>(p.res + (size_t)row * p.ldres + n0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rq[i] = __ldg(r4 + i);
-      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + part * kUnits * 64;
-#pragma unroll
-      for (int u = 0; u < kUnits; ++u) {
-        uint4 rn[8];
-        if (u + 1 < kUnits && has_res) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(p.res + (size_t)row * p.ldres + n0 + (u + 1) * 64);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) rn[i] = __ldg(r4 + i);
+#pragma unroll 1
+      for (int u = 0; u < kUnits; ++u, ++q) {
+        uint8_t* buf = my_stage + (Cfg::kSlabs == 2 ? (q & 1) * 4096 : 0);
+        if (lane == 0) {
+          if (has_res) {
+            tma_store_wait_read<0>();      // the other slab's store (unit q - 1) has been read out: the next residual may land in it
+            prefetch_res(q + 1);
+          } else {
+            tma_store_wait_read<Cfg::kSlabs - 1>();      // the previous store out of this slab has drained it
+          }
         }
-        uint8_t* buf = my_stage + (nstore & 1) * 4096;
-        ++nstore;
-        if (lane == 0) tma_store_wait_read<1>();   // the store issued two units ago has drained this slab
         __syncwarp();
+        if (has_res) mbar_wait(&my_rbar[q & 1], (q >> 1) & 1);
+        uint8_t* rowp = buf + lane * 128;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           const int col = n0 + u * 64 + hf * 32;
@@ -190,8 +207,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (has_res) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const uint4 q = rq[hf * 4 + i];
-                const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+                const uint4 rq = *reinterpret_cast<const uint4*>(rowp + (((hf * 4 + i) ^ (lane & 7)) << 4));
+                const float2 a = unpack_bf16(rq.x), b = unpack_bf16(rq.y), c = unpack_bf16(rq.z), d = unpack_bf16(rq.w);
                 v[8 * i] += a.x; v[8 * i + 1] += a.y; v[8 * i + 2] += b.x; v[8 * i + 3] += b.y;
                 v[8 * i + 4] += c.x; v[8 * i + 5] += c.y; v[8 * i + 6] += d.x; v[8 * i + 7] += d.y;
               }
@@ -204,7 +221,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
-          uint8_t* rowp = buf + lane * 128;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<uint4*>(rowp + (((hf * 4 + i) ^ (lane & 7)) << 4)) =
@@ -216,10 +232,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (lane == 0) {
           tma_store_2d(&tma_c, buf, n0 + u * 64, m0 + quad * 32);
           tma_store_commit();
-        }
-        if (u + 1 < kUnits) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) rq[i] = rn[i];
         }
       }
       tc_fence_before();
@@ -238,20 +250,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   }
 }
 
-template <int BN>
+template <int BN, bool DEEP>
 static void launch_conv(const bf16* A, int C, const bf16* W, const ConvParams& p, bf16* out, cudaStream_t st) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, DEEP>;
   static bool attr_set = false;
   if (!attr_set) {
-    VG_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    VG_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr_set = true;
   }
   CUtensorMap ta = make_tmap_2d(A, p.M, C, C, 128, false);
   CUtensorMap tb = make_tmap_2d(W, p.N, p.K, p.K, BN, false);
   CUtensorMap tc = make_tmap_2d(out, p.M, p.N, p.N, 32, false);
+  CUtensorMap tr = make_tmap_2d(p.res != nullptr ? (const void*)p.res : (const void*)out, p.M, p.N, p.ldres > 0 ? p.ldres : p.N, 32, false);
   const int tiles = ((p.M + 127) / 128) * (p.N / BN);
   const int grid = std::min(tiles, device_sm_count());
-  launch_pdl(conv_gemm_kernel<BN>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, st, ta, tb, tc, p);
+  launch_pdl(conv_gemm_kernel<BN, DEEP>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, st, ta, tb, tc, tr, p);
   VG_CUDA(cudaGetLastError());
 }
 
@@ -263,9 +276,10 @@ static void conv_gemm(const bf16* A, const ResNet::Conv& cv, int taps, int M, in
   ConvParams p;
   p.bias = cv.bias; p.res = res; p.ldres = cv.O; p.M = M; p.N = cv.O; p.K = cv.C * cv.taps; p.relu = relu ? 1 : 0;
   p.taps = taps; p.kpt = C / 64; p.Wp = Wp; p.Hp = Hp;
-  if (cv.O % 256 == 0) launch_conv<256>(A, C, cv.W, p, out, st);
-  else if (cv.O % 128 == 0) launch_conv<128>(A, C, cv.W, p, out, st);
-  else launch_conv<64>(A, C, cv.W, p, out, st);
+  const bool deep = res == nullptr && p.K >= 1024;
+  if (cv.O % 256 == 0) { if (deep) launch_conv<256, true>(A, C, cv.W, p, out, st); else launch_conv<256, false>(A, C, cv.W, p, out, st); }
+  else if (cv.O % 128 == 0) { if (deep) launch_conv<128, true>(A, C, cv.W, p, out, st); else launch_conv<128, false>(A, C, cv.W, p, out, st); }
+  else launch_conv<64, false>(A, C, cv.W, p, out, st);
 }
 
 // ------------------------------------------------------------------------------------------------ the other kernels
