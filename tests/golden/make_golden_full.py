@@ -21,14 +21,26 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 from oracle import vgqa_oracle as O  # noqa: E402
 
-CASES = [("full_vstgnet_T16_224_s0", 16, 224, 0, "a person jumping over the fence")]
+# (name, T, R, seed, sentence, (pad_right, pad_bottom)): padded pixels are zero and masked, as the reference's collate leaves them
+CASES = [("full_vstgnet_T16_224_s0", 16, 224, 0, "a person jumping over the fence", (0, 0)),
+         ("full_vstgnet_T8_224_masked_s1", 8, 224, 1, "the dog that runs behind the red car", (64, 32))]
 FRONT_END_CH = (2048, 768, 768)
 TEXT_TOWER = (12, 50265)
 
 
-def full_frames(seed, T, R):
+def full_frames(seed, T, R, pad=(0, 0)):
     rng = np.random.Generator(np.random.PCG64(17000 + seed))
-    return rng.standard_normal((T, 3, R, R), dtype=np.float32)
+    x = rng.standard_normal((T, 3, R, R), dtype=np.float32)
+    x[:, :, :, R - pad[0]:] = 0.0
+    x[:, :, R - pad[1]:, :] = 0.0
+    return x
+
+
+def full_mask(T, R, pad=(0, 0)):
+    m = np.zeros((T, R, R), bool)
+    m[:, :, R - pad[0]:] = True
+    m[:, R - pad[1]:, :] = True
+    return m
 
 
 def full_state_dict(seed):
@@ -41,7 +53,7 @@ def full_state_dict(seed):
 if __name__ == "__main__":
     import full_forward_cpu as FF
     torch.set_num_threads(os.cpu_count())
-    for name, T, R, seed, sentence in CASES:
+    for name, T, R, seed, sentence, pad in CASES:
         model, NestedTensor = FF.build_reference_model(T)
         sd = full_state_dict(seed)
         missing, unexpected = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
@@ -59,8 +71,8 @@ if __name__ == "__main__":
             taps["ids"] = enc["input_ids"].clone()
             return enc
         tok.batch_encode_plus = spy
-        x = full_frames(seed, T, R)
-        videos = NestedTensor(torch.from_numpy(x), torch.zeros(T, R, R, dtype=torch.bool), [T])
+        x = full_frames(seed, T, R, pad)
+        videos = NestedTensor(torch.from_numpy(x), torch.from_numpy(full_mask(T, R, pad)), [T])
         targets = [{"item_id": 0, "actioness": torch.ones(T)}]
         with torch.no_grad():
             out = model(videos, [sentence], targets)
@@ -69,7 +81,7 @@ if __name__ == "__main__":
         att = out["att_sequences"][0]
         c1 = torch.nonzero(att > model.theta).flatten().tolist() or list(range(T))
         c2 = torch.nonzero(act1 > 0.5).flatten().tolist() or list(range(T))
-        rec = dict(T=T, R=R, seed=seed, torch_version=torch.__version__, text_ids=taps["ids"].numpy().astype(np.int32),
+        rec = dict(T=T, R=R, seed=seed, pad=np.asarray(pad, np.int32), sentence=sentence, torch_version=torch.__version__, text_ids=taps["ids"].numpy().astype(np.int32),
                    choose1=np.asarray(c1, np.int32), choose2=np.asarray(c2, np.int32), actioness_pass1=act1.numpy(),
                    theta_margin=np.float32((att - model.theta).abs().min()), act_margin=np.float32((act1 - 0.5).abs().min()))
         for k in ("pred_boxes", "pred_sted", "pred_actioness", "logits_f_m", "logits_f_a", "logits_r_a", "logits_r_m", "att_sequences"):

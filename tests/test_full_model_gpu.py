@@ -7,7 +7,9 @@ import pytest
 import torch
 
 from conftest import golden_path
-from make_golden_full import FRONT_END_CH, full_frames, full_state_dict  # noqa: F401
+from make_golden_full import FRONT_END_CH, full_frames, full_mask, full_state_dict  # noqa: F401
+
+FIXTURES = ["full_vstgnet_T16_224_s0", "full_vstgnet_T8_224_masked_s1"]     # the second: right / bottom padding, masked (7x7 map: 2 columns, 1 row)
 
 pytestmark = pytest.mark.gpu
 
@@ -18,25 +20,32 @@ pytestmark = pytest.mark.gpu
 TOL = {"pred_boxes": 5e-3, "pred_sted": 4e-2, "pred_actioness": 4e-2, "logits_f_m": 4e-2, "logits_f_a": 4e-2, "logits_r_a": 4e-2,
        "logits_r_m": 4e-2, "att_sequences": 1e-2, "actioness_pass1": 1e-2}
 
-def test_whole_forward_from_pixels_matches_the_reference_model():
+@pytest.mark.parametrize("name", FIXTURES)
+def test_whole_forward_from_pixels_matches_the_reference_model(name):
     from vgqa_b200.engine import GroundingEngine
-    g = np.load(golden_path("full_vstgnet_T16_224_s0"))
+    g = np.load(golden_path(name))
     T, R, seed = (int(g[k]) for k in ("T", "R", "seed"))
+    pad = tuple(int(v) for v in g["pad"])
     ids = torch.from_numpy(g["text_ids"]).cuda()
     L = ids.shape[1]
     eng = GroundingEngine(full_state_dict(seed), max_clips=1, max_frames=T, max_hw=49, max_text=L)
-    frames = torch.from_numpy(full_frames(seed, T, R)).cuda()
+    frames = torch.from_numpy(full_frames(seed, T, R, pad)).cuda()
     vis_map = eng.resnet_backbone(frames).view(1, T, 7, 7, 2048)        # `vis_res_features` (channels-last bf16)
     vid_map = eng.swin_backbone(frames, 1)                               # `vid_features_all['3']`
+    kw = {}
+    if any(pad):   # BackboneBase.forward (backbone.py:92-96): nearest interpolation of the pixel mask to the map; [:, 0, 0] as grounding_net does
+        m = torch.nn.functional.interpolate(torch.from_numpy(full_mask(T, R, pad))[None].float(), size=(7, 7)).bool()[0]
+        m[:, 0, 0] = False
+        kw = {"vis_mask": m.reshape(T, 49).to(torch.uint8).cuda().contiguous(), "text_mask": torch.zeros(1, L, dtype=torch.uint8, device="cuda")}
     want = ["pred_boxes", "pred_sted", "pred_actioness", "logits_f_m", "logits_f_a", "logits_r_a", "logits_r_m", "att_sequences",
             "choose1", "choose2", "actioness_pass1", "aux_boxes", "aux_sted"]
-    o = eng.forward(vis_map, vid_map, None, None, raw=True, text_ids=ids, want=want)      # free-running: no decision is forced
+    o = eng.forward(vis_map, vid_map, None, None, raw=True, text_ids=ids, want=want, **kw)      # free-running: no decision is forced
     torch.cuda.synchronize()
     o = {k: v.float().cpu().numpy() for k, v in o.items()}
     ref = {"pred_boxes": g["pred_boxes"], "pred_sted": g["pred_sted"][0], "pred_actioness": g["pred_actioness"][0, :, 0],
            "logits_f_m": g["logits_f_m"], "logits_f_a": g["logits_f_a"], "logits_r_a": g["logits_r_a"][0], "logits_r_m": g["logits_r_m"][0],
            "att_sequences": g["att_sequences"][0], "actioness_pass1": g["actioness_pass1"]}
-    # the two frame selections are the reference's (its margins: |att - theta| >= 0.036, |actioness - 0.5| >= 0.14)
+    # the two frame selections are the reference's (its margins: |att - theta| >= 0.036, |actioness - 0.5| >= 0.04)
     sel = lambda w: np.flatnonzero(w.reshape(-1)[:T] > 0.5).tolist()
     assert sel(o["choose1"]) == g["choose1"].tolist() and sel(o["choose2"]) == g["choose2"].tolist()
     worst = {k: float(np.abs(o[k][0].reshape(r.shape) - r).max()) for k, r in ref.items()}
@@ -59,19 +68,21 @@ def test_whole_forward_from_pixels_matches_the_reference_model():
     eng.close()
 
 
-def test_vstgnet_dropin_with_every_extractor_in_the_library():
+@pytest.mark.parametrize("name", FIXTURES)
+def test_vstgnet_dropin_with_every_extractor_in_the_library(name):
     """`B200VSTGNet` given the whole state_dict: no PyTorch module of the model is called (the extractor modules passed in raise) —
     `videos.tensors` and the tokenizer's ids go into the library; output dict as grounding_net.py:164-203."""
     from make_golden import make_cfg
     from vgqa_b200 import modules as M
-    g = np.load(golden_path("full_vstgnet_T16_224_s0"))
+    g = np.load(golden_path(name))
     T, R, seed = (int(g[k]) for k in ("T", "R", "seed"))
+    pad, sentence = tuple(int(v) for v in g["pad"]), str(g["sentence"])
     ids = torch.from_numpy(g["text_ids"]).long()
 
     class TextEncoder:            # what the drop-in calls of the reference's RoBERTa wrapper: the tokenizer (bert.py:50,65)
         @staticmethod
         def tokenizer(texts, padding, return_tensors):
-            assert texts == [" a person jumping over the fence"]       # grounding_net.py:110: subject + " " + sentence
+            assert texts == [" " + sentence]       # grounding_net.py:110: subject + " " + sentence
             return {"input_ids": ids, "attention_mask": torch.ones_like(ids)}
 
     def boom(*a, **k):
@@ -80,8 +91,8 @@ def test_vstgnet_dropin_with_every_extractor_in_the_library():
     model = M.B200VSTGNet(make_cfg(), boom, boom, TextEncoder(), boom, boom, full_state_dict(seed), verb_label2={"0": {"sub": ""}},
                           max_frames=T, max_hw=49, max_text=ids.shape[1]).eval()
     assert model.fused_backbones and model.fused_front_end and model.fused_text_tower
-    videos = M.NestedTensor(torch.from_numpy(full_frames(seed, T, R)).cuda(), torch.zeros(T, R, R, dtype=torch.bool, device="cuda"), [T])
-    out = model(videos, ["a person jumping over the fence"], [{"item_id": 0, "actioness": torch.ones(T, device="cuda")}])
+    videos = M.NestedTensor(torch.from_numpy(full_frames(seed, T, R, pad)).cuda(), torch.from_numpy(full_mask(T, R, pad)).cuda(), [T])
+    out = model(videos, [sentence], [{"item_id": 0, "actioness": torch.ones(T, device="cuda")}])
     for k in ("pred_boxes", "pred_sted", "pred_actioness", "logits_f_m", "logits_f_a", "logits_r_a", "logits_r_m", "att_sequences"):
         got = out[k].float().cpu().numpy()
         assert got.shape == g[k].shape, (k, got.shape, g[k].shape)
