@@ -100,3 +100,26 @@ def test_vstgnet_dropin_with_every_extractor_in_the_library(name):
     assert len(out["aux_outputs"]) == 5 and out["pr"] == (1.0, 1.0)
     for i, a in enumerate(out["aux_outputs"]):
         assert float(np.abs(a["pred_boxes"].cpu().numpy() - g[f"aux{i}_pred_boxes"]).max()) <= TOL["pred_boxes"], i
+
+
+def test_predictor_from_frames_and_token_ids():
+    """`GroundingPredictor(raw_inputs=True)` fed with the sampled FRAMES and the token ids (grounding.py:142-244 after decoding /
+    resizing / tokenising): identical to feeding it the maps of the library's extractors computed pass by pass."""
+    from vgqa_b200.predict import GroundingPredictor
+    g = np.load(golden_path("full_vstgnet_T16_224_s0"))
+    T, R, seed = 8, 224, int(g["seed"])
+    ids = g["text_ids"][0]
+    pred = GroundingPredictor(full_state_dict(seed), sample_num=T, max_hw=49, max_text=len(ids), raw_inputs=True)
+    frames = torch.from_numpy(full_frames(seed, 2 * T, R)).cuda()
+    fids = list(range(5, 5 + 2 * T * 4, 4))
+    got = pred.predict_many([{"frames": frames, "text_ids": ids, "frame_ids": fids, "ori_size": (360, 640), "fps": 25.0}])[0]
+    eng = pred.engine
+    maps = [eng.extract_features(frames[par::2].contiguous(), 1) for par in (0, 1)]
+    nchw = lambda m: m[0].permute(0, 3, 1, 2).float()                      # [T, C, 7, 7] as the "vis" / "vid" items are laid out
+    vis = torch.stack([nchw(maps[0][0]), nchw(maps[1][0])], 1).reshape(2 * T, 2048, 7, 7)     # interleave the passes again
+    vid = torch.stack([nchw(maps[0][1]), nchw(maps[1][1])], 1).reshape(2 * T, 768, 7, 7)
+    ref = pred.predict_many([{"vis": vis, "vid": vid, "text_ids": ids, "frame_ids": fids, "ori_size": (360, 640), "fps": 25.0}])[0]
+    assert got["temporal"] == ref["temporal"] and got["temporal"]["score"] == 1.0
+    assert [t["frame"] for t in got["tube"]] == [t["frame"] for t in ref["tube"]] == list(range(fids[0], fids[-1] + 1))
+    np.testing.assert_allclose(np.asarray([t["bbox"] for t in got["tube"]]), np.asarray([t["bbox"] for t in ref["tube"]]), atol=1.0)   # pixels
+    pred.close()

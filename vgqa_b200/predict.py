@@ -6,8 +6,10 @@ every call, samples 2*TRAIN_SAMPLE_NUM frames, runs TWO forwards (even / odd fra
 two-clip batch (clips never interact — SURVEY §0 fact 5), decodes both passes with the library's PostProcess kernel and
 returns the reference's output schema.  Several queries can be served per call (`predict_many`): 2*Q clips in one batch.
 
-Inputs are the tensors at the hot-path boundary (outputs of input_proj / input_proj2 / the text resizer): video decoding,
-the backbones and RoBERTa stay the caller's (out of scope).
+Inputs are the tensors at the hot-path boundary (outputs of input_proj / input_proj2 / the text resizer), or — raw_inputs=True —
+the extractor outputs, or the sampled, resized and normalised FRAMES themselves plus the tokenizer's ids: with the extractor
+weights in the state_dict (`vis_encoder.0.body.*`, `vid.*`, `text_encoder.body.*`) ResNet101, Video-Swin-T and RoBERTa run inside
+the library as well.  Video decoding / resizing (decord, grounding.py:27-77) and the tokenizer stay the caller's.
 """
 from __future__ import annotations
 
@@ -39,7 +41,9 @@ class GroundingPredictor:
         by predict()), "ori_size": (h, w), "fps": float}.  All items share T, H, W, L.  "pos" ([1,256,H,W]) is optional: the
         library generates PositionEmbeddingSine itself (predict() resizes to a square, so nothing is padded, grounding.py:177).
         With raw_inputs=True the channel counts are those of the extractors (see __init__); an item may then carry
-        "text_ids" ([L] RoBERTa token ids) instead of "text" — the text tower runs inside the library too (all items or none).
+        "text_ids" ([L] RoBERTa token ids) instead of "text" — the text tower runs inside the library too (all items or none) —
+        and "frames" ([2T,3,R,R] fp32: the sampled frames after the reference's resize + normalisation, R = 224 / 448, T a multiple
+        of 8) instead of "vis" / "vid": both extractors then run inside the library (all items or none).
         Returns one {"temporal": {...}, "tube": [...]} dict per item (grounding.py:227-244)."""
         Q = len(items)
         if Q == 0:
@@ -50,19 +54,27 @@ class GroundingPredictor:
         f32 = lambda t: torch.as_tensor(t, dtype=torch.float32, device=dev)
         vis, vid, text, sizes = [], [], [], []
         use_ids = self.raw_inputs and all("text_ids" in it for it in items)
+        use_frames = self.raw_inputs and all("frames" in it for it in items)
         for it in items:
-            v, w = f32(it["vis"]), f32(it["vid"])
+            v = f32(it["frames"] if use_frames else it["vis"])
+            w = None if use_frames else f32(it["vid"])
             n = v.shape[0]
             if n < 2 or n % 2 != 0 or n // 2 > self.sample_num:
                 raise ValueError("predict() samples an even number of frames, at most 2*sample_num")   # grounding.py:137-138,157
             assert len(it["frame_ids"]) == n, "one frame id per sampled frame"
             for par in (0, 1):                       # even pass, odd pass (grounding.py:163-168)
-                vis.append(v[par::2]); vid.append(w[par::2])
+                vis.append(v[par::2])
+                if not use_frames:
+                    vid.append(w[par::2])
                 text.append(torch.as_tensor(it["text_ids"], dtype=torch.int32, device=dev) if use_ids else f32(it["text"]))
                 sizes.append([float(it["ori_size"][0]), float(it["ori_size"][1])])
         T = vis[0].shape[0]
         assert all(x.shape[0] == T for x in vis), "all queries of a call must sample the same number of frames"
-        vis, vid, text = torch.stack(vis).contiguous(), torch.stack(vid).contiguous(), torch.stack(text).contiguous()
+        text = torch.stack(text).contiguous()
+        if use_frames:   # every pass is a clip of its own for the extractors too (the Video-Swin windows span the frames of ONE pass)
+            vis, vid = self.engine.extract_features(torch.cat(vis).contiguous(), 2 * Q)
+        else:
+            vis, vid = torch.stack(vis).contiguous(), torch.stack(vid).contiguous()
         pos = f32(items[0]["pos"])[:1].contiguous() if items[0].get("pos") is not None else None
         o = self.engine.forward(vis, vid, None if use_ids else text, pos, ori_sizes_hw=torch.tensor(sizes, device=dev),
                                 want=["att_sequences", "boxes_px", "sted_idx"], raw=self.raw_inputs,
