@@ -47,15 +47,17 @@ def test_resnet101_matches_reference_golden(name):
 
 
 def test_resnet101_chunks_and_frames_are_independent():
-    """More than one pass of 128 frames: every frame's map equals the map of the same picture computed in a small batch, bit for bit
-    (a row's accumulation order does not depend on its tile or on its neighbours)."""
+    """More than one pass (a pass holds as many frames as the GPU has SMs): every frame's map equals the map of the same picture
+    computed in a small batch, bit for bit (a row's accumulation order does not depend on its tile or on its neighbours)."""
     seed, R = 1, 64
     base = torch.from_numpy(resnet_frames(seed, 3, R)).cuda()
     eng = _engine(seed, base)
     small = eng.resnet_backbone(base)
-    big = eng.resnet_backbone(base.repeat(44, 1, 1, 1)[:131].contiguous())
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    n = 2 * sms + 5                                              # three passes, the last one short
+    big = eng.resnet_backbone(base.repeat((n + 2) // 3, 1, 1, 1)[:n].contiguous())
     torch.cuda.synchronize()
-    for i in (0, 1, 2, 64, 127, 128, 129, 130):
+    for i in (0, 1, 2, sms - 1, sms, sms + 1, 2 * sms - 1, 2 * sms, n - 1):
         assert torch.equal(big[i], small[i % 3]), i
     eng.close()
 
