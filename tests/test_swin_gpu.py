@@ -35,7 +35,7 @@ def test_swin_stage_matches_reference_golden(name):
     assert float(err_all.max()) <= 1.25 * float(g["autocast_err_max"]) + 8e-3, float(err_all.max())   # + fp16 storage of the full map
     np.testing.assert_allclose(y16.float().cpu().numpy(), got, atol=4e-2)      # the bf16 copy handed to input_proj2
     # the rolled (odd) block really matters: without it the map differs by far more than the tolerance
-    assert eng.last_launch_count >= 2 * 7 + 2
+    assert eng.last_launch_count >= 2 * 7 + 1
     eng.close()
 
 

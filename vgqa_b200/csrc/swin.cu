@@ -11,8 +11,9 @@
 // Layout: channels-last fp32 residual stream x32 [clips, D, H, W, Cp] (Cp = channels padded to a multiple of 64: 96 → 128 in the
 // first stage, zero in the pad columns), exactly as in the encoder.  Kernels:
 //   * LayerNorm rows (one warp per token) → bf16 GEMM operand;
-//   * window partition + cyclic roll = ONE row gather (window_gather), window reverse + un-roll + residual add = ONE scatter-add;
-//     where a window is a run of whole frames and nothing is rolled (last stage at 7x7, even blocks) the partition is free;
+//   * window partition + cyclic roll ride on LayerNorm 1 (one pass: fp32 map row in, normalised bf16 row out at its window position);
+//     window reverse + un-roll + residual add ride on LayerNorm 2 (x[m] += y[r], LN of the sum in the same pass); where a window is
+//     a run of whole frames and nothing is rolled (last stage at 7x7, even blocks) the partition is free;
 //   * the tcgen05 GEMMs of the encoder (qkv, proj → fp32, fc1 + GELU, fc2 + fp32 residual, patch embedding, PatchMerging reduction);
 //   * the multi-tile tcgen05 attention of attn_tc_long.cu with `heads` heads, the bias table [heads][392][392] (divided by the
 //     scale, L2-resident) and the shift mask from per-token region ids (a few hundred bytes per distinct window kind);
@@ -30,53 +31,111 @@
 namespace vg {
 
 // ------------------------------------------------------------------------------------------------ kernels
-// LayerNorm over the C real columns of rows with stride ld (one warp per row): y16 (bf16, stride ldy, pad columns zeroed) and / or
-// y32 (fp32, stride ld, may alias x, pad columns zeroed)
-__global__ void __launch_bounds__(256) ln_rows_ld_kernel(const float* x, int ld, int C, const float* __restrict__ w,
-                                                         const float* __restrict__ b, float eps, float* y32, bf16* __restrict__ y16,
-                                                         int ldy, long long rows) {
-  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+struct WinGeom { int B, D, H, W, wd, wh, ww, sd, sh, sw; };
+__device__ __forceinline__ int win_src_row(const WinGeom& g, int r) {   // window-order row → row of the (unrolled) map; 32-bit: rows < 2^31
+  const unsigned N = g.wd * g.wh * g.ww;
+  const unsigned grp = (unsigned)r / N, n = (unsigned)r - grp * N;
+  const unsigned nWh = g.H / g.wh, nWw = g.W / g.ww, nWd = g.D / g.wd;
+  const unsigned q1 = grp / nWw, wwi = grp - q1 * nWw, q2 = q1 / nWh, hwi = q1 - q2 * nWh, b = q2 / nWd, dwi = q2 - b * nWd;
+  const unsigned t1 = n / g.ww, wl = n - t1 * g.ww, dd = t1 / g.wh, hh = t1 - dd * g.wh;
+  unsigned d = dwi * g.wd + dd + g.sd, h = hwi * g.wh + hh + g.sh, w = wwi * g.ww + wl + g.sw;   // the shifts are smaller than the sides
+  if (d >= (unsigned)g.D) d -= g.D;
+  if (h >= (unsigned)g.H) h -= g.H;
+  if (w >= (unsigned)g.W) w -= g.W;
+  return (int)(((b * g.D + d) * g.H + h) * g.W + w);
+}
+// LayerNorm fused with the window plumbing (rows r in WINDOW order; m = the map row that r comes from / goes to):
+//   MODE 1  (LN1 + window_partition(roll(x, -shift))):   y16[r] = LN(x[m])
+//   MODE 2  (x += roll(window_reverse(y), +shift), then LN2):   x[m] += add[r];  y16[m] = LN(x[m])
+//   MODE 0 / 3  (no window map, m = r):   y16[r] = LN(x[r])  /  x[r] = LN(x[r]) in place, fp32 (the patch embedding's norm)
+// Saves the bf16 round trip of a separate gather (MODE 1) and LayerNorm's re-read of the fp32 row (MODE 2).  A warp walks rows with a
+// grid stride and keeps RW rows (NJ float4 per lane each) in flight: one 512-byte row per warp at a time leaves the loads latency-bound
+// (2.3 TB/s measured on the 96-channel stage).
+template <int MODE, int NJ, int RW>
+__global__ void __launch_bounds__(256, 4) ln_window_kernel(float* x, int ld, int C, const float* __restrict__ w, const float* __restrict__ b,
+                                                        float eps, const float* __restrict__ add, bf16* __restrict__ y16, int ldy,
+                                                        WinGeom g, long long rows) {
   const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + r * ld);
-  const int n4 = C >> 2;
-  float4 v[8];                      // the row in registers (C <= 1024): one global read
-  float s = 0.f;
+  const long long nwarps = (long long)gridDim.x * 8, wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int n4 = C >> 2, np4 = ld >> 2, ny4 = ldy >> 2;
+  for (long long r0 = wid * RW; r0 < rows; r0 += nwarps * RW) {
+    long long m[RW];
+    float4 v[RW][NJ];
+    // lane k works out the map row of the group's row k (the index arithmetic is a dozen integer divisions: once per row, not per lane)
+    const long long rl = r0 + (lane < RW ? lane : 0);
+    const int rc = (int)(rl < rows ? rl : rows - 1);                   // a short last group repeats the last row (same values written twice)
+    const int ml = (MODE == 1 || MODE == 2) ? win_src_row(g, rc) : rc;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int i = lane + 32 * j;
-    v[j] = i < n4 ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    s += v[j].x + v[j].y + v[j].z + v[j].w;
-  }
-  const float mean = warp_sum(s) / (float)C;
-  float m2 = 0.f;
+    for (int k = 0; k < RW; ++k) {
+      m[k] = __shfl_sync(0xffffffffu, ml, k);
+      const float4* xr = reinterpret_cast<const float4*>(x + m[k] * ld);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (lane + 32 * j < n4) {
-      const float a = v[j].x - mean, bb = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
-      m2 += a * a + bb * bb + c * c + d * d;
+      for (int j = 0; j < NJ; ++j) {
+        const int i = lane + 32 * j;
+        v[k][j] = i < np4 ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(m2) / (float)C + eps);
-  const int np4 = (y16 != nullptr ? ldy : ld) >> 2;
+    if (MODE == 2) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int i = lane + 32 * j;
-    if (i >= np4) break;
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < n4) {
-      const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + i), bv = __ldg(reinterpret_cast<const float4*>(b) + i);
-      o = make_float4((v[j].x - mean) * rstd * ww.x + bv.x, (v[j].y - mean) * rstd * ww.y + bv.y, (v[j].z - mean) * rstd * ww.z + bv.z,
-                      (v[j].w - mean) * rstd * ww.w + bv.w);
+      for (int k = 0; k < RW; ++k) {
+        if (r0 + k >= rows) continue;                                // the repeated row must not be added twice
+        const float4* ar = reinterpret_cast<const float4*>(add + (r0 + k) * ld);
+        float4* xr = reinterpret_cast<float4*>(x + m[k] * ld);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int i = lane + 32 * j;
+          if (i < np4) {
+            const float4 a = __ldg(ar + i);
+            v[k][j] = make_float4(v[k][j].x + a.x, v[k][j].y + a.y, v[k][j].z + a.z, v[k][j].w + a.w);
+            xr[i] = v[k][j];                                         // pad columns: 0 + 0
+          }
+        }
+      }
     }
-    if (y32 != nullptr && i < (ld >> 2)) reinterpret_cast<float4*>(y32 + r * ld)[i] = o;
-    if (y16 != nullptr) reinterpret_cast<uint2*>(y16 + r * ldy)[i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+#pragma unroll
+    for (int k = 0; k < RW; ++k) {
+      if (r0 + k >= rows) continue;
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if (lane + 32 * j < n4) s += v[k][j].x + v[k][j].y + v[k][j].z + v[k][j].w;
+      const float mean = warp_sum(s) / (float)C;
+      float m2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if (lane + 32 * j < n4) {
+          const float a = v[k][j].x - mean, bb = v[k][j].y - mean, c = v[k][j].z - mean, d = v[k][j].w - mean;
+          m2 += a * a + bb * bb + c * c + d * d;
+        }
+      const float rstd = rsqrtf(warp_sum(m2) / (float)C + eps);
+      uint2* yr = MODE == 3 ? nullptr : reinterpret_cast<uint2*>(y16 + (MODE == 1 ? r0 + k : m[k]) * ldy);
+      float4* xo = reinterpret_cast<float4*>(x + m[k] * ld);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int i = lane + 32 * j;
+        if (i >= (MODE == 3 ? np4 : ny4)) break;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n4) {
+          const float4 gw = __ldg(reinterpret_cast<const float4*>(w) + i), gb = __ldg(reinterpret_cast<const float4*>(b) + i);   // L1-resident
+          o = make_float4((v[k][j].x - mean) * rstd * gw.x + gb.x, (v[k][j].y - mean) * rstd * gw.y + gb.y,
+                          (v[k][j].z - mean) * rstd * gw.z + gb.z, (v[k][j].w - mean) * rstd * gw.w + gb.w);
+        }
+        if (MODE == 3) xo[i] = o;
+        else yr[i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    }
   }
 }
-static void ln_rows_ld(const float* x, int ld, int C, const float* w, const float* b, float eps, float* y32, bf16* y16, int ldy,
-                       long long rows, cudaStream_t st) {
-  VG_CHECK(C % 4 == 0 && C <= 1024 && ld <= 1024, "ln_rows_ld: rows of at most 1024 channels");
-  ln_rows_ld_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, ld, C, w, b, eps, y32, y16, ldy, rows);
+template <int MODE>
+static void ln_window(float* x, int ld, int C, const float* w, const float* b, float eps, const float* add, bf16* y16, const WinGeom& g,
+                      long long rows, cudaStream_t st) {
+  const int nj = (ld / 4 + 31) / 32;
+  VG_CHECK(ld % 4 == 0 && nj <= 8 && rows < (1LL << 31), "ln_window: rows of at most 1024 channels, fewer than 2^31 rows");
+  auto grid = [&](int rw) { return (unsigned)std::min<long long>((rows + 8LL * rw - 1) / (8LL * rw), 148 * 4); };
+  if (nj == 1) ln_window_kernel<MODE, 1, 4><<<grid(4), 256, 0, st>>>(x, ld, C, w, b, eps, add, y16, ld, g, rows);
+  else if (nj == 2) ln_window_kernel<MODE, 2, 4><<<grid(4), 256, 0, st>>>(x, ld, C, w, b, eps, add, y16, ld, g, rows);
+  else if (nj <= 4) ln_window_kernel<MODE, 4, 2><<<grid(2), 256, 0, st>>>(x, ld, C, w, b, eps, add, y16, ld, g, rows);
+  else ln_window_kernel<MODE, 8, 1><<<grid(1), 256, 0, st>>>(x, ld, C, w, b, eps, add, y16, ld, g, rows);
   VG_CUDA(cudaGetLastError());
 }
 
@@ -99,72 +158,73 @@ __global__ void __launch_bounds__(256) patch_im2col_kernel(const float* __restri
   }
 }
 
-struct WinGeom { int B, D, H, W, wd, wh, ww, sd, sh, sw; };
-__device__ __forceinline__ long long win_src_row(const WinGeom& g, long long r) {   // window-order row → row of the (unrolled) map
-  const int N = g.wd * g.wh * g.ww;
-  const long long grp = r / N;
-  const int n = (int)(r - grp * N);
-  const int nWh = g.H / g.wh, nWw = g.W / g.ww, nWd = g.D / g.wd;
-  const int wwi = (int)(grp % nWw), hwi = (int)((grp / nWw) % nWh), dwi = (int)((grp / (nWw * nWh)) % nWd);
-  const long long b = grp / ((long long)nWw * nWh * nWd);
-  const int dd = n / (g.wh * g.ww), hh = (n / g.ww) % g.wh, wl = n % g.ww;
-  const int d = (dwi * g.wd + dd + g.sd) % g.D, h = (hwi * g.wh + hh + g.sh) % g.H, w = (wwi * g.ww + wl + g.sw) % g.W;
-  return ((b * g.D + d) * g.H + h) * g.W + w;
-}
-// window_partition(roll(x, -shift)) as one gather of bf16 rows (16-byte chunks)
-__global__ void __launch_bounds__(256) window_gather_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, WinGeom g, int cpr,
-                                                            long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / cpr;
-    const int off = (int)(i - r * cpr);
-    dst[i] = __ldg(src + win_src_row(g, r) * cpr + off);
-  }
-}
-// x += roll(window_reverse(y), +shift): every map row receives exactly one window row (fp32, 16-byte chunks)
-__global__ void __launch_bounds__(256) window_scatter_add_kernel(float4* __restrict__ x, const float4* __restrict__ y, WinGeom g, int cpr,
-                                                                 long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / cpr;
-    const int off = (int)(i - r * cpr);
-    float4* p = x + win_src_row(g, r) * cpr + off;
-    const float4 a = *p, q = __ldg(y + i);
-    *p = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
-  }
-}
 // PatchMerging (:291-308), even H and W: out[(b, d, h2, w2), k*C + c] = LayerNorm_4C(cat(x[2h2, 2w2], x[2h2+1, 2w2], x[2h2, 2w2+1],
-// x[2h2+1, 2w2+1])) as bf16; one warp per output token
-__global__ void __launch_bounds__(256) merge_ln_kernel(const float* __restrict__ x, int ld, int C, int H, int W, const float* __restrict__ w,
-                                                       const float* __restrict__ b, float eps, bf16* __restrict__ out, long long tokens) {
-  const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+// x[2h2+1, 2w2+1])) as bf16.  A warp walks output tokens with a grid stride, RW tokens (4 source rows of NJ float4 per lane each) in
+// registers at a time: one read of the map.
+template <int NJ, int RW>
+__global__ void __launch_bounds__(256, 4) merge_ln_kernel(const float* __restrict__ x, int ld, int C, int H, int W, const float* __restrict__ w,
+                                                          const float* __restrict__ b, float eps, bf16* __restrict__ out, long long tokens) {
   const int lane = threadIdx.x & 31;
-  if (t >= tokens) return;
-  const int H2 = H >> 1, W2 = W >> 1;
-  const long long bd = t / (H2 * W2);
-  const int rem = (int)(t - bd * H2 * W2), h2 = rem / W2, w2 = rem - h2 * W2;
-  const float* src[4];
+  const long long nwarps = (long long)gridDim.x * 8, wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int H2 = H >> 1, W2 = W >> 1, n4 = C >> 2;
+  for (long long t0 = wid * RW; t0 < tokens; t0 += nwarps * RW) {
+    float4 v[RW][4][NJ];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) src[k] = x + ((bd * H + 2 * h2 + (k & 1)) * W + 2 * w2 + (k >> 1)) * (long long)ld;
-  const int n4 = C >> 2;
-  float s = 0.f;
-  for (int k = 0; k < 4; ++k)
-    for (int i = lane; i < n4; i += 32) { const float4 v = reinterpret_cast<const float4*>(src[k])[i]; s += v.x + v.y + v.z + v.w; }
-  const float mean = warp_sum(s) / (float)(4 * C);
-  float m2 = 0.f;
-  for (int k = 0; k < 4; ++k)
-    for (int i = lane; i < n4; i += 32) {
-      const float4 v = reinterpret_cast<const float4*>(src[k])[i];
-      const float a = v.x - mean, bb = v.y - mean, c = v.z - mean, d = v.w - mean;
-      m2 += a * a + bb * bb + c * c + d * d;
+    for (int q = 0; q < RW; ++q) {
+      const long long t = t0 + q < tokens ? t0 + q : tokens - 1;
+      const long long bd = t / (H2 * W2);
+      const int rem = (int)(t - bd * H2 * W2), h2 = rem / W2, w2 = rem - h2 * W2;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4* src = reinterpret_cast<const float4*>(x + ((bd * H + 2 * h2 + (k & 1)) * W + 2 * w2 + (k >> 1)) * (long long)ld);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) v[q][k][j] = lane + 32 * j < n4 ? __ldg(src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-  const float rstd = rsqrtf(warp_sum(m2) / (float)(4 * C) + eps);
-  for (int k = 0; k < 4; ++k)
-    for (int i = lane; i < n4; i += 32) {
-      const float4 v = reinterpret_cast<const float4*>(src[k])[i];
-      const float4 ww = __ldg(reinterpret_cast<const float4*>(w + k * C) + i), bv = __ldg(reinterpret_cast<const float4*>(b + k * C) + i);
-      reinterpret_cast<uint2*>(out + t * 4 * C + k * C)[i] =
-          make_uint2(pack_bf16((v.x - mean) * rstd * ww.x + bv.x, (v.y - mean) * rstd * ww.y + bv.y),
-                     pack_bf16((v.z - mean) * rstd * ww.z + bv.z, (v.w - mean) * rstd * ww.w + bv.w));
+#pragma unroll
+    for (int q = 0; q < RW; ++q) {
+      if (t0 + q >= tokens) continue;
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) s += v[q][k][j].x + v[q][k][j].y + v[q][k][j].z + v[q][k][j].w;      // lanes beyond the row hold zeros
+      const float mean = warp_sum(s) / (float)(4 * C);
+      float m2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          if (lane + 32 * j < n4) {
+            const float a = v[q][k][j].x - mean, bb = v[q][k][j].y - mean, c = v[q][k][j].z - mean, d = v[q][k][j].w - mean;
+            m2 += a * a + bb * bb + c * c + d * d;
+          }
+      const float rstd = rsqrtf(warp_sum(m2) / (float)(4 * C) + eps);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int i = lane + 32 * j;
+          if (i < n4) {
+            const float4 ww = __ldg(reinterpret_cast<const float4*>(w + k * C) + i), bv = __ldg(reinterpret_cast<const float4*>(b + k * C) + i);
+            const float4 a = v[q][k][j];
+            reinterpret_cast<uint2*>(out + (t0 + q) * 4 * C + k * C)[i] =
+                make_uint2(pack_bf16((a.x - mean) * rstd * ww.x + bv.x, (a.y - mean) * rstd * ww.y + bv.y),
+                           pack_bf16((a.z - mean) * rstd * ww.z + bv.z, (a.w - mean) * rstd * ww.w + bv.w));
+          }
+        }
     }
+  }
+}
+static void merge_ln(const float* x, int ld, int C, int H, int W, const float* w, const float* b, float eps, bf16* out, long long tokens,
+                     cudaStream_t st) {
+  const int nj = (C / 4 + 31) / 32;
+  VG_CHECK(C % 4 == 0 && nj <= 3, "merge_ln: at most 384 channels before PatchMerging");
+  auto grid = [&](int rw) { return (unsigned)std::min<long long>((tokens + 8LL * rw - 1) / (8LL * rw), 148 * 4); };
+  if (nj == 1) merge_ln_kernel<1, 2><<<grid(2), 256, 0, st>>>(x, ld, C, H, W, w, b, eps, out, tokens);
+  else if (nj == 2) merge_ln_kernel<2, 1><<<grid(1), 256, 0, st>>>(x, ld, C, H, W, w, b, eps, out, tokens);
+  else merge_ln_kernel<3, 1><<<grid(1), 256, 0, st>>>(x, ld, C, H, W, w, b, eps, out, tokens);
+  VG_CUDA(cudaGetLastError());
 }
 // strided rows fp32 [rows, ld] → compact bf16 / fp32 [rows, C]
 __global__ void __launch_bounds__(256) rows_out_kernel(const float* __restrict__ x, int ld, int C, bf16* __restrict__ o16, float* __restrict__ o32,
@@ -329,28 +389,26 @@ void SwinNet::run_stage(int s, int clips, int D, int H, int W, cudaStream_t st_)
     const bool shifted = (i % 2 == 1) && (shd || shh || shw);
     const WinGeom g{clips, D, H, W, wd, wh, ww, shifted ? shd : 0, shifted ? shh : 0, shifted ? shw : 0};
     const bool gather = shifted || !contiguous;
-    ln_rows_ld(x32, Cp, C, k.n1w, k.n1b, 1e-5f, nullptr, xn, Cp, rows, st_);
     const bf16* a = xn;
-    if (gather) {
-      const long long n = rows * (Cp / 8);
-      window_gather_kernel<<<grid_for(n), 256, 0, st_>>>(reinterpret_cast<const uint4*>(xn), reinterpret_cast<uint4*>(xw), g, Cp / 8, n);
-      a = xw; ++launches;
+    if (gather) {   // LN1 + window partition + cyclic roll in one pass over the rows
+      ln_window<1>(x32, Cp, C, k.n1w, k.n1b, 1e-5f, nullptr, xw, g, rows, st_);
+      a = xw;
+    } else {
+      ln_window<0>(x32, Cp, C, k.n1w, k.n1b, 1e-5f, nullptr, xn, g, rows, st_);
     }
     { GemmEpi ep; ep.C = qkv; ep.ldc = S.Nqkv; ep.bias = k.bqkv; ep.bias_ld = S.Nqkv;
       gemm_bf16_tn(a, Cp, k.Wqkv, Cp, (int)rows, S.Nqkv, Cp, ep, st_); }
     window_attn_tc(qkv, S.Nqkv, ao, Cp, groups, N, S.heads, k.sbias, shifted ? mt->rid : nullptr, shifted ? mt->gset : nullptr, scale, st_);
-    if (gather) {   // proj → fp32 in window order, then window reverse + un-roll fused with the residual add
+    if (gather) {   // proj → fp32 in window order; window reverse + un-roll + residual add + LN2 in one pass over the rows
       GemmEpi ep; ep.C = y32; ep.ldc = Cp; ep.c_f32 = 1; ep.bias = k.bproj; ep.bias_ld = Cp;
       gemm_bf16_tn(ao, Cp, k.Wproj, Cp, (int)rows, Cp, Cp, ep, st_);
-      const long long n = rows * (Cp / 4);
-      window_scatter_add_kernel<<<grid_for(n), 256, 0, st_>>>(reinterpret_cast<float4*>(x32), reinterpret_cast<const float4*>(y32), g, Cp / 4, n);
-      ++launches;
+      ln_window<2>(x32, Cp, C, k.n2w, k.n2b, 1e-5f, y32, xn, g, rows, st_);
     } else {
       GemmEpi ep; ep.C = y32; ep.ldc = Cp; ep.c_f32 = 1; ep.bias = k.bproj; ep.bias_ld = Cp; ep.res32 = x32; ep.ldres32 = Cp;
       gemm_bf16_tn(ao, Cp, k.Wproj, Cp, (int)rows, Cp, Cp, ep, st_);
       std::swap(x32, y32);
+      ln_window<0>(x32, Cp, C, k.n2w, k.n2b, 1e-5f, nullptr, xn, g, rows, st_);
     }
-    ln_rows_ld(x32, Cp, C, k.n2w, k.n2b, 1e-5f, nullptr, xn, Cp, rows, st_);
     { GemmEpi ep; ep.C = hid; ep.ldc = 4 * C; ep.bias = k.bfc1; ep.bias_ld = 4 * C; ep.act = ACT_GELU;
       gemm_bf16_tn(xn, Cp, k.Wfc1, Cp, (int)rows, 4 * C, Cp, ep, st_); }
     { GemmEpi ep; ep.C = y32; ep.ldc = Cp; ep.c_f32 = 1; ep.bias = k.bfc2; ep.bias_ld = Cp; ep.res32 = x32; ep.ldres32 = Cp;
@@ -391,7 +449,7 @@ int SwinNet::forward_full(const float* frames, int clips, int T, int R, bf16* ou
     patch_im2col_kernel<<<grid_for(n16), 256, 0, st_>>>(frames, a0, R, n16);
     GemmEpi ep; ep.C = x32; ep.ldc = st[0].Cp; ep.c_f32 = 1; ep.bias = bpe; ep.bias_ld = st[0].Cp;
     gemm_bf16_tn(a0, 64, Wpe, 64, (int)rows, st[0].Cp, 64, ep, st_);
-    ln_rows_ld(x32, st[0].Cp, st[0].C, pnw, pnb, 1e-5f, x32, nullptr, 0, rows, st_);
+    ln_window<3>(x32, st[0].Cp, st[0].C, pnw, pnb, 1e-5f, nullptr, nullptr, WinGeom{}, rows, st_);
     launches += 3;
   }
   for (int s = 0; s < kStages; ++s) {
@@ -405,7 +463,7 @@ int SwinNet::forward_full(const float* frames, int clips, int T, int R, bf16* ou
     if (s + 1 < kStages) {   // PatchMerging (:291-308): 2x2 gather + LayerNorm(4C) → reduction GEMM → the next stage's stream
       VG_CHECK(H % 2 == 0, "Video-Swin: odd map side before PatchMerging");
       const long long tokens = rows / 4;
-      merge_ln_kernel<<<(unsigned)((tokens + 7) / 8), 256, 0, st_>>>(x32, S.Cp, S.C, H, H, S.mnw, S.mnb, 1e-5f, xm, tokens);
+      merge_ln(x32, S.Cp, S.C, H, H, S.mnw, S.mnb, 1e-5f, xm, tokens, st_);
       GemmEpi ep; ep.C = y32; ep.ldc = st[s + 1].Cp; ep.c_f32 = 1;
       gemm_bf16_tn(xm, 4 * S.C, S.Wred, 4 * S.C, (int)tokens, st[s + 1].Cp, 4 * S.C, ep, st_);
       std::swap(x32, y32);
