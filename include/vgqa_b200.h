@@ -200,8 +200,8 @@ int vgqa_swin_stage(vgqa_ctx* ctx, const float* x, int clips, int T, int H, int 
 /* The WHOLE Video-Swin-T extractor (`self.vid` of VSTGNet = VideoSwinTransformerBackbone, video_swin_transformer.py:626-685): PatchEmbed3D
  * with patch (1,4,4) + LayerNorm, four stages (depths 2/2/6/2, dims 96..768, window (8,7,7), shifted windows with the compute_mask
  * masks) and the PatchMerging layers between them; weights "vid.patch_embed.*", "vid.layers.{0-3}.blocks.*", "vid.downsamples.{0-2}.*".
- * frames: NCHW fp32 [clips*T, 3, R, R] (`videos.tensors`), R = 224 or 448 (map sides must stay multiples of the 7x7 window), T a
- * multiple of 8.  out_bf16 / out_f32: the last stage's map ('3' of the reference's output dict) channels-last [clips, T, R/32, R/32, 768]
+ * frames: NCHW fp32 [clips*T, 3, R, R] (`videos.tensors`), R a multiple of 32 from 224 on, T >= 8 (map sides that are not
+ * multiples of the (8,7,7) window are zero-padded for the attention half of every block, as the reference does, :205-211).  out_bf16 / out_f32: the last stage's map ('3' of the reference's output dict) channels-last [clips, T, R/32, R/32, 768]
  * (out_bf16 = the vid_raw / raw_layout = 1 input of vgqa_forward); stage_out: NULL or 4 device pointers (each may be NULL) that
  * receive the four stage outputs channels-last fp32 [clips, T, R/4/2^s, R/4/2^s, 96 * 2^s].  Device pointers. */
 int vgqa_swin_backbone(vgqa_ctx* ctx, const float* frames, int clips, int T, int R, void* out_bf16, float* out_f32,

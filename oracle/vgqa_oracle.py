@@ -663,14 +663,17 @@ def swin_shift_mask(D, H, W, win, shift) -> np.ndarray:
 
 def swin_stage(sd, x: np.ndarray, prefix: str = "vid.layers.3.", heads: int = 24, window=(8, 7, 7), depth: int = 2) -> np.ndarray:
     """BasicLayer.forward of one Video-Swin stage (no downsample) — video_swin_transformer.py:377-398 — on a channels-last map
-    x (B, D, H, W, C) whose sides are multiples of the (clamped) window:
-    per block (:210-275)  x += proj(W-MSA(LN1(x)));  x += fc2(gelu(fc1(LN2(x)))), window attention with the relative position bias
-    (:143-165), odd blocks on the cyclically rolled map with the -100 mask of compute_mask (:311-325)."""
+    x (B, D, H, W, C):
+    per block (:200-275)  x += proj(W-MSA(LN1(x)));  x += fc2(gelu(fc1(LN2(x)))), window attention with the relative position bias
+    (:143-165), odd blocks on the cyclically rolled map with the -100 mask of compute_mask (:311-325).  Sides that are not multiples
+    of the window: LN1(x) is zero-padded at the END of every axis up to the next multiple (:205-211; the padded tokens take part in
+    the attention as keys with q = k = v = the biases), the mask is computed on the padded sides (:383-386), the result is cropped
+    (:233-234)."""
     B, D, H, W, C = x.shape
     size = (D, H, W)
     win = tuple(min(window[i], size[i]) for i in range(3))           # get_window_size (:53-66)
     shift = tuple(0 if size[i] <= window[i] else window[i] // 2 for i in range(3))
-    assert all(size[i] % win[i] == 0 for i in range(3)), "oracle: sides must be multiples of the window (no padding path)"
+    Dp, Hp, Wp = (int(math.ceil(size[i] / win[i])) * win[i] for i in range(3))
     N = win[0] * win[1] * win[2]
     dh = C // heads
     idx = swin_relative_position_index(window)
@@ -678,12 +681,13 @@ def swin_stage(sd, x: np.ndarray, prefix: str = "vid.layers.3.", heads: int = 24
     # reference is only the same thing when the window is not clamped in H or W)
     assert win[1:] == tuple(window[1:]) or win == tuple(window), "oracle: spatially clamped windows are not restated"
     idx = idx[:N, :N]
-    mask = swin_shift_mask(D, H, W, win, shift) if any(shift) else None
+    mask = swin_shift_mask(Dp, Hp, Wp, win, shift) if any(shift) else None
     x = x.astype(F32)
     for i in range(depth):
         p = f"{prefix}blocks.{i}."
         sh = shift if (i % 2 == 1 and any(shift)) else None
         h = layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+        h = np.pad(h, ((0, 0), (0, Dp - D), (0, Hp - H), (0, Wp - W), (0, 0)))
         if sh:
             h = np.roll(h, (-sh[0], -sh[1], -sh[2]), axis=(1, 2, 3))
         winx = _swin_windows(h, win)
@@ -697,10 +701,10 @@ def swin_stage(sd, x: np.ndarray, prefix: str = "vid.layers.3.", heads: int = 24
             attn = (attn.reshape(B, nW, heads, N, N) + mask[None, :, None]).reshape(-1, heads, N, N)
         attn = softmax(attn, -1)
         o = (attn @ v).transpose(0, 2, 1, 3).reshape(-1, N, C)
-        o = _swin_unwindows(linear(o, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"]), win, B, D, H, W)
+        o = _swin_unwindows(linear(o, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"]), win, B, Dp, Hp, Wp)
         if sh:
             o = np.roll(o, sh, axis=(1, 2, 3))
-        x = x + o
+        x = x + o[:, :D, :H, :W]
         h = layer_norm(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
         h = gelu_erf(linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]))
         x = x + linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])

@@ -23,7 +23,8 @@ from oracle import vgqa_oracle as O  # noqa: E402
 
 # (name, T, R, seed, sentence, (pad_right, pad_bottom)): padded pixels are zero and masked, as the reference's collate leaves them
 CASES = [("full_vstgnet_T16_224_s0", 16, 224, 0, "a person jumping over the fence", (0, 0)),
-         ("full_vstgnet_T8_224_masked_s1", 8, 224, 1, "the dog that runs behind the red car", (64, 32))]
+         ("full_vstgnet_T8_224_masked_s1", 8, 224, 1, "the dog that runs behind the red car", (64, 32)),
+         ("full_vstgnet_T12_256_s2", 12, 256, 2, "two children play with a ball", (0, 0))]      # 8x8 maps; Video-Swin pads 12 → 16 frames, 64 → 70 ...
 FRONT_END_CH = (2048, 768, 768)
 TEXT_TOWER = (12, 50265)
 

@@ -18,7 +18,8 @@ sys.path.insert(0, HERE)
 from make_golden_swin import load_swin_module  # noqa: E402
 from oracle import vgqa_oracle as O  # noqa: E402
 
-CASES = [("swin_full_T16_224_s0", 1, 16, 224, 0)]
+CASES = [("swin_full_T16_224_s0", 1, 16, 224, 0),
+         ("swin_full_T12_256_s1", 1, 12, 256, 1)]      # 12 frames → 16, maps 64 / 32 / 16 / 8 → 70 / 35 / 21 / 14: the padding path
 
 
 def swin_frames(seed, clips, T, R):

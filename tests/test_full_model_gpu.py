@@ -9,7 +9,9 @@ import torch
 from conftest import golden_path
 from make_golden_full import FRONT_END_CH, full_frames, full_mask, full_state_dict  # noqa: F401
 
-FIXTURES = ["full_vstgnet_T16_224_s0", "full_vstgnet_T8_224_masked_s1"]     # the second: right / bottom padding, masked (7x7 map: 2 columns, 1 row)
+# the second: right / bottom padding, masked (7x7 map: 2 columns, 1 row); the third: 256 px (8x8 maps) and 12 frames — the Video-Swin
+# stages pad 12 → 16 frames and 64 / 32 / 16 / 8 → 70 / 35 / 21 / 14 positions
+FIXTURES = ["full_vstgnet_T16_224_s0", "full_vstgnet_T8_224_masked_s1", "full_vstgnet_T12_256_s2"]
 
 pytestmark = pytest.mark.gpu
 
@@ -28,15 +30,16 @@ def test_whole_forward_from_pixels_matches_the_reference_model(name):
     pad = tuple(int(v) for v in g["pad"])
     ids = torch.from_numpy(g["text_ids"]).cuda()
     L = ids.shape[1]
-    eng = GroundingEngine(full_state_dict(seed), max_clips=1, max_frames=T, max_hw=49, max_text=L)
+    h = R // 32
+    eng = GroundingEngine(full_state_dict(seed), max_clips=1, max_frames=T, max_hw=h * h, max_text=L)
     frames = torch.from_numpy(full_frames(seed, T, R, pad)).cuda()
-    vis_map = eng.resnet_backbone(frames).view(1, T, 7, 7, 2048)        # `vis_res_features` (channels-last bf16)
+    vis_map = eng.resnet_backbone(frames).view(1, T, h, h, 2048)        # `vis_res_features` (channels-last bf16)
     vid_map = eng.swin_backbone(frames, 1)                               # `vid_features_all['3']`
     kw = {}
     if any(pad):   # BackboneBase.forward (backbone.py:92-96): nearest interpolation of the pixel mask to the map; [:, 0, 0] as grounding_net does
-        m = torch.nn.functional.interpolate(torch.from_numpy(full_mask(T, R, pad))[None].float(), size=(7, 7)).bool()[0]
+        m = torch.nn.functional.interpolate(torch.from_numpy(full_mask(T, R, pad))[None].float(), size=(h, h)).bool()[0]
         m[:, 0, 0] = False
-        kw = {"vis_mask": m.reshape(T, 49).to(torch.uint8).cuda().contiguous(), "text_mask": torch.zeros(1, L, dtype=torch.uint8, device="cuda")}
+        kw = {"vis_mask": m.reshape(T, h * h).to(torch.uint8).cuda().contiguous(), "text_mask": torch.zeros(1, L, dtype=torch.uint8, device="cuda")}
     want = ["pred_boxes", "pred_sted", "pred_actioness", "logits_f_m", "logits_f_a", "logits_r_a", "logits_r_m", "att_sequences",
             "choose1", "choose2", "actioness_pass1", "aux_boxes", "aux_sted"]
     o = eng.forward(vis_map, vid_map, None, None, raw=True, text_ids=ids, want=want, **kw)      # free-running: no decision is forced
@@ -89,7 +92,7 @@ def test_vstgnet_dropin_with_every_extractor_in_the_library(name):
         raise AssertionError("a PyTorch extractor module was called")
 
     model = M.B200VSTGNet(make_cfg(), boom, boom, TextEncoder(), boom, boom, full_state_dict(seed), verb_label2={"0": {"sub": ""}},
-                          max_frames=T, max_hw=49, max_text=ids.shape[1]).eval()
+                          max_frames=T, max_hw=(R // 32) ** 2, max_text=ids.shape[1]).eval()
     assert model.fused_backbones and model.fused_front_end and model.fused_text_tower
     videos = M.NestedTensor(torch.from_numpy(full_frames(seed, T, R, pad)).cuda(), torch.from_numpy(full_mask(T, R, pad)).cuda(), [T])
     out = model(videos, [sentence], [{"item_id": 0, "actioness": torch.ones(T, device="cuda")}])

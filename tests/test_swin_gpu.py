@@ -58,18 +58,20 @@ def test_swin_stage_feeds_the_raw_forward():
     eng.close()
 
 
-def test_video_swin_backbone_matches_reference_golden():
-    """The WHOLE Video-Swin-T extractor (patch embedding, four stages with shifted 3-D windows and their masks, PatchMerging) on the
+@pytest.mark.parametrize("name", ["swin_full_T16_224_s0", "swin_full_T12_256_s1"])
+def test_video_swin_backbone_matches_reference_golden(name):
+    """The second fixture exercises the padding path: 12 frames (→ 16) at 256 px (maps 64 / 32 / 16 / 8 → 70 / 35 / 21 / 14).
+    The WHOLE Video-Swin-T extractor (patch embedding, four stages with shifted 3-D windows and their masks, PatchMerging) on the
     library's kernels against the golden of the reference's own `VideoSwinTransformerBackbone` (tests/golden/make_golden_swin_full.py):
     every 97th token row of all four stage outputs, and the last stage's map in full.  Yardstick per stage: the deviation of torch's
     own bf16-autocast run of the reference module from its fp32 run (stored in the fixture)."""
     from make_golden_swin_full import swin_frames
     from vgqa_b200.engine import GroundingEngine
-    g = np.load(golden_path("swin_full_T16_224_s0"))
+    g = np.load(golden_path(name))
     clips, T, R, seed = (int(g[k]) for k in ("clips", "T", "R", "seed"))
     sd = O.synth_state_dict(0)
     sd.update(O.synth_swin_backbone(seed))
-    eng = GroundingEngine(sd, max_clips=clips, max_frames=T, max_hw=49, max_text=8)
+    eng = GroundingEngine(sd, max_clips=clips, max_frames=T, max_hw=64, max_text=8)
     frames = torch.from_numpy(swin_frames(seed, clips, T, R)).cuda()
     out, stages = eng.swin_backbone(frames, clips, want_stages=True)
     torch.cuda.synchronize()

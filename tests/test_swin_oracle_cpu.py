@@ -23,11 +23,12 @@ def test_relative_position_index_shape_and_range():
     assert (np.diag(idx) == idx[0, 0]).all()
 
 
-def test_video_swin_backbone_oracle_matches_reference_golden():
+@pytest.mark.parametrize("name", ["swin_full_T16_224_s0", "swin_full_T12_256_s1"])
+def test_video_swin_backbone_oracle_matches_reference_golden(name):
     """The whole extractor (patch embedding, 4 stages with shifted 3-D windows + masks, PatchMerging) against the golden of the
     reference's own VideoSwinTransformerBackbone (every 97th token row of all four stage outputs)."""
     from make_golden_swin_full import swin_frames
-    g = np.load(golden_path("swin_full_T16_224_s0"))
+    g = np.load(golden_path(name))
     clips, T, R, seed = (int(g[k]) for k in ("clips", "T", "R", "seed"))
     outs = O.video_swin_backbone(O.synth_swin_backbone(seed), swin_frames(seed, clips, T, R), clips)
     for s in range(4):

@@ -18,7 +18,8 @@
 //   * the multi-tile tcgen05 attention of attn_tc_long.cu with `heads` heads, the bias table [heads][392][392] (divided by the
 //     scale, L2-resident) and the shift mask from per-token region ids (a few hundred bytes per distinct window kind);
 //   * PatchMerging: 2x2 gather + LayerNorm(4C) in one kernel, then the reduction GEMM.
-// Supported maps: sides that are multiples of the window after every stage (224 / 448 px clips, T a multiple of 8).
+// Map sides that are not multiples of the window take the reference's padding path (zero tokens at the end of every axis, for the
+// attention half of a block only); supported: T >= 8 and frame sides that are multiples of 32 from 224 on (no clamped windows).
 #include <algorithm>
 #include <cmath>
 #include <string>
@@ -31,22 +32,26 @@
 namespace vg {
 
 // ------------------------------------------------------------------------------------------------ kernels
-struct WinGeom { int B, D, H, W, wd, wh, ww, sd, sh, sw; };
-__device__ __forceinline__ int win_src_row(const WinGeom& g, int r) {   // window-order row → row of the (unrolled) map; 32-bit: rows < 2^31
+// D, H, W: the map; Dp, Hp, Wp: its sides rounded up to multiples of the window (the reference zero-pads LN1(x) at the END of every
+// axis, :205-211); the windows and the cyclic roll live on the padded grid
+struct WinGeom { int B, D, H, W, Dp, Hp, Wp, wd, wh, ww, sd, sh, sw; };
+// window-order row (padded grid) → row of the map, or -1 for a padding token; 32-bit arithmetic: rows < 2^31
+__device__ __forceinline__ int win_src_row(const WinGeom& g, int r) {
   const unsigned N = g.wd * g.wh * g.ww;
   const unsigned grp = (unsigned)r / N, n = (unsigned)r - grp * N;
-  const unsigned nWh = g.H / g.wh, nWw = g.W / g.ww, nWd = g.D / g.wd;
+  const unsigned nWh = g.Hp / g.wh, nWw = g.Wp / g.ww, nWd = g.Dp / g.wd;
   const unsigned q1 = grp / nWw, wwi = grp - q1 * nWw, q2 = q1 / nWh, hwi = q1 - q2 * nWh, b = q2 / nWd, dwi = q2 - b * nWd;
   const unsigned t1 = n / g.ww, wl = n - t1 * g.ww, dd = t1 / g.wh, hh = t1 - dd * g.wh;
   unsigned d = dwi * g.wd + dd + g.sd, h = hwi * g.wh + hh + g.sh, w = wwi * g.ww + wl + g.sw;   // the shifts are smaller than the sides
-  if (d >= (unsigned)g.D) d -= g.D;
-  if (h >= (unsigned)g.H) h -= g.H;
-  if (w >= (unsigned)g.W) w -= g.W;
+  if (d >= (unsigned)g.Dp) d -= g.Dp;
+  if (h >= (unsigned)g.Hp) h -= g.Hp;
+  if (w >= (unsigned)g.Wp) w -= g.Wp;
+  if (d >= (unsigned)g.D || h >= (unsigned)g.H || w >= (unsigned)g.W) return -1;
   return (int)(((b * g.D + d) * g.H + h) * g.W + w);
 }
 // LayerNorm fused with the window plumbing (rows r in WINDOW order; m = the map row that r comes from / goes to):
-//   MODE 1  (LN1 + window_partition(roll(x, -shift))):   y16[r] = LN(x[m])
-//   MODE 2  (x += roll(window_reverse(y), +shift), then LN2):   x[m] += add[r];  y16[m] = LN(x[m])
+//   MODE 1  (LN1 + window_partition(roll(pad(x), -shift))):   y16[r] = LN(x[m]), zeros for a padding token
+//   MODE 2  (x += crop(roll(window_reverse(y), +shift)), then LN2):   x[m] += add[r];  y16[m] = LN(x[m]); padding tokens are skipped
 //   MODE 0 / 3  (no window map, m = r):   y16[r] = LN(x[r])  /  x[r] = LN(x[r]) in place, fp32 (the patch embedding's norm)
 // Saves the bf16 round trip of a separate gather (MODE 1) and LayerNorm's re-read of the fp32 row (MODE 2).  A warp walks rows with a
 // grid stride and keeps RW rows (NJ float4 per lane each) in flight: one 512-byte row per warp at a time leaves the loads latency-bound
@@ -68,7 +73,7 @@ __global__ void __launch_bounds__(256, 4) ln_window_kernel(float* x, int ld, int
 #pragma unroll
     for (int k = 0; k < RW; ++k) {
       m[k] = __shfl_sync(0xffffffffu, ml, k);
-      const float4* xr = reinterpret_cast<const float4*>(x + m[k] * ld);
+      const float4* xr = reinterpret_cast<const float4*>(x + (m[k] < 0 ? 0 : m[k]) * ld);
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int i = lane + 32 * j;
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(256, 4) ln_window_kernel(float* x, int ld, int
     if (MODE == 2) {
 #pragma unroll
       for (int k = 0; k < RW; ++k) {
-        if (r0 + k >= rows) continue;                                // the repeated row must not be added twice
+        if (r0 + k >= rows || m[k] < 0) continue;                    // the repeated row must not be added twice; padding tokens are dropped
         const float4* ar = reinterpret_cast<const float4*>(add + (r0 + k) * ld);
         float4* xr = reinterpret_cast<float4*>(x + m[k] * ld);
 #pragma unroll
@@ -95,6 +100,13 @@ __global__ void __launch_bounds__(256, 4) ln_window_kernel(float* x, int ld, int
 #pragma unroll
     for (int k = 0; k < RW; ++k) {
       if (r0 + k >= rows) continue;
+      if (m[k] < 0) {                                                // a padding token: a zero row in window order (MODE 1), nothing otherwise
+        if (MODE == 1) {
+          uint2* yz = reinterpret_cast<uint2*>(y16 + (r0 + k) * ldy);
+          for (int i = lane; i < ny4; i += 32) yz[i] = make_uint2(0u, 0u);
+        }
+        continue;
+      }
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < NJ; ++j)
@@ -312,23 +324,30 @@ void SwinNet::pack(const HasFn& has, const GetFn& get, const std::function<bf16*
 }
 
 // ------------------------------------------------------------------------------------------------ workspace
-void SwinNet::ensure_workspace(size_t rows, int Cp, int Nqkv, bool with_frames) {
-  const size_t units = rows * (size_t)Cp;
-  const size_t need = std::max(units, rows * (size_t)Nqkv / 3 + 1);
-  if (need <= cap_units && (!with_frames || a0 != nullptr)) return;
+// units: the largest (rows incl. window padding) x (padded channels) of any stage; qkv_units: the same for the packed q|k|v rows
+void SwinNet::ensure_workspace(size_t units, size_t qkv_units, size_t frame_rows) {
+  if (units <= cap_units && qkv_units <= cap_qkv && frame_rows <= cap_frames) return;
+  units = std::max(units, cap_units); qkv_units = std::max(qkv_units, cap_qkv); frame_rows = std::max(frame_rows, cap_frames);
   release();
-  const size_t u = need;
+  const size_t u = units;
   VG_CUDA(cudaMalloc(&x32, u * 4)); VG_CUDA(cudaMalloc(&y32, u * 4));
   VG_CUDA(cudaMalloc(&xn, u * 2)); VG_CUDA(cudaMalloc(&xw, u * 2)); VG_CUDA(cudaMalloc(&ao, u * 2)); VG_CUDA(cudaMalloc(&xm, u * 2));
-  VG_CUDA(cudaMalloc(&qkv, u * 3 * 2 + 4096)); VG_CUDA(cudaMalloc(&hid, u * 4 * 2));
-  if (with_frames) VG_CUDA(cudaMalloc(&a0, rows * 64 * 2));
-  cap_units = u;
+  VG_CUDA(cudaMalloc(&qkv, qkv_units * 2 + 4096)); VG_CUDA(cudaMalloc(&hid, u * 4 * 2));
+  if (frame_rows) VG_CUDA(cudaMalloc(&a0, frame_rows * 64 * 2));
+  cap_units = u; cap_qkv = qkv_units; cap_frames = frame_rows;
+}
+// workspace demand of stage s on a (clips, D, H, W) map
+void SwinNet::stage_units(int s, int clips, int D, int H, int W, size_t& units, size_t& qkv_units) const {
+  const size_t Dp = (D + wd - 1) / wd * wd, Hp = (H + wh - 1) / wh * wh, Wp = (W + ww - 1) / ww * ww;
+  const size_t rows_p = (size_t)clips * Dp * Hp * Wp;
+  units = std::max(units, rows_p * st[s].Cp);
+  qkv_units = std::max(qkv_units, rows_p * st[s].Nqkv);
 }
 
 void SwinNet::release() {
   for (void* q : {(void*)x32, (void*)y32, (void*)xn, (void*)xw, (void*)qkv, (void*)ao, (void*)hid, (void*)xm, (void*)a0})
     if (q) cudaFree(q);
-  x32 = y32 = nullptr; xn = xw = qkv = ao = hid = xm = a0 = nullptr; cap_units = 0;
+  x32 = y32 = nullptr; xn = xw = qkv = ao = hid = xm = a0 = nullptr; cap_units = cap_qkv = cap_frames = 0;
   for (auto& m : masks) { if (m.second.rid) cudaFree(m.second.rid); if (m.second.gset) cudaFree(m.second.gset); }
   masks.clear();
 }
@@ -339,28 +358,30 @@ void SwinNet::run_stage(int s, int clips, int D, int H, int W, cudaStream_t st_)
   VG_CHECK(S.loaded, "Video-Swin: the weights of stage " + std::to_string(s) + " ('vid.layers." + std::to_string(s) + ".*') were not given");
   const int C = S.C, Cp = S.Cp;
   const int w_d = std::min(wd, D), w_h = std::min(wh, H), w_w = std::min(ww, W);     // get_window_size (:53-66)
-  VG_CHECK(w_d == wd && w_h == wh && w_w == ww, "Video-Swin: maps smaller than the window (8,7,7) are not supported");
-  VG_CHECK(D % wd == 0 && H % wh == 0 && W % ww == 0, "Video-Swin: map sides must be multiples of the window (8 frames, 7x7 positions)");
+  VG_CHECK(w_d == wd && w_h == wh && w_w == ww, "Video-Swin: maps smaller than the window (8 frames, 7x7 positions) are not supported");
+  // sides that are not multiples of the window are zero-padded at their end for the attention half (:205-211,233-234)
+  const int Dp = (D + wd - 1) / wd * wd, Hp = (H + wh - 1) / wh * wh, Wp = (W + ww - 1) / ww * ww;
+  const bool padded = Dp != D || Hp != H || Wp != W;
   const int shd = D > wd ? wd / 2 : 0, shh = H > wh ? wh / 2 : 0, shw = W > ww ? ww / 2 : 0;
-  const int N = wd * wh * ww, nW = (D / wd) * (H / wh) * (W / ww), groups = clips * nW;
-  const long long rows = (long long)clips * D * H * W;
-  const bool contiguous = H == wh && W == ww;          // a window = a run of whole frames: the partition is the identity
+  const int N = wd * wh * ww, nW = (Dp / wd) * (Hp / wh) * (Wp / ww), groups = clips * nW;
+  const long long rows = (long long)clips * D * H * W, rows_p = (long long)clips * Dp * Hp * Wp;
+  const bool contiguous = H == wh && W == ww && !padded;          // a window = a run of whole frames: the partition is the identity
   const float scale = 1.0f / std::sqrt((float)(C / S.heads));
   // region ids of the shifted windows (compute_mask, :311-325), built once per map shape
   MaskTab* mt = nullptr;
   if (shd || shh || shw) {
-    auto key = std::make_tuple(D, H, W, clips);
+    auto key = std::make_tuple(Dp, Hp, Wp, clips);
     MaskTab& m = masks[key];
     if (m.rid == nullptr) {
       auto region = [](int x, int X, int w, int sft) { return sft == 0 ? 0 : (x < X - w ? 0 : (x < X - sft ? 1 : 2)); };
       std::vector<std::vector<uint8_t>> sets(1, std::vector<uint8_t>(N, 0));
       std::vector<uint8_t> gs(nW);
       for (int g = 0; g < nW; ++g) {
-        const int wwi = g % (W / ww), hwi = (g / (W / ww)) % (H / wh), dwi = g / ((W / ww) * (H / wh));
+        const int wwi = g % (Wp / ww), hwi = (g / (Wp / ww)) % (Hp / wh), dwi = g / ((Wp / ww) * (Hp / wh));
         std::vector<uint8_t> v(N);
         for (int n = 0; n < N; ++n) {
           const int dd = n / (wh * ww), hh = (n / ww) % wh, wl = n % ww;
-          v[n] = (uint8_t)(region(dwi * wd + dd, D, wd, shd) * 9 + region(hwi * wh + hh, H, wh, shh) * 3 + region(wwi * ww + wl, W, ww, shw));
+          v[n] = (uint8_t)(region(dwi * wd + dd, Dp, wd, shd) * 9 + region(hwi * wh + hh, Hp, wh, shh) * 3 + region(wwi * ww + wl, Wp, ww, shw));
         }
         const bool constant = std::all_of(v.begin(), v.end(), [&](uint8_t q) { return q == v[0]; });
         int id = 0;
@@ -383,26 +404,27 @@ void SwinNet::run_stage(int s, int clips, int D, int H, int W, cudaStream_t st_)
     }
     mt = &m;
   }
-  if (Cp != C) VG_CUDA(cudaMemsetAsync(ao, 0, (size_t)rows * Cp * 2, st_));   // pad columns of the attention output stay zero
+  if (Cp != C) VG_CUDA(cudaMemsetAsync(ao, 0, (size_t)rows_p * Cp * 2, st_));   // pad columns of the attention output stay zero
   for (size_t i = 0; i < S.blocks.size(); ++i) {
     Block& k = S.blocks[i];
     const bool shifted = (i % 2 == 1) && (shd || shh || shw);
-    const WinGeom g{clips, D, H, W, wd, wh, ww, shifted ? shd : 0, shifted ? shh : 0, shifted ? shw : 0};
+    const WinGeom g{clips, D, H, W, Dp, Hp, Wp, wd, wh, ww, shifted ? shd : 0, shifted ? shh : 0, shifted ? shw : 0};
     const bool gather = shifted || !contiguous;
+    const long long rows_a = gather ? rows_p : rows;   // rows of the attention half (window order, padding tokens included)
     const bf16* a = xn;
     if (gather) {   // LN1 + window partition + cyclic roll in one pass over the rows
-      ln_window<1>(x32, Cp, C, k.n1w, k.n1b, 1e-5f, nullptr, xw, g, rows, st_);
+      ln_window<1>(x32, Cp, C, k.n1w, k.n1b, 1e-5f, nullptr, xw, g, rows_a, st_);
       a = xw;
     } else {
       ln_window<0>(x32, Cp, C, k.n1w, k.n1b, 1e-5f, nullptr, xn, g, rows, st_);
     }
     { GemmEpi ep; ep.C = qkv; ep.ldc = S.Nqkv; ep.bias = k.bqkv; ep.bias_ld = S.Nqkv;
-      gemm_bf16_tn(a, Cp, k.Wqkv, Cp, (int)rows, S.Nqkv, Cp, ep, st_); }
+      gemm_bf16_tn(a, Cp, k.Wqkv, Cp, (int)rows_a, S.Nqkv, Cp, ep, st_); }
     window_attn_tc(qkv, S.Nqkv, ao, Cp, groups, N, S.heads, k.sbias, shifted ? mt->rid : nullptr, shifted ? mt->gset : nullptr, scale, st_);
     if (gather) {   // proj → fp32 in window order; window reverse + un-roll + residual add + LN2 in one pass over the rows
       GemmEpi ep; ep.C = y32; ep.ldc = Cp; ep.c_f32 = 1; ep.bias = k.bproj; ep.bias_ld = Cp;
-      gemm_bf16_tn(ao, Cp, k.Wproj, Cp, (int)rows, Cp, Cp, ep, st_);
-      ln_window<2>(x32, Cp, C, k.n2w, k.n2b, 1e-5f, y32, xn, g, rows, st_);
+      gemm_bf16_tn(ao, Cp, k.Wproj, Cp, (int)rows_a, Cp, Cp, ep, st_);
+      ln_window<2>(x32, Cp, C, k.n2w, k.n2b, 1e-5f, y32, xn, g, rows_a, st_);
     } else {
       GemmEpi ep; ep.C = y32; ep.ldc = Cp; ep.c_f32 = 1; ep.bias = k.bproj; ep.bias_ld = Cp; ep.res32 = x32; ep.ldres32 = Cp;
       gemm_bf16_tn(ao, Cp, k.Wproj, Cp, (int)rows, Cp, Cp, ep, st_);
@@ -426,7 +448,7 @@ int SwinNet::forward_stage4(const float* x, int clips, int D, int H, int W, bf16
   VG_CHECK(clips >= 1 && D >= 1, "vgqa_swin_stage: bad shape");
   const int launches0 = launches;
   const long long rows = (long long)clips * D * H * W;
-  ensure_workspace((size_t)rows, S.Cp, S.Nqkv, false);
+  { size_t u = 0, q = 0; stage_units(3, clips, D, H, W, u, q); ensure_workspace(u, q, 0); }
   VG_CUDA(cudaMemcpyAsync(x32, x, (size_t)rows * S.C * 4, cudaMemcpyDeviceToDevice, st_));
   run_stage(3, clips, D, H, W, st_);
   const long long n4 = rows * (S.C / 4);
@@ -439,11 +461,16 @@ int SwinNet::forward_stage4(const float* x, int clips, int D, int H, int W, bf16
 int SwinNet::forward_full(const float* frames, int clips, int T, int R, bf16* out_bf16, float* out_f32, float* const* stage_out,
                           cudaStream_t st_) {
   VG_CHECK(full, "vgqa_swin_backbone needs the whole 'vid.*' state dict (patch_embed, layers.0-3, downsamples.0-2)");
-  VG_CHECK(clips >= 1 && T >= 1 && R >= 32 && R % 32 == 0, "vgqa_swin_backbone: the frame side must be a multiple of 32");
+  VG_CHECK(clips >= 1 && T >= wd && R >= 32 * wh && R % 32 == 0,
+           "vgqa_swin_backbone: at least 8 frames per clip and a frame side that is a multiple of 32, at least 224");
   const int launches0 = launches;
   int H = R / 4;
   long long rows = (long long)clips * T * H * H;
-  ensure_workspace((size_t)rows, st[0].Cp, st[0].Nqkv, true);
+  {
+    size_t u = 0, q = 0;
+    for (int s = 0, h = H; s < kStages; ++s, h /= 2) stage_units(s, clips, T, h, h, u, q);
+    ensure_workspace(u, q, (size_t)rows);
+  }
   {  // PatchEmbed3D (:426-443): 4x4 patches → GEMM [rows, 64] x [128, 64]^T + bias → LayerNorm(96), in place
     const long long n16 = rows * 16;
     patch_im2col_kernel<<<grid_for(n16), 256, 0, st_>>>(frames, a0, R, n16);

@@ -42,14 +42,15 @@ struct SwinNet {
   // workspace (allocated on first use, grown on demand; not part of the forward's arena)
   float *x32 = nullptr, *y32 = nullptr;
   bf16 *xn = nullptr, *xw = nullptr, *qkv = nullptr, *ao = nullptr, *hid = nullptr, *xm = nullptr, *a0 = nullptr;
-  size_t cap_units = 0;   // capacity in units of (rows x padded channels) of the largest stage
+  size_t cap_units = 0, cap_qkv = 0, cap_frames = 0;   // capacities: (rows x padded channels) of the largest stage, packed q|k|v elements, patch rows
   int launches = 0;
 
   using GetFn = std::function<const float*(const std::string&, std::vector<int64_t>)>;
   using HasFn = std::function<bool(const std::string&)>;
   void pack(const HasFn& has, const GetFn& get, const std::function<bf16*(const float*, size_t)>& to_bf16,
             const std::function<float*(const float*, size_t)>& to_f32);
-  void ensure_workspace(size_t rows, int Cp, int Nqkv, bool with_frames);
+  void ensure_workspace(size_t units, size_t qkv_units, size_t frame_rows);
+  void stage_units(int s, int clips, int D, int H, int W, size_t& units, size_t& qkv_units) const;
   void release();
   // one stage on the channels-last fp32 stream x32 [clips, D, H, W, Cp] (in place)
   void run_stage(int s, int clips, int D, int H, int W, cudaStream_t st);

@@ -333,7 +333,8 @@ class GroundingEngine:
 
     def swin_backbone(self, frames, clips, want_stages=False):
         """Whole Video-Swin-T extractor (csrc/swin.cu): frames fp32 NCHW [clips*T, 3, R, R] (device) → the last stage's map as
-        channels-last bf16 [clips, T, R/32, R/32, 768]; with want_stages also the four stage outputs (channels-last fp32)."""
+        channels-last bf16 [clips, T, R/32, R/32, 768]; with want_stages also the four stage outputs (channels-last fp32).
+        T >= 8, R a multiple of 32 from 224 on (sides that are not multiples of the (8,7,7) window are padded as the reference does)."""
         assert frames.dtype == torch.float32 and frames.dim() == 4 and frames.shape[1] == 3 and frames.is_contiguous()
         n, _, R, _ = frames.shape
         T = n // clips

@@ -195,7 +195,8 @@ class B200VSTGNet(torch.nn.Module):
     @torch.no_grad()
     def forward(self, videos, texts, targets, iteration_rate: int = -1):
         frames = videos.tensors
-        nhwc = self.fused_backbones and frames.shape[0] % 8 == 0 and frames.shape[-1] == frames.shape[-2] and frames.shape[-1] in (224, 448)
+        R = frames.shape[-1]
+        nhwc = self.fused_backbones and frames.shape[0] >= 8 and frames.shape[-2] == R and R % 32 == 0 and 224 <= R <= 512
         if nhwc:
             # the library's extractors: layer4 map of ResNet101 and the last Video-Swin-T stage, both channels-last bf16; the mask is
             # interpolated as BackboneBase.forward does (backbone.py:92-96) and the positional encoding is generated from it

@@ -42,8 +42,7 @@ class GroundingPredictor:
         library generates PositionEmbeddingSine itself (predict() resizes to a square, so nothing is padded, grounding.py:177).
         With raw_inputs=True the channel counts are those of the extractors (see __init__); an item may then carry
         "text_ids" ([L] RoBERTa token ids) instead of "text" — the text tower runs inside the library too (all items or none) —
-        and "frames" ([2T,3,R,R] fp32: the sampled frames after the reference's resize + normalisation, R = 224 / 448, T a multiple
-        of 8) instead of "vis" / "vid": both extractors then run inside the library (all items or none).
+        and "frames" ([2T,3,R,R] fp32: the sampled frames after the reference's resize + normalisation, R a multiple of 32 in 224..512, T >= 8) instead of "vis" / "vid": both extractors then run inside the library (all items or none).
         Returns one {"temporal": {...}, "tube": [...]} dict per item (grounding.py:227-244)."""
         Q = len(items)
         if Q == 0:
