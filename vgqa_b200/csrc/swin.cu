@@ -280,7 +280,7 @@ void SwinNet::pack(const HasFn& has, const GetFn& get, const std::function<bf16*
   };
   for (int s = 0; s < kStages; ++s) {
     Stage& S = st[s];
-    S.C = embed << s; S.Cp = pad64(S.C); S.Nqkv = pad64(3 * S.C); S.heads = heads[s];
+    S.C = embed << s; S.Cp = pad64(S.C); S.Nqkv = (3 * S.C + 127) / 128 * 128; S.heads = heads[s];   // q|k|v width padded to 128-column GEMM tiles
     const std::string lp = "vid.layers." + std::to_string(s) + ".";
     if (!has(lp + "blocks.0.attn.qkv.weight")) continue;
     const int C = S.C, Cp = S.Cp;
