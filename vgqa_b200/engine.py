@@ -371,6 +371,7 @@ class GroundingEngine:
         not fill the GPU with either network (layer3 of 32 frames is 64 tiles for 148 SMs), so up to 64 frames the two run
         concurrently on two streams."""
         n = frames.shape[0]
+        assert clips >= 1 and n % clips == 0, "frames must hold clips * T pictures"
         if n > 64:
             vis = self.resnet_backbone(frames)
             vid = self.swin_backbone(frames, clips)
