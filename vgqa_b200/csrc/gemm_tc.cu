@@ -452,7 +452,7 @@ void gemm_bf16_tn(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, 
     gemm_ln(A, lda, W, ldw, M, K, e, stream);
     return;
   }
-  if (gemm_ws_supported(N, K, e)) {
+  if (M > BM && gemm_ws_supported(N, K, e)) {   // a single row tile: 64-column streaming tiles below put more SMs on the weights
     gemm_ws(A, nullptr, 0, lda, W, ldw, M, N, K, e, stream);
     return;
   }
@@ -465,6 +465,10 @@ void gemm_bf16_tn(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, 
   if (e.ln_w != nullptr) {
     VG_CHECK(N == 256, "gemm: the fused LayerNorm epilogue needs N == 256");
     launch_gemm<256>(A, lda, W, ldw, M, N, K, ep, stream);
+  } else if (M <= BM && N % 64 == 0) {
+    // a single row tile (the text tower's handful of tokens, batch-1 heads): the launch is bound by how fast ONE SM can stream its
+    // K x BN weight slice — 64-column tiles put four times as many SMs on the weights as 256-column ones
+    launch_gemm<64>(A, lda, W, ldw, M, N, K, ep, stream);
   } else if (N % 256 == 0) {
     launch_gemm<256>(A, lda, W, ldw, M, N, K, ep, stream);
   } else if (N % 128 == 0) {
