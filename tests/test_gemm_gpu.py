@@ -129,7 +129,10 @@ def test_gemm_gelu_mul_strided():
                                                 (80000 + 77, 256, True, True, False, 0),  # ragged last tile
                                                 (3000, 2048, True, True, False, 0),     # few rows, long K: the CTA-pair (column-split) form
                                                 (76000, 512, False, False, False, 1),   # no residual, ReLU, bf16 output only
-                                                (77000, 64, True, False, True, 0)])
+                                                (77000, 64, True, False, True, 0),
+                                                (64, 2048, True, True, True, 0),        # one row tile: the four-CTA cluster form (batch-1 decoders)
+                                                (100, 256, True, True, False, 1),       # the same with a short K and ReLU
+                                                (128, 512, False, False, True, 0)])
 def test_gemm_residual_layernorm_all_outputs(M, K, res, c32, c2, act):
     """vgqa_gemm_ln (the `norm(x + sublayer(x))` launches of the forward) vs torch fp32: bf16 / fp32 / bf16(x+pos) outputs."""
     import ctypes

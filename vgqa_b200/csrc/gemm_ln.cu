@@ -33,7 +33,8 @@ struct LnCfg {
   static constexpr int kStages = NSPLIT == 1 ? 3 : 4;
   static constexpr int kABytes = LBM * LBK * 2, kBBytes = LBN * LBK * 2, kStageBytes = kABytes + kBBytes;
   static constexpr int kStaging = 4 * 16384;
-  static constexpr int kXch = NSPLIT == 1 ? 0 : 2 * 128 * 8;   // [2 tile parities][128 rows] (mean, M2) written by the peer CTA
+  // [2 tile parities][128 rows] (mean, M2) written by the peer CTA (NSPLIT = 2); [2][NSPLIT source ranks][128] for wider clusters
+  static constexpr int kXch = NSPLIT == 1 ? 0 : (NSPLIT == 2 ? 2 * 128 * 8 : 2 * NSPLIT * 128 * 8);
   static constexpr int kSmem = kStages * kStageBytes + kStaging + kXch + 3 * LBN * 4 + 1024 + 256;
 };
 
@@ -69,8 +70,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + kLnStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* res_bar = tempty_bar + 2;  // [4 warps][2]
-  uint64_t* xbar = res_bar + 8;        // NSPLIT = 2: the peer's 128 epilogue threads have delivered their moments
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 1);
+  uint64_t* xbar = res_bar + 8;        // [2]: the peers' epilogue threads have delivered their moments (NSPLIT = 2 uses [0] only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (p.M + LBM - 1) / LBM;
@@ -84,7 +85,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     for (int s = 0; s < kLnStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     for (int i = 0; i < 8; ++i) mbar_init(&res_bar[i], 1);
-    mbar_init(xbar, 128);
+    mbar_init(&xbar[0], 128 * (NSPLIT > 1 ? NSPLIT - 1 : 1));
+    mbar_init(&xbar[1], 128 * (NSPLIT > 1 ? NSPLIT - 1 : 1));
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * LBN);
@@ -232,7 +234,31 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const float dm = s1 * (1.0f / LBN);
       float mean = shift + dm;
       float var = fmaxf(s2 * (1.0f / LBN) - dm * dm, 0.f);
-      if (NSPLIT > 1) {
+      if (NSPLIT > 2) {
+        // (mean, M2) of this CTA's columns → every peer's exchange slot [parity][my rank][row]; then the NSPLIT partial moments of
+        // equal weight are combined: mean = avg(mean_q), M2 = sum M2_q + LBN * sum (mean_q - mean)^2.  One barrier per tile parity.
+        const int par = tile_i & 1, rowi = quad * 32 + lane;
+        const float m2 = var * (float)LBN;
+#pragma unroll
+        for (int q = 0; q < NSPLIT; ++q) {
+          if (q == rank) continue;
+          const uint32_t pa = mapa_u32(smem_u32(xch), (uint32_t)q) + (uint32_t)((par * NSPLIT + rank) * 128 + rowi) * 8u;
+          asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(pa), "f"(mean), "f"(m2) : "memory");
+          mbar_arrive_cluster(mapa_u32(smem_u32(&xbar[par]), (uint32_t)q));
+        }
+        mbar_wait_cluster(&xbar[par], (uint32_t)(tile_i >> 1) & 1u);
+        float mq[NSPLIT], msum = 0.f, m2s = 0.f;
+#pragma unroll
+        for (int q = 0; q < NSPLIT; ++q) {
+          const float2 o = q == rank ? make_float2(mean, m2) : xch[(par * NSPLIT + q) * 128 + rowi];
+          mq[q] = o.x; msum += o.x; m2s += o.y;
+        }
+        mean = msum * (1.0f / NSPLIT);
+        float dev = 0.f;
+#pragma unroll
+        for (int q = 0; q < NSPLIT; ++q) dev = fmaf(mq[q] - mean, mq[q] - mean, dev);
+        var = (m2s + (float)LBN * dev) * (1.0f / 256.0f);
+      } else if (NSPLIT > 1) {
         // (mean, M2) of this CTA's 128 columns → the peer's exchange slot; combine with the peer's (parallel-variance formula)
         const int slot = (tile_i & 1) * 128 + quad * 32 + lane;
         const float m2 = var * (float)LBN;
@@ -357,7 +383,10 @@ void gemm_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, const
   // few row tiles and a long K (the decoders' 2048 -> 256 projections): split the columns over CTA pairs
   static int split_ok = -1;
   if (split_ok < 0) { const char* s = getenv("VGQA_LN_SPLIT"); split_ok = (s == nullptr || s[0] != '0') ? 1 : 0; }
-  if (split_ok && num_m * 2 <= device_sm_count() && K >= 512)
+  if (split_ok && num_m == 1 && K >= 256)
+    // a single row tile (batch-1 decoders): a cluster of four CTAs streams a quarter of the K x 256 weights each
+    launch_ln<4>(ta, W, ldw, K, tres, tc, tc32, tc2, p, num_m, stream);
+  else if (split_ok && num_m * 2 <= device_sm_count() && K >= 512)
     launch_ln<2>(ta, W, ldw, K, tres, tc, tc32, tc2, p, num_m, stream);
   else
     launch_ln<1>(ta, W, ldw, K, tres, tc, tc32, tc2, p, num_m, stream);
